@@ -1,0 +1,910 @@
+// api.cu — the C ABI of include/b200gs.h: viewer / model handles, device memory, stream,
+// uploads, downloads and the per-frame launch sequence.  Mirrors the resource model of the
+// reference's gs::MultiModelViewer (src/tab/scene.rs:1969-1980, 2102-2139): one viewer = one
+// CUDA stream on one device; calls on a viewer are externally serialised (scene.rs:1926-1930).
+//
+// There is no CPU fallback: every compute entry point needs a CUDA device.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "host_api.h"
+
+// ---------------------------------------------------------------------------- errors
+static thread_local std::string g_last_error;
+void gs_set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+extern "C" const char* b200gs_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* b200gs_version(void) { return "b200gs 0.1 (sm_100a)"; }
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) {                                                                       \
+            gs_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));        \
+            return e__ == cudaErrorMemoryAllocation ? B200GS_ERR_OOM : B200GS_ERR_CUDA;                 \
+        }                                                                                               \
+    } while (0)
+#define REQUIRE(cond, msg)                          \
+    do {                                            \
+        if (!(cond)) {                              \
+            gs_set_error("%s: %s", __func__, msg);  \
+            return B200GS_ERR_INVALID;              \
+        }                                           \
+    } while (0)
+
+// ---------------------------------------------------------------------------- handles
+enum {  // viewer control block (u32 words), zeroed at the start of every render
+    VC_BIN_TICKET = 0,     // 64 words, one per model in the frame
+    VC_ENTRY_TOTAL = 64,   // 65 words: running (tile, splat) entry count after each model
+    VC_OVERFLOW = 130,
+    VC_TSORT_TICKET = 132, // 2 words
+    VC_EVALS = 136,        // u64
+    VC_TSORT_HIST = 256,   // 2 x 256
+    VC_WORDS = 768
+};
+enum {  // model control block layout
+    MC_CTRL = 0,               // GS_CTRL_WORDS
+    MC_SORT_TICKET = 16,       // 4
+    MC_SORT_HIST = 32,         // 4 x 256
+    MC_WORDS = 32 + 1024
+};
+constexpr uint32_t kMaxModelsPerFrame = 64;
+
+struct b200gs_model {
+    b200gs_viewer* v = nullptr;
+    std::string key;
+    uint64_t cap = 0;
+    uint8_t* recs = nullptr;
+    uint32_t* mask = nullptr;
+    uint32_t* selection = nullptr;
+    b200gs_edit_pod* edits = nullptr;
+    float pos[3] = {0, 0, 0}, quat[4] = {0, 0, 0, 1}, scale[3] = {1, 1, 1};
+    uint32_t* ctrl = nullptr;
+    uint32_t *keys_a = nullptr, *vals_a = nullptr, *keys_b = nullptr, *vals_b = nullptr, *idx = nullptr;
+    uint64_t *lb_pre = nullptr, *lb_sort = nullptr;
+    uint64_t arena_offset = 0;
+    bool preprocessed = false, sorted = false;
+};
+
+struct b200gs_viewer {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = GS_NUM_SMS_FALLBACK;
+    uint32_t sh = 0, cov = 0, rb = 0;
+    uint32_t W = 1, H = 1;
+    float view[16], proj[16], size[2];
+    float gsize = 1.0f;
+    uint32_t display_mode = 0, sh_deg = 3, no_sh0 = 0;
+    b200gs_edit_pod sel_edit;
+    float hl[4] = {0, 0, 0, 0}, bg[4] = {0, 0, 0, 0};
+    b200gs_query_pod query;
+    std::vector<b200gs_model*> models;
+    b200gs_splat* arena = nullptr;
+    uint64_t arena_cap = 0;
+    bool layout_dirty = true;
+    uint32_t *tk_a = nullptr, *tv_a = nullptr, *tk_b = nullptr, *tv_b = nullptr;
+    uint64_t entry_cap = 0, entry_cap_user = 0;
+    uint64_t *lb_bin = nullptr, *lb_tsort = nullptr;
+    uint64_t lb_bin_words = 0;
+    uint32_t* ranges = nullptr;
+    uint32_t ranges_tiles = 0;
+    uint32_t* vctrl = nullptr;
+    uint8_t* image = nullptr;  // internal RGBA8 target for render_frame_host
+    size_t image_bytes = 0;
+    uint32_t epoch = 0;
+    bool timing = false, count_evals = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    b200gs_timings last = {};
+    uint32_t* h_small = nullptr;  // pinned scratch
+};
+
+static void identity16(float* m) {
+    memset(m, 0, 64);
+    m[0] = m[5] = m[10] = m[15] = 1.0f;
+}
+
+static void quat_to_mat3(const float q[4], float R[3][3]) {  // glam Mat3::from_quat
+    float x = q[0], y = q[1], z = q[2], w = q[3];
+    float x2 = x + x, y2 = y + y, z2 = z + z;
+    float xx = x * x2, xy = x * y2, xz = x * z2;
+    float yy = y * y2, yz = y * z2, zz = z * z2;
+    float wx = w * x2, wy = w * y2, wz = w * z2;
+    R[0][0] = 1.0f - (yy + zz); R[0][1] = xy - wz;          R[0][2] = xz + wy;
+    R[1][0] = xy + wz;          R[1][1] = 1.0f - (xx + zz); R[1][2] = yz - wx;
+    R[2][0] = xz - wy;          R[2][1] = yz + wx;          R[2][2] = 1.0f - (xx + yy);
+}
+
+static GsFrame make_frame(const b200gs_viewer* v) {
+    GsFrame f;
+    memset(&f, 0, sizeof f);
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 4; c++) f.V[r][c] = v->view[c * 4 + r];
+    for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) f.P[r][c] = v->proj[c * 4 + r];
+    for (int a = 0; a < 3; a++) f.cam[a] = -(f.V[0][a] * f.V[0][3] + f.V[1][a] * f.V[1][3] + f.V[2][a] * f.V[2][3]);
+    f.W = v->size[0];
+    f.H = v->size[1];
+    f.fx = f.P[0][0] * f.W * 0.5f;
+    f.fy = f.P[1][1] * f.H * 0.5f;
+    f.limx = GS_CLAMP_XY / f.P[0][0];
+    f.limy = GS_CLAMP_XY / f.P[1][1];
+    f.sz2 = v->gsize * v->gsize;
+    f.display_mode = v->display_mode;
+    f.sh_deg = v->sh_deg;
+    f.no_sh0 = v->no_sh0;
+    f.sel_edit = v->sel_edit;
+    memcpy(f.hl, v->hl, 16);
+    memcpy(f.bg, v->bg, 16);
+    f.tiles_x = (v->W + GS_TILE - 1) / GS_TILE;
+    f.tiles_y = (v->H + GS_TILE - 1) / GS_TILE;
+    return f;
+}
+
+static GsModelXf make_xf(const b200gs_model* m) {
+    GsModelXf x;
+    quat_to_mat3(m->quat, x.R);
+    for (int a = 0; a < 3; a++) { x.t[a] = m->pos[a]; x.s[a] = m->scale[a]; }
+    for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) x.M[a][b] = x.R[a][b] * x.s[b];
+    return x;
+}
+
+static int set_device(const b200gs_viewer* v) {
+    CK(cudaSetDevice(v->device));
+    return B200GS_OK;
+}
+
+template <typename T>
+static int dev_alloc(T** p, size_t count, bool zero, cudaStream_t st) {
+    *p = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    CK(cudaMalloc((void**)p, bytes));
+    if (zero) CK(cudaMemsetAsync(*p, 0, bytes, st));
+    return B200GS_OK;
+}
+#define TRY(x)                        \
+    do {                              \
+        int rc__ = (x);               \
+        if (rc__ != B200GS_OK) return rc__; \
+    } while (0)
+
+// (re)build the viewer-level buffers whose size depends on the set of models / the viewport
+static int ensure_frame_buffers(b200gs_viewer* v) {
+    const uint32_t n_tiles = ((v->W + GS_TILE - 1) / GS_TILE) * ((v->H + GS_TILE - 1) / GS_TILE);
+    if (v->ranges_tiles < n_tiles) {
+        CK(cudaStreamSynchronize(v->stream));
+        if (v->ranges) CK(cudaFree(v->ranges));
+        TRY(dev_alloc(&v->ranges, (size_t)n_tiles * 2, true, v->stream));
+        v->ranges_tiles = n_tiles;
+    }
+    const size_t img = (size_t)v->W * v->H * 4;
+    if (v->image_bytes < img) {
+        CK(cudaStreamSynchronize(v->stream));
+        if (v->image) CK(cudaFree(v->image));
+        TRY(dev_alloc(&v->image, img, true, v->stream));
+        v->image_bytes = img;
+    }
+    if (!v->layout_dirty) return B200GS_OK;
+    CK(cudaStreamSynchronize(v->stream));
+    uint64_t total = 0, maxcap = 0;
+    for (auto* m : v->models) {
+        m->arena_offset = total;
+        total += m->cap;
+        maxcap = std::max(maxcap, m->cap);
+        m->preprocessed = m->sorted = false;
+    }
+    if (total > v->arena_cap) {
+        if (v->arena) CK(cudaFree(v->arena));
+        TRY(dev_alloc(&v->arena, total, false, v->stream));
+        v->arena_cap = total;
+    }
+    uint64_t want = v->entry_cap_user ? v->entry_cap_user : std::max<uint64_t>(total * 8, 1u << 20);
+    want = std::min<uint64_t>(want, 0x3fffffffull);
+    if (want != v->entry_cap) {
+        for (uint32_t** p : {&v->tk_a, &v->tv_a, &v->tk_b, &v->tv_b}) {
+            if (*p) CK(cudaFree(*p));
+            TRY(dev_alloc(p, want, false, v->stream));
+        }
+        if (v->lb_tsort) CK(cudaFree(v->lb_tsort));
+        TRY(dev_alloc(&v->lb_tsort, gs_sort_lookback_words((uint32_t)want, 2), true, v->stream));
+        v->entry_cap = want;
+    }
+    uint64_t lbw = (maxcap + 1023) / 1024 + 1;
+    if (lbw > v->lb_bin_words) {
+        if (v->lb_bin) CK(cudaFree(v->lb_bin));
+        TRY(dev_alloc(&v->lb_bin, lbw * kMaxModelsPerFrame, true, v->stream));
+        v->lb_bin_words = lbw;
+    }
+    v->layout_dirty = false;
+    return B200GS_OK;
+}
+
+// ---------------------------------------------------------------------------- library
+extern "C" int b200gs_device_count(int* out) {
+    REQUIRE(out, "null out");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+    *out = n;
+    return B200GS_OK;
+}
+
+extern "C" uint32_t b200gs_record_bytes(uint32_t sh, uint32_t cov3d) { return gs_record_bytes(sh, cov3d); }
+
+// ---------------------------------------------------------------------------- viewer
+extern "C" int b200gs_viewer_create(int device, uint32_t sh, uint32_t cov3d, uint32_t width, uint32_t height,
+                                    b200gs_viewer** out) {
+    REQUIRE(out, "null out");
+    *out = nullptr;
+    REQUIRE(gs_record_bytes(sh, cov3d) != 0, "invalid layout");
+    REQUIRE(width >= 1 && height >= 1 && width <= 16384 && height <= 16384, "invalid size");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        (void)cudaGetLastError();
+        gs_set_error("no CUDA device: the B200 render core has no CPU fallback");
+        return B200GS_ERR_CUDA;
+    }
+    REQUIRE(device >= 0 && device < n, "device out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        gs_set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return B200GS_ERR_CUDA;
+    }
+    auto* v = new b200gs_viewer();
+    v->device = device;
+    v->num_sms = prop.multiProcessorCount;
+    v->sh = sh; v->cov = cov3d; v->rb = gs_record_bytes(sh, cov3d);
+    v->W = width; v->H = height;
+    identity16(v->view);
+    identity16(v->proj);
+    v->size[0] = (float)width; v->size[1] = (float)height;
+    v->sel_edit = b200gs_edit_pod{0, {0.0f, 1.0f, 1.0f}, 0.0f, 0.0f, 1.0f, 1.0f};
+    memset(&v->query, 0, sizeof v->query);
+    cudaError_t e = cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&v->vctrl, VC_WORDS * 4);
+    if (e == cudaSuccess) e = cudaMemsetAsync(v->vctrl, 0, VC_WORDS * 4, v->stream);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&v->h_small, 4096);
+    for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&v->ev[i]);
+    if (e != cudaSuccess) {
+        gs_set_error("viewer_create: %s", cudaGetErrorString(e));
+        b200gs_viewer_destroy(v);
+        return B200GS_ERR_CUDA;
+    }
+    *out = v;
+    return B200GS_OK;
+}
+
+static void free_model(b200gs_model* m) {
+    void* ps[] = {m->recs, m->mask, m->selection, m->edits, m->ctrl, m->keys_a, m->vals_a, m->keys_b, m->vals_b, m->idx,
+                  m->lb_pre, m->lb_sort};
+    for (void* p : ps)
+        if (p) cudaFree(p);
+    delete m;
+}
+
+extern "C" int b200gs_viewer_destroy(b200gs_viewer* v) {
+    if (!v) return B200GS_OK;
+    cudaSetDevice(v->device);
+    if (v->stream) cudaStreamSynchronize(v->stream);
+    for (auto* m : v->models) free_model(m);
+    void* ps[] = {v->arena, v->tk_a, v->tv_a, v->tk_b, v->tv_b, v->lb_bin, v->lb_tsort, v->ranges, v->vctrl, v->image};
+    for (void* p : ps)
+        if (p) cudaFree(p);
+    if (v->h_small) cudaFreeHost(v->h_small);
+    for (auto& e : v->ev)
+        if (e) cudaEventDestroy(e);
+    if (v->stream) cudaStreamDestroy(v->stream);
+    delete v;
+    return B200GS_OK;
+}
+
+extern "C" int b200gs_resize(b200gs_viewer* v, uint32_t width, uint32_t height) {
+    REQUIRE(v, "null viewer");
+    REQUIRE(width >= 1 && height >= 1 && width <= 16384 && height <= 16384, "invalid size");
+    v->W = width; v->H = height;
+    v->size[0] = (float)width; v->size[1] = (float)height;
+    return B200GS_OK;
+}
+
+extern "C" int b200gs_set_camera(b200gs_viewer* v, const float view[16], const float proj[16], const float size[2]) {
+    REQUIRE(v && view && proj, "null argument");
+    memcpy(v->view, view, 64);
+    memcpy(v->proj, proj, 64);
+    if (size) {
+        REQUIRE(size[0] >= 1.0f && size[1] >= 1.0f, "invalid size");
+        v->size[0] = size[0]; v->size[1] = size[1];
+        v->W = (uint32_t)size[0]; v->H = (uint32_t)size[1];
+    }
+    return B200GS_OK;
+}
+
+extern "C" int b200gs_set_gaussian_transform(b200gs_viewer* v, float size, uint32_t display_mode, uint32_t sh_deg,
+                                             uint32_t no_sh0) {
+    REQUIRE(v, "null viewer");
+    REQUIRE(display_mode <= 2, "display_mode out of range");
+    REQUIRE(sh_deg <= 3, "sh_deg out of range (gs::GaussianShDegree::new)");
+    v->gsize = size; v->display_mode = display_mode; v->sh_deg = sh_deg; v->no_sh0 = no_sh0 ? 1 : 0;
+    return B200GS_OK;
+}
+extern "C" int b200gs_set_selection_edit(b200gs_viewer* v, const b200gs_edit_pod* pod) {
+    REQUIRE(v && pod, "null argument");
+    v->sel_edit = *pod;
+    return B200GS_OK;
+}
+extern "C" int b200gs_set_selection_highlight(b200gs_viewer* v, const float rgba[4]) {
+    REQUIRE(v && rgba, "null argument");
+    memcpy(v->hl, rgba, 16);
+    return B200GS_OK;
+}
+extern "C" int b200gs_set_query(b200gs_viewer* v, const b200gs_query_pod* pod) {
+    REQUIRE(v && pod, "null argument");
+    REQUIRE(pod->kind <= B200GS_QUERY_BRUSH, "query kind out of range");
+    v->query = *pod;
+    return B200GS_OK;
+}
+extern "C" int b200gs_set_background(b200gs_viewer* v, const float rgba[4]) {
+    REQUIRE(v && rgba, "null argument");
+    memcpy(v->bg, rgba, 16);
+    return B200GS_OK;
+}
+extern "C" int b200gs_set_tile_entry_capacity(b200gs_viewer* v, uint64_t entries) {
+    REQUIRE(v, "null viewer");
+    REQUIRE(entries < 0x40000000ull, "capacity too large");
+    v->entry_cap_user = entries;
+    v->layout_dirty = true;
+    return B200GS_OK;
+}
+extern "C" int b200gs_enable_timings(b200gs_viewer* v, int on, int count_evals) {
+    REQUIRE(v, "null viewer");
+    v->timing = on != 0;
+    v->count_evals = count_evals != 0;
+    return B200GS_OK;
+}
+extern "C" int b200gs_sync(b200gs_viewer* v) {
+    REQUIRE(v, "null viewer");
+    TRY(set_device(v));
+    CK(cudaStreamSynchronize(v->stream));
+    return B200GS_OK;
+}
+extern "C" void* b200gs_stream(b200gs_viewer* v) { return v ? (void*)v->stream : nullptr; }
+extern "C" void* b200gs_image_device(b200gs_viewer* v) {
+    if (!v || set_device(v) != B200GS_OK || ensure_frame_buffers(v) != B200GS_OK) return nullptr;
+    return v->image;
+}
+extern "C" int b200gs_host_alloc(size_t bytes, void** out) {
+    REQUIRE(out, "null out");
+    CK(cudaMallocHost(out, bytes ? bytes : 1));
+    return B200GS_OK;
+}
+extern "C" int b200gs_host_free(void* p) {
+    if (p) CK(cudaFreeHost(p));
+    return B200GS_OK;
+}
+
+// ---------------------------------------------------------------------------- models
+extern "C" int b200gs_model_create(b200gs_viewer* v, const char* key, uint64_t capacity, b200gs_model** out) {
+    REQUIRE(v && key && out, "null argument");
+    *out = nullptr;
+    REQUIRE(capacity < 0x3fffff00ull, "capacity too large");
+    REQUIRE(v->models.size() < kMaxModelsPerFrame, "too many models");
+    for (auto* m : v->models) REQUIRE(m->key != key, "duplicate model key");
+    TRY(set_device(v));
+    auto* m = new b200gs_model();
+    m->v = v; m->key = key; m->cap = capacity;
+    cudaStream_t st = v->stream;
+    // records: padded so that the last chunk's 16-byte-rounded TMA copy stays inside the buffer
+    size_t rec_bytes = (size_t)capacity * v->rb + 64;
+    int rc = dev_alloc(&m->recs, rec_bytes, true, st);
+    if (rc == B200GS_OK) rc = dev_alloc(&m->ctrl, MC_WORDS, true, st);
+    if (rc == B200GS_OK) rc = dev_alloc(&m->keys_a, capacity, false, st);
+    if (rc == B200GS_OK) rc = dev_alloc(&m->vals_a, capacity, false, st);
+    if (rc == B200GS_OK) rc = dev_alloc(&m->keys_b, capacity, false, st);
+    if (rc == B200GS_OK) rc = dev_alloc(&m->vals_b, capacity, false, st);
+    if (rc == B200GS_OK) rc = dev_alloc(&m->idx, capacity, false, st);
+    if (rc == B200GS_OK) rc = dev_alloc(&m->lb_pre, (capacity + 255) / 256 + 1, true, st);
+    if (rc == B200GS_OK) rc = dev_alloc(&m->lb_sort, gs_sort_lookback_words((uint32_t)capacity, 4), true, st);
+    if (rc != B200GS_OK) { free_model(m); return rc; }
+    v->models.push_back(m);
+    v->layout_dirty = true;
+    *out = m;
+    return B200GS_OK;
+}
+
+extern "C" int b200gs_model_destroy(b200gs_viewer* v, b200gs_model* m) {
+    REQUIRE(v && m, "null argument");
+    auto it = std::find(v->models.begin(), v->models.end(), m);
+    REQUIRE(it != v->models.end(), "model does not belong to this viewer");
+    TRY(set_device(v));
+    CK(cudaStreamSynchronize(v->stream));
+    v->models.erase(it);
+    free_model(m);
+    v->layout_dirty = true;
+    return B200GS_OK;
+}
+
+extern "C" b200gs_model* b200gs_model_find(b200gs_viewer* v, const char* key) {
+    if (!v || !key) return nullptr;
+    for (auto* m : v->models)
+        if (m->key == key) return m;
+    return nullptr;
+}
+
+extern "C" uint64_t b200gs_model_len(const b200gs_model* m) { return m ? m->cap : 0; }
+
+extern "C" int b200gs_model_upload_packed(b200gs_model* m, uint64_t start, const void* packed, uint64_t count) {
+    REQUIRE(m && (packed || count == 0), "null argument");
+    REQUIRE(start <= m->cap && count <= m->cap - start, "range exceeds the model's capacity");
+    if (count == 0) return B200GS_OK;
+    TRY(set_device(m->v));
+    CK(cudaMemcpyAsync(m->recs + start * m->v->rb, packed, count * m->v->rb, cudaMemcpyHostToDevice, m->v->stream));
+    CK(cudaStreamSynchronize(m->v->stream));  // the host buffer is only borrowed for the call
+    return B200GS_OK;
+}
+
+extern "C" int b200gs_model_upload_packed_device(b200gs_model* m, uint64_t start, const void* packed_dev, uint64_t count) {
+    REQUIRE(m && (packed_dev || count == 0), "null argument");
+    REQUIRE(start <= m->cap && count <= m->cap - start, "range exceeds the model's capacity");
+    if (count == 0) return B200GS_OK;
+    TRY(set_device(m->v));
+    CK(cudaMemcpyAsync(m->recs + start * m->v->rb, packed_dev, count * m->v->rb, cudaMemcpyDeviceToDevice, m->v->stream));
+    return B200GS_OK;
+}
+
+extern "C" int b200gs_model_update_range(b200gs_model* m, uint64_t start, const b200gs_gaussian* gaussians, uint64_t count) {
+    REQUIRE(m && (gaussians || count == 0), "null argument");
+    REQUIRE(start <= m->cap && count <= m->cap - start, "range exceeds the model's capacity");
+    if (count == 0) return B200GS_OK;
+    TRY(set_device(m->v));
+    // pack on the host in pinned chunks and stream them up (scene.rs:2069-2085)
+    const uint64_t chunk = 1u << 16;
+    const uint32_t rb = m->v->rb;
+    uint8_t* stage[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    int rc = B200GS_OK;
+    for (int i = 0; i < 2; i++) {
+        if (cudaMallocHost((void**)&stage[i], (size_t)chunk * rb) != cudaSuccess || cudaEventCreate(&done[i]) != cudaSuccess) {
+            gs_set_error("update_range: pinned staging allocation failed");
+            rc = B200GS_ERR_OOM;
+        }
+    }
+    for (uint64_t o = 0, k = 0; rc == B200GS_OK && o < count; o += chunk, k++) {
+        uint64_t c = std::min(chunk, count - o);
+        int b = (int)(k & 1);
+        if (k >= 2) cudaEventSynchronize(done[b]);
+        b200gs_pack_gaussians(m->v->sh, m->v->cov, gaussians + o, c, stage[b]);
+        cudaError_t e = cudaMemcpyAsync(m->recs + (start + o) * rb, stage[b], c * rb, cudaMemcpyHostToDevice, m->v->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(done[b], m->v->stream);
+        if (e != cudaSuccess) { gs_set_error("update_range: %s", cudaGetErrorString(e)); rc = B200GS_ERR_CUDA; }
+    }
+    cudaStreamSynchronize(m->v->stream);
+    for (int i = 0; i < 2; i++) {
+        if (stage[i]) cudaFreeHost(stage[i]);
+        if (done[i]) cudaEventDestroy(done[i]);
+    }
+    return rc;
+}
+
+extern "C" int b200gs_model_set_transform(b200gs_model* m, const float pos[3], const float quat_xyzw[4], const float scale[3]) {
+    REQUIRE(m && pos && quat_xyzw && scale, "null argument");
+    memcpy(m->pos, pos, 12);
+    memcpy(m->quat, quat_xyzw, 16);
+    memcpy(m->scale, scale, 12);
+    return B200GS_OK;
+}
+
+static int upload_words(b200gs_model* m, uint32_t** dst, const uint32_t* words, uint64_t nwords) {
+    uint64_t need = (m->cap + 31) / 32;
+    REQUIRE(words && nwords == need, "bitset must hold ceil(N/32) words");
+    TRY(set_device(m->v));
+    if (!*dst) TRY(dev_alloc(dst, need, true, m->v->stream));
+    CK(cudaMemcpyAsync(*dst, words, need * 4, cudaMemcpyHostToDevice, m->v->stream));
+    CK(cudaStreamSynchronize(m->v->stream));
+    return B200GS_OK;
+}
+extern "C" int b200gs_model_upload_mask(b200gs_model* m, const uint32_t* words, uint64_t nwords) {
+    REQUIRE(m, "null model");
+    return upload_words(m, &m->mask, words, nwords);
+}
+extern "C" int b200gs_model_upload_selection(b200gs_model* m, const uint32_t* words, uint64_t nwords) {
+    REQUIRE(m, "null model");
+    return upload_words(m, &m->selection, words, nwords);
+}
+
+static int ensure_edits(b200gs_model* m) {
+    if (m->edits) return B200GS_OK;
+    TRY(dev_alloc(&m->edits, m->cap, false, m->v->stream));
+    CK(gs_launch_fill_default_edits((uint32_t)m->cap, m->edits, m->v->stream));
+    return B200GS_OK;
+}
+extern "C" int b200gs_model_upload_edits(b200gs_model* m, uint64_t start, const b200gs_edit_pod* pods, uint64_t count) {
+    REQUIRE(m && (pods || count == 0), "null argument");
+    REQUIRE(start <= m->cap && count <= m->cap - start, "range exceeds the model's capacity");
+    TRY(set_device(m->v));
+    TRY(ensure_edits(m));
+    if (count) CK(cudaMemcpyAsync(m->edits + start, pods, count * sizeof(b200gs_edit_pod), cudaMemcpyHostToDevice, m->v->stream));
+    CK(cudaStreamSynchronize(m->v->stream));
+    return B200GS_OK;
+}
+
+extern "C" int b200gs_model_eval_mask(b200gs_model* m, const b200gs_mask_op* postfix, uint32_t n_ops,
+                                      const b200gs_mask_shape* shapes, uint32_t n_shapes) {
+    REQUIRE(m, "null model");
+    REQUIRE(n_ops <= 64, "too many mask ops");
+    REQUIRE((postfix || n_ops == 0) && (shapes || n_shapes == 0), "null argument");
+    // validate the postfix program on the host (stack depth, shape indices)
+    int sp = n_ops == 0 ? 1 : 0;
+    for (uint32_t o = 0; o < n_ops; o++) {
+        switch (postfix[o].kind) {
+            case B200GS_MASKOP_SHAPE: REQUIRE(postfix[o].arg < n_shapes, "shape index out of range"); sp++; break;
+            case B200GS_MASKOP_RESET: sp++; break;
+            case B200GS_MASKOP_COMPLEMENT: REQUIRE(sp >= 1, "malformed op tree"); break;
+            case B200GS_MASKOP_UNION: case B200GS_MASKOP_INTERSECTION: case B200GS_MASKOP_DIFFERENCE:
+            case B200GS_MASKOP_SYMDIFF: REQUIRE(sp >= 2, "malformed op tree"); sp--; break;
+            default: REQUIRE(false, "unknown mask op");
+        }
+        REQUIRE(sp <= 60, "op tree too deep");
+    }
+    REQUIRE(sp == 1, "malformed op tree");
+    TRY(set_device(m->v));
+    cudaStream_t st = m->v->stream;
+    uint64_t need = (m->cap + 31) / 32;
+    if (!m->mask) TRY(dev_alloc(&m->mask, need, true, st));
+    b200gs_mask_op* d_ops = nullptr;
+    b200gs_mask_shape* d_shapes = nullptr;
+    float* d_rot = nullptr;
+    std::vector<float> rot(9 * std::max<uint32_t>(n_shapes, 1));
+    for (uint32_t s = 0; s < n_shapes; s++) {
+        float R[3][3];
+        quat_to_mat3(shapes[s].quat, R);
+        memcpy(&rot[9 * s], R, 36);
+    }
+    TRY(dev_alloc(&d_ops, n_ops, false, st));
+    TRY(dev_alloc(&d_shapes, n_shapes, false, st));
+    TRY(dev_alloc(&d_rot, 9 * (size_t)n_shapes, false, st));
+    if (n_ops) CK(cudaMemcpyAsync(d_ops, postfix, n_ops * sizeof(b200gs_mask_op), cudaMemcpyHostToDevice, st));
+    if (n_shapes) {
+        CK(cudaMemcpyAsync(d_shapes, shapes, n_shapes * sizeof(b200gs_mask_shape), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_rot, rot.data(), 36 * (size_t)n_shapes, cudaMemcpyHostToDevice, st));
+    }
+    GsModelXf xf = make_xf(m);
+    CK(gs_launch_eval_mask(m->recs, (uint32_t)m->cap, m->v->rb, xf, d_ops, n_ops, d_shapes, d_rot, m->mask, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d_ops); cudaFree(d_shapes); cudaFree(d_rot);
+    return B200GS_OK;
+}
+
+extern "C" int b200gs_model_postprocess(b200gs_model* m) {
+    REQUIRE(m, "null model");
+    if (!m->selection || !(m->v->sel_edit.flag & B200GS_EDIT_ENABLED)) return B200GS_OK;
+    TRY(set_device(m->v));
+    TRY(ensure_edits(m));
+    CK(gs_launch_postprocess((uint32_t)m->cap, m->selection, m->edits, m->v->sel_edit, m->v->stream));
+    return B200GS_OK;
+}
+
+// ---------------------------------------------------------------------------- hot path
+extern "C" int b200gs_model_preprocess(b200gs_model* m, int use_unedited) {
+    REQUIRE(m, "null model");
+    b200gs_viewer* v = m->v;
+    TRY(set_device(v));
+    TRY(ensure_frame_buffers(v));
+    CK(cudaMemsetAsync(m->ctrl, 0, MC_WORDS * 4, v->stream));
+    GsFrame f = make_frame(v);
+    if (use_unedited) f.sel_edit = b200gs_edit_pod{0, {0.0f, 1.0f, 1.0f}, 0.0f, 0.0f, 1.0f, 1.0f};
+    GsModelXf xf = make_xf(m);
+    GsPreprocessArgs a;
+    a.recs = m->recs; a.n = (uint32_t)m->cap; a.sh = v->sh; a.cov = v->cov;
+    a.mask = m->mask; a.selection = m->selection; a.edits = use_unedited ? nullptr : m->edits;
+    a.ctrl = m->ctrl + MC_CTRL; a.lookback = m->lb_pre; a.epoch = ++v->epoch;
+    a.keys = m->keys_a; a.idx = m->idx; a.splats = v->arena + m->arena_offset;
+    if (v->timing) CK(cudaEventRecord(v->ev[0], v->stream));
+    CK(gs_launch_preprocess(a, f, xf, v->num_sms, v->stream));
+    if (v->timing) CK(cudaEventRecord(v->ev[1], v->stream));
+    m->preprocessed = true;
+    m->sorted = false;
+    return B200GS_OK;
+}
+
+extern "C" int b200gs_model_sort(b200gs_model* m) {
+    REQUIRE(m, "null model");
+    REQUIRE(m->preprocessed, "sort called before preprocess");
+    b200gs_viewer* v = m->v;
+    TRY(set_device(v));
+    GsSortArgs a;
+    a.keys_a = m->keys_a; a.vals_a = m->vals_a; a.keys_b = m->keys_b; a.vals_b = m->vals_b;
+    a.d_n = m->ctrl + MC_CTRL + GS_CTRL_VISIBLE; a.n_max = (uint32_t)m->cap;
+    a.hist = m->ctrl + MC_SORT_HIST; a.lookback = m->lb_sort; a.epoch = ++v->epoch;
+    a.tickets = m->ctrl + MC_SORT_TICKET; a.passes = 4; a.hist_prefilled = false; a.vals_identity = true;
+    CK(gs_launch_sort(a, v->num_sms, v->stream));
+    if (v->timing) CK(cudaEventRecord(v->ev[2], v->stream));
+    m->sorted = true;
+    return B200GS_OK;
+}
+
+extern "C" int b200gs_render(b200gs_viewer* v, b200gs_model* const* far_to_near, uint32_t n_models, void* rgba8_out, size_t pitch) {
+    REQUIRE(v && rgba8_out && (far_to_near || n_models == 0), "null argument");
+    REQUIRE(n_models <= kMaxModelsPerFrame, "too many models");
+    REQUIRE(pitch >= (size_t)v->W * 4, "pitch too small");
+    for (uint32_t i = 0; i < n_models; i++) {
+        REQUIRE(far_to_near[i] && far_to_near[i]->v == v, "model does not belong to this viewer");
+        REQUIRE(far_to_near[i]->sorted, "render called before preprocess + sort");
+    }
+    TRY(set_device(v));
+    TRY(ensure_frame_buffers(v));
+    for (uint32_t i = 0; i < n_models; i++) REQUIRE(far_to_near[i]->sorted, "model layout changed; preprocess + sort again");
+    cudaStream_t st = v->stream;
+    GsFrame f = make_frame(v);
+    const uint32_t n_tiles = f.tiles_x * f.tiles_y;
+    CK(cudaMemsetAsync(v->vctrl, 0, VC_WORDS * 4, st));
+    // nearest model first: its splats come first in every tile's front-to-back list
+    for (uint32_t k = 0; k < n_models; k++) {
+        b200gs_model* m = far_to_near[n_models - 1 - k];
+        GsBinArgs b;
+        b.sorted_slot = m->vals_a;
+        b.splats = v->arena + m->arena_offset;
+        b.d_v = m->ctrl + MC_CTRL + GS_CTRL_VISIBLE;
+        b.v_max = (uint32_t)m->cap;
+        b.splat_base = (uint32_t)m->arena_offset;
+        b.lookback = v->lb_bin + (size_t)k * v->lb_bin_words;
+        b.epoch = ++v->epoch;
+        b.ticket = v->vctrl + VC_BIN_TICKET + k;
+        b.entry_base_in = v->vctrl + VC_ENTRY_TOTAL + k;
+        b.entry_total_out = v->vctrl + VC_ENTRY_TOTAL + k + 1;
+        b.overflow = v->vctrl + VC_OVERFLOW;
+        b.tile_keys = v->tk_a; b.tile_vals = v->tv_a; b.capacity = (uint32_t)v->entry_cap;
+        CK(gs_launch_bin(b, f, v->num_sms, st));
+    }
+    GsSortArgs s;
+    s.keys_a = v->tk_a; s.vals_a = v->tv_a; s.keys_b = v->tk_b; s.vals_b = v->tv_b;
+    s.d_n = v->vctrl + VC_ENTRY_TOTAL + n_models; s.n_max = (uint32_t)v->entry_cap;
+    s.hist = v->vctrl + VC_TSORT_HIST; s.lookback = v->lb_tsort; s.epoch = ++v->epoch;
+    s.tickets = v->vctrl + VC_TSORT_TICKET; s.passes = 2; s.hist_prefilled = false; s.vals_identity = false;
+    CK(gs_launch_sort(s, v->num_sms, st));
+    CK(gs_launch_tile_ranges(v->tk_a, s.d_n, (uint32_t)v->entry_cap, v->ranges, n_tiles, v->num_sms, st));
+    if (v->timing) CK(cudaEventRecord(v->ev[3], st));
+    GsCompositeArgs c;
+    c.tile_vals = v->tv_a; c.ranges = v->ranges; c.splats = v->arena;
+    c.out = (uint8_t*)rgba8_out; c.pitch = pitch;
+    c.evals = v->count_evals ? (unsigned long long*)(v->vctrl + VC_EVALS) : nullptr;
+    CK(gs_launch_composite(c, f, st));
+    if (v->timing) CK(cudaEventRecord(v->ev[4], st));
+    return B200GS_OK;
+}
+
+extern "C" int b200gs_render_frame(b200gs_viewer* v, b200gs_model* const* far_to_near, uint32_t n_models, void* rgba8_out, size_t pitch) {
+    REQUIRE(v && (far_to_near || n_models == 0), "null argument");
+    for (uint32_t i = 0; i < n_models; i++) {
+        REQUIRE(far_to_near[i], "null model");
+        TRY(b200gs_model_preprocess(far_to_near[i], 0));
+        TRY(b200gs_model_sort(far_to_near[i]));
+    }
+    return b200gs_render(v, far_to_near, n_models, rgba8_out, pitch);
+}
+
+extern "C" int b200gs_render_frame_host(b200gs_viewer* v, b200gs_model* const* far_to_near, uint32_t n_models,
+                                        const float view[16], const float proj[16], void* rgba8_host) {
+    REQUIRE(v && rgba8_host, "null argument");
+    if (view && proj) TRY(b200gs_set_camera(v, view, proj, nullptr));
+    TRY(set_device(v));
+    TRY(ensure_frame_buffers(v));
+    TRY(b200gs_render_frame(v, far_to_near, n_models, v->image, (size_t)v->W * 4));
+    CK(cudaMemcpyAsync(rgba8_host, v->image, (size_t)v->W * v->H * 4, cudaMemcpyDeviceToHost, v->stream));
+    CK(cudaStreamSynchronize(v->stream));
+    return B200GS_OK;
+}
+
+extern "C" int b200gs_order_models(b200gs_viewer* v, b200gs_model* const* models, const float* centers, uint32_t n, uint32_t* order_out) {
+    REQUIRE(v && (models || n == 0) && (centers || n == 0) && (order_out || n == 0), "null argument");
+    GsFrame f = make_frame(v);
+    std::vector<float> d(n);
+    for (uint32_t i = 0; i < n; i++) {
+        REQUIRE(models[i], "null model");
+        GsModelXf x = make_xf(models[i]);
+        float cs[3] = {centers[3 * i] * x.s[0], centers[3 * i + 1] * x.s[1], centers[3 * i + 2] * x.s[2]};
+        float acc = 0.0f;
+        for (int r = 0; r < 3; r++) {
+            float w = x.R[r][0] * cs[0] + x.R[r][1] * cs[1] + x.R[r][2] * cs[2] + x.t[r];
+            float dd = w - f.cam[r];
+            acc = acc + dd * dd;
+        }
+        d[i] = acc;
+        order_out[i] = i;
+    }
+    std::stable_sort(order_out, order_out + n, [&](uint32_t a, uint32_t b) { return d[a] > d[b]; });
+    return B200GS_OK;
+}
+
+// ---------------------------------------------------------------------------- downloads
+static int visible_count(b200gs_model* m, uint64_t* out) {
+    b200gs_viewer* v = m->v;
+    TRY(set_device(v));
+    if (!m->preprocessed) { *out = 0; return B200GS_OK; }
+    CK(cudaMemcpyAsync(v->h_small, m->ctrl + MC_CTRL + GS_CTRL_VISIBLE, 4, cudaMemcpyDeviceToHost, v->stream));
+    CK(cudaStreamSynchronize(v->stream));
+    *out = v->h_small[0];
+    return B200GS_OK;
+}
+extern "C" int b200gs_model_visible_count(b200gs_model* m, uint64_t* out) {
+    REQUIRE(m && out, "null argument");
+    return visible_count(m, out);
+}
+static int download_u32(b200gs_model* m, const uint32_t* src, uint32_t* dst, uint64_t n) {
+    if (n) CK(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToHost, m->v->stream));
+    CK(cudaStreamSynchronize(m->v->stream));
+    return B200GS_OK;
+}
+extern "C" int b200gs_model_download_depth_keys(b200gs_model* m, uint32_t* keys, uint64_t cap, uint64_t* n) {
+    REQUIRE(m && n && (keys || cap == 0), "null argument");
+    uint64_t vc;
+    TRY(visible_count(m, &vc));
+    *n = vc;
+    REQUIRE(cap >= vc, "buffer too small");
+    return download_u32(m, m->keys_a, keys, vc);
+}
+extern "C" int b200gs_model_download_indices(b200gs_model* m, uint32_t* idx, uint64_t cap, uint64_t* n) {
+    REQUIRE(m && n && (idx || cap == 0), "null argument");
+    uint64_t vc;
+    TRY(visible_count(m, &vc));
+    *n = vc;
+    REQUIRE(cap >= vc, "buffer too small");
+    if (!m->sorted) return download_u32(m, m->idx, idx, vc);
+    std::vector<uint32_t> slots(vc), orig(vc);
+    TRY(download_u32(m, m->vals_a, slots.data(), vc));
+    TRY(download_u32(m, m->idx, orig.data(), vc));
+    for (uint64_t i = 0; i < vc; i++) idx[i] = slots[i] < vc ? orig[slots[i]] : 0xffffffffu;
+    return B200GS_OK;
+}
+extern "C" int b200gs_model_download_splats(b200gs_model* m, b200gs_splat* out, uint64_t cap, uint64_t* n) {
+    REQUIRE(m && n && (out || cap == 0), "null argument");
+    uint64_t vc;
+    TRY(visible_count(m, &vc));
+    *n = vc;
+    REQUIRE(cap >= vc, "buffer too small");
+    b200gs_viewer* v = m->v;
+    if (!m->sorted) {
+        if (vc) CK(cudaMemcpyAsync(out, v->arena + m->arena_offset, vc * sizeof(b200gs_splat), cudaMemcpyDeviceToHost, v->stream));
+        CK(cudaStreamSynchronize(v->stream));
+        return B200GS_OK;
+    }
+    std::vector<uint32_t> slots(vc);
+    std::vector<b200gs_splat> tmp(vc);
+    TRY(download_u32(m, m->vals_a, slots.data(), vc));
+    if (vc) CK(cudaMemcpyAsync(tmp.data(), v->arena + m->arena_offset, vc * sizeof(b200gs_splat), cudaMemcpyDeviceToHost, v->stream));
+    CK(cudaStreamSynchronize(v->stream));
+    for (uint64_t i = 0; i < vc; i++) {
+        if (slots[i] < vc) out[i] = tmp[slots[i]];
+        else memset(&out[i], 0xff, sizeof(b200gs_splat));
+    }
+    return B200GS_OK;
+}
+static int download_words(b200gs_model* m, const uint32_t* src, uint32_t fill, uint32_t* words, uint64_t cap_words, uint64_t* n) {
+    uint64_t need = (m->cap + 31) / 32;
+    *n = need;
+    REQUIRE(cap_words >= need, "buffer too small");
+    TRY(set_device(m->v));
+    if (!src) {
+        for (uint64_t i = 0; i < need; i++) words[i] = fill;
+        if (fill && (m->cap & 31) && need) words[need - 1] = (1u << (m->cap & 31)) - 1u;
+        return B200GS_OK;
+    }
+    return download_u32(m, src, words, need);
+}
+extern "C" int b200gs_model_download_mask(b200gs_model* m, uint32_t* words, uint64_t cap_words, uint64_t* n) {
+    REQUIRE(m && n && (words || cap_words == 0), "null argument");
+    return download_words(m, m->mask, 0xffffffffu, words, cap_words, n);  // MaskOpTree::Reset = all shown
+}
+extern "C" int b200gs_model_download_selection(b200gs_model* m, uint32_t* words, uint64_t cap_words, uint64_t* n) {
+    REQUIRE(m && n && (words || cap_words == 0), "null argument");
+    return download_words(m, m->selection, 0u, words, cap_words, n);
+}
+extern "C" int b200gs_model_download_edits(b200gs_model* m, b200gs_edit_pod* pods, uint64_t cap, uint64_t* n) {
+    REQUIRE(m && n && (pods || cap == 0), "null argument");
+    *n = m->cap;
+    REQUIRE(cap >= m->cap, "buffer too small");
+    TRY(set_device(m->v));
+    TRY(ensure_edits(m));
+    if (m->cap) CK(cudaMemcpyAsync(pods, m->edits, m->cap * sizeof(b200gs_edit_pod), cudaMemcpyDeviceToHost, m->v->stream));
+    CK(cudaStreamSynchronize(m->v->stream));
+    return B200GS_OK;
+}
+extern "C" int b200gs_model_download_packed(b200gs_model* m, uint64_t start, void* packed, uint64_t count) {
+    REQUIRE(m && (packed || count == 0), "null argument");
+    REQUIRE(start <= m->cap && count <= m->cap - start, "range exceeds the model's capacity");
+    TRY(set_device(m->v));
+    if (count) CK(cudaMemcpyAsync(packed, m->recs + start * m->v->rb, count * m->v->rb, cudaMemcpyDeviceToHost, m->v->stream));
+    CK(cudaStreamSynchronize(m->v->stream));
+    return B200GS_OK;
+}
+
+extern "C" int b200gs_last_timings(b200gs_viewer* v, b200gs_timings* out) {
+    REQUIRE(v && out, "null argument");
+    TRY(set_device(v));
+    CK(cudaStreamSynchronize(v->stream));
+    memset(out, 0, sizeof *out);
+    if (v->timing) {
+        float t;
+        if (cudaEventElapsedTime(&t, v->ev[0], v->ev[1]) == cudaSuccess) out->preprocess_ms = t;
+        if (cudaEventElapsedTime(&t, v->ev[1], v->ev[2]) == cudaSuccess) out->sort_ms = t;
+        if (cudaEventElapsedTime(&t, v->ev[2], v->ev[3]) == cudaSuccess) out->bin_ms = t;
+        if (cudaEventElapsedTime(&t, v->ev[3], v->ev[4]) == cudaSuccess) out->composite_ms = t;
+        if (cudaEventElapsedTime(&t, v->ev[0], v->ev[4]) == cudaSuccess) out->total_ms = t;
+        (void)cudaGetLastError();
+    }
+    uint64_t vis = 0;
+    for (auto* m : v->models) {
+        uint64_t c = 0;
+        if (m->preprocessed) TRY(visible_count(m, &c));
+        vis += c;
+    }
+    out->visible = vis;
+    CK(cudaMemcpyAsync(v->h_small, v->vctrl, VC_WORDS * 4, cudaMemcpyDeviceToHost, v->stream));
+    CK(cudaStreamSynchronize(v->stream));
+    uint32_t last = 0;
+    for (uint32_t k = 0; k <= kMaxModelsPerFrame; k++) last = std::max(last, v->h_small[VC_ENTRY_TOTAL + k]);
+    out->tile_entries = last;
+    uint64_t ev;
+    memcpy(&ev, &v->h_small[VC_EVALS], 8);
+    out->evals = ev;
+    out->overflow = v->h_small[VC_OVERFLOW];
+    return B200GS_OK;
+}
+
+// ---------------------------------------------------------------------------- raw sort
+extern "C" int b200gs_sort_pairs_device(b200gs_viewer* v, uint32_t* keys_dev, uint32_t* values_dev, uint64_t n, uint32_t bits) {
+    REQUIRE(v && (keys_dev || n == 0) && (values_dev || n == 0), "null argument");
+    REQUIRE(bits == 16 || bits == 32, "bits must be 16 or 32");
+    REQUIRE(n < 0x3fffff00ull, "too many elements");
+    if (n == 0) return B200GS_OK;
+    TRY(set_device(v));
+    cudaStream_t st = v->stream;
+    const uint32_t passes = bits / 8;
+    uint32_t *kb = nullptr, *vb = nullptr, *ctl = nullptr;
+    uint64_t* lb = nullptr;
+    TRY(dev_alloc(&kb, n, false, st));
+    TRY(dev_alloc(&vb, n, false, st));
+    TRY(dev_alloc(&ctl, 2048, true, st));
+    TRY(dev_alloc(&lb, gs_sort_lookback_words((uint32_t)n, passes), true, st));
+    uint32_t nn = (uint32_t)n;
+    CK(cudaMemcpyAsync(ctl, &nn, 4, cudaMemcpyHostToDevice, st));
+    GsSortArgs a;
+    a.keys_a = keys_dev; a.vals_a = values_dev; a.keys_b = kb; a.vals_b = vb;
+    a.d_n = ctl; a.n_max = nn; a.hist = ctl + 1024; a.lookback = lb; a.epoch = ++v->epoch;
+    a.tickets = ctl + 8; a.passes = passes; a.hist_prefilled = false; a.vals_identity = false;
+    CK(gs_launch_sort(a, v->num_sms, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(kb); cudaFree(vb); cudaFree(ctl); cudaFree(lb);
+    return B200GS_OK;
+}
+
+extern "C" int b200gs_sort_pairs_host(b200gs_viewer* v, uint32_t* keys, uint32_t* values, uint64_t n, uint32_t bits) {
+    REQUIRE(v && (keys || n == 0) && (values || n == 0), "null argument");
+    if (n == 0) return B200GS_OK;
+    TRY(set_device(v));
+    uint32_t *dk = nullptr, *dv = nullptr;
+    TRY(dev_alloc(&dk, n, false, v->stream));
+    TRY(dev_alloc(&dv, n, false, v->stream));
+    CK(cudaMemcpyAsync(dk, keys, n * 4, cudaMemcpyHostToDevice, v->stream));
+    CK(cudaMemcpyAsync(dv, values, n * 4, cudaMemcpyHostToDevice, v->stream));
+    int rc = b200gs_sort_pairs_device(v, dk, dv, n, bits);
+    if (rc == B200GS_OK) {
+        CK(cudaMemcpyAsync(keys, dk, n * 4, cudaMemcpyDeviceToHost, v->stream));
+        CK(cudaMemcpyAsync(values, dv, n * 4, cudaMemcpyDeviceToHost, v->stream));
+        CK(cudaStreamSynchronize(v->stream));
+    }
+    cudaFree(dk); cudaFree(dv);
+    return rc;
+}

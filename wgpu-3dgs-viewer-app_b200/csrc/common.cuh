@@ -1,0 +1,207 @@
+// common.cuh — shared declarations of the B200 (sm_100a) 3DGS render core.
+//
+// Product code.  Nothing here includes or links anything under oracle/.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200gs.h"
+
+// ---- constants of the path ([CANON] = Inria diff-gaussian-rasterization) ----
+#define GS_CULL_XY 1.3f                 // NDC x/y frustum margin
+#define GS_CLAMP_XY 1.3f                // Jacobian clamp, x/z and y/z to 1.3 tan(fov/2)
+#define GS_LOWPASS 0.3f                 // low-pass added to the cov2d diagonal
+#define GS_EXTENT_SIGMA 3.0f            // extent = ceil(3 sqrt(lambda_max))
+#define GS_MIN_DISC 0.1f
+#define GS_ALPHA_MAX 0.99f
+#define GS_ALPHA_MIN (1.0f / 255.0f)
+#define GS_T_EPS (1.0f / 1024.0f)       // front-to-back termination threshold
+#define GS_FLAT_D2 4.0f                 // Ellipse / Point display modes
+#define GS_POINT_RADIUS 1.5f
+
+#define GS_TILE 16                      // compositor tile edge in pixels
+#define GS_NUM_SMS_FALLBACK 148
+
+// Per-frame uniforms (CameraPod + GaussianTransformPod + selection pods of the reference,
+// scene.rs:785-835) pre-digested on the host so the kernels do no setup arithmetic.
+struct GsFrame {
+    float V[3][4];  // rows 0..2 of the view matrix
+    float P[4][4];  // projection, row-major
+    float cam[3];   // camera position in world space
+    float W, H;     // viewport in pixels
+    float fx, fy;   // P00*W/2, P11*H/2
+    float limx, limy;
+    float sz2;      // gaussian size²
+    uint32_t display_mode, sh_deg, no_sh0;
+    b200gs_edit_pod sel_edit;
+    float hl[4];
+    float bg[4];
+    uint32_t tiles_x, tiles_y;
+};
+
+// Per-model uniforms (ModelTransformPod, scene.rs:796-802)
+struct GsModelXf {
+    float R[3][3];
+    float t[3];
+    float s[3];
+    float M[3][3];  // R * diag(s)
+};
+
+// Control block of one model in device memory (u32 words)
+enum {
+    GS_CTRL_TICKET = 0,    // preprocess chunk ticket
+    GS_CTRL_VISIBLE = 1,   // V, written by the preprocess kernel
+    GS_CTRL_SORT_TICKET = 2, // +pass (4 words)
+    GS_CTRL_WORDS = 16
+};
+
+#define GS_LOOKBACK_FLAG_AGG (1u << 30)
+#define GS_LOOKBACK_FLAG_INCL (2u << 30)
+#define GS_LOOKBACK_VALUE_MASK ((1u << 30) - 1u)
+
+// ------------------------------------------------------------- launch API (csrc/*.cu)
+struct GsPreprocessArgs {
+    const uint8_t* recs; uint32_t n; uint32_t sh, cov;
+    const uint32_t* mask; const uint32_t* selection; const b200gs_edit_pod* edits;
+    uint32_t* ctrl;      // GS_CTRL_WORDS, zeroed before launch
+    uint64_t* lookback;  // one status word per 256-Gaussian chunk (epoch-tagged, never cleared)
+    uint32_t epoch;
+    uint32_t* keys; uint32_t* idx; b200gs_splat* splats;
+};
+cudaError_t gs_launch_preprocess(const GsPreprocessArgs& a, const GsFrame& f, const GsModelXf& m, int num_sms,
+                                 cudaStream_t st);
+
+// Onesweep LSD radix sort of (key,value) u32 pairs; n is read from the device (*d_n).
+struct GsSortArgs {
+    uint32_t* keys_a; uint32_t* vals_a;   // input, and final output
+    uint32_t* keys_b; uint32_t* vals_b;   // scratch (ping-pong)
+    const uint32_t* d_n; uint32_t n_max;  // element count on device, and its upper bound
+    uint32_t* hist;      // 4 x 256 global digit histogram (zeroed before launch unless prefilled)
+    uint64_t* lookback;  // passes x tiles x 256 status words (epoch-tagged, never cleared)
+    uint32_t epoch;
+    uint32_t* tickets;   // passes words, zeroed before launch
+    uint32_t passes;     // 1..4 (bits = 8*passes, starting at bit 0); must be even so the result lands in *_a
+    bool hist_prefilled; // histogram already accumulated by the producer
+    bool vals_identity;  // pass 0 synthesises value = input position instead of reading vals_a
+};
+size_t gs_sort_lookback_words(uint32_t n_max, uint32_t passes);
+cudaError_t gs_launch_sort(const GsSortArgs& a, int num_sms, cudaStream_t st);
+
+// Binning: expand depth-sorted splats into (tile, splat) entries in depth order.
+struct GsBinArgs {
+    const uint32_t* sorted_slot;   // per depth rank: slot of the splat in `splats` (compaction order), or null = identity
+    const b200gs_splat* splats;    // this model's splats (compaction order)
+    const uint32_t* d_v;           // visible count of this model on device
+    uint32_t v_max;
+    uint32_t splat_base;           // global id of this model's splat 0 in the frame arena
+    uint64_t* lookback;            // per-chunk status words (epoch-tagged, never cleared)
+    uint32_t epoch;
+    uint32_t* ticket;              // zeroed before launch
+    const uint32_t* entry_base_in; // entries already emitted by nearer models
+    uint32_t* entry_total_out;     // entry_base_in + this model's entries (a different word)
+    uint32_t* overflow;            // set to 1 when the capacity is exceeded
+    uint32_t* tile_keys; uint32_t* tile_vals; uint32_t capacity;
+};
+cudaError_t gs_launch_bin(const GsBinArgs& a, const GsFrame& f, int num_sms, cudaStream_t st);
+cudaError_t gs_launch_tile_ranges(const uint32_t* tile_keys, const uint32_t* d_entries, uint32_t capacity,
+                                  uint32_t* ranges /* 2 x tiles */, uint32_t n_tiles, int num_sms, cudaStream_t st);
+
+struct GsCompositeArgs {
+    const uint32_t* tile_vals;      // entries sorted by tile, depth order inside a tile
+    const uint32_t* ranges;         // [tile] = start, [n_tiles + tile] = end
+    const b200gs_splat* splats;     // frame arena
+    uint8_t* out; size_t pitch;     // RGBA8
+    unsigned long long* evals;      // optional work counter (may be null)
+};
+cudaError_t gs_launch_composite(const GsCompositeArgs& a, const GsFrame& f, cudaStream_t st);
+
+// Mask evaluation / postprocess (row N2)
+cudaError_t gs_launch_eval_mask(const uint8_t* recs, uint32_t n, uint32_t record_bytes, const GsModelXf& m,
+                                const b200gs_mask_op* ops_dev, uint32_t n_ops, const b200gs_mask_shape* shapes_dev,
+                                const float* shape_rot_dev, uint32_t* words, cudaStream_t st);
+cudaError_t gs_launch_postprocess(uint32_t n, const uint32_t* selection, b200gs_edit_pod* edits,
+                                  b200gs_edit_pod sel_edit, cudaStream_t st);
+cudaError_t gs_launch_fill_default_edits(uint32_t n, b200gs_edit_pod* edits, cudaStream_t st);
+
+// ------------------------------------------------------------------ device helpers
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t gs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void gs_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void gs_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void gs_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gs_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gs_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(gs_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D TMA bulk copy global -> shared (SASS: UBLKCP), completion on an mbarrier
+__device__ __forceinline__ void gs_tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     gs_smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(gs_smem_u32(bar))
+                 : "memory");
+}
+// ---- epoch-tagged look-back status words -------------------------------------------------
+// A status word is (epoch << 32) | (flag << 30) | value.  A word whose epoch differs from the
+// launch's epoch reads as "not published", so status arrays never need clearing between
+// launches: the host hands every launch a fresh epoch (buffers are zero-filled at allocation
+// and epochs start at 1).
+__device__ __forceinline__ uint64_t gs_ld_status(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void gs_st_status(uint64_t* p, uint32_t epoch, uint32_t flag_value) {
+    uint64_t v = ((uint64_t)epoch << 32) | flag_value;
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t gs_status_flag(uint64_t v, uint32_t epoch) {
+    return ((uint32_t)(v >> 32) == epoch) ? (((uint32_t)v) >> 30) : 0u;
+}
+
+// Decoupled look-back executed by ONE full warp.  Publishes this tile's aggregate, returns the
+// exclusive prefix and publishes the inclusive prefix.  All lanes return the same value.
+__device__ __forceinline__ uint32_t gs_lookback_warp(uint64_t* status, uint32_t epoch, uint32_t tile,
+                                                     uint32_t aggregate, int lane) {
+    if (tile == 0) {
+        if (lane == 0) gs_st_status(&status[0], epoch, GS_LOOKBACK_FLAG_INCL | aggregate);
+        return 0;
+    }
+    if (lane == 0) gs_st_status(&status[tile], epoch, GS_LOOKBACK_FLAG_AGG | aggregate);
+    uint32_t excl = 0;
+    int64_t p = (int64_t)tile - 1;
+    while (true) {
+        int64_t i = p - lane;
+        uint64_t v = (i >= 0) ? gs_ld_status(&status[i]) : (((uint64_t)epoch << 32) | GS_LOOKBACK_FLAG_INCL);
+        uint32_t flag = gs_status_flag(v, epoch);
+        uint32_t m_incl = __ballot_sync(0xffffffffu, flag == 2u);
+        uint32_t m_inv = __ballot_sync(0xffffffffu, flag == 0u);
+        uint32_t first = m_incl ? (uint32_t)(__ffs((int)m_incl) - 1) : 32u;
+        uint32_t needed = first >= 31u ? 0xffffffffu : ((2u << first) - 1u);
+        if (m_inv & needed) continue;  // a needed predecessor has not published yet: retry
+        uint32_t contrib = ((needed >> lane) & 1u) ? ((uint32_t)v & GS_LOOKBACK_VALUE_MASK) : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        excl += contrib;
+        if (first < 32u) break;
+        p -= 32;
+    }
+    if (lane == 0) gs_st_status(&status[tile], epoch, GS_LOOKBACK_FLAG_INCL | (excl + aggregate));
+    return excl;
+}
+#endif

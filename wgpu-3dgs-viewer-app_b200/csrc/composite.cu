@@ -1,0 +1,154 @@
+// composite.cu — K3: tile-binned front-to-back splat compositor.
+//
+// Replaces the fragment + ROP-blend half of renderer.render_with_pass (reference
+// src/tab/scene.rs:2302-2314; depth state scene.rs:1972-1978): the reference blends quads back
+// to front in hardware; here one CTA owns a 16x16 pixel tile, stages the tile's depth-sorted
+// splats in shared memory 256 at a time and blends them FRONT TO BACK
+//     C += c·α·T,  T -= α·T,   α = min(0.99, o·exp(-½ dᵀQd)),
+// dropping α < 1/255 and power > 0, and stops a pixel when T < 1/1024 (whole warp / whole CTA
+// exit as soon as all their pixels stopped).  Each warp owns an 8x4 pixel sub-tile and first
+// culls the staged splats against it 32 at a time with a ballot, so only splats whose extent
+// square overlaps the sub-tile are evaluated.  FP32-pipe + MUFU bound, not HBM bound.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <bool FLAT, bool COUNT>
+__global__ void __launch_bounds__(kThreads) k_composite(const uint32_t* __restrict__ tile_vals,
+                                                        const uint32_t* __restrict__ ranges,
+                                                        const b200gs_splat* __restrict__ splats, uint8_t* out,
+                                                        size_t pitch, uint32_t W, uint32_t H, uint32_t tiles_x,
+                                                        uint32_t n_tiles, float bg0, float bg1, float bg2, float bg3,
+                                                        unsigned long long* evals) {
+    __shared__ float4 sA[kThreads];  // mx, my, a', b'   (conic pre-scaled: power in log2 units)
+    __shared__ float4 sB[kThreads];  // c', opacity, red, green
+    __shared__ int4 sD[kThreads];    // x0, x1-x0, y0, y1-y0 (pixel bounds clipped to the viewport)
+    __shared__ float sC[kThreads];   // blue
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tile = blockIdx.x;
+    const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+    const uint32_t start = ranges[tile], end = ranges[n_tiles + tile];
+
+    // warp -> 8x4 sub-tile, lane -> pixel
+    const int wx0 = (int)(tx * GS_TILE) + (warp & 1) * 8, wy0 = (int)(ty * GS_TILE) + (warp >> 1) * 4;
+    const int wx1 = wx0 + 7, wy1 = wy0 + 3;
+    const int px = wx0 + (lane & 7), py = wy0 + (lane >> 3);
+    const float fpx = (float)px, fpy = (float)py;
+    const bool inside = px < (int)W && py < (int)H;
+
+    float T = 1.0f, Cr = 0.0f, Cg = 0.0f, Cb = 0.0f;
+    bool done = !inside;
+    unsigned long long my_evals = 0;
+    const float Wf = (float)W, Hf = (float)H;
+
+    for (uint32_t base = start; base < end; base += kThreads) {
+        const uint32_t cnt = min((uint32_t)kThreads, end - base);
+        if ((uint32_t)tid < cnt) {
+            const uint32_t id = tile_vals[base + tid];
+            const uint4* sp = reinterpret_cast<const uint4*>(splats + id);
+            const uint4 q0 = __ldg(sp), q1 = __ldg(sp + 1);
+            const float mx = __uint_as_float(q0.x), my = __uint_as_float(q0.y);
+            const float r = (float)(q0.z & 0xffffu);
+            const float op = __half2float(__ushort_as_half((unsigned short)(q0.z >> 16)));
+            const float cr = __half2float(__ushort_as_half((unsigned short)(q0.w & 0xffffu)));
+            const float cg = __half2float(__ushort_as_half((unsigned short)(q0.w >> 16)));
+            const float cb = __half2float(__ushort_as_half((unsigned short)(q1.w & 0xffffu)));
+            const float ca = __uint_as_float(q1.x), cbq = __uint_as_float(q1.y), cc = __uint_as_float(q1.z);
+            // same bounds expression as bin.cu / the oracle (exact in float)
+            float fx0 = ceilf(mx - r), fx1 = floorf(mx + r), fy0 = ceilf(my - r), fy1 = floorf(my + r);
+            if (fx0 < 0.0f) fx0 = 0.0f;
+            if (fy0 < 0.0f) fy0 = 0.0f;
+            if (fx1 > Wf - 1.0f) fx1 = Wf - 1.0f;
+            if (fy1 > Hf - 1.0f) fy1 = Hf - 1.0f;
+            sA[tid] = make_float4(mx, my, -0.5f * kLog2e * ca, -kLog2e * cbq);
+            sB[tid] = make_float4(-0.5f * kLog2e * cc, op, cr, cg);
+            sD[tid] = make_int4((int)fx0, (int)fx1 - (int)fx0, (int)fy0, (int)fy1 - (int)fy0);
+            sC[tid] = cb;
+        }
+        __syncthreads();
+
+        if (!__all_sync(0xffffffffu, done)) {
+            for (uint32_t g = 0; g < cnt; g += 32) {
+                const uint32_t s = g + lane;
+                bool ov = false;
+                if (s < cnt) {
+                    const int4 d = sD[s];
+                    ov = d.x <= wx1 && d.x + d.y >= wx0 && d.z <= wy1 && d.z + d.w >= wy0;
+                }
+                uint32_t m = __ballot_sync(0xffffffffu, ov);
+                while (m) {
+                    const int s2 = (int)g + __ffs((int)m) - 1;
+                    m &= m - 1;
+                    const float4 A = sA[s2];
+                    const float4 B = sB[s2];
+                    const int4 D = sD[s2];
+                    const float cb = sC[s2];
+                    const bool in = (uint32_t)(px - D.x) <= (uint32_t)D.y && (uint32_t)(py - D.z) <= (uint32_t)D.w;
+                    const float dx = fpx - A.x, dy = fpy - A.y;
+                    const float p2 = A.z * dx * dx + B.x * dy * dy + A.w * dx * dy;
+                    float al;
+                    if (FLAT) al = (p2 >= -0.5f * GS_FLAT_D2 * kLog2e) ? fminf(GS_ALPHA_MAX, B.y) : 0.0f;
+                    else al = fminf(GS_ALPHA_MAX, B.y * ex2_approx(p2));
+                    const bool ok = in && !done && p2 <= 0.0f && al >= GS_ALPHA_MIN;
+                    if (COUNT) my_evals += (in && !done) ? 1ull : 0ull;
+                    if (ok) {
+                        const float w = al * T;
+                        Cr += B.z * w;
+                        Cg += B.w * w;
+                        Cb += cb * w;
+                        T -= w;
+                        done = T < GS_T_EPS;
+                    }
+                }
+                if (__all_sync(0xffffffffu, done)) break;
+            }
+        }
+        if (__syncthreads_and(done)) break;
+    }
+
+    if (inside) {
+        const float r = Cr + bg0 * T, g = Cg + bg1 * T, b = Cb + bg2 * T, a = (1.0f - T) + bg3 * T;
+        auto q = [](float v) -> uint32_t {
+            v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
+            return (uint32_t)(v * 255.0f + 0.5f);
+        };
+        const uint32_t rgba = q(r) | (q(g) << 8) | (q(b) << 16) | (q(a) << 24);
+        *reinterpret_cast<uint32_t*>(out + (size_t)py * pitch + (size_t)px * 4) = rgba;
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) my_evals += __shfl_xor_sync(0xffffffffu, my_evals, o);
+        if (lane == 0 && my_evals) atomicAdd(evals, my_evals);
+    }
+}
+
+}  // namespace
+
+cudaError_t gs_launch_composite(const GsCompositeArgs& a, const GsFrame& f, cudaStream_t st) {
+    const uint32_t n_tiles = f.tiles_x * f.tiles_y;
+    const bool flat = f.display_mode != B200GS_DISPLAY_SPLAT;
+    const uint32_t W = (uint32_t)f.W, H = (uint32_t)f.H;
+#define GS_LAUNCH_COMPOSITE(FLAT, COUNT)                                                                              \
+    k_composite<FLAT, COUNT><<<n_tiles, kThreads, 0, st>>>(a.tile_vals, a.ranges, a.splats, a.out, a.pitch, W, H,      \
+                                                           f.tiles_x, n_tiles, f.bg[0], f.bg[1], f.bg[2], f.bg[3],     \
+                                                           a.evals)
+    if (flat) {
+        if (a.evals) GS_LAUNCH_COMPOSITE(true, true);
+        else GS_LAUNCH_COMPOSITE(true, false);
+    } else {
+        if (a.evals) GS_LAUNCH_COMPOSITE(false, true);
+        else GS_LAUNCH_COMPOSITE(false, false);
+    }
+#undef GS_LAUNCH_COMPOSITE
+    return cudaGetLastError();
+}

@@ -1,0 +1,409 @@
+// preprocess.cu — K1: the preprocess kernel of the B200 3DGS render core.
+//
+// Replaces viewer.preprocessor.preprocess(encoder, bind_group, N) (reference
+// src/tab/scene.rs:856-863, bindings :1835-1852) and, per the north star, the per-splat vertex
+// work of renderer.render_with_pass (scene.rs:2306-2313): model/view/projection transform,
+// frustum cull, mask + hidden-edit + selection test, 3D->2D covariance projection, conic and
+// extent, SH colour up to degree 3, edits and highlight.  Emits, for the V visible Gaussians in
+// ASCENDING INDEX ORDER (order-preserving compaction by decoupled look-back, so that the later
+// stable sort is deterministic): depth key, Gaussian index, and a 32-byte projected splat.
+//
+// Data movement: persistent CTAs; each 256-Gaussian chunk (256*R contiguous bytes, 16-byte
+// aligned because 256*R is a multiple of 1024) is pulled into shared memory with one 1-D TMA
+// bulk copy (cp.async.bulk -> UBLKCP) on an mbarrier, NSTAGE chunks in flight per CTA; each
+// thread then reads its own record from shared memory (word stride R/4).
+//
+// THIS FILE IS COMPILED WITH -fmad=false: every float operation rounds separately, in source
+// order, so that culling, depth keys and pixel bounds are bit-identical to the CPU oracle's
+// (which is built with -ffp-contract=off).  Do not re-associate the arithmetic.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kChunk = 256;
+
+template <int SH> struct ShBytes { static constexpr int v = SH == 0 ? 180 : SH == 1 ? 92 : SH == 2 ? 48 : 0; };
+template <int COV> struct CovBytes { static constexpr int v = COV == 0 ? 24 : 12; };
+
+__host__ __device__ constexpr int stages_for(int rb) {
+    int s = 110000 / (kChunk * rb);
+    return s < 2 ? 2 : (s > 4 ? 4 : s);
+}
+
+__device__ __forceinline__ float h2f_lo(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))); }
+__device__ __forceinline__ float h2f_hi(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
+__device__ __forceinline__ float clamp01(float x) { return x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x); }
+
+// SH coefficient k (0..44) of the record whose SH field starts at word pointer `w`
+template <int SH>
+__device__ __forceinline__ float sh_coef(const uint32_t* w, int k) {
+    if (SH == 0) return __uint_as_float(w[k]);
+    if (SH == 1) { uint32_t x = w[k >> 1]; return (k & 1) ? h2f_hi(x) : h2f_lo(x); }
+    if (SH == 2) { uint32_t x = w[k >> 2]; return (float)((x >> ((k & 3) * 8)) & 0xffu) * (2.0f / 255.0f) - 1.0f; }
+    return 0.0f;
+}
+
+__device__ void rgb_to_hsv(const float c[3], float hsv[3]) {
+    float mx = fmaxf(c[0], fmaxf(c[1], c[2])), mn = fminf(c[0], fminf(c[1], c[2]));
+    float d = mx - mn, h = 0.0f;
+    if (d > 0.0f) {
+        if (mx == c[0]) h = (c[1] - c[2]) / d;
+        else if (mx == c[1]) h = 2.0f + (c[2] - c[0]) / d;
+        else h = 4.0f + (c[0] - c[1]) / d;
+        h = h / 6.0f;
+        if (h < 0.0f) h = h + 1.0f;
+    }
+    hsv[0] = h;
+    hsv[1] = mx > 0.0f ? d / mx : 0.0f;
+    hsv[2] = mx;
+}
+__device__ void hsv_to_rgb(const float hsv[3], float c[3]) {
+    float h = hsv[0] * 6.0f, s = hsv[1], v = hsv[2];
+    float i = floorf(h), f = h - i;
+    int k = ((int)i) % 6;
+    if (k < 0) k += 6;
+    float p = v * (1.0f - s), q = v * (1.0f - s * f), t = v * (1.0f - s * (1.0f - f));
+    switch (k) {
+        case 0: c[0] = v; c[1] = t; c[2] = p; break;
+        case 1: c[0] = q; c[1] = v; c[2] = p; break;
+        case 2: c[0] = p; c[1] = v; c[2] = t; break;
+        case 3: c[0] = p; c[1] = q; c[2] = v; break;
+        case 4: c[0] = t; c[1] = p; c[2] = v; break;
+        default: c[0] = v; c[1] = p; c[2] = q; break;
+    }
+}
+// GaussianEditPod application (inputs: src/app.rs:1533-1564): colour -> contrast -> exposure ->
+// gamma -> alpha.
+__device__ void apply_edit(const b200gs_edit_pod& e, float rgb[3], float& op) {
+    if (!(e.flag & B200GS_EDIT_ENABLED)) return;
+    if (e.flag & B200GS_EDIT_OVERRIDE_COLOR) {
+        rgb[0] = e.color[0]; rgb[1] = e.color[1]; rgb[2] = e.color[2];
+    } else {
+        float hsv[3];
+        rgb_to_hsv(rgb, hsv);
+        float h = hsv[0] + e.color[0];
+        hsv[0] = h - floorf(h);
+        hsv[1] = clamp01(hsv[1] * e.color[1]);
+        hsv[2] = hsv[2] * e.color[2];
+        hsv_to_rgb(hsv, rgb);
+    }
+    float ex = exp2f(e.exposure);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        float v = (rgb[c] - 0.5f) * (1.0f + e.contrast) + 0.5f;
+        v = v * ex;
+        v = powf(fmaxf(v, 0.0f), e.gamma);
+        rgb[c] = v;
+    }
+    op = clamp01(op * e.alpha);
+}
+
+template <int SH, int COV>
+__global__ void __launch_bounds__(kChunk) k_preprocess(const uint8_t* __restrict__ recs, uint32_t n,
+                                                       const uint32_t* __restrict__ mask,
+                                                       const uint32_t* __restrict__ selection,
+                                                       const b200gs_edit_pod* __restrict__ edits,
+                                                       const __grid_constant__ GsFrame f,
+                                                       const __grid_constant__ GsModelXf m, uint32_t* ctrl,
+                                                       uint64_t* lookback, uint32_t epoch,
+                                                       uint32_t* __restrict__ keys,
+                                                       uint32_t* __restrict__ idx, b200gs_splat* __restrict__ splats) {
+    constexpr int RB = 16 + ShBytes<SH>::v + CovBytes<COV>::v;  // record bytes
+    constexpr int RW = RB / 4;                                  // record words
+    constexpr int NSTAGE = stages_for(RB);
+    constexpr uint32_t STAGE_BYTES = kChunk * RB;
+
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* stage_mem = smem;  // NSTAGE * STAGE_BYTES
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
+    uint32_t* s_chunk = reinterpret_cast<uint32_t*>(bars + NSTAGE);  // NSTAGE
+    uint32_t* s_wcount_all = s_chunk + NSTAGE;                       // 2 x 8 warp counts (double-buffered)
+    uint32_t* s_base_all = s_wcount_all + 16;                        // 2
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t nchunks = (n + kChunk - 1) / kChunk;
+
+    auto issue = [&](int stage, uint32_t c) {
+        uint32_t cnt = min((uint32_t)kChunk, n - c * kChunk);
+        uint32_t bytes = (cnt * RB + 15u) & ~15u;  // buffer is padded, see api.cu
+        gs_mbar_expect_tx(&bars[stage], bytes);
+        gs_tma_load_1d(stage_mem + (size_t)stage * STAGE_BYTES, recs + (size_t)c * STAGE_BYTES, bytes, &bars[stage]);
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; s++) gs_mbar_init(&bars[s], 1);
+        gs_fence_mbar_init();
+        for (int s = 0; s < NSTAGE; s++) {
+            uint32_t c = atomicAdd(&ctrl[GS_CTRL_TICKET], 1u);
+            s_chunk[s] = c;
+            if (c < nchunks) issue(s, c);
+        }
+    }
+    __syncthreads();
+
+    for (uint32_t it = 0;; it++) {
+        const int stage = it % NSTAGE;
+        // double-buffered by iteration parity: a fast warp may start iteration it+1 while a slow
+        // one still reads iteration it's counts in the output phase
+        uint32_t* s_wcount = s_wcount_all + (it & 1u) * 8;
+        uint32_t* s_base = s_base_all + (it & 1u);
+        const uint32_t c = s_chunk[stage];
+        if (c >= nchunks) break;
+        gs_mbar_wait(&bars[stage], (it / NSTAGE) & 1u);
+
+        const uint32_t i = c * kChunk + tid;
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)stage * STAGE_BYTES) + tid * RW;
+
+        // ---------------- phase 1: mask / hidden / frustum cull, depth key ----------------
+        bool vis = i < n;
+        bool selected = false;
+        b200gs_edit_pod ed;
+        ed.flag = 0;
+        if (vis && mask) vis = (mask[i >> 5] >> (i & 31)) & 1u;
+        if (vis && selection) selected = (selection[i >> 5] >> (i & 31)) & 1u;
+        if (vis && edits) {
+            const uint4* ep = reinterpret_cast<const uint4*>(edits + i);
+            uint4 e0 = ep[0], e1 = ep[1];
+            ed.flag = e0.x; ed.color[0] = __uint_as_float(e0.y); ed.color[1] = __uint_as_float(e0.z);
+            ed.color[2] = __uint_as_float(e0.w); ed.contrast = __uint_as_float(e1.x);
+            ed.exposure = __uint_as_float(e1.y); ed.gamma = __uint_as_float(e1.z); ed.alpha = __uint_as_float(e1.w);
+            if ((ed.flag & B200GS_EDIT_ENABLED) && (ed.flag & B200GS_EDIT_HIDDEN)) vis = false;
+        }
+        if (vis && selected && (f.sel_edit.flag & B200GS_EDIT_ENABLED) && (f.sel_edit.flag & B200GS_EDIT_HIDDEN))
+            vis = false;
+
+        float pw[3], pv[3], nx = 0.0f, ny = 0.0f, nz = 0.0f;
+        if (vis) {
+            float p0 = __uint_as_float(w[0]), p1 = __uint_as_float(w[1]), p2 = __uint_as_float(w[2]);
+            // world = q*(s⊙p)+t  (src/app.rs:1044-1046)
+            float ps0 = m.s[0] * p0, ps1 = m.s[1] * p1, ps2 = m.s[2] * p2;
+#pragma unroll
+            for (int r = 0; r < 3; r++) pw[r] = m.R[r][0] * ps0 + m.R[r][1] * ps1 + m.R[r][2] * ps2 + m.t[r];
+#pragma unroll
+            for (int r = 0; r < 3; r++) pv[r] = f.V[r][0] * pw[0] + f.V[r][1] * pw[1] + f.V[r][2] * pw[2] + f.V[r][3];
+            float pc[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) pc[r] = f.P[r][0] * pv[0] + f.P[r][1] * pv[1] + f.P[r][2] * pv[2] + f.P[r][3];
+            if (!(pc[3] > 0.0f)) vis = false;
+            else {
+                nx = pc[0] / pc[3]; ny = pc[1] / pc[3]; nz = pc[2] / pc[3];
+                vis = nz > 0.0f && nz < 1.0f && fabsf(nx) <= GS_CULL_XY && fabsf(ny) <= GS_CULL_XY;
+            }
+        }
+        const uint32_t ballot = __ballot_sync(0xffffffffu, vis);
+        if (lane == 0) s_wcount[warp] = __popc(ballot);
+        __syncthreads();  // (A)
+
+        // ---------------- phase 2: projected splat for the visible ones ----------------
+        uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
+        if (vis) {
+            const uint32_t* shw = w + 4;
+            const uint32_t* cw = w + 4 + ShBytes<SH>::v / 4;
+            float cv[6];
+            if (COV == 0) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) cv[k] = __uint_as_float(cw[k]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 3; k++) { uint32_t x = cw[k]; cv[2 * k] = h2f_lo(x); cv[2 * k + 1] = h2f_hi(x); }
+            }
+            // Σ' = (R_m S_m) Σ (R_m S_m)^T · size²  (upper triangle)
+            float S[3][3] = {{cv[0], cv[1], cv[2]}, {cv[1], cv[3], cv[4]}, {cv[2], cv[4], cv[5]}};
+            float B[3][3], Sw[3][3];
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int k = 0; k < 3; k++) B[r][k] = m.M[r][0] * S[0][k] + m.M[r][1] * S[1][k] + m.M[r][2] * S[2][k];
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int k = r; k < 3; k++)
+                    Sw[r][k] = (B[r][0] * m.M[k][0] + B[r][1] * m.M[k][1] + B[r][2] * m.M[k][2]) * f.sz2;
+            Sw[1][0] = Sw[0][1]; Sw[2][0] = Sw[0][2]; Sw[2][1] = Sw[1][2];
+
+            // Jacobian of the pixel mapping (view space RH, looking down -z; rows flipped in y)
+            float tz = -pv[2];
+            float txz = pv[0] / tz, tyz = pv[1] / tz;
+            txz = fminf(f.limx, fmaxf(-f.limx, txz));
+            tyz = fminf(f.limy, fmaxf(-f.limy, tyz));
+            float xc = txz * tz, yc = tyz * tz;
+            float tz2 = tz * tz;
+            float J00 = f.fx / tz, J02 = (f.fx * xc) / tz2;
+            float J11 = -(f.fy / tz), J12 = -((f.fy * yc) / tz2);
+            float T0[3], T1[3], U0[3], U1[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                T0[k] = J00 * f.V[0][k] + J02 * f.V[2][k];
+                T1[k] = J11 * f.V[1][k] + J12 * f.V[2][k];
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                U0[k] = T0[0] * Sw[0][k] + T0[1] * Sw[1][k] + T0[2] * Sw[2][k];
+                U1[k] = T1[0] * Sw[0][k] + T1[1] * Sw[1][k] + T1[2] * Sw[2][k];
+            }
+            float a = U0[0] * T0[0] + U0[1] * T0[1] + U0[2] * T0[2];
+            float b = U0[0] * T1[0] + U0[1] * T1[1] + U0[2] * T1[2];
+            float d = U1[0] * T1[0] + U1[1] * T1[1] + U1[2] * T1[2];
+            a = a + GS_LOWPASS;
+            d = d + GS_LOWPASS;
+            float det = a * d - b * b;
+            float ca = 0.0f, cb = 0.0f, cc = 0.0f, radf = 0.0f;
+            if (det > 0.0f) {
+                float di = 1.0f / det;
+                ca = d * di; cb = -b * di; cc = a * di;
+                float mid = 0.5f * (a + d);
+                float disc = mid * mid - det;
+                if (disc < GS_MIN_DISC) disc = GS_MIN_DISC;
+                float lam = mid + sqrtf(disc);
+                radf = ceilf(GS_EXTENT_SIGMA * sqrtf(lam));
+            }
+            if (f.display_mode == B200GS_DISPLAY_POINT) {
+                ca = GS_FLAT_D2 / (GS_POINT_RADIUS * GS_POINT_RADIUS); cb = 0.0f; cc = ca;
+                radf = ceilf(GS_POINT_RADIUS);
+            }
+            if (!(radf <= 65535.0f)) radf = 65535.0f;
+
+            // colour: baked SH0 (u8) + bands 1..sh_deg, view direction in world space
+            float dx = pw[0] - f.cam[0], dy = pw[1] - f.cam[1], dz = pw[2] - f.cam[2];
+            float dl = sqrtf(dx * dx + dy * dy + dz * dz);
+            dx = dx / dl; dy = dy / dl; dz = dz / dl;
+            float bs[15];
+#pragma unroll
+            for (int k = 0; k < 15; k++) bs[k] = 0.0f;
+            const uint32_t deg = SH == 3 ? 0u : f.sh_deg;
+            if (deg >= 1) {
+                bs[0] = -0.4886025119029199f * dy;
+                bs[1] = 0.4886025119029199f * dz;
+                bs[2] = -0.4886025119029199f * dx;
+            }
+            if (deg >= 2) {
+                float xx = dx * dx, yy = dy * dy, zz = dz * dz, xy = dx * dy, yz = dy * dz, xz = dx * dz;
+                bs[3] = 1.0925484305920792f * xy;
+                bs[4] = -1.0925484305920792f * yz;
+                bs[5] = 0.31539156525252005f * (2.0f * zz - xx - yy);
+                bs[6] = -1.0925484305920792f * xz;
+                bs[7] = 0.5462742152960396f * (xx - yy);
+                if (deg >= 3) {
+                    bs[8] = -0.5900435899266435f * dy * (3.0f * xx - yy);
+                    bs[9] = 2.890611442640554f * xy * dz;
+                    bs[10] = -0.4570457994644658f * dy * (4.0f * zz - xx - yy);
+                    bs[11] = 0.3731763325901154f * dz * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+                    bs[12] = -0.4570457994644658f * dx * (4.0f * zz - xx - yy);
+                    bs[13] = 1.445305721320277f * dz * (xx - yy);
+                    bs[14] = -0.5900435899266435f * dx * (xx - 3.0f * yy);
+                }
+            }
+            const uint32_t colw = w[3];
+            float rgb[3];
+            const int ncoef = deg >= 3 ? 15 : (deg == 2 ? 8 : (deg == 1 ? 3 : 0));
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) rgb[ch] = f.no_sh0 ? 0.0f : (float)((colw >> (8 * ch)) & 0xffu) / 255.0f;
+            if (SH != 3) {
+#pragma unroll
+                for (int k = 0; k < 15; k++) {
+                    if (k < ncoef) {
+#pragma unroll
+                        for (int ch = 0; ch < 3; ch++) rgb[ch] = rgb[ch] + bs[k] * sh_coef<SH>(shw, 3 * k + ch);
+                    }
+                }
+            }
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) rgb[ch] = clamp01(rgb[ch]);
+            float op = (float)(colw >> 24) / 255.0f;
+            if (edits) apply_edit(ed, rgb, op);
+            if (selected) {
+                apply_edit(f.sel_edit, rgb, op);
+                float ha = f.hl[3];
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) rgb[ch] = rgb[ch] + (f.hl[ch] - rgb[ch]) * ha;
+            }
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) rgb[ch] = clamp01(rgb[ch]);
+
+            float mx = ((nx + 1.0f) * f.W - 1.0f) * 0.5f;
+            float my = ((1.0f - ny) * f.H - 1.0f) * 0.5f;
+            q0.x = __float_as_uint(mx);
+            q0.y = __float_as_uint(my);
+            q0.z = (uint32_t)radf | ((uint32_t)__half_as_ushort(__float2half_rn(op)) << 16);
+            q0.w = (uint32_t)__half_as_ushort(__float2half_rn(rgb[0])) |
+                   ((uint32_t)__half_as_ushort(__float2half_rn(rgb[1])) << 16);
+            q1.x = __float_as_uint(ca);
+            q1.y = __float_as_uint(cb);
+            q1.z = __float_as_uint(cc);
+            q1.w = (uint32_t)__half_as_ushort(__float2half_rn(rgb[2])) | ((selected ? 1u : 0u) << 16);
+        }
+        __syncthreads();  // (B) every read of this stage's shared memory is done
+
+        // refill the stage, then resolve this chunk's output base by decoupled look-back
+        if (tid == 0) {
+            uint32_t c2 = atomicAdd(&ctrl[GS_CTRL_TICKET], 1u);
+            s_chunk[stage] = c2;
+            if (c2 < nchunks) issue(stage, c2);
+        }
+        if (warp == 1) {
+            uint32_t wc = lane < 8 ? s_wcount[lane] : 0u;
+            uint32_t total = wc;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+            total = __shfl_sync(0xffffffffu, total, 0);
+            uint32_t excl = gs_lookback_warp(lookback, epoch, c, total, lane);
+            if (lane == 0) {
+                *s_base = excl;
+                if (c == nchunks - 1) ctrl[GS_CTRL_VISIBLE] = excl + total;
+            }
+        }
+        __syncthreads();  // (C)
+
+        if (vis) {
+            uint32_t off = *s_base;
+            for (int k = 0; k < warp; k++) off += s_wcount[k];
+            off += __popc(ballot & ((1u << lane) - 1u));
+            keys[off] = __float_as_uint(nz);
+            idx[off] = i;
+            uint4* sp = reinterpret_cast<uint4*>(splats + off);
+            sp[0] = q0;
+            sp[1] = q1;
+        }
+    }
+    if (n == 0 && blockIdx.x == 0 && tid == 0) ctrl[GS_CTRL_VISIBLE] = 0;
+}
+
+template <int SH, int COV>
+cudaError_t launch_t(const GsPreprocessArgs& a, const GsFrame& f, const GsModelXf& m, int num_sms, cudaStream_t st) {
+    constexpr int RB = 16 + ShBytes<SH>::v + CovBytes<COV>::v;
+    constexpr int NSTAGE = stages_for(RB);
+    constexpr size_t smem = (size_t)NSTAGE * kChunk * RB + NSTAGE * 8 + NSTAGE * 4 + 16 * 4 + 2 * 4 + 16;
+    auto kern = k_preprocess<SH, COV>;
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kChunk, smem);
+        if (e != cudaSuccess) return e;
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    uint32_t nchunks = (a.n + kChunk - 1) / kChunk;
+    uint32_t grid = (uint32_t)(blocks_per_sm * num_sms);
+    if (grid > nchunks) grid = nchunks;
+    if (grid < 1) grid = 1;
+    kern<<<grid, kChunk, smem, st>>>(a.recs, a.n, a.mask, a.selection, a.edits, f, m, a.ctrl, a.lookback, a.epoch, a.keys,
+                                     a.idx, a.splats);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t gs_launch_preprocess(const GsPreprocessArgs& a, const GsFrame& f, const GsModelXf& m, int num_sms,
+                                 cudaStream_t st) {
+    switch (a.sh * 2 + a.cov) {
+        case 0: return launch_t<0, 0>(a, f, m, num_sms, st);
+        case 1: return launch_t<0, 1>(a, f, m, num_sms, st);
+        case 2: return launch_t<1, 0>(a, f, m, num_sms, st);
+        case 3: return launch_t<1, 1>(a, f, m, num_sms, st);
+        case 4: return launch_t<2, 0>(a, f, m, num_sms, st);
+        case 5: return launch_t<2, 1>(a, f, m, num_sms, st);
+        case 6: return launch_t<3, 0>(a, f, m, num_sms, st);
+        case 7: return launch_t<3, 1>(a, f, m, num_sms, st);
+    }
+    return cudaErrorInvalidValue;
+}

@@ -1,0 +1,254 @@
+// sort.cu — K2: onesweep-style LSD radix sort of (u32 key, u32 value) pairs.
+//
+// Replaces viewer.radix_sorter.sort(encoder, bind_group, radix_sort_indirect_args)
+// (reference src/tab/scene.rs:865-869): stable ascending sort of the depth keys (f32 bits as
+// u32) with the Gaussian indices as payload; the element count lives on the device (the
+// reference sizes an indirect dispatch from it), here `*d_n`.
+//
+// Design: one histogram kernel (all digit histograms in one read of the keys), then one
+// kernel per 8-bit digit.  A digit pass is a single sweep: each 4096-key tile ranks its keys
+// with warp-level __match_any_sync histograms, publishes its per-digit counts and resolves
+// its global offsets by decoupled look-back over epoch-tagged status words (chained scan, no
+// separate scan kernel, no second read of the keys), then scatters keys and values through
+// shared memory so that global writes are runs of consecutive addresses.  Tiles are handed
+// out by an atomic ticket so that every predecessor a tile waits on is owned by a running CTA.
+// The same kernels sort the (tile id, splat) entries of the binning stage with 2 passes.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kKpt = 16;                       // keys per thread
+constexpr int kTile = kThreads * kKpt;         // 4096 keys per tile
+constexpr int kRadix = 256;
+
+// ------------------------------------------------------------------ histogram kernel
+// hist[pass][digit] += count, for `passes` digits.  Warp-aggregated (match_any) shared-memory
+// atomics: depth keys share their top bytes, so naive atomics would serialise on one bin.
+__global__ void __launch_bounds__(kThreads) k_sort_hist(const uint32_t* __restrict__ keys, const uint32_t* d_n,
+                                                        uint32_t n_max, uint32_t* hist, uint32_t passes) {
+    __shared__ uint32_t s_hist[4 * kRadix];
+    for (int i = threadIdx.x; i < 4 * kRadix; i += kThreads) s_hist[i] = 0;
+    __syncthreads();
+    uint32_t n = *d_n;
+    if (n > n_max) n = n_max;
+    const int lane = threadIdx.x & 31;
+    // each warp walks 32-key groups, grid-stride
+    const uint32_t warps_total = gridDim.x * kWarps;
+    const uint32_t gw = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const uint32_t ngroups = (n + 31) / 32;
+    for (uint32_t g = gw; g < ngroups; g += warps_total) {
+        uint32_t i = g * 32 + lane;
+        bool ok = i < n;
+        uint32_t k = ok ? keys[i] : 0u;
+        uint32_t act = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            for (uint32_t p = 0; p < passes; p++) {
+                uint32_t d = (k >> (8 * p)) & 0xffu;
+                uint32_t peers = __match_any_sync(act, d);
+                if ((uint32_t)lane == (uint32_t)(__ffs((int)peers) - 1)) atomicAdd(&s_hist[p * kRadix + d], __popc(peers));
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (int)passes * kRadix; i += kThreads) {
+        uint32_t c = s_hist[i];
+        if (c) atomicAdd(&hist[i], c);
+    }
+}
+
+// ---------------------------------------------------------------------- digit pass
+struct PassSmem {
+    uint32_t warp_hist[kWarps][kRadix];  // per-warp digit counts -> per-warp exclusive offsets
+    uint32_t exch[kTile];                // key / value exchange buffer
+    uint32_t tile_start[kRadix];         // first position of each digit inside the sorted tile
+    int32_t global_off[kRadix];          // global index = global_off[digit] + position in sorted tile
+    uint32_t scan_tmp[kWarps];
+    uint32_t tile_id;
+};
+
+__global__ void __launch_bounds__(kThreads) k_sort_pass(const uint32_t* __restrict__ keys_in,
+                                                        const uint32_t* __restrict__ vals_in,
+                                                        uint32_t* __restrict__ keys_out,
+                                                        uint32_t* __restrict__ vals_out, const uint32_t* d_n,
+                                                        uint32_t n_max, const uint32_t* __restrict__ hist,
+                                                        uint64_t* lookback, uint32_t epoch, uint32_t* ticket,
+                                                        uint32_t shift) {
+    __shared__ PassSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t n = *d_n;
+    if (n > n_max) n = n_max;
+    const uint32_t ntiles = (n + kTile - 1) / kTile;
+
+    // exclusive prefix of the global histogram of this digit (thread d owns digit d)
+    uint32_t gbase;
+    {
+        uint32_t c = hist[tid];
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) sm.scan_tmp[warp] = incl;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (int k = 0; k < warp; k++) wbase += sm.scan_tmp[k];
+        gbase = wbase + incl - c;
+        __syncthreads();
+    }
+
+    while (true) {
+        if (tid == 0) sm.tile_id = atomicAdd(ticket, 1u);
+#pragma unroll
+        for (int k = 0; k < kRadix / 32; k++) sm.warp_hist[warp][k * 32 + lane] = 0;
+        __syncthreads();
+        const uint32_t tile = sm.tile_id;
+        if (tile >= ntiles) break;
+        const uint32_t tile_base = tile * kTile;
+        const uint32_t valid = min((uint32_t)kTile, n - tile_base);
+
+        // ---- load (warp-striped: slot = warp*512 + k*32 + lane keeps index order inside a warp)
+        uint32_t key[kKpt], val[kKpt];
+        const uint32_t wbase_idx = warp * (32 * kKpt);
+#pragma unroll
+        for (int k = 0; k < kKpt; k++) {
+            uint32_t s = wbase_idx + k * 32 + lane;
+            key[k] = s < valid ? keys_in[tile_base + s] : 0xffffffffu;
+        }
+#pragma unroll
+        for (int k = 0; k < kKpt; k++) {
+            uint32_t s = wbase_idx + k * 32 + lane;
+            val[k] = s < valid ? (vals_in ? vals_in[tile_base + s] : tile_base + s) : 0u;
+        }
+
+        // ---- rank inside the warp, digit by digit, in index order (stable)
+        uint32_t rank[kKpt];
+#pragma unroll
+        for (int k = 0; k < kKpt; k++) {
+            uint32_t d = (key[k] >> shift) & 0xffu;
+            uint32_t peers = __match_any_sync(0xffffffffu, d);
+            int leader = __ffs((int)peers) - 1;
+            uint32_t old = 0;
+            if (lane == leader) {
+                old = sm.warp_hist[warp][d];
+                sm.warp_hist[warp][d] = old + __popc(peers);
+            }
+            old = __shfl_sync(0xffffffffu, old, leader);
+            rank[k] = old + __popc(peers & ((1u << lane) - 1u));
+            __syncwarp();
+        }
+        __syncthreads();
+
+        // ---- per digit (thread d): exclusive scan over warps, tile total
+        uint32_t count = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < kWarps; w2++) {
+            uint32_t t = sm.warp_hist[w2][tid];
+            sm.warp_hist[w2][tid] = count;
+            count += t;
+        }
+        // ---- exclusive scan of the tile totals over digits
+        uint32_t incl = count;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) sm.scan_tmp[warp] = incl;
+        __syncthreads();
+        uint32_t wb = 0;
+        for (int k = 0; k < warp; k++) wb += sm.scan_tmp[k];
+        const uint32_t tstart = wb + incl - count;
+        sm.tile_start[tid] = tstart;
+
+        // ---- decoupled look-back for digit `tid`
+        uint64_t* lb = lookback + (size_t)tid;
+        uint32_t excl = 0;
+        if (tile == 0) {
+            gs_st_status(&lb[0], epoch, GS_LOOKBACK_FLAG_INCL | count);
+        } else {
+            gs_st_status(&lb[(size_t)tile * kRadix], epoch, GS_LOOKBACK_FLAG_AGG | count);
+            int64_t p = (int64_t)tile - 1;
+            while (true) {
+                uint64_t v = gs_ld_status(&lb[(size_t)p * kRadix]);
+                uint32_t fl = gs_status_flag(v, epoch);
+                if (fl == 0u) continue;
+                excl += (uint32_t)v & GS_LOOKBACK_VALUE_MASK;
+                if (fl == 2u) break;
+                p--;
+            }
+            gs_st_status(&lb[(size_t)tile * kRadix], epoch, GS_LOOKBACK_FLAG_INCL | (excl + count));
+        }
+        sm.global_off[tid] = (int32_t)(gbase + excl) - (int32_t)tstart;
+        __syncthreads();
+
+        // ---- scatter keys into tile-sorted order in shared memory
+        uint32_t pos[kKpt];
+#pragma unroll
+        for (int k = 0; k < kKpt; k++) {
+            uint32_t d = (key[k] >> shift) & 0xffu;
+            pos[k] = sm.tile_start[d] + sm.warp_hist[warp][d] + rank[k];
+            sm.exch[pos[k]] = key[k];
+        }
+        __syncthreads();
+        uint32_t gpos[kKpt];
+#pragma unroll
+        for (int k = 0; k < kKpt; k++) {
+            uint32_t p = k * kThreads + tid;
+            uint32_t kk = sm.exch[p];
+            uint32_t d = (kk >> shift) & 0xffu;
+            gpos[k] = (uint32_t)(sm.global_off[d] + (int32_t)p);
+            if (p < valid) keys_out[gpos[k]] = kk;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kKpt; k++) sm.exch[pos[k]] = val[k];
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kKpt; k++) {
+            uint32_t p = k * kThreads + tid;
+            if (p < valid) vals_out[gpos[k]] = sm.exch[p];
+        }
+        __syncthreads();  // exch / warp_hist / tile_id are reused by the next tile
+    }
+}
+
+}  // namespace
+
+size_t gs_sort_lookback_words(uint32_t n_max, uint32_t passes) {
+    size_t tiles = ((size_t)n_max + kTile - 1) / kTile;
+    if (tiles < 1) tiles = 1;
+    return tiles * kRadix * passes;
+}
+
+cudaError_t gs_launch_sort(const GsSortArgs& a, int num_sms, cudaStream_t st) {
+    if (a.passes < 1 || a.passes > 4 || (a.passes & 1)) return cudaErrorInvalidValue;
+    size_t tiles = ((size_t)a.n_max + kTile - 1) / kTile;
+    if (tiles < 1) tiles = 1;
+    if (!a.hist_prefilled) {
+        uint32_t grid = (uint32_t)(num_sms * 4);
+        uint32_t need = (uint32_t)((a.n_max + kThreads - 1) / kThreads);
+        if (grid > need) grid = need < 1 ? 1 : need;
+        k_sort_hist<<<grid, kThreads, 0, st>>>(a.keys_a, a.d_n, a.n_max, a.hist, a.passes);
+    }
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_sort_pass, kThreads, 0);
+        if (e != cudaSuccess) return e;
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    uint32_t grid = (uint32_t)(blocks_per_sm * num_sms);
+    if (grid > tiles) grid = (uint32_t)tiles;
+    for (uint32_t p = 0; p < a.passes; p++) {
+        const uint32_t* ki = (p & 1) ? a.keys_b : a.keys_a;
+        const uint32_t* vi = (p & 1) ? a.vals_b : ((p == 0 && a.vals_identity) ? nullptr : a.vals_a);
+        uint32_t* ko = (p & 1) ? a.keys_a : a.keys_b;
+        uint32_t* vo = (p & 1) ? a.vals_a : a.vals_b;
+        k_sort_pass<<<grid, kThreads, 0, st>>>(ki, vi, ko, vo, a.d_n, a.n_max, a.hist + p * kRadix,
+                                               a.lookback + (size_t)p * tiles * kRadix, a.epoch, a.tickets + p,
+                                               8 * p);
+    }
+    return cudaGetLastError();
+}
