@@ -76,7 +76,8 @@ def lib():
 
 
 def _p(a):
-    return None if a is None else C.c_void_p(a.ctypes.data)
+    # data_as keeps a reference to the array, so temporaries stay alive for the call
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
 def default_edit():

@@ -1,0 +1,424 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against
+the CPU oracle on the same seeded inputs.  Bars (BASELINE.json north_star):
+  * visible count, compaction order, depth keys, sorted index order: BIT-EXACT
+  * RGBA: max |Δ| <= 2/255 per channel and PSNR >= 50 dB (tests/util.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from util import (SEED_100K, SEED_1M, SEED_6M, SEEDS_CFG4, assert_image_close, bits_set, make_gaussians, pack_bits, psnr)
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SPLAT_FIELDS = ("mx", "my", "radius", "ca", "cb", "cc", "opacity_h", "r_h", "g_h", "b_h", "flags")
+
+
+def _splats_equal(a, b):
+    assert len(a) == len(b)
+    for f in SPLAT_FIELDS:
+        x, y = np.ascontiguousarray(a[f]), np.ascontiguousarray(b[f])
+        assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), "splat field %s differs" % f
+
+
+def _splats_close(a, b, bounds_exact=True):
+    """colour / conic / opacity are floating point: tolerance; bounds inputs stay exact"""
+    assert len(a) == len(b)
+    if bounds_exact:
+        for f in ("mx", "my", "radius"):
+            assert np.array_equal(np.ascontiguousarray(a[f]).view(np.uint8), np.ascontiguousarray(b[f]).view(np.uint8)), f
+    for f in ("ca", "cb", "cc"):
+        assert np.allclose(a[f], b[f], rtol=1e-5, atol=1e-7), f
+    for f in ("opacity_h", "r_h", "g_h", "b_h"):
+        assert np.max(np.abs(a[f].astype(np.float32) - b[f].astype(np.float32)), initial=0) <= 2e-3, f
+
+
+def _full_parity(G, O, n, seed, W, H, sh=2, cov=1, cam=None, check_image=True, **frame_kw):
+    ply = G.synth_scene(seed, n)
+    g = G.gaussian_from_ply(ply)
+    packed = G.pack_gaussians(sh, cov, g)
+    cam = cam or G.OrbitCamera.orbit()
+    view, proj = cam.view(), cam.projection(np.float32(W) / np.float32(H))
+    f = O.make_frame(view, proj, W, H, **frame_kw)
+    om = O.ModelRef(sh, cov, packed, n)
+    oi, ok, osp = O.preprocess(f, om)
+    with G.Viewer(W, H, sh, cov) as v:
+        m = v.add_model("scene", n)
+        m.upload_packed(0, packed)
+        v.update_camera(cam)
+        v.update_gaussian_transform(frame_kw.get("gaussian_size", 1.0), frame_kw.get("display_mode", 0),
+                                    frame_kw.get("sh_deg", 3), bool(frame_kw.get("no_sh0", 0)))
+        if "background" in frame_kw:
+            v.set_background(frame_kw["background"])
+        m.preprocess()
+        assert m.visible_count() == len(oi)                       # visible-splat count: exact
+        assert np.array_equal(m.indices(), oi)                    # order-preserving compaction
+        assert np.array_equal(m.depth_keys(), ok)                 # depth keys: bit-exact
+        _splats_equal(m.splats(), osp)
+        m.sort()
+        ok2, oi2, osp2 = O.sort(ok, oi, osp)
+        assert np.array_equal(m.depth_keys(), ok2)
+        assert np.array_equal(m.indices(), oi2)                   # sorted index order: bit-exact
+        _splats_equal(m.splats(), osp2)
+        img = v.render_frame_host([m]).copy()
+        if check_image:
+            ref, _ = O.composite(f, osp2, front_to_back=False)    # reference-style back-to-front
+            assert_image_close(img, ref)
+        t = v.last_timings()
+        assert t.overflow == 0
+    return img
+
+
+def test_config1_100k_720p_all_stages(G, O):
+    """BASELINE.json configs[0]: 100k-Gaussian SH3 scene at 1280x720 (Norm8 SH + Half Cov3d)."""
+    _full_parity(G, O, 100_000, SEED_100K, 1280, 720)
+
+
+def test_config2_1m_1080p_all_stages(G, O):
+    """BASELINE.json configs[1]: 1M-Gaussian SH3 scene, single view 1920x1080."""
+    _full_parity(G, O, 1_000_000, SEED_1M, 1920, 1080)
+
+
+def test_config3_6m_1080p_all_stages(G, O):
+    """BASELINE.json configs[2] at full size: 6M Gaussians at 1920x1080 — every stage still compared
+    with the oracle (it finishes in seconds on the host cores)."""
+    _full_parity(G, O, 6_000_000, SEED_6M, 1920, 1080)
+
+
+def test_config3_4k_image(G, O):
+    """BASELINE.json configs[2], 3840x2160 leg, on a 1M subset so that the oracle image is quick."""
+    _full_parity(G, O, 1_000_000, SEED_6M, 3840, 2160)
+
+
+@pytest.mark.parametrize("sh,cov", [(s, c) for s in range(4) for c in range(2)])
+def test_all_eight_layouts(G, O, sh, cov):
+    """The 8 GaussianPod layouts of reference src/app.rs:250-257."""
+    _full_parity(G, O, 20_011, 0xB2000077, 640, 360, sh=sh, cov=cov)
+
+
+@pytest.mark.parametrize("kw", [dict(sh_deg=0), dict(sh_deg=1), dict(sh_deg=2), dict(no_sh0=1), dict(gaussian_size=0.5),
+                                dict(gaussian_size=2.0), dict(display_mode=1), dict(display_mode=2),
+                                dict(background=(0.2, 0.4, 0.6, 1.0))])
+def test_gaussian_transform_settings(G, O, kw):
+    """update_gaussian_transform(size, display_mode, sh_deg, no_sh0) — reference scene.rs:803-809;
+    UI ranges src/tab/transform.rs:110-145."""
+    _full_parity(G, O, 30_000, 0xB2000078, 800, 450, **kw)
+
+
+def test_other_cameras_and_odd_viewport(G, O):
+    for cam, (W, H) in [(G.OrbitCamera.orbit(3.0, -10.0, 200.0), (333, 217)), (G.OrbitCamera.orbit(8.0, 60.0, 90.0), (1000, 16)),
+                        (G.OrbitCamera.orbit(0.7, 5.0, 10.0), (640, 480))]:
+        _full_parity(G, O, 50_000, SEED_100K, W, H, cam=cam)
+
+
+def test_golden_fixture_matches_gpu(G):
+    """Committed oracle bytes (tests/golden/oracle_small.npz) vs the CUDA path — no oracle run."""
+    z = np.load(os.path.join(GOLDEN, "oracle_small.npz"))
+    n, W, H = int(z["n"]), int(z["W"]), int(z["H"])
+    g = G.gaussian_from_ply(G.synth_scene(int(z["seed"]), n))
+    for sh, cov in ((2, 1), (1, 0), (0, 0), (3, 1)):
+        with G.Viewer(W, H, sh, cov) as v:
+            m = v.add_model("g", n)
+            m.update_range(0, g)                                   # host packs, then H2D
+            v.update_camera(G.OrbitCamera.orbit())
+            img = v.render_frame_host([m]).copy()
+            tag = "%d%d" % (sh, cov)
+            assert np.array_equal(m.indices(), z["idx_" + tag])
+            assert np.array_equal(m.depth_keys(), z["keys_" + tag])
+            assert_image_close(img, z["img_" + tag])
+
+
+def test_single_splat_closed_form_on_gpu(G):
+    """The analytic known-answer of tests/test_oracle.py, rendered by the CUDA path."""
+    import math
+    W = H = 65
+    s, D, o8 = 0.2, 5.0, 230
+    g = make_gaussians(G.GAUSSIAN, [[0, 0, 0]], scale=s, color=(255, 128, 0, o8))
+    with G.Viewer(W, H, G.SH_SINGLE, G.COV3D_SINGLE) as v:
+        m = v.add_model("one", 1)
+        m.update_range(0, g)
+        v.update_camera(G.OrbitCamera(pos=(0, 0, D)))
+        img = v.render_frame_host([m]).copy()
+        assert m.visible_count() == 1
+    fy = (1 / math.tan(math.radians(30))) * H / 2
+    var = (fy * s / D) ** 2 + 0.3
+    yy, xx = np.mgrid[0:H, 0:W]
+    r2 = (xx - (W - 1) / 2) ** 2 + (yy - (H - 1) / 2) ** 2
+    alpha = np.minimum(0.99, (o8 / 255) * np.exp(-0.5 * r2 / var))
+    rad = math.ceil(3 * math.sqrt(var + math.sqrt(0.1)))
+    alpha[(np.abs(xx - (W - 1) / 2) > rad) | (np.abs(yy - (H - 1) / 2) > rad) | (alpha < 1 / 255)] = 0
+    ref = np.concatenate([alpha[..., None] * np.array([1.0, 128 / 255, 0.0]), alpha[..., None]], -1)
+    assert np.max(np.abs(img.astype(np.float64) / 255 - ref)) <= 1.01 / 255
+
+
+# ------------------------------------------------------------------ config 4: multi-model
+def _config4(G, O, n_per_model, W, H):
+    """BASELINE.json configs[3] / SURVEY.md §8d: three models with transforms, a colour edit on a
+    selected half of model 2, and the composite mask `0 | 1 - 2` on model 1."""
+    xf = [((-2, 0, 0), (0, 30, 0), (1, 1, 1)), ((0, 0, 0), (10, 0, 45), (1.2, 0.8, 1)), ((2, 0.5, 0), (0, -60, 0), (0.7, 0.7, 0.7))]
+    cam = G.OrbitCamera.orbit()
+    view, proj = cam.view(), cam.projection(np.float32(W) / np.float32(H))
+    f = O.make_frame(view, proj, W, H)
+    shapes = np.zeros(3, G.MASK_SHAPE)
+    shapes["kind"] = [G.MASK_BOX, G.MASK_ELLIPSOID, G.MASK_BOX]
+    shapes["pos"] = [(-1, 0, 0), (1, 0, 0.5), (1, 0, 0)]
+    shapes["quat"] = [G.quat_from_euler_zyx_deg([0, 20, 0]), (0, 0, 0, 1), (0, 0, 0, 1)]
+    shapes["scale"] = [(3, 3, 6), (4, 3, 5), (1.5, 4, 1.5)]
+    ops = np.array([(0, 0), (0, 1), (0, 2), (3, 0), (1, 0)], G.MASK_OP)         # 0 1 2 - |
+    edit = dict(flag=1, color=(0.5, 1.2, 0.9), contrast=0.2, exposure=0.5, gamma=1.2, alpha=0.8)
+    v = G.Viewer(W, H)
+    gm, om, centers = [], [], []
+    for k in range(3):
+        g = G.gaussian_from_ply(G.synth_scene(SEEDS_CFG4[k], n_per_model))
+        packed = G.pack_gaussians(2, 1, g)
+        q = G.quat_from_euler_zyx_deg(xf[k][1])
+        m = v.add_model("model%d" % k, n_per_model)
+        m.upload_packed(0, packed)
+        m.set_transform(xf[k][0], q, xf[k][2])
+        kw = {}
+        if k == 1:
+            m.eval_mask(ops, shapes)
+            mask_gpu = m.download_mask()
+            ref_model = O.ModelRef(2, 1, packed, n_per_model, pos=xf[k][0], quat=q, scale=xf[k][2])
+            mask_ref = O.eval_mask(ref_model, ops.astype(O.MASK_OP), shapes.astype(O.MASK_SHAPE))
+            assert np.array_equal(mask_gpu, mask_ref)             # mask bitset: bit-exact
+            assert 0 < bits_set(mask_ref, n_per_model).sum() < n_per_model
+            kw["mask"] = mask_ref
+        if k == 2:
+            sel = pack_bits(g["pos"][:, 0] > 0)                    # "rect-selected half"
+            edits = np.zeros(n_per_model, G.EDIT)
+            edits["color"], edits["gamma"], edits["alpha"] = (0, 1, 1), 1, 1
+            chosen = bits_set(sel, n_per_model)
+            for key, val in edit.items():
+                edits[key][chosen] = val
+            m.upload_edits(0, edits)
+            kw["edits"] = edits.astype(O.EDIT)
+        gm.append(m)
+        om.append(O.ModelRef(2, 1, packed, n_per_model, pos=xf[k][0], quat=q, scale=xf[k][2], **kw))
+        centers.append(g["pos"].mean(0))
+    v.update_camera(cam)
+    order_g = v.order_models(gm, np.array(centers, np.float32))
+    order_o = O.order_models(f, om, np.array(centers, np.float32))
+    assert [gm.index(x) for x in order_g] == order_o.tolist()     # farthest centre first
+    far_to_near_o = [om[i] for i in order_o]
+    return v, f, order_g, far_to_near_o
+
+
+def test_config4_three_models_edits_mask(G, O):
+    v, f, gms, oms = _config4(G, O, 150_000, 1920, 1080)
+    try:
+        img = v.render_frame_host(gms).copy()
+        for gmod, omod in zip(gms, oms):
+            oi, ok, osp = O.preprocess(f, omod)
+            ok, oi, osp = O.sort(ok, oi, osp)
+            assert np.array_equal(gmod.indices(), oi) and np.array_equal(gmod.depth_keys(), ok)
+            _splats_close(gmod.splats(), osp)                      # edited colours: powf/exp2f tolerance
+        ref, total, _ = O.render_frame(f, oms, front_to_back=False)
+        assert v.last_timings().visible == total
+        assert_image_close(img, ref)
+        # layering is per model, not a global depth sort: reversing the order changes the image
+        img_rev = v.render_frame_host(gms[::-1]).copy()
+        assert psnr(img_rev, ref) < 45
+    finally:
+        v.close()
+
+
+def test_config4_full_size_properties(G, O):
+    """3 x 2M at 1080p: visible counts and sorted order per model exact; image within tolerance."""
+    v, f, gms, oms = _config4(G, O, 2_000_000, 1920, 1080)
+    try:
+        img = v.render_frame_host(gms).copy()
+        for gmod, omod in zip(gms, oms):
+            oi, ok, _ = O.preprocess(f, omod)
+            ok, oi, _ = O.sort(ok, oi)
+            assert np.array_equal(gmod.indices(), oi) and np.array_equal(gmod.depth_keys(), ok)
+        ref, _, _ = O.render_frame(f, oms, front_to_back=False)
+        assert_image_close(img, ref)
+        assert np.array_equal(img, v.render_frame_host(gms))       # idempotent: same bytes again
+    finally:
+        v.close()
+
+
+def test_selection_highlight_hidden_and_unedited(G, O):
+    W, H, n = 640, 360, 40_000
+    g = G.gaussian_from_ply(G.synth_scene(0xB2000079, n))
+    packed = G.pack_gaussians(2, 1, g)
+    sel = pack_bits(g["pos"][:, 1] > 0)
+    mask = pack_bits(np.arange(n) % 3 != 0)
+    cam = G.OrbitCamera.orbit()
+    view, proj = cam.view(), cam.projection(np.float32(W) / np.float32(H))
+    with G.Viewer(W, H) as v:
+        m = v.add_model("m", n)
+        m.upload_packed(0, packed)
+        m.upload_selection(sel)
+        m.upload_mask(mask)
+        v.update_camera(cam)
+        assert np.array_equal(m.download_mask(), mask) and np.array_equal(m.download_selection(), sel)
+        # highlight only (reference scene.rs:822-829)
+        v.update_selection_highlight((1.0, 0.0, 1.0, 0.5))
+        f = O.make_frame(view, proj, W, H, highlight=(1.0, 0.0, 1.0, 0.5))
+        om = O.ModelRef(2, 1, packed, n, mask=mask, selection=sel)
+        img = v.render_frame_host([m]).copy()
+        oi, ok, osp = O.preprocess(f, om)
+        ok, oi, osp = O.sort(ok, oi, osp)
+        assert np.array_equal(m.indices(), oi)
+        _splats_close(m.splats(), osp)
+        assert_image_close(img, O.composite(f, osp)[0])
+        # a live selection edit that hides the selection (GaussianEditFlag::HIDDEN, app.rs:1548-1551)
+        pod = G.EditPod.new(G.EDIT_ENABLED | G.EDIT_HIDDEN)
+        v.update_selection_edit(pod)
+        v.update_selection_highlight((0, 0, 0, 0))
+        f2 = O.make_frame(view, proj, W, H, selection_edit=O.edit_pod(flag=3))
+        m.preprocess()
+        oi2, _, _ = O.preprocess(f2, om)
+        assert np.array_equal(m.indices(), oi2) and len(oi2) < len(oi)
+        # show_unedited (reference scene.rs:843-849, 858-861): blank edit buffer + default pod
+        m.preprocess(use_unedited=True)
+        f3 = O.make_frame(view, proj, W, H)
+        oi3, _, _ = O.preprocess(f3, om)
+        assert np.array_equal(m.indices(), oi3)
+        # postprocess commits the selection edit into the per-Gaussian edit buffer (scene.rs:604-610)
+        pod2 = G.EditPod.new(G.EDIT_ENABLED | G.EDIT_OVERRIDE_COLOR, color=(0.1, 0.9, 0.2), alpha=0.7)
+        v.update_selection_edit(pod2)
+        m.postprocess()
+        ed = m.download_edits()
+        chosen = bits_set(sel, n)
+        assert np.all(ed["flag"][chosen] == 5) and np.all(ed["flag"][~chosen] == 0)
+        assert np.allclose(ed["color"][chosen], (0.1, 0.9, 0.2)) and np.allclose(ed["alpha"][chosen], 0.7)
+
+
+# ------------------------------------------------------------------ sort
+@pytest.mark.parametrize("n", [1, 2, 255, 4095, 4096, 4097, 100_003, 1 << 20, 5_000_000])
+def test_sort_pairs_matches_stable_sort(G, O, n):
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    vals = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    with G.Viewer(16, 16) as v:
+        k, val = v.sort_pairs(keys, vals)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(k, keys[order]) and np.array_equal(val, vals[order])
+    if n <= 200_000:
+        ko, vo = O.sort_pairs(keys, vals)
+        assert np.array_equal(k, ko) and np.array_equal(val, vo)
+
+
+def test_sort_ties_collisions_and_16bit(G):
+    rng = np.random.default_rng(5)
+    n = 300_000
+    with G.Viewer(16, 16) as v:
+        for keys in (np.zeros(n, np.uint32), np.full(n, 0xFFFFFFFF, np.uint32),
+                     rng.integers(0, 4, n).astype(np.uint32) << 24, rng.integers(0, 7, n).astype(np.uint32),
+                     np.arange(n, dtype=np.uint32)[::-1].copy(),
+                     np.float32(rng.uniform(0.9, 1.0, n)).view(np.uint32)):      # depth-like keys: shared top bytes
+            vals = np.arange(n, dtype=np.uint32)
+            k, val = v.sort_pairs(keys, vals)
+            order = np.argsort(keys, kind="stable")
+            assert np.array_equal(k, keys[order]) and np.array_equal(val, order.astype(np.uint32))   # ties keep input order
+        keys = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+        k, val = v.sort_pairs(keys, np.arange(n, dtype=np.uint32), bits=16)
+        order = np.argsort(keys & 0xFFFF, kind="stable")
+        assert np.array_equal(val, order.astype(np.uint32))
+
+
+# ------------------------------------------------------------------ edge cases & ABI behaviour
+def test_edge_cases(G, O):
+    W, H = 320, 200
+    cam = G.OrbitCamera.orbit()
+    with G.Viewer(W, H) as v:
+        v.update_camera(cam)
+        # nothing uploaded yet: capacity is rendered as zero records (streaming-upload contract,
+        # reference scene.rs:341-380): zero opacity, so a transparent image
+        m = v.add_model("empty", 1000)
+        img = v.render_frame_host([m]).copy()
+        assert not img.any()
+        # a model entirely behind the camera: V = 0
+        g = make_gaussians(G.GAUSSIAN, np.tile(np.array(cam.pos, np.float32) * 2.0, (513, 1)), scale=0.01)
+        m2 = v.add_model("behind", 513)
+        m2.update_range(0, g)
+        img = v.render_frame_host([m2]).copy()
+        assert m2.visible_count() == 0 and not img.any()
+        # no models at all: background only
+        v.set_background((1.0, 0.5, 0.25, 1.0))
+        img = v.render_frame_host([]).copy()
+        assert np.all(img == np.array([255, 128, 64, 255], np.uint8))
+        v.set_background((0, 0, 0, 0))
+        # ragged sizes around the 256-Gaussian chunk
+        for n in (1, 255, 256, 257, 1023):
+            ply = G.synth_scene(77, n)
+            gg = G.gaussian_from_ply(ply)
+            packed = G.pack_gaussians(2, 1, gg)
+            mm = v.add_model("r%d" % n, n)
+            mm.upload_packed(0, packed)
+            mm.preprocess()
+            f = O.make_frame(cam.view(), cam.projection(np.float32(W) / np.float32(H)), W, H)
+            oi, ok, _ = O.preprocess(f, O.ModelRef(2, 1, packed, n))
+            assert np.array_equal(mm.indices(), oi) and np.array_equal(mm.depth_keys(), ok)
+            v.remove_model("r%d" % n)
+        # partial upload: update_range into the middle of the buffer
+        n = 5000
+        gg = G.gaussian_from_ply(G.synth_scene(78, n))
+        mm = v.add_model("partial", n)
+        mm.update_range(1000, gg[1000:3000])
+        back = mm.download_packed(1000, 2000)
+        assert back.tobytes() == G.pack_gaussians(2, 1, gg[1000:3000]).tobytes()
+
+
+def test_huge_splat_and_tile_capacity_overflow(G, O):
+    """A splat covering the whole screen touches every tile; a tiny entry capacity must flag
+    overflow instead of corrupting memory."""
+    W, H = 640, 360
+    g = make_gaussians(G.GAUSSIAN, [[0, 0, 0], [0.1, 0, 0.5]], scale=3.0, color=(200, 100, 50, 128))
+    cam = G.OrbitCamera(pos=(0, 0, 2.0))
+    with G.Viewer(W, H, G.SH_NONE, G.COV3D_SINGLE) as v:
+        m = v.add_model("big", 2)
+        m.update_range(0, g)
+        v.update_camera(cam)
+        img = v.render_frame_host([m]).copy()
+        t = v.last_timings()
+        assert t.tile_entries == 2 * ((W + 15) // 16) * ((H + 15) // 16) and t.overflow == 0
+        f = O.make_frame(cam.view(), cam.projection(np.float32(W) / np.float32(H)), W, H)
+        ref, _, _ = O.render_frame(f, [O.ModelRef(3, 0, G.pack_gaussians(3, 0, g), 2)])
+        assert_image_close(img, ref)
+        v.set_tile_entry_capacity(100)
+        v.render_frame_host([m])
+        assert v.last_timings().overflow == 1
+
+
+def test_call_order_errors(G):
+    with G.Viewer(64, 64) as v:
+        m = v.add_model("m", 10)
+        with pytest.raises(G.GsError):
+            m.sort()                                               # sort before preprocess
+        m.preprocess()
+        with pytest.raises(G.GsError):
+            v.render([m], v.image_device())                        # render before sort
+        with pytest.raises(G.GsError):
+            v.add_model("m", 10)                                   # duplicate key
+        with pytest.raises(G.GsError):
+            m.upload_packed(5, np.zeros(10 * v.record_bytes, np.uint8))   # range exceeds capacity
+        with pytest.raises(G.GsError):
+            m.upload_mask(np.zeros(5, np.uint32))                  # wrong bitset length
+        with pytest.raises(G.GsError):
+            v.update_gaussian_transform(1.0, 0, 4, False)          # GaussianShDegree::new(4) is None
+        with pytest.raises(G.GsError):
+            m.eval_mask(np.array([(1, 0)], G.MASK_OP), np.zeros(0, G.MASK_SHAPE))   # malformed tree
+
+
+def test_resize_and_determinism(G, O):
+    n = 60_000
+    packed = G.pack_gaussians(2, 1, G.gaussian_from_ply(G.synth_scene(SEED_100K, n)))
+    cam = G.OrbitCamera.orbit()
+    with G.Viewer(320, 180) as v:
+        m = v.add_model("m", n)
+        m.upload_packed(0, packed)
+        imgs = {}
+        for (W, H) in [(320, 180), (1280, 720), (320, 180)]:
+            v.resize(W, H)
+            v.update_camera(cam)
+            img = v.render_frame_host([m]).copy()
+            f = O.make_frame(cam.view(), cam.projection(np.float32(W) / np.float32(H)), W, H)
+            ref, _, _ = O.render_frame(f, [O.ModelRef(2, 1, packed, n)])
+            assert_image_close(img, ref)
+            if (W, H) in imgs:
+                assert np.array_equal(img, imgs[(W, H)])           # same view -> same bytes
+            imgs[(W, H)] = img
