@@ -424,7 +424,8 @@ static int pre_one(const orc_frame* f, const orc_model* m, const pre_ctx* c, uin
     for (int r = 0; r < 3; r++) pv[r] = c->V[r][0] * pw[0] + c->V[r][1] * pw[1] + c->V[r][2] * pw[2] + c->V[r][3];
     for (int r = 0; r < 4; r++) pc[r] = c->P[r][0] * pv[0] + c->P[r][1] * pv[1] + c->P[r][2] * pv[2] + c->P[r][3];
     if (!(pc[3] > 0.0f)) return 0;
-    float nx = pc[0] / pc[3], ny = pc[1] / pc[3], nz = pc[2] / pc[3];
+    float iw = 1.0f / pc[3]; /* one IEEE reciprocal, then multiplies */
+    float nx = pc[0] * iw, ny = pc[1] * iw, nz = pc[2] * iw;
     /* frustum cull [RECALLED §8c.5] */
     if (!(nz > 0.0f && nz < 1.0f && fabsf(nx) <= ORC_CULL_XY && fabsf(ny) <= ORC_CULL_XY)) return 0;
     /* depth key [§8c.6]: bits(ndc.z), ascending = near -> far */
@@ -443,13 +444,14 @@ static int pre_one(const orc_frame* f, const orc_model* m, const pre_ctx* c, uin
 
     /* Jacobian of the pixel mapping [CANON §8c.7]; view space is RH, looking down -z */
     float tz = -pv[2];
-    float txz = pv[0] / tz, tyz = pv[1] / tz;
+    float itz = 1.0f / tz;
+    float txz = pv[0] * itz, tyz = pv[1] * itz;
     txz = fminf(c->limx, fmaxf(-c->limx, txz));
     tyz = fminf(c->limy, fmaxf(-c->limy, tyz));
     float xc = txz * tz, yc = tyz * tz;
-    float tz2 = tz * tz;
-    float J00 = c->fx / tz, J02 = (c->fx * xc) / tz2;
-    float J11 = -(c->fy / tz), J12 = -((c->fy * yc) / tz2);
+    float itz2 = itz * itz;
+    float J00 = c->fx * itz, J02 = (c->fx * xc) * itz2;
+    float J11 = -(c->fy * itz), J12 = -((c->fy * yc) * itz2);
     float T0[3], T1[3];
     for (int k = 0; k < 3; k++) {
         T0[k] = J00 * c->V[0][k] + J02 * c->V[2][k];

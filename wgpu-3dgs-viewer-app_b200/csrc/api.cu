@@ -149,6 +149,10 @@ static GsFrame make_frame(const b200gs_viewer* v) {
     memcpy(f.bg, v->bg, 16);
     f.tiles_x = (v->W + GS_TILE - 1) / GS_TILE;
     f.tiles_y = (v->H + GS_TILE - 1) / GS_TILE;
+    const float (*P)[4] = f.P;
+    f.std_proj = (P[0][1] == 0.0f && P[0][2] == 0.0f && P[0][3] == 0.0f && P[1][0] == 0.0f && P[1][2] == 0.0f &&
+                  P[1][3] == 0.0f && P[2][0] == 0.0f && P[2][1] == 0.0f && P[3][0] == 0.0f && P[3][1] == 0.0f &&
+                  P[3][3] == 0.0f) ? 1u : 0u;
     return f;
 }
 
@@ -158,6 +162,12 @@ static GsModelXf make_xf(const b200gs_model* m) {
     for (int a = 0; a < 3; a++) { x.t[a] = m->pos[a]; x.s[a] = m->scale[a]; }
     for (int a = 0; a < 3; a++)
         for (int b = 0; b < 3; b++) x.M[a][b] = x.R[a][b] * x.s[b];
+    x.identity = 1u;
+    for (int a = 0; a < 3; a++) {
+        if (x.t[a] != 0.0f || x.s[a] != 1.0f) x.identity = 0u;
+        for (int b = 0; b < 3; b++)
+            if (x.R[a][b] != (a == b ? 1.0f : 0.0f)) x.identity = 0u;
+    }
     return x;
 }
 
@@ -611,6 +621,7 @@ extern "C" int b200gs_model_preprocess(b200gs_model* m, int use_unedited) {
     a.mask = m->mask; a.selection = m->selection; a.edits = use_unedited ? nullptr : m->edits;
     a.ctrl = m->ctrl + MC_CTRL; a.lookback = m->lb_pre; a.epoch = ++v->epoch;
     a.keys = m->keys_a; a.idx = m->idx; a.splats = v->arena + m->arena_offset;
+    a.sort_hist = m->ctrl + MC_SORT_HIST;
     if (v->timing) CK(cudaEventRecord(v->ev[0], v->stream));
     CK(gs_launch_preprocess(a, f, xf, v->num_sms, v->stream));
     if (v->timing) CK(cudaEventRecord(v->ev[1], v->stream));
@@ -622,13 +633,14 @@ extern "C" int b200gs_model_preprocess(b200gs_model* m, int use_unedited) {
 extern "C" int b200gs_model_sort(b200gs_model* m) {
     REQUIRE(m, "null model");
     REQUIRE(m->preprocessed, "sort called before preprocess");
+    if (m->sorted) return B200GS_OK;  // already sorted since the last preprocess
     b200gs_viewer* v = m->v;
     TRY(set_device(v));
     GsSortArgs a;
     a.keys_a = m->keys_a; a.vals_a = m->vals_a; a.keys_b = m->keys_b; a.vals_b = m->vals_b;
     a.d_n = m->ctrl + MC_CTRL + GS_CTRL_VISIBLE; a.n_max = (uint32_t)m->cap;
     a.hist = m->ctrl + MC_SORT_HIST; a.lookback = m->lb_sort; a.epoch = ++v->epoch;
-    a.tickets = m->ctrl + MC_SORT_TICKET; a.passes = 4; a.hist_prefilled = false; a.vals_identity = true;
+    a.tickets = m->ctrl + MC_SORT_TICKET; a.passes = 4; a.hist_prefilled = true; a.vals_identity = true;
     CK(gs_launch_sort(a, v->num_sms, v->stream));
     if (v->timing) CK(cudaEventRecord(v->ev[2], v->stream));
     m->sorted = true;

@@ -39,6 +39,7 @@ struct GsFrame {
     float hl[4];
     float bg[4];
     uint32_t tiles_x, tiles_y;
+    uint32_t std_proj;  // 1: only P00,P11,P22,P23,P32 are non-zero (glam perspective_rh): kernels skip the zero terms
 };
 
 // Per-model uniforms (ModelTransformPod, scene.rs:796-802)
@@ -47,6 +48,7 @@ struct GsModelXf {
     float t[3];
     float s[3];
     float M[3][3];  // R * diag(s)
+    uint32_t identity;  // 1: R = I, s = 1, t = 0 exactly: kernels skip the model transform
 };
 
 // Control block of one model in device memory (u32 words)
@@ -69,6 +71,7 @@ struct GsPreprocessArgs {
     uint64_t* lookback;  // one status word per 256-Gaussian chunk (epoch-tagged, never cleared)
     uint32_t epoch;
     uint32_t* keys; uint32_t* idx; b200gs_splat* splats;
+    uint32_t* sort_hist;  // 4 x 256 digit histogram of the emitted keys (zeroed before launch), or null
 };
 cudaError_t gs_launch_preprocess(const GsPreprocessArgs& a, const GsFrame& f, const GsModelXf& m, int num_sms,
                                  cudaStream_t st);
@@ -163,12 +166,12 @@ __device__ __forceinline__ void gs_tma_load_1d(void* dst_smem, const void* src_g
 // and epochs start at 1).
 __device__ __forceinline__ uint64_t gs_ld_status(const uint64_t* p) {
     uint64_t v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void gs_st_status(uint64_t* p, uint32_t epoch, uint32_t flag_value) {
     uint64_t v = ((uint64_t)epoch << 32) | flag_value;
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t gs_status_flag(uint64_t v, uint32_t epoch) {
     return ((uint32_t)(v >> 32) == epoch) ? (((uint32_t)v) >> 30) : 0u;

@@ -8,14 +8,19 @@
 // ASCENDING INDEX ORDER (order-preserving compaction by decoupled look-back, so that the later
 // stable sort is deterministic): depth key, Gaussian index, and a 32-byte projected splat.
 //
-// Data movement: persistent CTAs; each 256-Gaussian chunk (256*R contiguous bytes, 16-byte
-// aligned because 256*R is a multiple of 1024) is pulled into shared memory with one 1-D TMA
-// bulk copy (cp.async.bulk -> UBLKCP) on an mbarrier, NSTAGE chunks in flight per CTA; each
-// thread then reads its own record from shared memory (word stride R/4).
+// Data movement: persistent CTAs of 8 compute warps + 1 control warp; each 256-Gaussian chunk
+// (256*R contiguous bytes, 16-byte aligned because 256*R is a multiple of 1024) is pulled into
+// shared memory with one 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) on an mbarrier, NSTAGE
+// chunks in flight per CTA; each compute thread then reads its own record from shared memory
+// (word stride R/4).  The control warp owns tickets, TMA issue and the decoupled look-back, so
+// the look-back latency overlaps the compute warps' heavy phase (named barriers, no
+// __syncthreads in the loop).
 //
-// THIS FILE IS COMPILED WITH -fmad=false: every float operation rounds separately, in source
-// order, so that culling, depth keys and pixel bounds are bit-identical to the CPU oracle's
-// (which is built with -ffp-contract=off).  Do not re-associate the arithmetic.
+// THIS FILE IS COMPILED WITH -fmad=false: in the EXACT class (position chain, cull, depth key,
+// pixel centre, covariance -> conic/extent) every float operation rounds separately, in source
+// order, so that those results are bit-identical to the CPU oracle's (built with
+// -ffp-contract=off).  Do not re-associate that arithmetic.  The TOLERANCE class (SH colour,
+// edits) uses explicit __fmaf_rn / rsqrtf and is compared within the RGBA tolerance.
 #include "common.cuh"
 
 namespace {
@@ -26,8 +31,8 @@ template <int SH> struct ShBytes { static constexpr int v = SH == 0 ? 180 : SH =
 template <int COV> struct CovBytes { static constexpr int v = COV == 0 ? 24 : 12; };
 
 __host__ __device__ constexpr int stages_for(int rb) {
-    int s = 110000 / (kChunk * rb);
-    return s < 2 ? 2 : (s > 4 ? 4 : s);
+    int s = 70000 / (kChunk * rb);  // <= ~70 KB of stages per CTA: 3 CTAs per SM for the common layouts
+    return s < 2 ? 2 : (s > 3 ? 3 : s);
 }
 
 __device__ __forceinline__ float h2f_lo(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))); }
@@ -98,16 +103,30 @@ __device__ void apply_edit(const b200gs_edit_pod& e, float rgb[3], float& op) {
     op = clamp01(op * e.alpha);
 }
 
+// named barriers (id 0 is __syncthreads)
+constexpr int kBarCounts = 1;   // compute warps -> control warp: per-warp visible counts are in smem
+constexpr int kBarBase = 2;     // control warp -> compute warps: this chunk's output base is in smem
+constexpr int kBarFree = 3;     // (+ iteration parity) compute warps -> control warp: stage can be refilled
+constexpr int kThreads = kChunk + 32;  // 8 compute warps + 1 control warp
+
+__device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kThreads) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kThreads) : "memory"); }
+
+// byte k of x as a float, without I2F: PRMT builds 0x4B0000bb (= 8388608 + b), one FADD removes the bias
+__device__ __forceinline__ float byte_to_float(uint32_t x, int k) {
+    return __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7440u | (uint32_t)k)) - 8388608.0f;
+}
+
 template <int SH, int COV>
-__global__ void __launch_bounds__(kChunk) k_preprocess(const uint8_t* __restrict__ recs, uint32_t n,
-                                                       const uint32_t* __restrict__ mask,
-                                                       const uint32_t* __restrict__ selection,
-                                                       const b200gs_edit_pod* __restrict__ edits,
-                                                       const __grid_constant__ GsFrame f,
-                                                       const __grid_constant__ GsModelXf m, uint32_t* ctrl,
-                                                       uint64_t* lookback, uint32_t epoch,
-                                                       uint32_t* __restrict__ keys,
-                                                       uint32_t* __restrict__ idx, b200gs_splat* __restrict__ splats) {
+__global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restrict__ recs, uint32_t n,
+                                                         const uint32_t* __restrict__ mask,
+                                                         const uint32_t* __restrict__ selection,
+                                                         const b200gs_edit_pod* __restrict__ edits,
+                                                         const __grid_constant__ GsFrame f,
+                                                         const __grid_constant__ GsModelXf m, uint32_t* ctrl,
+                                                         uint64_t* lookback, uint32_t epoch,
+                                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ idx,
+                                                         b200gs_splat* __restrict__ splats, uint32_t* sort_hist) {
     constexpr int RB = 16 + ShBytes<SH>::v + CovBytes<COV>::v;  // record bytes
     constexpr int RW = RB / 4;                                  // record words
     constexpr int NSTAGE = stages_for(RB);
@@ -117,11 +136,13 @@ __global__ void __launch_bounds__(kChunk) k_preprocess(const uint8_t* __restrict
     uint8_t* stage_mem = smem;  // NSTAGE * STAGE_BYTES
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
     uint32_t* s_chunk = reinterpret_cast<uint32_t*>(bars + NSTAGE);  // NSTAGE
-    uint32_t* s_wcount_all = s_chunk + NSTAGE;                       // 2 x 8 warp counts (double-buffered)
+    uint32_t* s_wcount_all = s_chunk + NSTAGE;                       // 2 x 8 warp counts (by iteration parity)
     uint32_t* s_base_all = s_wcount_all + 16;                        // 2
+    uint32_t* s_hist = s_base_all + 2;                               // 4 x 256 (only if sort_hist)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t nchunks = (n + kChunk - 1) / kChunk;
+    const bool is_control = warp == kChunk / 32;
 
     auto issue = [&](int stage, uint32_t c) {
         uint32_t cnt = min((uint32_t)kChunk, n - c * kChunk);
@@ -130,7 +151,7 @@ __global__ void __launch_bounds__(kChunk) k_preprocess(const uint8_t* __restrict
         gs_tma_load_1d(stage_mem + (size_t)stage * STAGE_BYTES, recs + (size_t)c * STAGE_BYTES, bytes, &bars[stage]);
     };
 
-    if (tid == 0) {
+    if (tid == kChunk) {
         for (int s = 0; s < NSTAGE; s++) gs_mbar_init(&bars[s], 1);
         gs_fence_mbar_init();
         for (int s = 0; s < NSTAGE; s++) {
@@ -139,230 +160,300 @@ __global__ void __launch_bounds__(kChunk) k_preprocess(const uint8_t* __restrict
             if (c < nchunks) issue(s, c);
         }
     }
+    if (sort_hist)
+        for (int i = tid; i < 1024; i += kThreads) s_hist[i] = 0;
     __syncthreads();
 
-    for (uint32_t it = 0;; it++) {
-        const int stage = it % NSTAGE;
-        // double-buffered by iteration parity: a fast warp may start iteration it+1 while a slow
-        // one still reads iteration it's counts in the output phase
-        uint32_t* s_wcount = s_wcount_all + (it & 1u) * 8;
-        uint32_t* s_base = s_base_all + (it & 1u);
-        const uint32_t c = s_chunk[stage];
-        if (c >= nchunks) break;
-        gs_mbar_wait(&bars[stage], (it / NSTAGE) & 1u);
-
-        const uint32_t i = c * kChunk + tid;
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)stage * STAGE_BYTES) + tid * RW;
-
-        // ---------------- phase 1: mask / hidden / frustum cull, depth key ----------------
-        bool vis = i < n;
-        bool selected = false;
-        b200gs_edit_pod ed;
-        ed.flag = 0;
-        if (vis && mask) vis = (mask[i >> 5] >> (i & 31)) & 1u;
-        if (vis && selection) selected = (selection[i >> 5] >> (i & 31)) & 1u;
-        if (vis && edits) {
-            const uint4* ep = reinterpret_cast<const uint4*>(edits + i);
-            uint4 e0 = ep[0], e1 = ep[1];
-            ed.flag = e0.x; ed.color[0] = __uint_as_float(e0.y); ed.color[1] = __uint_as_float(e0.z);
-            ed.color[2] = __uint_as_float(e0.w); ed.contrast = __uint_as_float(e1.x);
-            ed.exposure = __uint_as_float(e1.y); ed.gamma = __uint_as_float(e1.z); ed.alpha = __uint_as_float(e1.w);
-            if ((ed.flag & B200GS_EDIT_ENABLED) && (ed.flag & B200GS_EDIT_HIDDEN)) vis = false;
-        }
-        if (vis && selected && (f.sel_edit.flag & B200GS_EDIT_ENABLED) && (f.sel_edit.flag & B200GS_EDIT_HIDDEN))
-            vis = false;
-
-        float pw[3], pv[3], nx = 0.0f, ny = 0.0f, nz = 0.0f;
-        if (vis) {
-            float p0 = __uint_as_float(w[0]), p1 = __uint_as_float(w[1]), p2 = __uint_as_float(w[2]);
-            // world = q*(s⊙p)+t  (src/app.rs:1044-1046)
-            float ps0 = m.s[0] * p0, ps1 = m.s[1] * p1, ps2 = m.s[2] * p2;
-#pragma unroll
-            for (int r = 0; r < 3; r++) pw[r] = m.R[r][0] * ps0 + m.R[r][1] * ps1 + m.R[r][2] * ps2 + m.t[r];
-#pragma unroll
-            for (int r = 0; r < 3; r++) pv[r] = f.V[r][0] * pw[0] + f.V[r][1] * pw[1] + f.V[r][2] * pw[2] + f.V[r][3];
-            float pc[4];
-#pragma unroll
-            for (int r = 0; r < 4; r++) pc[r] = f.P[r][0] * pv[0] + f.P[r][1] * pv[1] + f.P[r][2] * pv[2] + f.P[r][3];
-            if (!(pc[3] > 0.0f)) vis = false;
-            else {
-                nx = pc[0] / pc[3]; ny = pc[1] / pc[3]; nz = pc[2] / pc[3];
-                vis = nz > 0.0f && nz < 1.0f && fabsf(nx) <= GS_CULL_XY && fabsf(ny) <= GS_CULL_XY;
-            }
-        }
-        const uint32_t ballot = __ballot_sync(0xffffffffu, vis);
-        if (lane == 0) s_wcount[warp] = __popc(ballot);
-        __syncthreads();  // (A)
-
-        // ---------------- phase 2: projected splat for the visible ones ----------------
-        uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
-        if (vis) {
-            const uint32_t* shw = w + 4;
-            const uint32_t* cw = w + 4 + ShBytes<SH>::v / 4;
-            float cv[6];
-            if (COV == 0) {
-#pragma unroll
-                for (int k = 0; k < 6; k++) cv[k] = __uint_as_float(cw[k]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 3; k++) { uint32_t x = cw[k]; cv[2 * k] = h2f_lo(x); cv[2 * k + 1] = h2f_hi(x); }
-            }
-            // Σ' = (R_m S_m) Σ (R_m S_m)^T · size²  (upper triangle)
-            float S[3][3] = {{cv[0], cv[1], cv[2]}, {cv[1], cv[3], cv[4]}, {cv[2], cv[4], cv[5]}};
-            float B[3][3], Sw[3][3];
-#pragma unroll
-            for (int r = 0; r < 3; r++)
-#pragma unroll
-                for (int k = 0; k < 3; k++) B[r][k] = m.M[r][0] * S[0][k] + m.M[r][1] * S[1][k] + m.M[r][2] * S[2][k];
-#pragma unroll
-            for (int r = 0; r < 3; r++)
-#pragma unroll
-                for (int k = r; k < 3; k++)
-                    Sw[r][k] = (B[r][0] * m.M[k][0] + B[r][1] * m.M[k][1] + B[r][2] * m.M[k][2]) * f.sz2;
-            Sw[1][0] = Sw[0][1]; Sw[2][0] = Sw[0][2]; Sw[2][1] = Sw[1][2];
-
-            // Jacobian of the pixel mapping (view space RH, looking down -z; rows flipped in y)
-            float tz = -pv[2];
-            float txz = pv[0] / tz, tyz = pv[1] / tz;
-            txz = fminf(f.limx, fmaxf(-f.limx, txz));
-            tyz = fminf(f.limy, fmaxf(-f.limy, tyz));
-            float xc = txz * tz, yc = tyz * tz;
-            float tz2 = tz * tz;
-            float J00 = f.fx / tz, J02 = (f.fx * xc) / tz2;
-            float J11 = -(f.fy / tz), J12 = -((f.fy * yc) / tz2);
-            float T0[3], T1[3], U0[3], U1[3];
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                T0[k] = J00 * f.V[0][k] + J02 * f.V[2][k];
-                T1[k] = J11 * f.V[1][k] + J12 * f.V[2][k];
-            }
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                U0[k] = T0[0] * Sw[0][k] + T0[1] * Sw[1][k] + T0[2] * Sw[2][k];
-                U1[k] = T1[0] * Sw[0][k] + T1[1] * Sw[1][k] + T1[2] * Sw[2][k];
-            }
-            float a = U0[0] * T0[0] + U0[1] * T0[1] + U0[2] * T0[2];
-            float b = U0[0] * T1[0] + U0[1] * T1[1] + U0[2] * T1[2];
-            float d = U1[0] * T1[0] + U1[1] * T1[1] + U1[2] * T1[2];
-            a = a + GS_LOWPASS;
-            d = d + GS_LOWPASS;
-            float det = a * d - b * b;
-            float ca = 0.0f, cb = 0.0f, cc = 0.0f, radf = 0.0f;
-            if (det > 0.0f) {
-                float di = 1.0f / det;
-                ca = d * di; cb = -b * di; cc = a * di;
-                float mid = 0.5f * (a + d);
-                float disc = mid * mid - det;
-                if (disc < GS_MIN_DISC) disc = GS_MIN_DISC;
-                float lam = mid + sqrtf(disc);
-                radf = ceilf(GS_EXTENT_SIGMA * sqrtf(lam));
-            }
-            if (f.display_mode == B200GS_DISPLAY_POINT) {
-                ca = GS_FLAT_D2 / (GS_POINT_RADIUS * GS_POINT_RADIUS); cb = 0.0f; cc = ca;
-                radf = ceilf(GS_POINT_RADIUS);
-            }
-            if (!(radf <= 65535.0f)) radf = 65535.0f;
-
-            // colour: baked SH0 (u8) + bands 1..sh_deg, view direction in world space
-            float dx = pw[0] - f.cam[0], dy = pw[1] - f.cam[1], dz = pw[2] - f.cam[2];
-            float dl = sqrtf(dx * dx + dy * dy + dz * dz);
-            dx = dx / dl; dy = dy / dl; dz = dz / dl;
-            float bs[15];
-#pragma unroll
-            for (int k = 0; k < 15; k++) bs[k] = 0.0f;
-            const uint32_t deg = SH == 3 ? 0u : f.sh_deg;
-            if (deg >= 1) {
-                bs[0] = -0.4886025119029199f * dy;
-                bs[1] = 0.4886025119029199f * dz;
-                bs[2] = -0.4886025119029199f * dx;
-            }
-            if (deg >= 2) {
-                float xx = dx * dx, yy = dy * dy, zz = dz * dz, xy = dx * dy, yz = dy * dz, xz = dx * dz;
-                bs[3] = 1.0925484305920792f * xy;
-                bs[4] = -1.0925484305920792f * yz;
-                bs[5] = 0.31539156525252005f * (2.0f * zz - xx - yy);
-                bs[6] = -1.0925484305920792f * xz;
-                bs[7] = 0.5462742152960396f * (xx - yy);
-                if (deg >= 3) {
-                    bs[8] = -0.5900435899266435f * dy * (3.0f * xx - yy);
-                    bs[9] = 2.890611442640554f * xy * dz;
-                    bs[10] = -0.4570457994644658f * dy * (4.0f * zz - xx - yy);
-                    bs[11] = 0.3731763325901154f * dz * (2.0f * zz - 3.0f * xx - 3.0f * yy);
-                    bs[12] = -0.4570457994644658f * dx * (4.0f * zz - xx - yy);
-                    bs[13] = 1.445305721320277f * dz * (xx - yy);
-                    bs[14] = -0.5900435899266435f * dx * (xx - 3.0f * yy);
-                }
-            }
-            const uint32_t colw = w[3];
-            float rgb[3];
-            const int ncoef = deg >= 3 ? 15 : (deg == 2 ? 8 : (deg == 1 ? 3 : 0));
-#pragma unroll
-            for (int ch = 0; ch < 3; ch++) rgb[ch] = f.no_sh0 ? 0.0f : (float)((colw >> (8 * ch)) & 0xffu) / 255.0f;
-            if (SH != 3) {
-#pragma unroll
-                for (int k = 0; k < 15; k++) {
-                    if (k < ncoef) {
-#pragma unroll
-                        for (int ch = 0; ch < 3; ch++) rgb[ch] = rgb[ch] + bs[k] * sh_coef<SH>(shw, 3 * k + ch);
-                    }
-                }
-            }
-#pragma unroll
-            for (int ch = 0; ch < 3; ch++) rgb[ch] = clamp01(rgb[ch]);
-            float op = (float)(colw >> 24) / 255.0f;
-            if (edits) apply_edit(ed, rgb, op);
-            if (selected) {
-                apply_edit(f.sel_edit, rgb, op);
-                float ha = f.hl[3];
-#pragma unroll
-                for (int ch = 0; ch < 3; ch++) rgb[ch] = rgb[ch] + (f.hl[ch] - rgb[ch]) * ha;
-            }
-#pragma unroll
-            for (int ch = 0; ch < 3; ch++) rgb[ch] = clamp01(rgb[ch]);
-
-            float mx = ((nx + 1.0f) * f.W - 1.0f) * 0.5f;
-            float my = ((1.0f - ny) * f.H - 1.0f) * 0.5f;
-            q0.x = __float_as_uint(mx);
-            q0.y = __float_as_uint(my);
-            q0.z = (uint32_t)radf | ((uint32_t)__half_as_ushort(__float2half_rn(op)) << 16);
-            q0.w = (uint32_t)__half_as_ushort(__float2half_rn(rgb[0])) |
-                   ((uint32_t)__half_as_ushort(__float2half_rn(rgb[1])) << 16);
-            q1.x = __float_as_uint(ca);
-            q1.y = __float_as_uint(cb);
-            q1.z = __float_as_uint(cc);
-            q1.w = (uint32_t)__half_as_ushort(__float2half_rn(rgb[2])) | ((selected ? 1u : 0u) << 16);
-        }
-        __syncthreads();  // (B) every read of this stage's shared memory is done
-
-        // refill the stage, then resolve this chunk's output base by decoupled look-back
-        if (tid == 0) {
-            uint32_t c2 = atomicAdd(&ctrl[GS_CTRL_TICKET], 1u);
-            s_chunk[stage] = c2;
-            if (c2 < nchunks) issue(stage, c2);
-        }
-        if (warp == 1) {
-            uint32_t wc = lane < 8 ? s_wcount[lane] : 0u;
+    if (is_control) {
+        // ------------------------------------------------------------ control warp
+        // Resolves each chunk's output base by decoupled look-back WHILE the compute warps are in
+        // their heavy phase, then refills the stage with the next ticket's chunk by TMA.
+        for (uint32_t it = 0;; it++) {
+            const int stage = it % NSTAGE;
+            const uint32_t par = it & 1u;
+            const uint32_t c = s_chunk[stage];
+            if (c >= nchunks) break;
+            bar_sync(kBarCounts);
+            uint32_t wc = lane < 8 ? s_wcount_all[par * 8 + lane] : 0u;
             uint32_t total = wc;
 #pragma unroll
             for (int o = 4; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
             total = __shfl_sync(0xffffffffu, total, 0);
-            uint32_t excl = gs_lookback_warp(lookback, epoch, c, total, lane);
+            const uint32_t excl = gs_lookback_warp(lookback, epoch, c, total, lane);
             if (lane == 0) {
-                *s_base = excl;
+                s_base_all[par] = excl;
                 if (c == nchunks - 1) ctrl[GS_CTRL_VISIBLE] = excl + total;
             }
+            bar_arrive(kBarBase);
+            bar_sync(kBarFree + (int)par);
+            if (lane == 0) {
+                uint32_t c2 = atomicAdd(&ctrl[GS_CTRL_TICKET], 1u);
+                s_chunk[stage] = c2;
+                if (c2 < nchunks) issue(stage, c2);
+            }
+            __syncwarp();
         }
-        __syncthreads();  // (C)
+    } else {
+        // ------------------------------------------------------------ compute warps
+        for (uint32_t it = 0;; it++) {
+            const int stage = it % NSTAGE;
+            const uint32_t par = it & 1u;
+            const uint32_t c = s_chunk[stage];
+            if (c >= nchunks) break;
+            gs_mbar_wait(&bars[stage], (it / NSTAGE) & 1u);
 
-        if (vis) {
-            uint32_t off = *s_base;
-            for (int k = 0; k < warp; k++) off += s_wcount[k];
-            off += __popc(ballot & ((1u << lane) - 1u));
-            keys[off] = __float_as_uint(nz);
-            idx[off] = i;
-            uint4* sp = reinterpret_cast<uint4*>(splats + off);
-            sp[0] = q0;
-            sp[1] = q1;
+            const uint32_t i = c * kChunk + tid;
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)stage * STAGE_BYTES) + tid * RW;
+
+            // ---------------- phase 1: mask / hidden / frustum cull, depth key (exact class) -------
+            bool vis = i < n;
+            bool selected = false;
+            b200gs_edit_pod ed;
+            ed.flag = 0;
+            if (vis && mask) vis = (mask[i >> 5] >> (i & 31)) & 1u;
+            if (vis && selection) selected = (selection[i >> 5] >> (i & 31)) & 1u;
+            if (vis && edits) {
+                const uint4* ep = reinterpret_cast<const uint4*>(edits + i);
+                uint4 e0 = ep[0], e1 = ep[1];
+                ed.flag = e0.x; ed.color[0] = __uint_as_float(e0.y); ed.color[1] = __uint_as_float(e0.z);
+                ed.color[2] = __uint_as_float(e0.w); ed.contrast = __uint_as_float(e1.x);
+                ed.exposure = __uint_as_float(e1.y); ed.gamma = __uint_as_float(e1.z); ed.alpha = __uint_as_float(e1.w);
+                if ((ed.flag & B200GS_EDIT_ENABLED) && (ed.flag & B200GS_EDIT_HIDDEN)) vis = false;
+            }
+            if (vis && selected && (f.sel_edit.flag & B200GS_EDIT_ENABLED) && (f.sel_edit.flag & B200GS_EDIT_HIDDEN))
+                vis = false;
+
+            float pw[3], pv[3], nx = 0.0f, ny = 0.0f, nz = 0.0f;
+            if (vis) {
+                const float p0 = __uint_as_float(w[0]), p1 = __uint_as_float(w[1]), p2 = __uint_as_float(w[2]);
+                if (m.identity) {  // bit-identical to the general form when R = I, s = 1, t = 0
+                    pw[0] = p0; pw[1] = p1; pw[2] = p2;
+                } else {
+                    // world = q*(s⊙p)+t  (src/app.rs:1044-1046)
+                    const float ps0 = m.s[0] * p0, ps1 = m.s[1] * p1, ps2 = m.s[2] * p2;
+#pragma unroll
+                    for (int r = 0; r < 3; r++) pw[r] = m.R[r][0] * ps0 + m.R[r][1] * ps1 + m.R[r][2] * ps2 + m.t[r];
+                }
+#pragma unroll
+                for (int r = 0; r < 3; r++) pv[r] = f.V[r][0] * pw[0] + f.V[r][1] * pw[1] + f.V[r][2] * pw[2] + f.V[r][3];
+                float pc[4];
+                if (f.std_proj) {  // zero terms of glam's perspective_rh skipped: same bits
+                    pc[0] = f.P[0][0] * pv[0];
+                    pc[1] = f.P[1][1] * pv[1];
+                    pc[2] = f.P[2][2] * pv[2] + f.P[2][3];
+                    pc[3] = f.P[3][2] * pv[2];
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 4; r++) pc[r] = f.P[r][0] * pv[0] + f.P[r][1] * pv[1] + f.P[r][2] * pv[2] + f.P[r][3];
+                }
+                if (!(pc[3] > 0.0f)) vis = false;
+                else {
+                    const float iw = 1.0f / pc[3];
+                    nx = pc[0] * iw; ny = pc[1] * iw; nz = pc[2] * iw;
+                    vis = nz > 0.0f && nz < 1.0f && fabsf(nx) <= GS_CULL_XY && fabsf(ny) <= GS_CULL_XY;
+                }
+            }
+            const uint32_t ballot = __ballot_sync(0xffffffffu, vis);
+            if (lane == 0) s_wcount_all[par * 8 + warp] = __popc(ballot);
+            bar_arrive(kBarCounts);
+
+            // ---------------- phase 2: projected splat for the visible ones ----------------
+            uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
+            if (vis) {
+                const uint32_t* shw = w + 4;
+                const uint32_t* cw = w + 4 + ShBytes<SH>::v / 4;
+                float cv[6];
+                if (COV == 0) {
+#pragma unroll
+                    for (int k = 0; k < 6; k++) cv[k] = __uint_as_float(cw[k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 3; k++) { uint32_t x = cw[k]; cv[2 * k] = h2f_lo(x); cv[2 * k + 1] = h2f_hi(x); }
+                }
+                // Σ' = (R_m S_m) Σ (R_m S_m)^T · size²  (upper triangle; exact class)
+                float Sw[3][3];
+                if (m.identity) {
+                    Sw[0][0] = cv[0] * f.sz2; Sw[0][1] = cv[1] * f.sz2; Sw[0][2] = cv[2] * f.sz2;
+                    Sw[1][1] = cv[3] * f.sz2; Sw[1][2] = cv[4] * f.sz2; Sw[2][2] = cv[5] * f.sz2;
+                } else {
+                    const float S[3][3] = {{cv[0], cv[1], cv[2]}, {cv[1], cv[3], cv[4]}, {cv[2], cv[4], cv[5]}};
+                    float B[3][3];
+#pragma unroll
+                    for (int r = 0; r < 3; r++)
+#pragma unroll
+                        for (int k = 0; k < 3; k++) B[r][k] = m.M[r][0] * S[0][k] + m.M[r][1] * S[1][k] + m.M[r][2] * S[2][k];
+#pragma unroll
+                    for (int r = 0; r < 3; r++)
+#pragma unroll
+                        for (int k = r; k < 3; k++)
+                            Sw[r][k] = (B[r][0] * m.M[k][0] + B[r][1] * m.M[k][1] + B[r][2] * m.M[k][2]) * f.sz2;
+                }
+                Sw[1][0] = Sw[0][1]; Sw[2][0] = Sw[0][2]; Sw[2][1] = Sw[1][2];
+
+                // Jacobian of the pixel mapping (view space RH, looking down -z; rows flipped in y)
+                const float tz = -pv[2];
+                const float itz = 1.0f / tz;
+                float txz = pv[0] * itz, tyz = pv[1] * itz;
+                txz = fminf(f.limx, fmaxf(-f.limx, txz));
+                tyz = fminf(f.limy, fmaxf(-f.limy, tyz));
+                const float xc = txz * tz, yc = tyz * tz;
+                const float itz2 = itz * itz;
+                const float J00 = f.fx * itz, J02 = (f.fx * xc) * itz2;
+                const float J11 = -(f.fy * itz), J12 = -((f.fy * yc) * itz2);
+                float T0[3], T1[3], U0[3], U1[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    T0[k] = J00 * f.V[0][k] + J02 * f.V[2][k];
+                    T1[k] = J11 * f.V[1][k] + J12 * f.V[2][k];
+                }
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    U0[k] = T0[0] * Sw[0][k] + T0[1] * Sw[1][k] + T0[2] * Sw[2][k];
+                    U1[k] = T1[0] * Sw[0][k] + T1[1] * Sw[1][k] + T1[2] * Sw[2][k];
+                }
+                float a = U0[0] * T0[0] + U0[1] * T0[1] + U0[2] * T0[2];
+                const float b = U0[0] * T1[0] + U0[1] * T1[1] + U0[2] * T1[2];
+                float d = U1[0] * T1[0] + U1[1] * T1[1] + U1[2] * T1[2];
+                a = a + GS_LOWPASS;
+                d = d + GS_LOWPASS;
+                const float det = a * d - b * b;
+                float ca = 0.0f, cb = 0.0f, cc = 0.0f, radf = 0.0f;
+                if (det > 0.0f) {
+                    const float di = 1.0f / det;
+                    ca = d * di; cb = -b * di; cc = a * di;
+                    const float mid = 0.5f * (a + d);
+                    float disc = mid * mid - det;
+                    if (disc < GS_MIN_DISC) disc = GS_MIN_DISC;
+                    const float lam = mid + sqrtf(disc);
+                    radf = ceilf(GS_EXTENT_SIGMA * sqrtf(lam));
+                }
+                if (f.display_mode == B200GS_DISPLAY_POINT) {
+                    ca = GS_FLAT_D2 / (GS_POINT_RADIUS * GS_POINT_RADIUS); cb = 0.0f; cc = ca;
+                    radf = ceilf(GS_POINT_RADIUS);
+                }
+                if (!(radf <= 65535.0f)) radf = 65535.0f;
+
+                // ---- colour (tolerance class: FMA and rsqrt allowed): baked SH0 (u8) + bands 1..deg,
+                // view direction in world space
+                float dx = pw[0] - f.cam[0], dy = pw[1] - f.cam[1], dz = pw[2] - f.cam[2];
+                const float il = rsqrtf(__fmaf_rn(dx, dx, __fmaf_rn(dy, dy, dz * dz)));
+                dx *= il; dy *= il; dz *= il;
+                const uint32_t colw = w[3];
+                float rgb[3];
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) rgb[ch] = f.no_sh0 ? 0.0f : byte_to_float(colw, ch) * (1.0f / 255.0f);
+                const uint32_t deg = SH == 3 ? 0u : f.sh_deg;
+                if (SH != 3 && deg >= 1) {
+                    float bs[15];
+                    bs[0] = -0.4886025119029199f * dy;
+                    bs[1] = 0.4886025119029199f * dz;
+                    bs[2] = -0.4886025119029199f * dx;
+                    int ncoef = 3;
+                    if (deg >= 2) {
+                        const float xx = dx * dx, yy = dy * dy, zz = dz * dz, xy = dx * dy, yz = dy * dz, xz = dx * dz;
+                        bs[3] = 1.0925484305920792f * xy;
+                        bs[4] = -1.0925484305920792f * yz;
+                        bs[5] = 0.31539156525252005f * (2.0f * zz - xx - yy);
+                        bs[6] = -1.0925484305920792f * xz;
+                        bs[7] = 0.5462742152960396f * (xx - yy);
+                        ncoef = 8;
+                        if (deg >= 3) {
+                            bs[8] = -0.5900435899266435f * dy * (3.0f * xx - yy);
+                            bs[9] = 2.890611442640554f * xy * dz;
+                            bs[10] = -0.4570457994644658f * dy * (4.0f * zz - xx - yy);
+                            bs[11] = 0.3731763325901154f * dz * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+                            bs[12] = -0.4570457994644658f * dx * (4.0f * zz - xx - yy);
+                            bs[13] = 1.445305721320277f * dz * (xx - yy);
+                            bs[14] = -0.5900435899266435f * dx * (xx - 3.0f * yy);
+                            ncoef = 15;
+                        }
+                    }
+                    float acc[3] = {0.0f, 0.0f, 0.0f};
+                    if (SH == 2) {
+                        // Σ b_k (q_k·2/255 − 1) = (2/255)·Σ b_k q_k − Σ b_k : one PRMT + FADD + FFMA per coefficient
+                        float sum_b = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < 15; k++) {
+                            if (k < ncoef) {
+                                sum_b += bs[k];
+#pragma unroll
+                                for (int ch = 0; ch < 3; ch++) {
+                                    const int e = 3 * k + ch;
+                                    acc[ch] = __fmaf_rn(bs[k], byte_to_float(shw[e >> 2], e & 3), acc[ch]);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int ch = 0; ch < 3; ch++) rgb[ch] += __fmaf_rn(acc[ch], 2.0f / 255.0f, -sum_b);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 15; k++) {
+                            if (k < ncoef) {
+#pragma unroll
+                                for (int ch = 0; ch < 3; ch++) acc[ch] = __fmaf_rn(bs[k], sh_coef<SH>(shw, 3 * k + ch), acc[ch]);
+                            }
+                        }
+#pragma unroll
+                        for (int ch = 0; ch < 3; ch++) rgb[ch] += acc[ch];
+                    }
+                }
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) rgb[ch] = clamp01(rgb[ch]);
+                float op = (float)(colw >> 24) * (1.0f / 255.0f);
+                if (edits) apply_edit(ed, rgb, op);
+                if (selected) {
+                    apply_edit(f.sel_edit, rgb, op);
+                    const float ha = f.hl[3];
+#pragma unroll
+                    for (int ch = 0; ch < 3; ch++) rgb[ch] = rgb[ch] + (f.hl[ch] - rgb[ch]) * ha;
+                }
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) rgb[ch] = clamp01(rgb[ch]);
+
+                const float mx = ((nx + 1.0f) * f.W - 1.0f) * 0.5f;
+                const float my = ((1.0f - ny) * f.H - 1.0f) * 0.5f;
+                q0.x = __float_as_uint(mx);
+                q0.y = __float_as_uint(my);
+                q0.z = (uint32_t)radf | ((uint32_t)__half_as_ushort(__float2half_rn(op)) << 16);
+                q0.w = (uint32_t)__half_as_ushort(__float2half_rn(rgb[0])) |
+                       ((uint32_t)__half_as_ushort(__float2half_rn(rgb[1])) << 16);
+                q1.x = __float_as_uint(ca);
+                q1.y = __float_as_uint(cb);
+                q1.z = __float_as_uint(cc);
+                q1.w = (uint32_t)__half_as_ushort(__float2half_rn(rgb[2])) | ((selected ? 1u : 0u) << 16);
+            }
+            bar_arrive(kBarFree + (int)par);  // every read of this stage's shared memory is done
+
+            // digit histograms of the emitted keys for the depth sort (saves its histogram kernel);
+            // warp-aggregated: depth keys share their top bytes
+            if (sort_hist && vis) {
+                const uint32_t key = __float_as_uint(nz);
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    const uint32_t dgt = (key >> (8 * p)) & 0xffu;
+                    const uint32_t peers = __match_any_sync(ballot, dgt);
+                    if (lane == __ffs((int)peers) - 1) atomicAdd(&s_hist[p * 256 + dgt], (uint32_t)__popc(peers));
+                }
+            }
+
+            bar_sync(kBarBase);
+            if (vis) {
+                uint32_t off = s_base_all[par];
+                for (int k = 0; k < warp; k++) off += s_wcount_all[par * 8 + k];
+                off += __popc(ballot & ((1u << lane) - 1u));
+                keys[off] = __float_as_uint(nz);
+                idx[off] = i;
+                uint4* sp = reinterpret_cast<uint4*>(splats + off);
+                sp[0] = q0;
+                sp[1] = q1;
+            }
+        }
+    }
+    if (sort_hist) {
+        __syncthreads();
+        for (int i = tid; i < 1024; i += kThreads) {
+            const uint32_t cnt = s_hist[i];
+            if (cnt) atomicAdd(&sort_hist[i], cnt);
         }
     }
     if (n == 0 && blockIdx.x == 0 && tid == 0) ctrl[GS_CTRL_VISIBLE] = 0;
@@ -372,13 +463,13 @@ template <int SH, int COV>
 cudaError_t launch_t(const GsPreprocessArgs& a, const GsFrame& f, const GsModelXf& m, int num_sms, cudaStream_t st) {
     constexpr int RB = 16 + ShBytes<SH>::v + CovBytes<COV>::v;
     constexpr int NSTAGE = stages_for(RB);
-    constexpr size_t smem = (size_t)NSTAGE * kChunk * RB + NSTAGE * 8 + NSTAGE * 4 + 16 * 4 + 2 * 4 + 16;
+    constexpr size_t smem = (size_t)NSTAGE * kChunk * RB + NSTAGE * 8 + NSTAGE * 4 + 16 * 4 + 2 * 4 + 1024 * 4 + 16;
     auto kern = k_preprocess<SH, COV>;
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kChunk, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kThreads, smem);
         if (e != cudaSuccess) return e;
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
@@ -386,8 +477,8 @@ cudaError_t launch_t(const GsPreprocessArgs& a, const GsFrame& f, const GsModelX
     uint32_t grid = (uint32_t)(blocks_per_sm * num_sms);
     if (grid > nchunks) grid = nchunks;
     if (grid < 1) grid = 1;
-    kern<<<grid, kChunk, smem, st>>>(a.recs, a.n, a.mask, a.selection, a.edits, f, m, a.ctrl, a.lookback, a.epoch, a.keys,
-                                     a.idx, a.splats);
+    kern<<<grid, kThreads, smem, st>>>(a.recs, a.n, a.mask, a.selection, a.edits, f, m, a.ctrl, a.lookback, a.epoch,
+                                       a.keys, a.idx, a.splats, a.sort_hist);
     return cudaGetLastError();
 }
 
