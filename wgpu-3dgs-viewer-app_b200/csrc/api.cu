@@ -46,13 +46,14 @@ extern "C" const char* b200gs_version(void) { return "b200gs 0.1 (sm_100a)"; }
 
 // ---------------------------------------------------------------------------- handles
 enum {  // viewer control block (u32 words), zeroed at the start of every render
-    VC_BIN_TICKET = 0,     // 64 words, one per model in the frame
-    VC_ENTRY_TOTAL = 64,   // 65 words: running (tile, splat) entry count after each model
-    VC_OVERFLOW = 130,
-    VC_TSORT_TICKET = 132, // 2 words
-    VC_EVALS = 136,        // u64
-    VC_TSORT_HIST = 256,   // 2 x 256
-    VC_WORDS = 768
+    VC_BIN_TICKET = 0,     // 2 x 64 words: (count, emit) tickets per model in the frame
+    VC_ENTRY_TOTAL = 128,  // 65 words: running (tile, splat) entry count after each model
+    VC_OVERFLOW = 194,
+    VC_TSORT_TICKET = 196, // 2 words
+    VC_EVALS = 200,        // u64
+    VC_CAND_TOTAL = 208,   // 64 words: candidate tiles per model
+    VC_TSORT_HIST = 512,   // 2 x 256
+    VC_WORDS = 1024
 };
 enum {  // model control block layout
     MC_CTRL = 0,               // GS_CTRL_WORDS
@@ -96,8 +97,10 @@ struct b200gs_viewer {
     bool layout_dirty = true;
     uint32_t *tk_a = nullptr, *tv_a = nullptr, *tk_b = nullptr, *tv_b = nullptr;
     uint64_t entry_cap = 0, entry_cap_user = 0;
-    uint64_t *lb_bin = nullptr, *lb_tsort = nullptr;
+    uint64_t *lb_bin = nullptr, *lb_tsort = nullptr, *lb_emit = nullptr;
     uint64_t lb_bin_words = 0;
+    uint32_t *cand_off = nullptr, *block_rank = nullptr;
+    uint64_t cand_off_words = 0, block_cap = 0;
     uint32_t* ranges = nullptr;
     uint32_t ranges_tiles = 0;
     uint32_t* vctrl = nullptr;
@@ -229,6 +232,12 @@ static int ensure_frame_buffers(b200gs_viewer* v) {
         }
         if (v->lb_tsort) CK(cudaFree(v->lb_tsort));
         TRY(dev_alloc(&v->lb_tsort, gs_sort_lookback_words((uint32_t)want, 2), true, v->stream));
+        // candidate space of the binning stage: up to 2 candidates per kept entry before the tail is dropped
+        v->block_cap = gs_bin_block_words((uint32_t)std::min<uint64_t>(want * 2, 0x7fffffffull));
+        if (v->block_rank) CK(cudaFree(v->block_rank));
+        TRY(dev_alloc(&v->block_rank, v->block_cap, true, v->stream));
+        if (v->lb_emit) CK(cudaFree(v->lb_emit));
+        TRY(dev_alloc(&v->lb_emit, v->block_cap * kMaxModelsPerFrame / 8 + v->block_cap, true, v->stream));
         v->entry_cap = want;
     }
     uint64_t lbw = (maxcap + 1023) / 1024 + 1;
@@ -236,6 +245,11 @@ static int ensure_frame_buffers(b200gs_viewer* v) {
         if (v->lb_bin) CK(cudaFree(v->lb_bin));
         TRY(dev_alloc(&v->lb_bin, lbw * kMaxModelsPerFrame, true, v->stream));
         v->lb_bin_words = lbw;
+    }
+    if (maxcap + 1 > v->cand_off_words) {
+        if (v->cand_off) CK(cudaFree(v->cand_off));
+        TRY(dev_alloc(&v->cand_off, maxcap + 1, true, v->stream));
+        v->cand_off_words = maxcap + 1;
     }
     v->layout_dirty = false;
     return B200GS_OK;
@@ -311,7 +325,8 @@ extern "C" int b200gs_viewer_destroy(b200gs_viewer* v) {
     cudaSetDevice(v->device);
     if (v->stream) cudaStreamSynchronize(v->stream);
     for (auto* m : v->models) free_model(m);
-    void* ps[] = {v->arena, v->tk_a, v->tv_a, v->tk_b, v->tv_b, v->lb_bin, v->lb_tsort, v->ranges, v->vctrl, v->image};
+    void* ps[] = {v->arena, v->tk_a, v->tv_a, v->tk_b, v->tv_b, v->lb_bin, v->lb_tsort, v->lb_emit, v->cand_off, v->block_rank,
+                  v->ranges, v->vctrl, v->image};
     for (void* p : ps)
         if (p) cudaFree(p);
     if (v->h_small) cudaFreeHost(v->h_small);
@@ -672,19 +687,25 @@ extern "C" int b200gs_render(b200gs_viewer* v, b200gs_model* const* far_to_near,
         b.v_max = (uint32_t)m->cap;
         b.splat_base = (uint32_t)m->arena_offset;
         b.lookback = v->lb_bin + (size_t)k * v->lb_bin_words;
+        b.lookback_emit = v->lb_emit;   // reused across models: every launch has its own epoch
         b.epoch = ++v->epoch;
-        b.ticket = v->vctrl + VC_BIN_TICKET + k;
+        b.ticket = v->vctrl + VC_BIN_TICKET + 2 * k;
+        b.cand_off = v->cand_off;       // models are expanded one after the other on the stream
+        b.block_rank = v->block_rank;
+        b.block_cap = (uint32_t)v->block_cap;
+        b.cand_total = v->vctrl + VC_CAND_TOTAL + k;
         b.entry_base_in = v->vctrl + VC_ENTRY_TOTAL + k;
         b.entry_total_out = v->vctrl + VC_ENTRY_TOTAL + k + 1;
         b.overflow = v->vctrl + VC_OVERFLOW;
         b.tile_keys = v->tk_a; b.tile_vals = v->tv_a; b.capacity = (uint32_t)v->entry_cap;
+        b.tile_hist = v->vctrl + VC_TSORT_HIST;
         CK(gs_launch_bin(b, f, v->num_sms, st));
     }
     GsSortArgs s;
     s.keys_a = v->tk_a; s.vals_a = v->tv_a; s.keys_b = v->tk_b; s.vals_b = v->tv_b;
     s.d_n = v->vctrl + VC_ENTRY_TOTAL + n_models; s.n_max = (uint32_t)v->entry_cap;
     s.hist = v->vctrl + VC_TSORT_HIST; s.lookback = v->lb_tsort; s.epoch = ++v->epoch;
-    s.tickets = v->vctrl + VC_TSORT_TICKET; s.passes = 2; s.hist_prefilled = false; s.vals_identity = false;
+    s.tickets = v->vctrl + VC_TSORT_TICKET; s.passes = 2; s.hist_prefilled = true; s.vals_identity = false;
     CK(gs_launch_sort(s, v->num_sms, st));
     CK(gs_launch_tile_ranges(v->tk_a, s.d_n, (uint32_t)v->entry_cap, v->ranges, n_tiles, v->num_sms, st));
     if (v->timing) CK(cudaEventRecord(v->ev[3], st));

@@ -3,86 +3,126 @@
 // Part of the replacement of renderer.render_with_pass (reference src/tab/scene.rs:2302-2314):
 // the reference draws one instanced quad per visible Gaussian in sorted order and lets the
 // rasteriser find the covered pixels; here every depth-sorted splat is expanded into one
-// (tile id, splat id) entry per 16x16 tile its extent square touches.  Entries are produced
-// IN DEPTH ORDER (order-preserving expansion: block scan + decoupled look-back), so a STABLE
-// sort by tile id alone (2 onesweep passes over 16 bits, sort.cu) yields per-tile lists that are
-// still front-to-back.  Models are expanded nearest first, each appended after the previous
-// one, which reproduces the reference's per-model layering (scene.rs:533-558).
+// (tile id, splat id) entry per 16x16 tile it can actually touch.  Entries are produced IN
+// DEPTH ORDER, so a STABLE sort by tile id alone (2 onesweep passes over 16 bits, sort.cu)
+// yields per-tile lists that are still front-to-back.  Models are expanded nearest first, each
+// appended after the previous one, which reproduces the reference's per-model layering
+// (scene.rs:533-558).
+//
+// Depth order puts the nearest = largest splats into the first ranks, so a rank-chunked
+// expansion is badly imbalanced (the first 1024 ranks hold ~40x the mean work).  The
+// expansion is therefore done over the CANDIDATE index space in two balanced kernels:
+//   k_bin_count : per depth rank, the number of candidate tiles (the tile rectangle of the extent
+//                 square) -> exclusive prefix cand_off[rank] (block scan + decoupled look-back),
+//                 plus, for every 2048-candidate block, the rank that owns its first candidate.
+//   k_bin_emit  : one CTA per block of 2048 consecutive candidates, one candidate per thread slot:
+//                 exact footprint test (a tile is kept only if some pixel of tile ∩ extent square
+//                 can reach alpha >= 1/255 — skipped tiles cannot change the image), order-
+//                 preserving compaction, decoupled look-back over the blocks' kept counts,
+//                 coalesced write-out through shared memory, and the digit histograms of the
+//                 tile sort accumulated on the way out.
 #include "common.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kIpt = 4;                      // depth ranks per thread
+constexpr int kIpt = 4;                      // depth ranks per thread in k_bin_count
 constexpr int kChunk = kThreads * kIpt;      // 1024 ranks per chunk
-constexpr uint32_t kBigSplat = 32;           // > this many tiles: expanded by the whole warp
+constexpr int kCpt = 8;                      // candidates per thread in k_bin_emit
+constexpr uint32_t kBlock = kThreads * kCpt; // 2048 candidates per block
 
-struct TileRect { uint32_t tx0, ty0, nx, ny; };
+struct Cand {
+    float mx, my, a, b, c, tau;   // ellipse
+    float nbc, nba;               // -b/c, -b/a
+    float fx0, fx1, fy0, fy1;     // pixel bounds of the extent square clipped to the viewport
+    uint32_t tx0, ty0, nx, ny;    // candidate tile rectangle
+};
 
-// Pixel bounds of a splat: the integer pixels of the screen-aligned square of half-size
-// `radius` around (mx,my), clipped to the viewport — same expression as the compositor's.
-__device__ __forceinline__ TileRect tile_rect(float mx, float my, uint32_t radius, float W, float H) {
-    TileRect t = {0, 0, 0, 0};
-    if (radius == 0) return t;
-    float r = (float)radius;
-    float fx0 = ceilf(mx - r), fx1 = floorf(mx + r), fy0 = ceilf(my - r), fy1 = floorf(my + r);
-    if (fx0 < 0.0f) fx0 = 0.0f;
-    if (fy0 < 0.0f) fy0 = 0.0f;
-    if (fx1 > W - 1.0f) fx1 = W - 1.0f;
-    if (fy1 > H - 1.0f) fy1 = H - 1.0f;
-    if (!(fx0 <= fx1 && fy0 <= fy1)) return t;
-    t.tx0 = (uint32_t)fx0 / GS_TILE;
-    t.ty0 = (uint32_t)fy0 / GS_TILE;
-    t.nx = (uint32_t)fx1 / GS_TILE - t.tx0 + 1;
-    t.ny = (uint32_t)fy1 / GS_TILE - t.ty0 + 1;
-    return t;
+// candidate tile rectangle of a projected splat (first 16 bytes); false if it cannot touch anything
+__device__ __forceinline__ bool make_rect(const uint4& q0, float W, float H, bool flat, Cand& c) {
+    const uint32_t radius = q0.z & 0xffffu;
+    if (radius == 0) return false;
+    c.mx = __uint_as_float(q0.x);
+    c.my = __uint_as_float(q0.y);
+    const float op = __half2float(__ushort_as_half((unsigned short)(q0.z >> 16)));
+    c.tau = gs_footprint_tau(op, flat);
+    if (c.tau < 0.0f) return false;
+    // same bounds expression as the compositor / the oracle (exact in float)
+    const float r = (float)radius;
+    c.fx0 = ceilf(c.mx - r); c.fx1 = floorf(c.mx + r); c.fy0 = ceilf(c.my - r); c.fy1 = floorf(c.my + r);
+    if (c.fx0 < 0.0f) c.fx0 = 0.0f;
+    if (c.fy0 < 0.0f) c.fy0 = 0.0f;
+    if (c.fx1 > W - 1.0f) c.fx1 = W - 1.0f;
+    if (c.fy1 > H - 1.0f) c.fy1 = H - 1.0f;
+    if (!(c.fx0 <= c.fx1 && c.fy0 <= c.fy1)) return false;
+    c.tx0 = (uint32_t)c.fx0 / GS_TILE;
+    c.ty0 = (uint32_t)c.fy0 / GS_TILE;
+    c.nx = (uint32_t)c.fx1 / GS_TILE - c.tx0 + 1;
+    c.ny = (uint32_t)c.fy1 / GS_TILE - c.ty0 + 1;
+    return true;
 }
 
-__global__ void __launch_bounds__(kThreads) k_bin_expand(const uint32_t* __restrict__ sorted_slot,
-                                                         const b200gs_splat* __restrict__ splats,
-                                                         const uint32_t* d_v, uint32_t v_max, uint32_t splat_base,
-                                                         uint64_t* lookback, uint32_t epoch, uint32_t* ticket,
-                                                         const uint32_t* entry_base_in, uint32_t* entry_total_out,
-                                                         uint32_t* overflow, uint32_t* __restrict__ tile_keys,
-                                                         uint32_t* __restrict__ tile_vals, uint32_t capacity,
-                                                         float W, float H, uint32_t tiles_x) {
+// can candidate tile (x, y) of the rectangle be touched?  (gs_min_q_rect with the divisions hoisted)
+__device__ __forceinline__ bool tile_hit(const Cand& c, uint32_t x, uint32_t y) {
+    const float tx = (float)((c.tx0 + x) * GS_TILE), ty = (float)((c.ty0 + y) * GS_TILE);
+    const float dx0 = fmaxf(tx, c.fx0) - c.mx, dx1 = fminf(tx + (float)(GS_TILE - 1), c.fx1) - c.mx;
+    const float dy0 = fmaxf(ty, c.fy0) - c.my, dy1 = fminf(ty + (float)(GS_TILE - 1), c.fy1) - c.my;
+    const bool inx = dx0 <= 0.0f && dx1 >= 0.0f, iny = dy0 <= 0.0f && dy1 >= 0.0f;
+    if (inx && iny) return true;
+    float best = 3.0e38f;
+    if (!inx) {
+        const float dx = dx0 > 0.0f ? dx0 : dx1;
+        const float dy = fminf(dy1, fmaxf(dy0, c.nbc * dx));
+        best = c.a * dx * dx + 2.0f * c.b * dx * dy + c.c * dy * dy;
+    }
+    if (!iny) {
+        const float dy = dy0 > 0.0f ? dy0 : dy1;
+        const float dx = fminf(dx1, fmaxf(dx0, c.nba * dy));
+        best = fminf(best, c.a * dx * dx + 2.0f * c.b * dx * dy + c.c * dy * dy);
+    }
+    return best <= c.tau;
+}
+
+// ------------------------------------------------------------------ kernel A: candidate counts
+__global__ void __launch_bounds__(kThreads) k_bin_count(const uint32_t* __restrict__ sorted_slot,
+                                                        const b200gs_splat* __restrict__ splats,
+                                                        const uint32_t* d_v, uint32_t v_max, uint64_t* lookback,
+                                                        uint32_t epoch, uint32_t* ticket, uint32_t* __restrict__ cand_off,
+                                                        uint32_t* __restrict__ block_rank, uint32_t block_cap,
+                                                        uint32_t* cand_total, float W, float H, uint32_t flat) {
     __shared__ uint32_t s_wsum[kThreads / 32];
     __shared__ uint32_t s_chunk, s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t v = *d_v;
     if (v > v_max) v = v_max;
     const uint32_t nchunks = (v + kChunk - 1) / kChunk;
-    const uint32_t ebase = *entry_base_in;
     if (v == 0) {
-        if (blockIdx.x == 0 && tid == 0) *entry_total_out = ebase;
+        if (blockIdx.x == 0 && tid == 0) *cand_total = 0;
         return;
     }
-
     while (true) {
+        __syncthreads();
         if (tid == 0) s_chunk = atomicAdd(ticket, 1u);
         __syncthreads();
         const uint32_t c = s_chunk;
         if (c >= nchunks) break;
-
         const uint32_t r0 = c * kChunk + tid * kIpt;
-        TileRect tr[kIpt];
-        uint32_t id[kIpt], cnt[kIpt], sum = 0;
+        uint32_t cnt[kIpt], sum = 0;
+        uint4 q0[kIpt];
 #pragma unroll
         for (int k = 0; k < kIpt; k++) {
-            uint32_t r = r0 + k;
-            cnt[k] = 0;
-            id[k] = 0;
-            tr[k] = TileRect{0, 0, 0, 0};
-            if (r < v) {
-                uint32_t slot = sorted_slot ? sorted_slot[r] : r;
-                uint4 q0 = *reinterpret_cast<const uint4*>(splats + slot);
-                tr[k] = tile_rect(__uint_as_float(q0.x), __uint_as_float(q0.y), q0.z & 0xffffu, W, H);
-                cnt[k] = tr[k].nx * tr[k].ny;
-                id[k] = splat_base + slot;
+            q0[k] = make_uint4(0, 0, 0, 0);
+            if (r0 + k < v) {
+                const uint32_t slot = sorted_slot ? sorted_slot[r0 + k] : r0 + k;
+                q0[k] = __ldg(reinterpret_cast<const uint4*>(splats + slot));
             }
+        }
+#pragma unroll
+        for (int k = 0; k < kIpt; k++) {
+            Cand cd;
+            cnt[k] = (r0 + k < v && make_rect(q0[k], W, H, flat != 0, cd)) ? cd.nx * cd.ny : 0u;
             sum += cnt[k];
         }
-        // block exclusive scan of `sum`
         uint32_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -91,61 +131,209 @@ __global__ void __launch_bounds__(kThreads) k_bin_expand(const uint32_t* __restr
         }
         if (lane == 31) s_wsum[warp] = incl;
         __syncthreads();
-        if (warp == 0) {
-            uint32_t ws = lane < kThreads / 32 ? s_wsum[lane] : 0u;
-            uint32_t tot = ws;
+        uint32_t chunk_total = 0, woff = 0;
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-            tot = __shfl_sync(0xffffffffu, tot, 0);
-            uint32_t excl = gs_lookback_warp(lookback, epoch, c, tot, lane);
+        for (int k = 0; k < kThreads / 32; k++) {
+            const uint32_t t = s_wsum[k];
+            if (k < warp) woff += t;
+            chunk_total += t;
+        }
+        if (warp == 0) {
+            const uint32_t excl = gs_lookback_warp(lookback, epoch, c, chunk_total, lane);
             if (lane == 0) {
                 s_base = excl;
-                if (c == nchunks - 1) {
-                    uint32_t total = ebase + excl + tot;
-                    if (total > capacity) { *overflow = 1u; total = capacity; }
-                    *entry_total_out = total;
+                if (c == nchunks - 1) *cand_total = excl + chunk_total;
+            }
+        }
+        __syncthreads();
+        uint32_t o = s_base + woff + incl - sum;
+#pragma unroll
+        for (int k = 0; k < kIpt; k++) {
+            if (r0 + k < v) {
+                cand_off[r0 + k] = o;
+                if (cnt[k]) {
+                    // this rank owns the first candidate of every block whose start falls in its run
+                    const uint32_t first = (o + kBlock - 1) / kBlock, last = (o + cnt[k] - 1) / kBlock;
+                    for (uint32_t b = first; b <= last && b < block_cap; b++) block_rank[b] = r0 + k;
+                }
+            }
+            o += cnt[k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ kernel B: test + emit
+__global__ void __launch_bounds__(kThreads) k_bin_emit(const uint32_t* __restrict__ sorted_slot,
+                                                       const b200gs_splat* __restrict__ splats,
+                                                       const uint32_t* d_v, uint32_t v_max, uint32_t splat_base,
+                                                       const uint32_t* __restrict__ cand_off,
+                                                       const uint32_t* __restrict__ block_rank, uint32_t block_cap,
+                                                       const uint32_t* cand_total_p, uint64_t* lookback, uint32_t epoch,
+                                                       uint32_t* ticket, const uint32_t* entry_base_in,
+                                                       uint32_t* entry_total_out, uint32_t* overflow,
+                                                       uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ tile_vals,
+                                                       uint32_t capacity, uint32_t* tile_hist, float W, float H,
+                                                       uint32_t tiles_x, uint32_t flat) {
+    __shared__ int32_t s_owner[kBlock];       // rank owning each candidate (after the max-scan)
+    __shared__ uint32_t s_keys[kBlock];
+    __shared__ uint32_t s_vals[kBlock];
+    __shared__ uint32_t s_hist[512];
+    __shared__ uint32_t s_cnt[kCpt][kThreads / 32];
+    __shared__ int32_t s_wmax[kThreads / 32];
+    __shared__ uint32_t s_blk, s_base, s_kept;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t v = *d_v;
+    if (v > v_max) v = v_max;
+    const uint32_t total = v ? *cand_total_p : 0u;
+    uint32_t nblocks = (total + kBlock - 1) / kBlock;
+    if (nblocks > block_cap - 1) {  // candidate space larger than the scratch: drop the tail, flag it
+        nblocks = block_cap - 1;
+        if (blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1u;
+    }
+    const uint32_t ebase = *entry_base_in;
+    if (nblocks == 0) {
+        if (blockIdx.x == 0 && tid == 0) *entry_total_out = ebase;
+        return;
+    }
+    for (int i = tid; i < 512; i += kThreads) s_hist[i] = 0;
+
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_blk = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t b = s_blk;
+        if (b >= nblocks) break;
+        const uint32_t cbase = b * kBlock;
+        const uint32_t nc = min(kBlock, total - cbase);
+
+        // ---- owners: rank r starts at cand_off[r]; mark the starts, then an inclusive max-scan
+        for (uint32_t i = tid; i < kBlock; i += kThreads) s_owner[i] = -1;
+        __syncthreads();
+        const uint32_t r_lo = block_rank[b];
+        const uint32_t r_hi = (b + 1 < nblocks) ? block_rank[b + 1] : v - 1;
+        if (tid == 0) s_owner[0] = (int32_t)r_lo;
+        for (uint32_t r = r_lo + 1 + tid; r <= r_hi; r += kThreads) {
+            const uint32_t o = cand_off[r];
+            const uint32_t nxt = (r + 1 < v) ? cand_off[r + 1] : total;
+            if (nxt > o && o >= cbase && o < cbase + kBlock) s_owner[o - cbase] = (int32_t)r;
+        }
+        __syncthreads();
+        {
+            // thread t scans its 8 consecutive slots, then warps / block combine
+            int32_t loc[kCpt], run = -1;
+#pragma unroll
+            for (int k = 0; k < kCpt; k++) { run = max(run, s_owner[tid * kCpt + k]); loc[k] = run; }
+            int32_t inc = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc = max(inc, t);
+            }
+            if (lane == 31) s_wmax[warp] = inc;
+            __syncthreads();
+            int32_t pre = -1;
+            for (int k = 0; k < warp; k++) pre = max(pre, s_wmax[k]);
+            const int32_t excl = __shfl_up_sync(0xffffffffu, inc, 1);
+            pre = max(pre, lane ? excl : -1);
+#pragma unroll
+            for (int k = 0; k < kCpt; k++) s_owner[tid * kCpt + k] = max(loc[k], pre);
+        }
+        __syncthreads();
+
+        // ---- one candidate per thread slot (p = k*256 + tid: consecutive lanes share splats)
+        uint32_t key[kCpt], val[kCpt];
+        bool keep[kCpt];
+#pragma unroll
+        for (int k = 0; k < kCpt; k++) {
+            const uint32_t p = k * kThreads + tid;
+            keep[k] = false;
+            key[k] = val[k] = 0;
+            if (p < nc) {
+                const uint32_t r = (uint32_t)s_owner[p];
+                const uint32_t slot = sorted_slot ? sorted_slot[r] : r;
+                const uint4* sp = reinterpret_cast<const uint4*>(splats + slot);
+                const uint4 q0 = __ldg(sp), q1 = __ldg(sp + 1);
+                Cand cd;
+                if (make_rect(q0, W, H, flat != 0, cd)) {
+                    cd.a = __uint_as_float(q1.x); cd.b = __uint_as_float(q1.y); cd.c = __uint_as_float(q1.z);
+                    cd.nbc = -cd.b / cd.c; cd.nba = -cd.b / cd.a;
+                    const uint32_t e = cbase + p - cand_off[r];
+                    const uint32_t y = e / cd.nx, x = e - y * cd.nx;
+                    keep[k] = tile_hit(cd, x, y);
+                    key[k] = (cd.ty0 + y) * tiles_x + cd.tx0 + x;
+                    val[k] = splat_base + slot;
+                }
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, keep[k]);
+            if (lane == 0) s_cnt[k][warp] = __popc(bal);
+        }
+        __syncthreads();
+        // ---- exclusive scan of the 64 (k, warp) counts in candidate order; block total
+        if (warp == 0) {
+            uint32_t a0 = s_cnt[lane >> 3][lane & 7], a1 = s_cnt[(lane >> 3) + 4][lane & 7];
+            uint32_t i0 = a0, i1 = a1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+                if (lane >= o) { i0 += t0; i1 += t1; }
+            }
+            const uint32_t half = __shfl_sync(0xffffffffu, i0, 31);
+            const uint32_t kept = half + __shfl_sync(0xffffffffu, i1, 31);
+            s_cnt[lane >> 3][lane & 7] = i0 - a0;
+            s_cnt[(lane >> 3) + 4][lane & 7] = half + i1 - a1;
+            if (lane == 0) {
+                s_kept = kept;
+                gs_lookback_publish(lookback, epoch, b, kept);
+            }
+        }
+        __syncthreads();
+        const uint32_t kept_total = s_kept;
+        // ---- stage the kept entries in candidate order
+#pragma unroll
+        for (int k = 0; k < kCpt; k++) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, keep[k]);
+            if (keep[k]) {
+                const uint32_t o = s_cnt[k][warp] + __popc(bal & ((1u << lane) - 1u));
+                s_keys[o] = key[k];
+                s_vals[o] = val[k];
+            }
+        }
+        if (warp == 0) {
+            const uint32_t excl = gs_lookback_resolve(lookback, epoch, b, kept_total, lane);
+            if (lane == 0) {
+                s_base = excl;
+                if (b == nblocks - 1) {
+                    uint32_t t = ebase + excl + kept_total;
+                    if (t > capacity) { *overflow = 1u; t = capacity; }
+                    *entry_total_out = t;
                 }
             }
         }
         __syncthreads();
-        uint32_t off = ebase + s_base + incl - sum;
-        for (int k = 0; k < warp; k++) off += s_wsum[k];
-
-        // small splats: the owning thread writes its run; big ones are spread over the warp
+        const uint32_t gbase = ebase + s_base;
+        // ---- coalesced write-out + digit histograms for the tile sort
+        for (uint32_t i0 = 0; i0 < kept_total; i0 += kThreads) {
+            const uint32_t i = i0 + tid;
+            const uint32_t g = gbase + i;
+            const bool ok = i < kept_total && g < capacity;
+            const uint32_t act = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const uint32_t kk = s_keys[i];
+                tile_keys[g] = kk;
+                tile_vals[g] = s_vals[i];
 #pragma unroll
-        for (int k = 0; k < kIpt; k++) {
-            const bool big = cnt[k] > kBigSplat;
-            if (!big) {
-                uint32_t o = off;
-                for (uint32_t y = 0; y < tr[k].ny; y++)
-                    for (uint32_t x = 0; x < tr[k].nx; x++, o++)
-                        if (o < capacity) {
-                            tile_keys[o] = (tr[k].ty0 + y) * tiles_x + tr[k].tx0 + x;
-                            tile_vals[o] = id[k];
-                        }
-            }
-            uint32_t bigmask = __ballot_sync(0xffffffffu, big);
-            while (bigmask) {
-                int src = __ffs((int)bigmask) - 1;
-                bigmask &= bigmask - 1;
-                uint32_t b_off = __shfl_sync(0xffffffffu, off, src);
-                uint32_t b_cnt = __shfl_sync(0xffffffffu, cnt[k], src);
-                uint32_t b_nx = __shfl_sync(0xffffffffu, tr[k].nx, src);
-                uint32_t b_tx0 = __shfl_sync(0xffffffffu, tr[k].tx0, src);
-                uint32_t b_ty0 = __shfl_sync(0xffffffffu, tr[k].ty0, src);
-                uint32_t b_id = __shfl_sync(0xffffffffu, id[k], src);
-                for (uint32_t e = lane; e < b_cnt; e += 32) {
-                    uint32_t o = b_off + e;
-                    if (o < capacity) {
-                        uint32_t y = e / b_nx, x = e - y * b_nx;
-                        tile_keys[o] = (b_ty0 + y) * tiles_x + b_tx0 + x;
-                        tile_vals[o] = b_id;
-                    }
+                for (int p = 0; p < 2; p++) {
+                    const uint32_t d = (kk >> (8 * p)) & 0xffu;
+                    const uint32_t peers = __match_any_sync(act, d);
+                    if (lane == __ffs((int)peers) - 1) atomicAdd(&s_hist[p * 256 + d], (uint32_t)__popc(peers));
                 }
             }
-            off += cnt[k];
         }
-        __syncthreads();  // s_chunk / s_wsum / s_base reused
+    }
+    __syncthreads();
+    for (int i = tid; i < 512; i += kThreads) {
+        const uint32_t cnt = s_hist[i];
+        if (cnt) atomicAdd(&tile_hist[i], cnt);
     }
 }
 
@@ -164,20 +352,30 @@ __global__ void __launch_bounds__(256) k_tile_ranges(const uint32_t* __restrict_
 
 }  // namespace
 
+size_t gs_bin_block_words(uint32_t capacity_candidates) { return (size_t)capacity_candidates / kBlock + 2; }
+
 cudaError_t gs_launch_bin(const GsBinArgs& a, const GsFrame& f, int num_sms, cudaStream_t st) {
-    static int blocks_per_sm = 0;
-    if (blocks_per_sm == 0) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_bin_expand, kThreads, 0);
+    static int bps_count = 0, bps_emit = 0;
+    if (bps_count == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_count, k_bin_count, kThreads, 0);
         if (e != cudaSuccess) return e;
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_emit, k_bin_emit, kThreads, 0);
+        if (e != cudaSuccess) return e;
+        if (bps_count < 1) bps_count = 1;
+        if (bps_emit < 1) bps_emit = 1;
     }
+    const uint32_t flat = f.display_mode != B200GS_DISPLAY_SPLAT ? 1u : 0u;
     uint32_t nchunks = (a.v_max + kChunk - 1) / kChunk;
-    uint32_t grid = (uint32_t)(blocks_per_sm * num_sms);
+    uint32_t grid = (uint32_t)(bps_count * num_sms);
     if (grid > nchunks) grid = nchunks;
     if (grid < 1) grid = 1;
-    k_bin_expand<<<grid, kThreads, 0, st>>>(a.sorted_slot, a.splats, a.d_v, a.v_max, a.splat_base, a.lookback, a.epoch,
-                                            a.ticket, a.entry_base_in, a.entry_total_out, a.overflow, a.tile_keys,
-                                            a.tile_vals, a.capacity, f.W, f.H, f.tiles_x);
+    k_bin_count<<<grid, kThreads, 0, st>>>(a.sorted_slot, a.splats, a.d_v, a.v_max, a.lookback, a.epoch, a.ticket,
+                                           a.cand_off, a.block_rank, a.block_cap, a.cand_total, f.W, f.H, flat);
+    k_bin_emit<<<(uint32_t)(bps_emit * num_sms), kThreads, 0, st>>>(
+        a.sorted_slot, a.splats, a.d_v, a.v_max, a.splat_base, a.cand_off, a.block_rank, a.block_cap, a.cand_total,
+        a.lookback_emit,
+        a.epoch, a.ticket + 1, a.entry_base_in, a.entry_total_out, a.overflow, a.tile_keys, a.tile_vals, a.capacity,
+        a.tile_hist, f.W, f.H, f.tiles_x, flat);
     return cudaGetLastError();
 }
 

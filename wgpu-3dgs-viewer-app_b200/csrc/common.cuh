@@ -99,14 +99,21 @@ struct GsBinArgs {
     const uint32_t* d_v;           // visible count of this model on device
     uint32_t v_max;
     uint32_t splat_base;           // global id of this model's splat 0 in the frame arena
-    uint64_t* lookback;            // per-chunk status words (epoch-tagged, never cleared)
+    uint64_t* lookback;            // k_bin_count: per-1024-rank-chunk status words (epoch-tagged, never cleared)
+    uint64_t* lookback_emit;       // k_bin_emit: per-2048-candidate-block status words
     uint32_t epoch;
-    uint32_t* ticket;              // zeroed before launch
+    uint32_t* ticket;              // 2 words (count, emit), zeroed before launch
+    uint32_t* cand_off;            // v_max words: exclusive prefix of the candidate counts
+    uint32_t* block_rank;          // block_cap words: first owning rank of every 2048-candidate block
+    uint32_t block_cap;
+    uint32_t* cand_total;          // 1 word
     const uint32_t* entry_base_in; // entries already emitted by nearer models
     uint32_t* entry_total_out;     // entry_base_in + this model's entries (a different word)
     uint32_t* overflow;            // set to 1 when the capacity is exceeded
     uint32_t* tile_keys; uint32_t* tile_vals; uint32_t capacity;
+    uint32_t* tile_hist;           // 2 x 256 digit histogram of the emitted tile ids (zeroed before the frame)
 };
+size_t gs_bin_block_words(uint32_t capacity_candidates);
 cudaError_t gs_launch_bin(const GsBinArgs& a, const GsFrame& f, int num_sms, cudaStream_t st);
 cudaError_t gs_launch_tile_ranges(const uint32_t* tile_keys, const uint32_t* d_entries, uint32_t capacity,
                                   uint32_t* ranges /* 2 x tiles */, uint32_t n_tiles, int num_sms, cudaStream_t st);
@@ -177,15 +184,14 @@ __device__ __forceinline__ uint32_t gs_status_flag(uint64_t v, uint32_t epoch) {
     return ((uint32_t)(v >> 32) == epoch) ? (((uint32_t)v) >> 30) : 0u;
 }
 
-// Decoupled look-back executed by ONE full warp.  Publishes this tile's aggregate, returns the
-// exclusive prefix and publishes the inclusive prefix.  All lanes return the same value.
-__device__ __forceinline__ uint32_t gs_lookback_warp(uint64_t* status, uint32_t epoch, uint32_t tile,
-                                                     uint32_t aggregate, int lane) {
-    if (tile == 0) {
-        if (lane == 0) gs_st_status(&status[0], epoch, GS_LOOKBACK_FLAG_INCL | aggregate);
-        return 0;
-    }
-    if (lane == 0) gs_st_status(&status[tile], epoch, GS_LOOKBACK_FLAG_AGG | aggregate);
+// Decoupled look-back executed by ONE full warp, split in two so that callers can put work
+// between publishing their aggregate and needing the prefix.  All lanes return the same value.
+__device__ __forceinline__ void gs_lookback_publish(uint64_t* status, uint32_t epoch, uint32_t tile, uint32_t aggregate) {
+    gs_st_status(&status[tile], epoch, (tile == 0 ? GS_LOOKBACK_FLAG_INCL : GS_LOOKBACK_FLAG_AGG) | aggregate);
+}
+__device__ __forceinline__ uint32_t gs_lookback_resolve(uint64_t* status, uint32_t epoch, uint32_t tile,
+                                                        uint32_t aggregate, int lane) {
+    if (tile == 0) return 0;
     uint32_t excl = 0;
     int64_t p = (int64_t)tile - 1;
     while (true) {
@@ -206,5 +212,42 @@ __device__ __forceinline__ uint32_t gs_lookback_warp(uint64_t* status, uint32_t 
     }
     if (lane == 0) gs_st_status(&status[tile], epoch, GS_LOOKBACK_FLAG_INCL | (excl + aggregate));
     return excl;
+}
+__device__ __forceinline__ uint32_t gs_lookback_warp(uint64_t* status, uint32_t epoch, uint32_t tile,
+                                                     uint32_t aggregate, int lane) {
+    if (lane == 0) gs_lookback_publish(status, epoch, tile, aggregate);
+    return gs_lookback_resolve(status, epoch, tile, aggregate, lane);
+}
+
+// ---- exact footprint test ---------------------------------------------------------------
+// A splat contributes to a pixel only if alpha = o*exp(-q/2) >= 1/255, i.e. q <= tau with
+// q = a dx^2 + 2 b dx dy + c dy^2 and tau = 2 ln(255 o) (flat display modes: tau = GS_FLAT_D2).
+// gs_min_q_rect returns the minimum of q over a pixel rectangle (inclusive float bounds): if it
+// exceeds tau (plus slack for rounding) no pixel of the rectangle can be touched, so skipping
+// the rectangle leaves the image unchanged.  Convex q: when the centre is outside the rectangle
+// the minimum lies on an edge facing the centre.
+__device__ __forceinline__ float gs_min_q_rect(float mx, float my, float a, float b, float c, float x0, float x1,
+                                               float y0, float y1) {
+    const float dx0 = x0 - mx, dx1 = x1 - mx, dy0 = y0 - my, dy1 = y1 - my;
+    const bool inx = dx0 <= 0.0f && dx1 >= 0.0f, iny = dy0 <= 0.0f && dy1 >= 0.0f;
+    if (inx && iny) return 0.0f;
+    float best = 3.0e38f;
+    if (!inx) {
+        const float dx = dx0 > 0.0f ? dx0 : dx1;
+        const float dy = fminf(dy1, fmaxf(dy0, -b * dx / c));
+        best = a * dx * dx + 2.0f * b * dx * dy + c * dy * dy;
+    }
+    if (!iny) {
+        const float dy = dy0 > 0.0f ? dy0 : dy1;
+        const float dx = fminf(dx1, fmaxf(dx0, -b * dy / a));
+        best = fminf(best, a * dx * dx + 2.0f * b * dx * dy + c * dy * dy);
+    }
+    return best;
+}
+// footprint threshold (with slack so that rounding can never cull a contributing pixel)
+__device__ __forceinline__ float gs_footprint_tau(float opacity, bool flat) {
+    if (!(opacity * 255.0f >= 1.0f)) return -1.0f;  // alpha < 1/255 everywhere
+    const float t = flat ? GS_FLAT_D2 : 2.0f * __logf(opacity * 255.0f);
+    return t * 1.001f + 0.01f;
 }
 #endif

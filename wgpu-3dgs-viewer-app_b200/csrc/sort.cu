@@ -170,14 +170,29 @@ __global__ void __launch_bounds__(kThreads) k_sort_pass(const uint32_t* __restri
             gs_st_status(&lb[0], epoch, GS_LOOKBACK_FLAG_INCL | count);
         } else {
             gs_st_status(&lb[(size_t)tile * kRadix], epoch, GS_LOOKBACK_FLAG_AGG | count);
+            // walk back over the predecessors, kLb status words per round trip (independent loads)
+            constexpr int kLb = 4;
             int64_t p = (int64_t)tile - 1;
-            while (true) {
-                uint64_t v = gs_ld_status(&lb[(size_t)p * kRadix]);
-                uint32_t fl = gs_status_flag(v, epoch);
-                if (fl == 0u) continue;
-                excl += (uint32_t)v & GS_LOOKBACK_VALUE_MASK;
-                if (fl == 2u) break;
-                p--;
+            bool done = false;
+            while (!done) {
+                uint64_t v[kLb];
+#pragma unroll
+                for (int j = 0; j < kLb; j++)
+                    v[j] = (p - j >= 0) ? gs_ld_status(&lb[(size_t)(p - j) * kRadix])
+                                        : (((uint64_t)epoch << 32) | GS_LOOKBACK_FLAG_INCL);
+                int used = 0;
+#pragma unroll
+                for (int j = 0; j < kLb; j++) {
+                    if (!done && used == j) {
+                        const uint32_t fl = gs_status_flag(v[j], epoch);
+                        if (fl != 0u) {
+                            excl += (uint32_t)v[j] & GS_LOOKBACK_VALUE_MASK;
+                            used = j + 1;
+                            done = fl == 2u;
+                        }
+                    }
+                }
+                p -= used;
             }
             gs_st_status(&lb[(size_t)tile * kRadix], epoch, GS_LOOKBACK_FLAG_INCL | (excl + count));
         }
