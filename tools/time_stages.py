@@ -1,0 +1,26 @@
+"""Median per-stage device times for the bench workload: python tools/time_stages.py [N] [frames]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import ctypes as C
+import b200gs as G
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 6_000_000
+frames = int(sys.argv[2]) if len(sys.argv) > 2 else 24
+W, H = 1920, 1080
+packed = G.pack_gaussians(G.SH_NORM8, G.COV3D_HALF, G.gaussian_from_ply(G.synth_scene(0xB2000006, N)))
+cams = G.view_batch()
+with G.Viewer(W, H) as v:
+    m = v.add_model("scene", N)
+    m.upload_packed(0, packed)
+    v.enable_timings(True, False)
+    rows = []
+    for i in range(frames):
+        v.update_camera(cams[i % 8])
+        v.render_frame([m])
+        t = v.last_timings()
+        rows.append((t.preprocess_ms, t.sort_ms, t.bin_ms, t.composite_ms, t.total_ms))
+    dbg = (C.c_uint32 * 16)()
+    G.lib().b200gs_debug_model_ctrl(m.h, dbg)
+    print("ctrl:", list(dbg), "chunks", (N + 255) // 256)
+    r = np.median(np.array(rows[4:]), 0)
+    print("median ms: pre %.3f sort %.3f bin %.3f comp %.3f total %.3f" % tuple(r))

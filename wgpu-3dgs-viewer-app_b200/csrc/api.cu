@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -50,6 +51,7 @@ enum {  // viewer control block (u32 words), zeroed at the start of every render
     VC_ENTRY_TOTAL = 128,  // 65 words: running (tile, splat) entry count after each model
     VC_OVERFLOW = 194,
     VC_TSORT_TICKET = 196, // 2 words
+    VC_TSORT_IN_B = 198,   // 1 = tile-sorted entries are in the *_b buffers
     VC_EVALS = 200,        // u64
     VC_CAND_TOTAL = 208,   // 64 words: candidate tiles per model
     VC_TSORT_HIST = 512,   // 2 x 256
@@ -99,7 +101,8 @@ struct b200gs_viewer {
     uint64_t entry_cap = 0, entry_cap_user = 0;
     uint64_t *lb_bin = nullptr, *lb_tsort = nullptr, *lb_emit = nullptr;
     uint64_t lb_bin_words = 0;
-    uint32_t *cand_off = nullptr, *block_rank = nullptr;
+    uint2* cand_off = nullptr;
+    uint32_t* block_rank = nullptr;
     uint64_t cand_off_words = 0, block_cap = 0;
     uint32_t* ranges = nullptr;
     uint32_t ranges_tiles = 0;
@@ -635,6 +638,7 @@ extern "C" int b200gs_model_preprocess(b200gs_model* m, int use_unedited) {
     a.recs = m->recs; a.n = (uint32_t)m->cap; a.sh = v->sh; a.cov = v->cov;
     a.mask = m->mask; a.selection = m->selection; a.edits = use_unedited ? nullptr : m->edits;
     a.ctrl = m->ctrl + MC_CTRL; a.lookback = m->lb_pre; a.epoch = ++v->epoch;
+    if (getenv("B200GS_DEBUG_UNORDERED")) a.epoch = 0xffffffffu;
     a.keys = m->keys_a; a.idx = m->idx; a.splats = v->arena + m->arena_offset;
     a.sort_hist = m->ctrl + MC_SORT_HIST;
     if (v->timing) CK(cudaEventRecord(v->ev[0], v->stream));
@@ -656,6 +660,7 @@ extern "C" int b200gs_model_sort(b200gs_model* m) {
     a.d_n = m->ctrl + MC_CTRL + GS_CTRL_VISIBLE; a.n_max = (uint32_t)m->cap;
     a.hist = m->ctrl + MC_SORT_HIST; a.lookback = m->lb_sort; a.epoch = ++v->epoch;
     a.tickets = m->ctrl + MC_SORT_TICKET; a.passes = 4; a.hist_prefilled = true; a.vals_identity = true;
+    a.result_in_b = m->ctrl + MC_CTRL + GS_CTRL_SORT_IN_B;
     CK(gs_launch_sort(a, v->num_sms, v->stream));
     if (v->timing) CK(cudaEventRecord(v->ev[2], v->stream));
     m->sorted = true;
@@ -682,6 +687,8 @@ extern "C" int b200gs_render(b200gs_viewer* v, b200gs_model* const* far_to_near,
         b200gs_model* m = far_to_near[n_models - 1 - k];
         GsBinArgs b;
         b.sorted_slot = m->vals_a;
+        b.sorted_slot_b = m->vals_b;
+        b.sorted_in_b = m->ctrl + MC_CTRL + GS_CTRL_SORT_IN_B;
         b.splats = v->arena + m->arena_offset;
         b.d_v = m->ctrl + MC_CTRL + GS_CTRL_VISIBLE;
         b.v_max = (uint32_t)m->cap;
@@ -706,11 +713,12 @@ extern "C" int b200gs_render(b200gs_viewer* v, b200gs_model* const* far_to_near,
     s.d_n = v->vctrl + VC_ENTRY_TOTAL + n_models; s.n_max = (uint32_t)v->entry_cap;
     s.hist = v->vctrl + VC_TSORT_HIST; s.lookback = v->lb_tsort; s.epoch = ++v->epoch;
     s.tickets = v->vctrl + VC_TSORT_TICKET; s.passes = 2; s.hist_prefilled = true; s.vals_identity = false;
+    s.result_in_b = v->vctrl + VC_TSORT_IN_B;
     CK(gs_launch_sort(s, v->num_sms, st));
-    CK(gs_launch_tile_ranges(v->tk_a, s.d_n, (uint32_t)v->entry_cap, v->ranges, n_tiles, v->num_sms, st));
+    CK(gs_launch_tile_ranges(v->tk_a, v->tk_b, s.result_in_b, s.d_n, (uint32_t)v->entry_cap, v->ranges, n_tiles, v->num_sms, st));
     if (v->timing) CK(cudaEventRecord(v->ev[3], st));
     GsCompositeArgs c;
-    c.tile_vals = v->tv_a; c.ranges = v->ranges; c.splats = v->arena;
+    c.tile_vals = v->tv_a; c.tile_vals_b = v->tv_b; c.tile_in_b = s.result_in_b; c.ranges = v->ranges; c.splats = v->arena;
     c.out = (uint8_t*)rgba8_out; c.pitch = pitch;
     c.evals = v->count_evals ? (unsigned long long*)(v->vctrl + VC_EVALS) : nullptr;
     CK(gs_launch_composite(c, f, st));
@@ -775,6 +783,16 @@ extern "C" int b200gs_model_visible_count(b200gs_model* m, uint64_t* out) {
     REQUIRE(m && out, "null argument");
     return visible_count(m, out);
 }
+// after a sort the data may sit in the *_b buffers (a degenerate digit pass was skipped)
+static int sorted_in_b(b200gs_model* m, bool* out) {
+    *out = false;
+    if (!m->sorted) return B200GS_OK;
+    b200gs_viewer* v = m->v;
+    CK(cudaMemcpyAsync(v->h_small, m->ctrl + MC_CTRL + GS_CTRL_SORT_IN_B, 4, cudaMemcpyDeviceToHost, v->stream));
+    CK(cudaStreamSynchronize(v->stream));
+    *out = v->h_small[0] != 0;
+    return B200GS_OK;
+}
 static int download_u32(b200gs_model* m, const uint32_t* src, uint32_t* dst, uint64_t n) {
     if (n) CK(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToHost, m->v->stream));
     CK(cudaStreamSynchronize(m->v->stream));
@@ -786,7 +804,9 @@ extern "C" int b200gs_model_download_depth_keys(b200gs_model* m, uint32_t* keys,
     TRY(visible_count(m, &vc));
     *n = vc;
     REQUIRE(cap >= vc, "buffer too small");
-    return download_u32(m, m->keys_a, keys, vc);
+    bool in_b;
+    TRY(sorted_in_b(m, &in_b));
+    return download_u32(m, in_b ? m->keys_b : m->keys_a, keys, vc);
 }
 extern "C" int b200gs_model_download_indices(b200gs_model* m, uint32_t* idx, uint64_t cap, uint64_t* n) {
     REQUIRE(m && n && (idx || cap == 0), "null argument");
@@ -796,7 +816,9 @@ extern "C" int b200gs_model_download_indices(b200gs_model* m, uint32_t* idx, uin
     REQUIRE(cap >= vc, "buffer too small");
     if (!m->sorted) return download_u32(m, m->idx, idx, vc);
     std::vector<uint32_t> slots(vc), orig(vc);
-    TRY(download_u32(m, m->vals_a, slots.data(), vc));
+    bool in_b;
+    TRY(sorted_in_b(m, &in_b));
+    TRY(download_u32(m, in_b ? m->vals_b : m->vals_a, slots.data(), vc));
     TRY(download_u32(m, m->idx, orig.data(), vc));
     for (uint64_t i = 0; i < vc; i++) idx[i] = slots[i] < vc ? orig[slots[i]] : 0xffffffffu;
     return B200GS_OK;
@@ -815,7 +837,9 @@ extern "C" int b200gs_model_download_splats(b200gs_model* m, b200gs_splat* out, 
     }
     std::vector<uint32_t> slots(vc);
     std::vector<b200gs_splat> tmp(vc);
-    TRY(download_u32(m, m->vals_a, slots.data(), vc));
+    bool in_b;
+    TRY(sorted_in_b(m, &in_b));
+    TRY(download_u32(m, in_b ? m->vals_b : m->vals_a, slots.data(), vc));
     if (vc) CK(cudaMemcpyAsync(tmp.data(), v->arena + m->arena_offset, vc * sizeof(b200gs_splat), cudaMemcpyDeviceToHost, v->stream));
     CK(cudaStreamSynchronize(v->stream));
     for (uint64_t i = 0; i < vc; i++) {
@@ -860,6 +884,16 @@ extern "C" int b200gs_model_download_packed(b200gs_model* m, uint64_t start, voi
     TRY(set_device(m->v));
     if (count) CK(cudaMemcpyAsync(packed, m->recs + start * m->v->rb, count * m->v->rb, cudaMemcpyDeviceToHost, m->v->stream));
     CK(cudaStreamSynchronize(m->v->stream));
+    return B200GS_OK;
+}
+
+// developer aid (not part of the public header): the 16 control words of a model
+extern "C" B200GS_API int b200gs_debug_model_ctrl(b200gs_model* m, uint32_t* out16) {
+    REQUIRE(m && out16, "null argument");
+    TRY(set_device(m->v));
+    CK(cudaMemcpyAsync(m->v->h_small, m->ctrl, 64, cudaMemcpyDeviceToHost, m->v->stream));
+    CK(cudaStreamSynchronize(m->v->stream));
+    memcpy(out16, m->v->h_small, 64);
     return B200GS_OK;
 }
 
@@ -917,8 +951,15 @@ extern "C" int b200gs_sort_pairs_device(b200gs_viewer* v, uint32_t* keys_dev, ui
     a.keys_a = keys_dev; a.vals_a = values_dev; a.keys_b = kb; a.vals_b = vb;
     a.d_n = ctl; a.n_max = nn; a.hist = ctl + 1024; a.lookback = lb; a.epoch = ++v->epoch;
     a.tickets = ctl + 8; a.passes = passes; a.hist_prefilled = false; a.vals_identity = false;
+    a.result_in_b = ctl + 16;
     CK(gs_launch_sort(a, v->num_sms, st));
+    CK(cudaMemcpyAsync(v->h_small, ctl + 16, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (v->h_small[0]) {  // an odd number of passes ran: the result is in the scratch buffers
+        CK(cudaMemcpyAsync(keys_dev, kb, n * 4, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(values_dev, vb, n * 4, cudaMemcpyDeviceToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    }
     cudaFree(kb); cudaFree(vb); cudaFree(ctl); cudaFree(lb);
     return B200GS_OK;
 }

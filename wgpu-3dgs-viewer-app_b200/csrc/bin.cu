@@ -84,15 +84,18 @@ __device__ __forceinline__ bool tile_hit(const Cand& c, uint32_t x, uint32_t y) 
 }
 
 // ------------------------------------------------------------------ kernel A: candidate counts
-__global__ void __launch_bounds__(kThreads) k_bin_count(const uint32_t* __restrict__ sorted_slot,
+__global__ void __launch_bounds__(kThreads) k_bin_count(const uint32_t* __restrict__ sorted_a,
+                                                        const uint32_t* __restrict__ sorted_b,
+                                                        const uint32_t* sorted_in_b,
                                                         const b200gs_splat* __restrict__ splats,
                                                         const uint32_t* d_v, uint32_t v_max, uint64_t* lookback,
-                                                        uint32_t epoch, uint32_t* ticket, uint32_t* __restrict__ cand_off,
+                                                        uint32_t epoch, uint32_t* ticket, uint2* __restrict__ cand_off,
                                                         uint32_t* __restrict__ block_rank, uint32_t block_cap,
                                                         uint32_t* cand_total, float W, float H, uint32_t flat) {
     __shared__ uint32_t s_wsum[kThreads / 32];
     __shared__ uint32_t s_chunk, s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t* __restrict__ sorted_slot = (sorted_in_b && *sorted_in_b) ? sorted_b : sorted_a;
     uint32_t v = *d_v;
     if (v > v_max) v = v_max;
     const uint32_t nchunks = (v + kChunk - 1) / kChunk;
@@ -100,73 +103,90 @@ __global__ void __launch_bounds__(kThreads) k_bin_count(const uint32_t* __restri
         if (blockIdx.x == 0 && tid == 0) *cand_total = 0;
         return;
     }
+    // Software-pipelined by one chunk: chunk k+1 is counted and its aggregate published BEFORE chunk
+    // k's prefix is resolved, so the look-back never waits for chunks drawn at the same moment.
+    bool have_prev = false;
+    uint32_t p_c = 0, p_total = 0, p_r0 = 0, p_local = 0, p_cnt[kIpt], p_slot[kIpt];
+#pragma unroll
+    for (int k = 0; k < kIpt; k++) p_cnt[k] = p_slot[k] = 0;
     while (true) {
         __syncthreads();
         if (tid == 0) s_chunk = atomicAdd(ticket, 1u);
         __syncthreads();
         const uint32_t c = s_chunk;
-        if (c >= nchunks) break;
+        const bool valid = c < nchunks;
+        uint32_t cnt[kIpt], slot[kIpt], sum = 0, chunk_total = 0, local = 0;
         const uint32_t r0 = c * kChunk + tid * kIpt;
-        uint32_t cnt[kIpt], sum = 0;
-        uint4 q0[kIpt];
 #pragma unroll
-        for (int k = 0; k < kIpt; k++) {
-            q0[k] = make_uint4(0, 0, 0, 0);
-            if (r0 + k < v) {
-                const uint32_t slot = sorted_slot ? sorted_slot[r0 + k] : r0 + k;
-                q0[k] = __ldg(reinterpret_cast<const uint4*>(splats + slot));
+        for (int k = 0; k < kIpt; k++) cnt[k] = slot[k] = 0;
+        if (valid) {
+            uint4 q0[kIpt];
+#pragma unroll
+            for (int k = 0; k < kIpt; k++) slot[k] = (r0 + k < v) ? (sorted_slot ? sorted_slot[r0 + k] : r0 + k) : 0u;
+#pragma unroll
+            for (int k = 0; k < kIpt; k++) {
+                q0[k] = make_uint4(0, 0, 0, 0);
+                if (r0 + k < v) q0[k] = __ldg(reinterpret_cast<const uint4*>(splats + slot[k]));
             }
-        }
 #pragma unroll
-        for (int k = 0; k < kIpt; k++) {
-            Cand cd;
-            cnt[k] = (r0 + k < v && make_rect(q0[k], W, H, flat != 0, cd)) ? cd.nx * cd.ny : 0u;
-            sum += cnt[k];
-        }
-        uint32_t incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) s_wsum[warp] = incl;
-        __syncthreads();
-        uint32_t chunk_total = 0, woff = 0;
-#pragma unroll
-        for (int k = 0; k < kThreads / 32; k++) {
-            const uint32_t t = s_wsum[k];
-            if (k < warp) woff += t;
-            chunk_total += t;
-        }
-        if (warp == 0) {
-            const uint32_t excl = gs_lookback_warp(lookback, epoch, c, chunk_total, lane);
-            if (lane == 0) {
-                s_base = excl;
-                if (c == nchunks - 1) *cand_total = excl + chunk_total;
+            for (int k = 0; k < kIpt; k++) {
+                Cand cd;
+                cnt[k] = (r0 + k < v && make_rect(q0[k], W, H, flat != 0, cd)) ? cd.nx * cd.ny : 0u;
+                sum += cnt[k];
             }
-        }
-        __syncthreads();
-        uint32_t o = s_base + woff + incl - sum;
+            uint32_t incl = sum;
 #pragma unroll
-        for (int k = 0; k < kIpt; k++) {
-            if (r0 + k < v) {
-                cand_off[r0 + k] = o;
-                if (cnt[k]) {
-                    // this rank owns the first candidate of every block whose start falls in its run
-                    const uint32_t first = (o + kBlock - 1) / kBlock, last = (o + cnt[k] - 1) / kBlock;
-                    for (uint32_t b = first; b <= last && b < block_cap; b++) block_rank[b] = r0 + k;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            uint32_t woff = 0;
+#pragma unroll
+            for (int k = 0; k < kThreads / 32; k++) {
+                const uint32_t t = s_wsum[k];
+                if (k < warp) woff += t;
+                chunk_total += t;
+            }
+            if (tid == 0) gs_lookback_publish(lookback, epoch, c, chunk_total);
+            local = woff + incl - sum;
+        }
+        if (have_prev) {
+            if (warp == 0) {
+                const uint32_t excl = gs_lookback_resolve(lookback, epoch, p_c, p_total, lane);
+                if (lane == 0) {
+                    s_base = excl;
+                    if (p_c == nchunks - 1) *cand_total = excl + p_total;
                 }
             }
-            o += cnt[k];
+            __syncthreads();
+            uint32_t o = s_base + p_local;
+#pragma unroll
+            for (int k = 0; k < kIpt; k++) {
+                if (p_r0 + k < v) {
+                    cand_off[p_r0 + k] = make_uint2(o, p_slot[k]);
+                    if (p_cnt[k]) {
+                        // this rank owns the first candidate of every block whose start falls in its run
+                        const uint32_t first = (o + kBlock - 1) / kBlock, last = (o + p_cnt[k] - 1) / kBlock;
+                        for (uint32_t b = first; b <= last && b < block_cap; b++) block_rank[b] = p_r0 + k;
+                    }
+                }
+                o += p_cnt[k];
+            }
         }
+        if (!valid) break;
+        have_prev = true;
+        p_c = c; p_total = chunk_total; p_r0 = r0; p_local = local;
+#pragma unroll
+        for (int k = 0; k < kIpt; k++) { p_cnt[k] = cnt[k]; p_slot[k] = slot[k]; }
     }
 }
 
 // ------------------------------------------------------------------ kernel B: test + emit
-__global__ void __launch_bounds__(kThreads) k_bin_emit(const uint32_t* __restrict__ sorted_slot,
-                                                       const b200gs_splat* __restrict__ splats,
+__global__ void __launch_bounds__(kThreads) k_bin_emit(const b200gs_splat* __restrict__ splats,
                                                        const uint32_t* d_v, uint32_t v_max, uint32_t splat_base,
-                                                       const uint32_t* __restrict__ cand_off,
+                                                       const uint2* __restrict__ cand_off,
                                                        const uint32_t* __restrict__ block_rank, uint32_t block_cap,
                                                        const uint32_t* cand_total_p, uint64_t* lookback, uint32_t epoch,
                                                        uint32_t* ticket, const uint32_t* entry_base_in,
@@ -175,8 +195,8 @@ __global__ void __launch_bounds__(kThreads) k_bin_emit(const uint32_t* __restric
                                                        uint32_t capacity, uint32_t* tile_hist, float W, float H,
                                                        uint32_t tiles_x, uint32_t flat) {
     __shared__ int32_t s_owner[kBlock];       // rank owning each candidate (after the max-scan)
-    __shared__ uint32_t s_keys[kBlock];
-    __shared__ uint32_t s_vals[kBlock];
+    __shared__ uint32_t s_keys[2][kBlock];    // kept entries of the block, double-buffered:
+    __shared__ uint32_t s_vals[2][kBlock];    // block b+1 is staged before block b is written out
     __shared__ uint32_t s_hist[512];
     __shared__ uint32_t s_cnt[kCpt][kThreads / 32];
     __shared__ int32_t s_wmax[kThreads / 32];
@@ -197,12 +217,19 @@ __global__ void __launch_bounds__(kThreads) k_bin_emit(const uint32_t* __restric
     }
     for (int i = tid; i < 512; i += kThreads) s_hist[i] = 0;
 
-    while (true) {
+    // Software-pipelined by one block: block b+1 is tested, counted, published and staged BEFORE
+    // block b's prefix is resolved and its entries are written out.
+    bool have_prev = false;
+    uint32_t p_b = 0, p_kept = 0;
+    for (uint32_t iter = 0;; iter++) {
+        const uint32_t buf = iter & 1u;
         __syncthreads();
         if (tid == 0) s_blk = atomicAdd(ticket, 1u);
         __syncthreads();
         const uint32_t b = s_blk;
-        if (b >= nblocks) break;
+        const bool valid = b < nblocks;
+        uint32_t kept_total = 0;
+        if (valid) {
         const uint32_t cbase = b * kBlock;
         const uint32_t nc = min(kBlock, total - cbase);
 
@@ -213,8 +240,8 @@ __global__ void __launch_bounds__(kThreads) k_bin_emit(const uint32_t* __restric
         const uint32_t r_hi = (b + 1 < nblocks) ? block_rank[b + 1] : v - 1;
         if (tid == 0) s_owner[0] = (int32_t)r_lo;
         for (uint32_t r = r_lo + 1 + tid; r <= r_hi; r += kThreads) {
-            const uint32_t o = cand_off[r];
-            const uint32_t nxt = (r + 1 < v) ? cand_off[r + 1] : total;
+            const uint32_t o = cand_off[r].x;
+            const uint32_t nxt = (r + 1 < v) ? cand_off[r + 1].x : total;
             if (nxt > o && o >= cbase && o < cbase + kBlock) s_owner[o - cbase] = (int32_t)r;
         }
         __syncthreads();
@@ -250,14 +277,15 @@ __global__ void __launch_bounds__(kThreads) k_bin_emit(const uint32_t* __restric
             key[k] = val[k] = 0;
             if (p < nc) {
                 const uint32_t r = (uint32_t)s_owner[p];
-                const uint32_t slot = sorted_slot ? sorted_slot[r] : r;
+                const uint2 os = __ldg(&cand_off[r]);  // {first candidate, splat slot} of the owning rank
+                const uint32_t slot = os.y;
                 const uint4* sp = reinterpret_cast<const uint4*>(splats + slot);
                 const uint4 q0 = __ldg(sp), q1 = __ldg(sp + 1);
                 Cand cd;
                 if (make_rect(q0, W, H, flat != 0, cd)) {
                     cd.a = __uint_as_float(q1.x); cd.b = __uint_as_float(q1.y); cd.c = __uint_as_float(q1.z);
-                    cd.nbc = -cd.b / cd.c; cd.nba = -cd.b / cd.a;
-                    const uint32_t e = cbase + p - cand_off[r];
+                    cd.nbc = __fdividef(-cd.b, cd.c); cd.nba = __fdividef(-cd.b, cd.a);  // tau carries the slack
+                    const uint32_t e = cbase + p - os.x;
                     const uint32_t y = e / cd.nx, x = e - y * cd.nx;
                     keep[k] = tile_hit(cd, x, y);
                     key[k] = (cd.ty0 + y) * tiles_x + cd.tx0 + x;
@@ -287,48 +315,56 @@ __global__ void __launch_bounds__(kThreads) k_bin_emit(const uint32_t* __restric
             }
         }
         __syncthreads();
-        const uint32_t kept_total = s_kept;
+        kept_total = s_kept;
         // ---- stage the kept entries in candidate order
 #pragma unroll
         for (int k = 0; k < kCpt; k++) {
             const uint32_t bal = __ballot_sync(0xffffffffu, keep[k]);
             if (keep[k]) {
                 const uint32_t o = s_cnt[k][warp] + __popc(bal & ((1u << lane) - 1u));
-                s_keys[o] = key[k];
-                s_vals[o] = val[k];
+                s_keys[buf][o] = key[k];
+                s_vals[buf][o] = val[k];
             }
         }
-        if (warp == 0) {
-            const uint32_t excl = gs_lookback_resolve(lookback, epoch, b, kept_total, lane);
-            if (lane == 0) {
-                s_base = excl;
-                if (b == nblocks - 1) {
-                    uint32_t t = ebase + excl + kept_total;
-                    if (t > capacity) { *overflow = 1u; t = capacity; }
-                    *entry_total_out = t;
+        }  // valid
+        if (have_prev) {
+            const uint32_t pbuf = buf ^ 1u;
+            if (warp == 0) {
+                const uint32_t excl = gs_lookback_resolve(lookback, epoch, p_b, p_kept, lane);
+                if (lane == 0) {
+                    s_base = excl;
+                    if (p_b == nblocks - 1) {
+                        uint32_t t = ebase + excl + p_kept;
+                        if (t > capacity) { *overflow = 1u; t = capacity; }
+                        *entry_total_out = t;
+                    }
                 }
             }
-        }
-        __syncthreads();
-        const uint32_t gbase = ebase + s_base;
-        // ---- coalesced write-out + digit histograms for the tile sort
-        for (uint32_t i0 = 0; i0 < kept_total; i0 += kThreads) {
-            const uint32_t i = i0 + tid;
-            const uint32_t g = gbase + i;
-            const bool ok = i < kept_total && g < capacity;
-            const uint32_t act = __ballot_sync(0xffffffffu, ok);
-            if (ok) {
-                const uint32_t kk = s_keys[i];
-                tile_keys[g] = kk;
-                tile_vals[g] = s_vals[i];
+            __syncthreads();
+            const uint32_t gbase = ebase + s_base;
+            // ---- coalesced write-out + digit histograms for the tile sort
+            for (uint32_t i0 = 0; i0 < p_kept; i0 += kThreads) {
+                const uint32_t i = i0 + tid;
+                const uint32_t g = gbase + i;
+                const bool ok = i < p_kept && g < capacity;
+                const uint32_t act = __ballot_sync(0xffffffffu, ok);
+                if (ok) {
+                    const uint32_t kk = s_keys[pbuf][i];
+                    tile_keys[g] = kk;
+                    tile_vals[g] = s_vals[pbuf][i];
 #pragma unroll
-                for (int p = 0; p < 2; p++) {
-                    const uint32_t d = (kk >> (8 * p)) & 0xffu;
-                    const uint32_t peers = __match_any_sync(act, d);
-                    if (lane == __ffs((int)peers) - 1) atomicAdd(&s_hist[p * 256 + d], (uint32_t)__popc(peers));
+                    for (int p = 0; p < 2; p++) {
+                        const uint32_t d = (kk >> (8 * p)) & 0xffu;
+                        const uint32_t peers = __match_any_sync(act, d);
+                        if (lane == __ffs((int)peers) - 1) atomicAdd(&s_hist[p * 256 + d], (uint32_t)__popc(peers));
+                    }
                 }
             }
         }
+        if (!valid) break;
+        have_prev = true;
+        p_b = b;
+        p_kept = kept_total;
     }
     __syncthreads();
     for (int i = tid; i < 512; i += kThreads) {
@@ -338,8 +374,10 @@ __global__ void __launch_bounds__(kThreads) k_bin_emit(const uint32_t* __restric
 }
 
 // ranges[tile] = first entry, ranges[n_tiles + tile] = one past the last entry (both 0 if none)
-__global__ void __launch_bounds__(256) k_tile_ranges(const uint32_t* __restrict__ tile_keys, const uint32_t* d_entries,
+__global__ void __launch_bounds__(256) k_tile_ranges(const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b,
+                                                     const uint32_t* in_b, const uint32_t* d_entries,
                                                      uint32_t capacity, uint32_t* ranges, uint32_t n_tiles) {
+    const uint32_t* __restrict__ tile_keys = *in_b ? keys_b : keys_a;
     uint32_t n = *d_entries;
     if (n > capacity) n = capacity;
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
@@ -369,20 +407,21 @@ cudaError_t gs_launch_bin(const GsBinArgs& a, const GsFrame& f, int num_sms, cud
     uint32_t grid = (uint32_t)(bps_count * num_sms);
     if (grid > nchunks) grid = nchunks;
     if (grid < 1) grid = 1;
-    k_bin_count<<<grid, kThreads, 0, st>>>(a.sorted_slot, a.splats, a.d_v, a.v_max, a.lookback, a.epoch, a.ticket,
+    k_bin_count<<<grid, kThreads, 0, st>>>(a.sorted_slot, a.sorted_slot_b, a.sorted_in_b, a.splats, a.d_v, a.v_max, a.lookback, a.epoch, a.ticket,
                                            a.cand_off, a.block_rank, a.block_cap, a.cand_total, f.W, f.H, flat);
     k_bin_emit<<<(uint32_t)(bps_emit * num_sms), kThreads, 0, st>>>(
-        a.sorted_slot, a.splats, a.d_v, a.v_max, a.splat_base, a.cand_off, a.block_rank, a.block_cap, a.cand_total,
+        a.splats, a.d_v, a.v_max, a.splat_base, a.cand_off, a.block_rank, a.block_cap, a.cand_total,
         a.lookback_emit,
         a.epoch, a.ticket + 1, a.entry_base_in, a.entry_total_out, a.overflow, a.tile_keys, a.tile_vals, a.capacity,
         a.tile_hist, f.W, f.H, f.tiles_x, flat);
     return cudaGetLastError();
 }
 
-cudaError_t gs_launch_tile_ranges(const uint32_t* tile_keys, const uint32_t* d_entries, uint32_t capacity,
-                                  uint32_t* ranges, uint32_t n_tiles, int num_sms, cudaStream_t st) {
+cudaError_t gs_launch_tile_ranges(const uint32_t* keys_a, const uint32_t* keys_b, const uint32_t* in_b,
+                                  const uint32_t* d_entries, uint32_t capacity, uint32_t* ranges, uint32_t n_tiles,
+                                  int num_sms, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(ranges, 0, (size_t)n_tiles * 2 * sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
-    k_tile_ranges<<<num_sms * 8, 256, 0, st>>>(tile_keys, d_entries, capacity, ranges, n_tiles);
+    k_tile_ranges<<<num_sms * 8, 256, 0, st>>>(keys_a, keys_b, in_b, d_entries, capacity, ranges, n_tiles);
     return cudaGetLastError();
 }

@@ -55,7 +55,7 @@ struct GsModelXf {
 enum {
     GS_CTRL_TICKET = 0,    // preprocess chunk ticket
     GS_CTRL_VISIBLE = 1,   // V, written by the preprocess kernel
-    GS_CTRL_SORT_TICKET = 2, // +pass (4 words)
+    GS_CTRL_SORT_IN_B = 2,   // 1 = sorted keys/values are in the *_b buffers
     GS_CTRL_WORDS = 16
 };
 
@@ -85,7 +85,8 @@ struct GsSortArgs {
     uint64_t* lookback;  // passes x tiles x 256 status words (epoch-tagged, never cleared)
     uint32_t epoch;
     uint32_t* tickets;   // passes words, zeroed before launch
-    uint32_t passes;     // 1..4 (bits = 8*passes, starting at bit 0); must be even so the result lands in *_a
+    uint32_t passes;     // 1..4 (bits = 8*passes, starting at bit 0)
+    uint32_t* result_in_b; // device flag written by the last pass: 1 = the sorted data is in keys_b/vals_b
     bool hist_prefilled; // histogram already accumulated by the producer
     bool vals_identity;  // pass 0 synthesises value = input position instead of reading vals_a
 };
@@ -94,7 +95,9 @@ cudaError_t gs_launch_sort(const GsSortArgs& a, int num_sms, cudaStream_t st);
 
 // Binning: expand depth-sorted splats into (tile, splat) entries in depth order.
 struct GsBinArgs {
-    const uint32_t* sorted_slot;   // per depth rank: slot of the splat in `splats` (compaction order), or null = identity
+    const uint32_t* sorted_slot;   // per depth rank: slot of the splat in `splats` (compaction order)
+    const uint32_t* sorted_slot_b; // the sort's other buffer, selected when *sorted_in_b != 0
+    const uint32_t* sorted_in_b;   // device flag written by the sort (GsSortArgs::result_in_b)
     const b200gs_splat* splats;    // this model's splats (compaction order)
     const uint32_t* d_v;           // visible count of this model on device
     uint32_t v_max;
@@ -103,7 +106,7 @@ struct GsBinArgs {
     uint64_t* lookback_emit;       // k_bin_emit: per-2048-candidate-block status words
     uint32_t epoch;
     uint32_t* ticket;              // 2 words (count, emit), zeroed before launch
-    uint32_t* cand_off;            // v_max words: exclusive prefix of the candidate counts
+    uint2* cand_off;               // v_max x {exclusive prefix of the candidate counts, splat slot}
     uint32_t* block_rank;          // block_cap words: first owning rank of every 2048-candidate block
     uint32_t block_cap;
     uint32_t* cand_total;          // 1 word
@@ -115,11 +118,14 @@ struct GsBinArgs {
 };
 size_t gs_bin_block_words(uint32_t capacity_candidates);
 cudaError_t gs_launch_bin(const GsBinArgs& a, const GsFrame& f, int num_sms, cudaStream_t st);
-cudaError_t gs_launch_tile_ranges(const uint32_t* tile_keys, const uint32_t* d_entries, uint32_t capacity,
-                                  uint32_t* ranges /* 2 x tiles */, uint32_t n_tiles, int num_sms, cudaStream_t st);
+cudaError_t gs_launch_tile_ranges(const uint32_t* keys_a, const uint32_t* keys_b, const uint32_t* in_b,
+                                  const uint32_t* d_entries, uint32_t capacity, uint32_t* ranges /* 2 x tiles */,
+                                  uint32_t n_tiles, int num_sms, cudaStream_t st);
 
 struct GsCompositeArgs {
     const uint32_t* tile_vals;      // entries sorted by tile, depth order inside a tile
+    const uint32_t* tile_vals_b;    // the tile sort's other buffer, selected when *tile_in_b != 0
+    const uint32_t* tile_in_b;
     const uint32_t* ranges;         // [tile] = start, [n_tiles + tile] = end
     const b200gs_splat* splats;     // frame arena
     uint8_t* out; size_t pitch;     // RGBA8
@@ -190,25 +196,43 @@ __device__ __forceinline__ void gs_lookback_publish(uint64_t* status, uint32_t e
     gs_st_status(&status[tile], epoch, (tile == 0 ? GS_LOOKBACK_FLAG_INCL : GS_LOOKBACK_FLAG_AGG) | aggregate);
 }
 __device__ __forceinline__ uint32_t gs_lookback_resolve(uint64_t* status, uint32_t epoch, uint32_t tile,
-                                                        uint32_t aggregate, int lane) {
+                                                        uint32_t aggregate, int lane, uint32_t* dbg = nullptr) {
+    // Each round inspects the 128 predecessors p .. p-127 with 4 independent loads per lane
+    // (group j holds p-32j-lane), so a walk over the few hundred tiles that are in flight at once
+    // costs a handful of L2 round trips instead of one per 32 tiles.
     if (tile == 0) return 0;
+    constexpr int kGroups = 4;
     uint32_t excl = 0;
     int64_t p = (int64_t)tile - 1;
     while (true) {
-        int64_t i = p - lane;
-        uint64_t v = (i >= 0) ? gs_ld_status(&status[i]) : (((uint64_t)epoch << 32) | GS_LOOKBACK_FLAG_INCL);
-        uint32_t flag = gs_status_flag(v, epoch);
-        uint32_t m_incl = __ballot_sync(0xffffffffu, flag == 2u);
-        uint32_t m_inv = __ballot_sync(0xffffffffu, flag == 0u);
-        uint32_t first = m_incl ? (uint32_t)(__ffs((int)m_incl) - 1) : 32u;
-        uint32_t needed = first >= 31u ? 0xffffffffu : ((2u << first) - 1u);
-        if (m_inv & needed) continue;  // a needed predecessor has not published yet: retry
-        uint32_t contrib = ((needed >> lane) & 1u) ? ((uint32_t)v & GS_LOOKBACK_VALUE_MASK) : 0u;
+        if (dbg && lane == 0) atomicAdd(&dbg[0], 1u);
+        uint64_t v[kGroups];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-        excl += contrib;
-        if (first < 32u) break;
-        p -= 32;
+        for (int j = 0; j < kGroups; j++) {
+            const int64_t i = p - 32 * j - lane;
+            v[j] = (i >= 0) ? gs_ld_status(&status[i]) : (((uint64_t)epoch << 32) | GS_LOOKBACK_FLAG_INCL);
+        }
+        bool done = false, stalled = false;
+#pragma unroll
+        for (int j = 0; j < kGroups; j++) {
+            if (!done && !stalled) {
+                const uint32_t flag = gs_status_flag(v[j], epoch);
+                const uint32_t m_incl = __ballot_sync(0xffffffffu, flag == 2u);
+                const uint32_t m_inv = __ballot_sync(0xffffffffu, flag == 0u);
+                const uint32_t first = m_incl ? (uint32_t)(__ffs((int)m_incl) - 1) : 32u;
+                const uint32_t needed = first >= 31u ? 0xffffffffu : ((2u << first) - 1u);
+                if (m_inv & needed) { stalled = true; if (dbg && lane == 0) atomicAdd(&dbg[1], 1u); }  // not published yet: retry from here
+                else {
+                    uint32_t contrib = ((needed >> lane) & 1u) ? ((uint32_t)v[j] & GS_LOOKBACK_VALUE_MASK) : 0u;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+                    excl += contrib;
+                    if (first < 32u) done = true;
+                    else p -= 32;
+                }
+            }
+        }
+        if (done) break;
     }
     if (lane == 0) gs_st_status(&status[tile], epoch, GS_LOOKBACK_FLAG_INCL | (excl + aggregate));
     return excl;

@@ -7,8 +7,9 @@
 //     C += c·α·T,  T -= α·T,   α = min(0.99, o·exp(-½ dᵀQd)),
 // dropping α < 1/255 and power > 0, and stops a pixel when T < 1/1024 (whole warp / whole CTA
 // exit as soon as all their pixels stopped).  Each warp owns an 8x4 pixel sub-tile and first
-// culls the staged splats against it 32 at a time with a ballot, so only splats whose extent
-// square overlaps the sub-tile are evaluated.  FP32-pipe + MUFU bound, not HBM bound.
+// culls the staged splats against it 32 at a time with a ballot (exact ellipse-vs-rectangle
+// footprint test, one splat per lane), so only splats that can reach alpha >= 1/255 inside the
+// sub-tile are evaluated.  FP32-pipe + MUFU bound, not HBM bound.
 #include "common.cuh"
 
 namespace {
@@ -23,7 +24,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 template <bool FLAT, bool COUNT>
-__global__ void __launch_bounds__(kThreads) k_composite(const uint32_t* __restrict__ tile_vals,
+__global__ void __launch_bounds__(kThreads) k_composite(const uint32_t* __restrict__ tile_vals_a,
+                                                        const uint32_t* __restrict__ tile_vals_b,
+                                                        const uint32_t* tile_in_b,
                                                         const uint32_t* __restrict__ ranges,
                                                         const b200gs_splat* __restrict__ splats, uint8_t* out,
                                                         size_t pitch, uint32_t W, uint32_t H, uint32_t tiles_x,
@@ -32,9 +35,10 @@ __global__ void __launch_bounds__(kThreads) k_composite(const uint32_t* __restri
     __shared__ float4 sA[kThreads];  // mx, my, a', b'   (conic pre-scaled: power in log2 units)
     __shared__ float4 sB[kThreads];  // c', opacity, red, green
     __shared__ int4 sD[kThreads];    // x0, x1-x0, y0, y1-y0 (pixel bounds clipped to the viewport)
-    __shared__ float sC[kThreads];   // blue
+    __shared__ float2 sC[kThreads];  // blue, footprint threshold (in the units of the pre-scaled conic)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t* __restrict__ tile_vals = *tile_in_b ? tile_vals_b : tile_vals_a;
     const uint32_t tile = blockIdx.x;
     const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
     const uint32_t start = ranges[tile], end = ranges[n_tiles + tile];
@@ -73,7 +77,7 @@ __global__ void __launch_bounds__(kThreads) k_composite(const uint32_t* __restri
             sA[tid] = make_float4(mx, my, -0.5f * kLog2e * ca, -kLog2e * cbq);
             sB[tid] = make_float4(-0.5f * kLog2e * cc, op, cr, cg);
             sD[tid] = make_int4((int)fx0, (int)fx1 - (int)fx0, (int)fy0, (int)fy1 - (int)fy0);
-            sC[tid] = cb;
+            sC[tid] = make_float2(cb, 0.5f * kLog2e * gs_footprint_tau(op, FLAT));
         }
         __syncthreads();
 
@@ -82,8 +86,27 @@ __global__ void __launch_bounds__(kThreads) k_composite(const uint32_t* __restri
                 const uint32_t s = g + lane;
                 bool ov = false;
                 if (s < cnt) {
+                    // exact footprint test of splat s against this warp's 8x4 sub-tile (∩ extent square)
                     const int4 d = sD[s];
-                    ov = d.x <= wx1 && d.x + d.y >= wx0 && d.z <= wy1 && d.z + d.w >= wy0;
+                    const int x0 = max(d.x, wx0), x1 = min(d.x + d.y, wx1), y0 = max(d.z, wy0), y1 = min(d.z + d.w, wy1);
+                    if (x0 <= x1 && y0 <= y1) {
+                        const float4 A = sA[s];
+                        const float pa = -A.z, pb = -0.5f * A.w, pc = -sB[s].x;  // 0.5*log2e * (a, b, c)
+                        const float dx0 = (float)x0 - A.x, dx1 = (float)x1 - A.x, dy0 = (float)y0 - A.y, dy1 = (float)y1 - A.y;
+                        const bool inx = dx0 <= 0.0f && dx1 >= 0.0f, iny = dy0 <= 0.0f && dy1 >= 0.0f;
+                        float best = (inx && iny) ? 0.0f : 3.0e38f;
+                        if (!inx) {
+                            const float dx = dx0 > 0.0f ? dx0 : dx1;
+                            const float dy = fminf(dy1, fmaxf(dy0, __fdividef(-pb * dx, pc)));
+                            best = pa * dx * dx + 2.0f * pb * dx * dy + pc * dy * dy;
+                        }
+                        if (!iny) {
+                            const float dy = dy0 > 0.0f ? dy0 : dy1;
+                            const float dx = fminf(dx1, fmaxf(dx0, __fdividef(-pb * dy, pa)));
+                            best = fminf(best, pa * dx * dx + 2.0f * pb * dx * dy + pc * dy * dy);
+                        }
+                        ov = best <= sC[s].y;
+                    }
                 }
                 uint32_t m = __ballot_sync(0xffffffffu, ov);
                 while (m) {
@@ -92,7 +115,7 @@ __global__ void __launch_bounds__(kThreads) k_composite(const uint32_t* __restri
                     const float4 A = sA[s2];
                     const float4 B = sB[s2];
                     const int4 D = sD[s2];
-                    const float cb = sC[s2];
+                    const float cb = sC[s2].x;
                     const bool in = (uint32_t)(px - D.x) <= (uint32_t)D.y && (uint32_t)(py - D.z) <= (uint32_t)D.w;
                     const float dx = fpx - A.x, dy = fpy - A.y;
                     const float p2 = A.z * dx * dx + B.x * dy * dy + A.w * dx * dy;
@@ -139,7 +162,7 @@ cudaError_t gs_launch_composite(const GsCompositeArgs& a, const GsFrame& f, cuda
     const bool flat = f.display_mode != B200GS_DISPLAY_SPLAT;
     const uint32_t W = (uint32_t)f.W, H = (uint32_t)f.H;
 #define GS_LAUNCH_COMPOSITE(FLAT, COUNT)                                                                              \
-    k_composite<FLAT, COUNT><<<n_tiles, kThreads, 0, st>>>(a.tile_vals, a.ranges, a.splats, a.out, a.pitch, W, H,      \
+    k_composite<FLAT, COUNT><<<n_tiles, kThreads, 0, st>>>(a.tile_vals, a.tile_vals_b, a.tile_in_b, a.ranges, a.splats, a.out, a.pitch, W, H,      \
                                                            f.tiles_x, n_tiles, f.bg[0], f.bg[1], f.bg[2], f.bg[3],     \
                                                            a.evals)
     if (flat) {

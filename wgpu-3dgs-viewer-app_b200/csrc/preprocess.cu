@@ -30,10 +30,6 @@ constexpr int kChunk = 256;
 template <int SH> struct ShBytes { static constexpr int v = SH == 0 ? 180 : SH == 1 ? 92 : SH == 2 ? 48 : 0; };
 template <int COV> struct CovBytes { static constexpr int v = COV == 0 ? 24 : 12; };
 
-__host__ __device__ constexpr int stages_for(int rb) {
-    int s = 70000 / (kChunk * rb);  // <= ~70 KB of stages per CTA: 3 CTAs per SM for the common layouts
-    return s < 2 ? 2 : (s > 3 ? 3 : s);
-}
 
 __device__ __forceinline__ float h2f_lo(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))); }
 __device__ __forceinline__ float h2f_hi(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
@@ -103,10 +99,11 @@ __device__ void apply_edit(const b200gs_edit_pod& e, float rgb[3], float& op) {
     op = clamp01(op * e.alpha);
 }
 
-// named barriers (id 0 is __syncthreads)
-constexpr int kBarCounts = 1;   // compute warps -> control warp: per-warp visible counts are in smem
-constexpr int kBarBase = 2;     // control warp -> compute warps: this chunk's output base is in smem
-constexpr int kBarFree = 3;     // (+ iteration parity) compute warps -> control warp: stage can be refilled
+// named barriers (id 0 is __syncthreads); each kind has 4 ids, indexed by chunk sequence number & 3,
+// because up to 3 generations of one kind can be outstanding (see the loop comments)
+constexpr int kBarCounts = 1;   // compute warps -> control warp: per-warp visible counts of chunk j are in smem
+constexpr int kBarBase = 5;     // control warp -> compute warps: chunk j's output base is in smem
+constexpr int kBarFree = 9;     // compute warps -> control warp: chunk j's stage can be refilled
 constexpr int kThreads = kChunk + 32;  // 8 compute warps + 1 control warp
 
 __device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kThreads) : "memory"); }
@@ -115,6 +112,59 @@ __device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0
 // byte k of x as a float, without I2F: PRMT builds 0x4B0000bb (= 8388608 + b), one FADD removes the bias
 __device__ __forceinline__ float byte_to_float(uint32_t x, int k) {
     return __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7440u | (uint32_t)k)) - 8388608.0f;
+}
+
+// EXACT class: model/view/projection chain, frustum cull.  Returns visibility; pw/pv/ndc out.
+__device__ __forceinline__ bool project_and_cull(const uint32_t* w, const GsFrame& f, const GsModelXf& m, float pw[3],
+                                                 float pv[3], float& nx, float& ny, float& nz) {
+    const float p0 = __uint_as_float(w[0]), p1 = __uint_as_float(w[1]), p2 = __uint_as_float(w[2]);
+    if (m.identity) {  // bit-identical to the general form when R = I, s = 1, t = 0
+        pw[0] = p0; pw[1] = p1; pw[2] = p2;
+    } else {
+        // world = q*(s⊙p)+t  (src/app.rs:1044-1046)
+        const float ps0 = m.s[0] * p0, ps1 = m.s[1] * p1, ps2 = m.s[2] * p2;
+#pragma unroll
+        for (int r = 0; r < 3; r++) pw[r] = m.R[r][0] * ps0 + m.R[r][1] * ps1 + m.R[r][2] * ps2 + m.t[r];
+    }
+#pragma unroll
+    for (int r = 0; r < 3; r++) pv[r] = f.V[r][0] * pw[0] + f.V[r][1] * pw[1] + f.V[r][2] * pw[2] + f.V[r][3];
+    float pc[4];
+    if (f.std_proj) {  // zero terms of glam's perspective_rh skipped: same bits
+        pc[0] = f.P[0][0] * pv[0];
+        pc[1] = f.P[1][1] * pv[1];
+        pc[2] = f.P[2][2] * pv[2] + f.P[2][3];
+        pc[3] = f.P[3][2] * pv[2];
+    } else {
+#pragma unroll
+        for (int r = 0; r < 4; r++) pc[r] = f.P[r][0] * pv[0] + f.P[r][1] * pv[1] + f.P[r][2] * pv[2] + f.P[r][3];
+    }
+    if (!(pc[3] > 0.0f)) return false;
+    const float iw = 1.0f / pc[3];
+    nx = pc[0] * iw; ny = pc[1] * iw; nz = pc[2] * iw;
+    return nz > 0.0f && nz < 1.0f && fabsf(nx) <= GS_CULL_XY && fabsf(ny) <= GS_CULL_XY;
+}
+
+// mask / hidden-edit / selection tests that precede the frustum cull (reference preprocess bindings,
+// src/tab/scene.rs:1835-1852; flags src/app.rs:1548-1551)
+__device__ __forceinline__ bool pre_tests(uint32_t i, uint32_t n, const uint32_t* __restrict__ mask,
+                                          const uint32_t* __restrict__ selection,
+                                          const b200gs_edit_pod* __restrict__ edits, const GsFrame& f, bool& selected,
+                                          b200gs_edit_pod& ed) {
+    bool vis = i < n;
+    selected = false;
+    ed.flag = 0;
+    if (vis && mask) vis = (mask[i >> 5] >> (i & 31)) & 1u;
+    if (vis && selection) selected = (selection[i >> 5] >> (i & 31)) & 1u;
+    if (vis && edits) {
+        const uint4* ep = reinterpret_cast<const uint4*>(edits + i);
+        const uint4 e0 = ep[0], e1 = ep[1];
+        ed.flag = e0.x; ed.color[0] = __uint_as_float(e0.y); ed.color[1] = __uint_as_float(e0.z);
+        ed.color[2] = __uint_as_float(e0.w); ed.contrast = __uint_as_float(e1.x);
+        ed.exposure = __uint_as_float(e1.y); ed.gamma = __uint_as_float(e1.z); ed.alpha = __uint_as_float(e1.w);
+        if ((ed.flag & B200GS_EDIT_ENABLED) && (ed.flag & B200GS_EDIT_HIDDEN)) vis = false;
+    }
+    if (vis && selected && (f.sel_edit.flag & B200GS_EDIT_ENABLED) && (f.sel_edit.flag & B200GS_EDIT_HIDDEN)) vis = false;
+    return vis;
 }
 
 template <int SH, int COV>
@@ -129,16 +179,16 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
                                                          b200gs_splat* __restrict__ splats, uint32_t* sort_hist) {
     constexpr int RB = 16 + ShBytes<SH>::v + CovBytes<COV>::v;  // record bytes
     constexpr int RW = RB / 4;                                  // record words
-    constexpr int NSTAGE = stages_for(RB);
+    constexpr int NSTAGE = 3;                                   // chunk j, chunk j+1 (counted ahead), one in flight
     constexpr uint32_t STAGE_BYTES = kChunk * RB;
 
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* stage_mem = smem;  // NSTAGE * STAGE_BYTES
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
     uint32_t* s_chunk = reinterpret_cast<uint32_t*>(bars + NSTAGE);  // NSTAGE
-    uint32_t* s_wcount_all = s_chunk + NSTAGE;                       // 2 x 8 warp counts (by iteration parity)
-    uint32_t* s_base_all = s_wcount_all + 16;                        // 2
-    uint32_t* s_hist = s_base_all + 2;                               // 4 x 256 (only if sort_hist)
+    uint32_t* s_wcount_all = s_chunk + NSTAGE + 1;                   // 4 x 8 warp counts (by sequence number & 3)
+    uint32_t* s_base_all = s_wcount_all + 32;                        // 4
+    uint32_t* s_hist = s_base_all + 4;                               // 4 x 256 (only if sort_hist)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t nchunks = (n + kChunk - 1) / kChunk;
@@ -164,98 +214,94 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
         for (int i = tid; i < 1024; i += kThreads) s_hist[i] = 0;
     __syncthreads();
 
+    // The CTA works through the chunks it drew, j = 0, 1, 2, ... (stage j % 3).  The cull/count of
+    // chunk j+1 runs BEFORE the heavy phase of chunk j, so chunk j+1's visible count is published a
+    // whole iteration before its output base is needed: the decoupled look-back (control warp)
+    // overlaps a full heavy phase and is off the critical path.
     if (is_control) {
         // ------------------------------------------------------------ control warp
-        // Resolves each chunk's output base by decoupled look-back WHILE the compute warps are in
-        // their heavy phase, then refills the stage with the next ticket's chunk by TMA.
-        for (uint32_t it = 0;; it++) {
-            const int stage = it % NSTAGE;
-            const uint32_t par = it & 1u;
-            const uint32_t c = s_chunk[stage];
-            if (c >= nchunks) break;
-            bar_sync(kBarCounts);
-            uint32_t wc = lane < 8 ? s_wcount_all[par * 8 + lane] : 0u;
-            uint32_t total = wc;
+        // publish(j+1) happens one iteration BEFORE resolve(j+1): by the time a chunk's prefix is
+        // resolved, its predecessors (drawn at the same moment by other CTAs) have long published.
+        auto publish = [&](uint32_t j, uint32_t c) -> uint32_t {
+            bar_sync(kBarCounts + (int)(j & 3u));  // counts of chunk j are in smem
+            uint32_t total = lane < 8 ? s_wcount_all[(j & 3u) * 8 + lane] : 0u;
 #pragma unroll
             for (int o = 4; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
             total = __shfl_sync(0xffffffffu, total, 0);
-            const uint32_t excl = gs_lookback_warp(lookback, epoch, c, total, lane);
+            if (lane == 0) gs_lookback_publish(lookback, epoch, c, total);
+            return total;
+        };
+        uint32_t c = s_chunk[0];
+        uint32_t total = c < nchunks ? publish(0, c) : 0u;
+        for (uint32_t j = 0; c < nchunks; j++) {
+            // the compute warps count chunk j+1 at the start of their iteration j
+            const uint32_t c_next = s_chunk[(j + 1) % NSTAGE];
+            const uint32_t total_next = c_next < nchunks ? publish(j + 1, c_next) : 0u;
+            if (j > 0) {
+                // chunk j-1's stage was read for the last time in its heavy phase: refill it
+                bar_sync(kBarFree + (int)((j - 1) & 3u));
+                if (lane == 0) {
+                    const uint32_t c2 = atomicAdd(&ctrl[GS_CTRL_TICKET], 1u);
+                    s_chunk[(j - 1) % NSTAGE] = c2;
+                    if (c2 < nchunks) issue((int)((j - 1) % NSTAGE), c2);
+                }
+                __syncwarp();
+            }
+            uint32_t excl;
+            if (epoch == 0xffffffffu) {  // measurement aid: unordered compaction (atomic), no look-back chain
+                excl = lane == 0 ? atomicAdd(&ctrl[8], total) : 0u;
+                excl = __shfl_sync(0xffffffffu, excl, 0);
+            } else {
+                const long long t0 = clock64();
+                excl = gs_lookback_resolve(lookback, epoch, c, total, lane, ctrl + 9);
+                if (lane == 0) atomicAdd(&ctrl[11], (uint32_t)((clock64() - t0) >> 4));
+            }
             if (lane == 0) {
-                s_base_all[par] = excl;
+                s_base_all[j & 3u] = excl;
                 if (c == nchunks - 1) ctrl[GS_CTRL_VISIBLE] = excl + total;
             }
-            bar_arrive(kBarBase);
-            bar_sync(kBarFree + (int)par);
-            if (lane == 0) {
-                uint32_t c2 = atomicAdd(&ctrl[GS_CTRL_TICKET], 1u);
-                s_chunk[stage] = c2;
-                if (c2 < nchunks) issue(stage, c2);
-            }
-            __syncwarp();
+            bar_arrive(kBarBase + (int)(j & 3u));
+            c = c_next;
+            total = total_next;
         }
     } else {
         // ------------------------------------------------------------ compute warps
+        // count-ahead of chunk j: cull only, publish the warp's visible count
+        auto count_ahead = [&](uint32_t j) {
+            const int stage = j % NSTAGE;
+            const uint32_t c = s_chunk[stage];
+            if (c >= nchunks) return;
+            gs_mbar_wait(&bars[stage], (j / NSTAGE) & 1u);
+            const uint32_t i = c * kChunk + tid;
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)stage * STAGE_BYTES) + tid * RW;
+            bool selected;
+            b200gs_edit_pod ed;
+            bool vis = pre_tests(i, n, mask, selection, edits, f, selected, ed);
+            if (vis) {
+                float pw[3], pv[3], nx, ny, nz;
+                vis = project_and_cull(w, f, m, pw, pv, nx, ny, nz);
+            }
+            const uint32_t ballot = __ballot_sync(0xffffffffu, vis);
+            if (lane == 0) s_wcount_all[(j & 3u) * 8 + warp] = __popc(ballot);
+            bar_arrive(kBarCounts + (int)(j & 3u));
+        };
+        count_ahead(0);
         for (uint32_t it = 0;; it++) {
             const int stage = it % NSTAGE;
-            const uint32_t par = it & 1u;
             const uint32_t c = s_chunk[stage];
             if (c >= nchunks) break;
-            gs_mbar_wait(&bars[stage], (it / NSTAGE) & 1u);
+            count_ahead(it + 1);
 
             const uint32_t i = c * kChunk + tid;
             const uint32_t* w = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)stage * STAGE_BYTES) + tid * RW;
 
-            // ---------------- phase 1: mask / hidden / frustum cull, depth key (exact class) -------
-            bool vis = i < n;
-            bool selected = false;
+            // ---------------- phase 1 again (cheap, exact class): same decisions as the count-ahead
+            bool selected;
             b200gs_edit_pod ed;
-            ed.flag = 0;
-            if (vis && mask) vis = (mask[i >> 5] >> (i & 31)) & 1u;
-            if (vis && selection) selected = (selection[i >> 5] >> (i & 31)) & 1u;
-            if (vis && edits) {
-                const uint4* ep = reinterpret_cast<const uint4*>(edits + i);
-                uint4 e0 = ep[0], e1 = ep[1];
-                ed.flag = e0.x; ed.color[0] = __uint_as_float(e0.y); ed.color[1] = __uint_as_float(e0.z);
-                ed.color[2] = __uint_as_float(e0.w); ed.contrast = __uint_as_float(e1.x);
-                ed.exposure = __uint_as_float(e1.y); ed.gamma = __uint_as_float(e1.z); ed.alpha = __uint_as_float(e1.w);
-                if ((ed.flag & B200GS_EDIT_ENABLED) && (ed.flag & B200GS_EDIT_HIDDEN)) vis = false;
-            }
-            if (vis && selected && (f.sel_edit.flag & B200GS_EDIT_ENABLED) && (f.sel_edit.flag & B200GS_EDIT_HIDDEN))
-                vis = false;
-
+            bool vis = pre_tests(i, n, mask, selection, edits, f, selected, ed);
             float pw[3], pv[3], nx = 0.0f, ny = 0.0f, nz = 0.0f;
-            if (vis) {
-                const float p0 = __uint_as_float(w[0]), p1 = __uint_as_float(w[1]), p2 = __uint_as_float(w[2]);
-                if (m.identity) {  // bit-identical to the general form when R = I, s = 1, t = 0
-                    pw[0] = p0; pw[1] = p1; pw[2] = p2;
-                } else {
-                    // world = q*(s⊙p)+t  (src/app.rs:1044-1046)
-                    const float ps0 = m.s[0] * p0, ps1 = m.s[1] * p1, ps2 = m.s[2] * p2;
-#pragma unroll
-                    for (int r = 0; r < 3; r++) pw[r] = m.R[r][0] * ps0 + m.R[r][1] * ps1 + m.R[r][2] * ps2 + m.t[r];
-                }
-#pragma unroll
-                for (int r = 0; r < 3; r++) pv[r] = f.V[r][0] * pw[0] + f.V[r][1] * pw[1] + f.V[r][2] * pw[2] + f.V[r][3];
-                float pc[4];
-                if (f.std_proj) {  // zero terms of glam's perspective_rh skipped: same bits
-                    pc[0] = f.P[0][0] * pv[0];
-                    pc[1] = f.P[1][1] * pv[1];
-                    pc[2] = f.P[2][2] * pv[2] + f.P[2][3];
-                    pc[3] = f.P[3][2] * pv[2];
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 4; r++) pc[r] = f.P[r][0] * pv[0] + f.P[r][1] * pv[1] + f.P[r][2] * pv[2] + f.P[r][3];
-                }
-                if (!(pc[3] > 0.0f)) vis = false;
-                else {
-                    const float iw = 1.0f / pc[3];
-                    nx = pc[0] * iw; ny = pc[1] * iw; nz = pc[2] * iw;
-                    vis = nz > 0.0f && nz < 1.0f && fabsf(nx) <= GS_CULL_XY && fabsf(ny) <= GS_CULL_XY;
-                }
-            }
+            if (vis) vis = project_and_cull(w, f, m, pw, pv, nx, ny, nz);
             const uint32_t ballot = __ballot_sync(0xffffffffu, vis);
-            if (lane == 0) s_wcount_all[par * 8 + warp] = __popc(ballot);
-            bar_arrive(kBarCounts);
 
             // ---------------- phase 2: projected splat for the visible ones ----------------
             uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
@@ -422,7 +468,7 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
                 q1.z = __float_as_uint(cc);
                 q1.w = (uint32_t)__half_as_ushort(__float2half_rn(rgb[2])) | ((selected ? 1u : 0u) << 16);
             }
-            bar_arrive(kBarFree + (int)par);  // every read of this stage's shared memory is done
+            bar_arrive(kBarFree + (int)(it & 3u));  // every read of this stage's shared memory is done
 
             // digit histograms of the emitted keys for the depth sort (saves its histogram kernel);
             // warp-aggregated: depth keys share their top bytes
@@ -436,10 +482,10 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
                 }
             }
 
-            bar_sync(kBarBase);
+            bar_sync(kBarBase + (int)(it & 3u));
             if (vis) {
-                uint32_t off = s_base_all[par];
-                for (int k = 0; k < warp; k++) off += s_wcount_all[par * 8 + k];
+                uint32_t off = s_base_all[it & 3u];
+                for (int k = 0; k < warp; k++) off += s_wcount_all[(it & 3u) * 8 + k];
                 off += __popc(ballot & ((1u << lane) - 1u));
                 keys[off] = __float_as_uint(nz);
                 idx[off] = i;
@@ -462,8 +508,8 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
 template <int SH, int COV>
 cudaError_t launch_t(const GsPreprocessArgs& a, const GsFrame& f, const GsModelXf& m, int num_sms, cudaStream_t st) {
     constexpr int RB = 16 + ShBytes<SH>::v + CovBytes<COV>::v;
-    constexpr int NSTAGE = stages_for(RB);
-    constexpr size_t smem = (size_t)NSTAGE * kChunk * RB + NSTAGE * 8 + NSTAGE * 4 + 16 * 4 + 2 * 4 + 1024 * 4 + 16;
+    constexpr int NSTAGE = 3;
+    constexpr size_t smem = (size_t)NSTAGE * kChunk * RB + NSTAGE * 8 + (NSTAGE + 1) * 4 + 32 * 4 + 4 * 4 + 1024 * 4 + 16;
     auto kern = k_preprocess<SH, COV>;
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {

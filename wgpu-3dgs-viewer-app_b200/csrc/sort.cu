@@ -68,18 +68,39 @@ struct PassSmem {
     uint32_t tile_id;
 };
 
-__global__ void __launch_bounds__(kThreads) k_sort_pass(const uint32_t* __restrict__ keys_in,
-                                                        const uint32_t* __restrict__ vals_in,
-                                                        uint32_t* __restrict__ keys_out,
-                                                        uint32_t* __restrict__ vals_out, const uint32_t* d_n,
-                                                        uint32_t n_max, const uint32_t* __restrict__ hist,
-                                                        uint64_t* lookback, uint32_t epoch, uint32_t* ticket,
-                                                        uint32_t shift) {
+__global__ void __launch_bounds__(kThreads) k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a,
+                                                        uint32_t* __restrict__ keys_b, uint32_t* __restrict__ vals_b,
+                                                        const uint32_t* d_n, uint32_t n_max,
+                                                        const uint32_t* __restrict__ hist_all, uint32_t pass,
+                                                        uint32_t passes, uint64_t* lookback, uint32_t epoch,
+                                                        uint32_t* ticket, uint32_t* result_in_b, uint32_t vals_identity) {
     __shared__ PassSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t n = *d_n;
     if (n > n_max) n = n_max;
     const uint32_t ntiles = (n + kTile - 1) / kTile;
+    const uint32_t shift = 8 * pass;
+
+    // A digit whose histogram has a single non-empty bin leaves the order unchanged: the pass is
+    // skipped (depth keys share their top byte).  Every CTA derives the same plan from the global
+    // histograms: which passes run, hence which buffer holds this pass's input.
+    uint32_t executed_before = 0;
+    bool skip_me = false;
+    for (uint32_t q = 0; q < passes; q++) {
+        const int degenerate = __syncthreads_or(n > 0 && hist_all[q * kRadix + tid] == n);
+        if (q < pass) executed_before += degenerate ? 0u : 1u;
+        if (q == pass) skip_me = degenerate != 0;
+    }
+    const bool src_b = (executed_before & 1u) != 0;
+    if (pass == passes - 1 && blockIdx.x == 0 && tid == 0)
+        *result_in_b = ((executed_before + (skip_me ? 0u : 1u)) & 1u);
+    if (skip_me || n == 0) return;
+    const uint32_t* __restrict__ keys_in = src_b ? keys_b : keys_a;
+    const uint32_t* __restrict__ vals_in = src_b ? vals_b : vals_a;
+    uint32_t* __restrict__ keys_out = src_b ? keys_a : keys_b;
+    uint32_t* __restrict__ vals_out = src_b ? vals_a : vals_b;
+    const bool synth_vals = vals_identity && executed_before == 0;  // first executed pass: value = input position
+    const uint32_t* __restrict__ hist = hist_all + pass * kRadix;
 
     // exclusive prefix of the global histogram of this digit (thread d owns digit d)
     uint32_t gbase;
@@ -120,7 +141,7 @@ __global__ void __launch_bounds__(kThreads) k_sort_pass(const uint32_t* __restri
 #pragma unroll
         for (int k = 0; k < kKpt; k++) {
             uint32_t s = wbase_idx + k * 32 + lane;
-            val[k] = s < valid ? (vals_in ? vals_in[tile_base + s] : tile_base + s) : 0u;
+            val[k] = s < valid ? (synth_vals ? tile_base + s : vals_in[tile_base + s]) : 0u;
         }
 
         // ---- rank inside the warp, digit by digit, in index order (stable)
@@ -239,7 +260,7 @@ size_t gs_sort_lookback_words(uint32_t n_max, uint32_t passes) {
 }
 
 cudaError_t gs_launch_sort(const GsSortArgs& a, int num_sms, cudaStream_t st) {
-    if (a.passes < 1 || a.passes > 4 || (a.passes & 1)) return cudaErrorInvalidValue;
+    if (a.passes < 1 || a.passes > 4 || !a.result_in_b) return cudaErrorInvalidValue;
     size_t tiles = ((size_t)a.n_max + kTile - 1) / kTile;
     if (tiles < 1) tiles = 1;
     if (!a.hist_prefilled) {
@@ -257,13 +278,9 @@ cudaError_t gs_launch_sort(const GsSortArgs& a, int num_sms, cudaStream_t st) {
     uint32_t grid = (uint32_t)(blocks_per_sm * num_sms);
     if (grid > tiles) grid = (uint32_t)tiles;
     for (uint32_t p = 0; p < a.passes; p++) {
-        const uint32_t* ki = (p & 1) ? a.keys_b : a.keys_a;
-        const uint32_t* vi = (p & 1) ? a.vals_b : ((p == 0 && a.vals_identity) ? nullptr : a.vals_a);
-        uint32_t* ko = (p & 1) ? a.keys_a : a.keys_b;
-        uint32_t* vo = (p & 1) ? a.vals_a : a.vals_b;
-        k_sort_pass<<<grid, kThreads, 0, st>>>(ki, vi, ko, vo, a.d_n, a.n_max, a.hist + p * kRadix,
+        k_sort_pass<<<grid, kThreads, 0, st>>>(a.keys_a, a.vals_a, a.keys_b, a.vals_b, a.d_n, a.n_max, a.hist, p, a.passes,
                                                a.lookback + (size_t)p * tiles * kRadix, a.epoch, a.tickets + p,
-                                               8 * p);
+                                               a.result_in_b, a.vals_identity ? 1u : 0u);
     }
     return cudaGetLastError();
 }
