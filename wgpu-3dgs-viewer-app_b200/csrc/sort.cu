@@ -6,7 +6,7 @@
 // reference sizes an indirect dispatch from it), here `*d_n`.
 //
 // Design: one histogram kernel (all digit histograms in one read of the keys), then one
-// kernel per 8-bit digit.  A digit pass is a single sweep: each 4096-key tile ranks its keys
+// kernel per 8-bit digit.  A digit pass is a single sweep: each 3072-key tile ranks its keys
 // with warp-level __match_any_sync histograms, publishes its per-digit counts and resolves
 // its global offsets by decoupled look-back over epoch-tagged status words (chained scan, no
 // separate scan kernel, no second read of the keys), then scatters keys and values through
@@ -19,8 +19,8 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kKpt = 16;                       // keys per thread
-constexpr int kTile = kThreads * kKpt;         // 4096 keys per tile
+constexpr int kKpt = 12;                       // keys per thread
+constexpr int kTile = kThreads * kKpt;         // 3072 keys per tile
 constexpr int kRadix = 256;
 
 // ------------------------------------------------------------------ histogram kernel
@@ -59,22 +59,28 @@ __global__ void __launch_bounds__(kThreads) k_sort_hist(const uint32_t* __restri
 }
 
 // ---------------------------------------------------------------------- digit pass
+// Software-pipelined by one tile with double-buffered shared memory: tile t+1 is loaded, counted
+// (its per-digit aggregates PUBLISHED), ranked and scattered into its exchange buffer BEFORE tile
+// t's look-back is resolved and tile t is written out, so a look-back only ever waits for
+// aggregates that were published a whole tile-time earlier.
 struct PassSmem {
-    uint32_t warp_hist[kWarps][kRadix];  // per-warp digit counts -> per-warp exclusive offsets
-    uint32_t exch[kTile];                // key / value exchange buffer
-    uint32_t tile_start[kRadix];         // first position of each digit inside the sorted tile
+    uint32_t warp_hist[kWarps][kRadix];  // per-warp digit counts -> running per-warp offsets
+    uint32_t exch_k[2][kTile];           // keys / values in tile-sorted order, double-buffered
+    uint32_t exch_v[2][kTile];
+    uint32_t tile_start[2][kRadix];      // first position of each digit inside the sorted tile
     int32_t global_off[kRadix];          // global index = global_off[digit] + position in sorted tile
     uint32_t scan_tmp[kWarps];
     uint32_t tile_id;
 };
 
-__global__ void __launch_bounds__(kThreads) k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a,
-                                                        uint32_t* __restrict__ keys_b, uint32_t* __restrict__ vals_b,
-                                                        const uint32_t* d_n, uint32_t n_max,
-                                                        const uint32_t* __restrict__ hist_all, uint32_t pass,
-                                                        uint32_t passes, uint64_t* lookback, uint32_t epoch,
-                                                        uint32_t* ticket, uint32_t* result_in_b, uint32_t vals_identity) {
-    __shared__ PassSmem sm;
+__global__ void __launch_bounds__(kThreads, 3) k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a,
+                                                           uint32_t* __restrict__ keys_b, uint32_t* __restrict__ vals_b,
+                                                           const uint32_t* d_n, uint32_t n_max,
+                                                           const uint32_t* __restrict__ hist_all, uint32_t pass,
+                                                           uint32_t passes, uint64_t* lookback, uint32_t epoch,
+                                                           uint32_t* ticket, uint32_t* result_in_b, uint32_t vals_identity) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    PassSmem& sm = *reinterpret_cast<PassSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t n = *d_n;
     if (n > n_max) n = n_max;
@@ -117,137 +123,131 @@ __global__ void __launch_bounds__(kThreads) k_sort_pass(uint32_t* __restrict__ k
         uint32_t wbase = 0;
         for (int k = 0; k < warp; k++) wbase += sm.scan_tmp[k];
         gbase = wbase + incl - c;
-        __syncthreads();
     }
+    uint64_t* lb = lookback + (size_t)tid;
 
-    while (true) {
+    bool have_prev = false;
+    uint32_t p_tile = 0, p_count = 0, p_valid = 0;
+    for (uint32_t iter = 0;; iter++) {
+        const uint32_t buf = iter & 1u;
+        __syncthreads();  // previous iteration's ranking / write-out are done
         if (tid == 0) sm.tile_id = atomicAdd(ticket, 1u);
 #pragma unroll
         for (int k = 0; k < kRadix / 32; k++) sm.warp_hist[warp][k * 32 + lane] = 0;
         __syncthreads();
         const uint32_t tile = sm.tile_id;
-        if (tile >= ntiles) break;
-        const uint32_t tile_base = tile * kTile;
-        const uint32_t valid = min((uint32_t)kTile, n - tile_base);
-
-        // ---- load (warp-striped: slot = warp*512 + k*32 + lane keeps index order inside a warp)
-        uint32_t key[kKpt], val[kKpt];
-        const uint32_t wbase_idx = warp * (32 * kKpt);
+        const bool valid_tile = tile < ntiles;
+        uint32_t count = 0, valid = 0;
+        if (valid_tile) {
+            const uint32_t tile_base = tile * kTile;
+            valid = min((uint32_t)kTile, n - tile_base);
+            // ---- load keys (warp-striped: slot = warp*32*KPT + k*32 + lane keeps index order inside a warp)
+            uint32_t key[kKpt];
+            const uint32_t wbase_idx = warp * (32 * kKpt);
 #pragma unroll
-        for (int k = 0; k < kKpt; k++) {
-            uint32_t s = wbase_idx + k * 32 + lane;
-            key[k] = s < valid ? keys_in[tile_base + s] : 0xffffffffu;
-        }
-#pragma unroll
-        for (int k = 0; k < kKpt; k++) {
-            uint32_t s = wbase_idx + k * 32 + lane;
-            val[k] = s < valid ? (synth_vals ? tile_base + s : vals_in[tile_base + s]) : 0u;
-        }
-
-        // ---- rank inside the warp, digit by digit, in index order (stable)
-        uint32_t rank[kKpt];
-#pragma unroll
-        for (int k = 0; k < kKpt; k++) {
-            uint32_t d = (key[k] >> shift) & 0xffu;
-            uint32_t peers = __match_any_sync(0xffffffffu, d);
-            int leader = __ffs((int)peers) - 1;
-            uint32_t old = 0;
-            if (lane == leader) {
-                old = sm.warp_hist[warp][d];
-                sm.warp_hist[warp][d] = old + __popc(peers);
+            for (int k = 0; k < kKpt; k++) {
+                const uint32_t s = wbase_idx + k * 32 + lane;
+                key[k] = s < valid ? keys_in[tile_base + s] : 0xffffffffu;
             }
-            old = __shfl_sync(0xffffffffu, old, leader);
-            rank[k] = old + __popc(peers & ((1u << lane) - 1u));
-            __syncwarp();
+            // ---- early counts (per-warp histograms), so the aggregates can be published at once
+#pragma unroll
+            for (int k = 0; k < kKpt; k++) atomicAdd(&sm.warp_hist[warp][(key[k] >> shift) & 0xffu], 1u);
+            __syncthreads();
+            // per digit (thread d): exclusive scan over warps, tile total
+#pragma unroll
+            for (int w2 = 0; w2 < kWarps; w2++) {
+                const uint32_t t = sm.warp_hist[w2][tid];
+                sm.warp_hist[w2][tid] = count;
+                count += t;
+            }
+            // publish this tile's aggregate for digit `tid`
+            gs_st_status(&lb[(size_t)tile * kRadix], epoch, (tile == 0 ? GS_LOOKBACK_FLAG_INCL : GS_LOOKBACK_FLAG_AGG) | count);
+            // exclusive scan of the tile totals over digits
+            uint32_t incl = count;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) sm.scan_tmp[warp] = incl;
+            __syncthreads();
+            uint32_t wb = 0;
+            for (int k = 0; k < warp; k++) wb += sm.scan_tmp[k];
+            sm.tile_start[buf][tid] = wb + incl - count;
+            __syncthreads();
+            // ---- values (loaded late to keep registers low), then rank + scatter into the exchange buffer
+            uint32_t val[kKpt];
+#pragma unroll
+            for (int k = 0; k < kKpt; k++) {
+                const uint32_t s = wbase_idx + k * 32 + lane;
+                val[k] = s < valid ? (synth_vals ? tile_base + s : vals_in[tile_base + s]) : 0u;
+            }
+#pragma unroll
+            for (int k = 0; k < kKpt; k++) {
+                const uint32_t d = (key[k] >> shift) & 0xffu;
+                const uint32_t peers = __match_any_sync(0xffffffffu, d);
+                const int leader = __ffs((int)peers) - 1;
+                uint32_t old = 0;
+                if (lane == leader) {
+                    old = sm.warp_hist[warp][d];
+                    sm.warp_hist[warp][d] = old + __popc(peers);
+                }
+                old = __shfl_sync(0xffffffffu, old, leader);
+                const uint32_t pos = sm.tile_start[buf][d] + old + __popc(peers & ((1u << lane) - 1u));
+                sm.exch_k[buf][pos] = key[k];
+                sm.exch_v[buf][pos] = val[k];
+                __syncwarp();
+            }
         }
-        __syncthreads();
-
-        // ---- per digit (thread d): exclusive scan over warps, tile total
-        uint32_t count = 0;
+        if (have_prev) {
+            // ---- resolve the previous tile's look-back for digit `tid`, kLb status words per round trip
+            const uint32_t pbuf = buf ^ 1u;
+            uint32_t excl = 0;
+            if (p_tile > 0) {
+                constexpr int kLb = 4;
+                int64_t p = (int64_t)p_tile - 1;
+                bool done = false;
+                while (!done) {
+                    uint64_t v[kLb];
 #pragma unroll
-        for (int w2 = 0; w2 < kWarps; w2++) {
-            uint32_t t = sm.warp_hist[w2][tid];
-            sm.warp_hist[w2][tid] = count;
-            count += t;
-        }
-        // ---- exclusive scan of the tile totals over digits
-        uint32_t incl = count;
+                    for (int j = 0; j < kLb; j++)
+                        v[j] = (p - j >= 0) ? gs_ld_status(&lb[(size_t)(p - j) * kRadix])
+                                            : (((uint64_t)epoch << 32) | GS_LOOKBACK_FLAG_INCL);
+                    int used = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) sm.scan_tmp[warp] = incl;
-        __syncthreads();
-        uint32_t wb = 0;
-        for (int k = 0; k < warp; k++) wb += sm.scan_tmp[k];
-        const uint32_t tstart = wb + incl - count;
-        sm.tile_start[tid] = tstart;
-
-        // ---- decoupled look-back for digit `tid`
-        uint64_t* lb = lookback + (size_t)tid;
-        uint32_t excl = 0;
-        if (tile == 0) {
-            gs_st_status(&lb[0], epoch, GS_LOOKBACK_FLAG_INCL | count);
-        } else {
-            gs_st_status(&lb[(size_t)tile * kRadix], epoch, GS_LOOKBACK_FLAG_AGG | count);
-            // walk back over the predecessors, kLb status words per round trip (independent loads)
-            constexpr int kLb = 4;
-            int64_t p = (int64_t)tile - 1;
-            bool done = false;
-            while (!done) {
-                uint64_t v[kLb];
-#pragma unroll
-                for (int j = 0; j < kLb; j++)
-                    v[j] = (p - j >= 0) ? gs_ld_status(&lb[(size_t)(p - j) * kRadix])
-                                        : (((uint64_t)epoch << 32) | GS_LOOKBACK_FLAG_INCL);
-                int used = 0;
-#pragma unroll
-                for (int j = 0; j < kLb; j++) {
-                    if (!done && used == j) {
-                        const uint32_t fl = gs_status_flag(v[j], epoch);
-                        if (fl != 0u) {
-                            excl += (uint32_t)v[j] & GS_LOOKBACK_VALUE_MASK;
-                            used = j + 1;
-                            done = fl == 2u;
+                    for (int j = 0; j < kLb; j++) {
+                        if (!done && used == j) {
+                            const uint32_t fl = gs_status_flag(v[j], epoch);
+                            if (fl != 0u) {
+                                excl += (uint32_t)v[j] & GS_LOOKBACK_VALUE_MASK;
+                                used = j + 1;
+                                done = fl == 2u;
+                            }
                         }
                     }
+                    p -= used;
                 }
-                p -= used;
+                gs_st_status(&lb[(size_t)p_tile * kRadix], epoch, GS_LOOKBACK_FLAG_INCL | (excl + p_count));
             }
-            gs_st_status(&lb[(size_t)tile * kRadix], epoch, GS_LOOKBACK_FLAG_INCL | (excl + count));
-        }
-        sm.global_off[tid] = (int32_t)(gbase + excl) - (int32_t)tstart;
-        __syncthreads();
-
-        // ---- scatter keys into tile-sorted order in shared memory
-        uint32_t pos[kKpt];
+            sm.global_off[tid] = (int32_t)(gbase + excl) - (int32_t)sm.tile_start[pbuf][tid];
+            __syncthreads();
+            // ---- write out the previous tile: consecutive positions of one digit are consecutive addresses
 #pragma unroll
-        for (int k = 0; k < kKpt; k++) {
-            uint32_t d = (key[k] >> shift) & 0xffu;
-            pos[k] = sm.tile_start[d] + sm.warp_hist[warp][d] + rank[k];
-            sm.exch[pos[k]] = key[k];
+            for (int k = 0; k < kKpt; k++) {
+                const uint32_t p = k * kThreads + tid;
+                if (p < p_valid) {
+                    const uint32_t kk = sm.exch_k[pbuf][p];
+                    const uint32_t g = (uint32_t)(sm.global_off[(kk >> shift) & 0xffu] + (int32_t)p);
+                    keys_out[g] = kk;
+                    vals_out[g] = sm.exch_v[pbuf][p];
+                }
+            }
         }
-        __syncthreads();
-        uint32_t gpos[kKpt];
-#pragma unroll
-        for (int k = 0; k < kKpt; k++) {
-            uint32_t p = k * kThreads + tid;
-            uint32_t kk = sm.exch[p];
-            uint32_t d = (kk >> shift) & 0xffu;
-            gpos[k] = (uint32_t)(sm.global_off[d] + (int32_t)p);
-            if (p < valid) keys_out[gpos[k]] = kk;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < kKpt; k++) sm.exch[pos[k]] = val[k];
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < kKpt; k++) {
-            uint32_t p = k * kThreads + tid;
-            if (p < valid) vals_out[gpos[k]] = sm.exch[p];
-        }
-        __syncthreads();  // exch / warp_hist / tile_id are reused by the next tile
+        if (!valid_tile) break;
+        have_prev = true;
+        p_tile = tile;
+        p_count = count;
+        p_valid = valid;
     }
 }
 
@@ -271,14 +271,16 @@ cudaError_t gs_launch_sort(const GsSortArgs& a, int num_sms, cudaStream_t st) {
     }
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_sort_pass, kThreads, 0);
+        cudaError_t e = cudaFuncSetAttribute(k_sort_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_sort_pass, kThreads, sizeof(PassSmem));
         if (e != cudaSuccess) return e;
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
     uint32_t grid = (uint32_t)(blocks_per_sm * num_sms);
     if (grid > tiles) grid = (uint32_t)tiles;
     for (uint32_t p = 0; p < a.passes; p++) {
-        k_sort_pass<<<grid, kThreads, 0, st>>>(a.keys_a, a.vals_a, a.keys_b, a.vals_b, a.d_n, a.n_max, a.hist, p, a.passes,
+        k_sort_pass<<<grid, kThreads, sizeof(PassSmem), st>>>(a.keys_a, a.vals_a, a.keys_b, a.vals_b, a.d_n, a.n_max, a.hist, p, a.passes,
                                                a.lookback + (size_t)p * tiles * kRadix, a.epoch, a.tickets + p,
                                                a.result_in_b, a.vals_identity ? 1u : 0u);
     }
