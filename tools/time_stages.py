@@ -19,8 +19,5 @@ with G.Viewer(W, H) as v:
         v.render_frame([m])
         t = v.last_timings()
         rows.append((t.preprocess_ms, t.sort_ms, t.bin_ms, t.composite_ms, t.total_ms))
-    dbg = (C.c_uint32 * 16)()
-    G.lib().b200gs_debug_model_ctrl(m.h, dbg)
-    print("ctrl:", list(dbg), "chunks", (N + 255) // 256)
     r = np.median(np.array(rows[4:]), 0)
     print("median ms: pre %.3f sort %.3f bin %.3f comp %.3f total %.3f" % tuple(r))

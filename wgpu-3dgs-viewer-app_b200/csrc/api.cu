@@ -8,7 +8,6 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -638,7 +637,6 @@ extern "C" int b200gs_model_preprocess(b200gs_model* m, int use_unedited) {
     a.recs = m->recs; a.n = (uint32_t)m->cap; a.sh = v->sh; a.cov = v->cov;
     a.mask = m->mask; a.selection = m->selection; a.edits = use_unedited ? nullptr : m->edits;
     a.ctrl = m->ctrl + MC_CTRL; a.lookback = m->lb_pre; a.epoch = ++v->epoch;
-    if (getenv("B200GS_DEBUG_UNORDERED")) a.epoch = 0xffffffffu;
     a.keys = m->keys_a; a.idx = m->idx; a.splats = v->arena + m->arena_offset;
     a.sort_hist = m->ctrl + MC_SORT_HIST;
     if (v->timing) CK(cudaEventRecord(v->ev[0], v->stream));
@@ -884,16 +882,6 @@ extern "C" int b200gs_model_download_packed(b200gs_model* m, uint64_t start, voi
     TRY(set_device(m->v));
     if (count) CK(cudaMemcpyAsync(packed, m->recs + start * m->v->rb, count * m->v->rb, cudaMemcpyDeviceToHost, m->v->stream));
     CK(cudaStreamSynchronize(m->v->stream));
-    return B200GS_OK;
-}
-
-// developer aid (not part of the public header): the 16 control words of a model
-extern "C" B200GS_API int b200gs_debug_model_ctrl(b200gs_model* m, uint32_t* out16) {
-    REQUIRE(m && out16, "null argument");
-    TRY(set_device(m->v));
-    CK(cudaMemcpyAsync(m->v->h_small, m->ctrl, 64, cudaMemcpyDeviceToHost, m->v->stream));
-    CK(cudaStreamSynchronize(m->v->stream));
-    memcpy(out16, m->v->h_small, 64);
     return B200GS_OK;
 }
 

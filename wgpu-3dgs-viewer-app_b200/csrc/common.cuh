@@ -196,7 +196,7 @@ __device__ __forceinline__ void gs_lookback_publish(uint64_t* status, uint32_t e
     gs_st_status(&status[tile], epoch, (tile == 0 ? GS_LOOKBACK_FLAG_INCL : GS_LOOKBACK_FLAG_AGG) | aggregate);
 }
 __device__ __forceinline__ uint32_t gs_lookback_resolve(uint64_t* status, uint32_t epoch, uint32_t tile,
-                                                        uint32_t aggregate, int lane, uint32_t* dbg = nullptr) {
+                                                        uint32_t aggregate, int lane) {
     // Each round inspects the 128 predecessors p .. p-127 with 4 independent loads per lane
     // (group j holds p-32j-lane), so a walk over the few hundred tiles that are in flight at once
     // costs a handful of L2 round trips instead of one per 32 tiles.
@@ -205,7 +205,6 @@ __device__ __forceinline__ uint32_t gs_lookback_resolve(uint64_t* status, uint32
     uint32_t excl = 0;
     int64_t p = (int64_t)tile - 1;
     while (true) {
-        if (dbg && lane == 0) atomicAdd(&dbg[0], 1u);
         uint64_t v[kGroups];
 #pragma unroll
         for (int j = 0; j < kGroups; j++) {
@@ -221,7 +220,7 @@ __device__ __forceinline__ uint32_t gs_lookback_resolve(uint64_t* status, uint32
                 const uint32_t m_inv = __ballot_sync(0xffffffffu, flag == 0u);
                 const uint32_t first = m_incl ? (uint32_t)(__ffs((int)m_incl) - 1) : 32u;
                 const uint32_t needed = first >= 31u ? 0xffffffffu : ((2u << first) - 1u);
-                if (m_inv & needed) { stalled = true; if (dbg && lane == 0) atomicAdd(&dbg[1], 1u); }  // not published yet: retry from here
+                if (m_inv & needed) stalled = true;  // a needed predecessor has not published yet: retry from here
                 else {
                     uint32_t contrib = ((needed >> lane) & 1u) ? ((uint32_t)v[j] & GS_LOOKBACK_VALUE_MASK) : 0u;
 #pragma unroll

@@ -247,15 +247,7 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
                 }
                 __syncwarp();
             }
-            uint32_t excl;
-            if (epoch == 0xffffffffu) {  // measurement aid: unordered compaction (atomic), no look-back chain
-                excl = lane == 0 ? atomicAdd(&ctrl[8], total) : 0u;
-                excl = __shfl_sync(0xffffffffu, excl, 0);
-            } else {
-                const long long t0 = clock64();
-                excl = gs_lookback_resolve(lookback, epoch, c, total, lane, ctrl + 9);
-                if (lane == 0) atomicAdd(&ctrl[11], (uint32_t)((clock64() - t0) >> 4));
-            }
+            const uint32_t excl = gs_lookback_resolve(lookback, epoch, c, total, lane);
             if (lane == 0) {
                 s_base_all[j & 3u] = excl;
                 if (c == nchunks - 1) ctrl[GS_CTRL_VISIBLE] = excl + total;
