@@ -74,7 +74,7 @@ class ClockSampler(threading.Thread):
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
                 self.rows.append([x.strip() for x in line.split(",")])
                 if self.stop_flag:
@@ -188,8 +188,8 @@ def run_ours(a, rank, world, local_rank):
 
     # ---- this rank's contiguous block of the 1024-view batch
     cams = G.view_batch()
-    per = len(cams) // world
-    block = cams[rank * per:(rank + 1) * per]
+    lo, hi = G.partition_views(len(cams), world, rank)
+    block = cams[lo:hi]
     asp = np.float32(W) / np.float32(H)
     mats = [(c.view(), c.projection(asp)) for c in block]
 

@@ -212,6 +212,14 @@ def view_batch(n_az=32, n_el=8, radii=(3.0, 4.5, 6.0, 8.0), el_range=(-10.0, 60.
     return cams
 
 
+def partition_views(n_views, world_size, rank):
+    """Contiguous block [lo, hi) of a view batch owned by `rank` (views are the
+    independent units; every GPU holds a full scene replica)."""
+    per, extra = divmod(n_views, world_size)
+    lo = rank * per + min(rank, extra)
+    return lo, lo + per + (1 if rank < extra else 0)
+
+
 def read_ply(path, chunk=1 << 20):
     """Gaussians::read_ply_header + read_ply_gaussians (reference src/app.rs:1056-1070): yields
     chunks of PLY vertices as they are parsed (streaming)."""
