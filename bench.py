@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="diagnostic: skip the NCCL image gather")
     return ap.parse_args()
 
 
@@ -210,7 +211,7 @@ def run_ours(a, rank, world, local_rank):
             view, proj = mats[(s * B + j) % len(mats)]
             v.update_camera_matrices(view, proj, (W, H))
             v.render_frame([m], base + j * img_bytes, W * 4)
-        if world > 1:
+        if world > 1 and not a.no_gather:
             pending[slot] = dist.gather(ring[slot], gathered[slot] if rank == 0 else None, dst=0, async_op=True)
 
     def barrier():

@@ -427,3 +427,13 @@ def test_resize_and_determinism(G, O):
             if (W, H) in imgs:
                 assert np.array_equal(img, imgs[(W, H)])           # same view -> same bytes
             imgs[(W, H)] = img
+
+
+def test_cpp_gs_mirror_renders_a_frame(G, tmp_path):
+    """The C++ gs:: mirror drives one frame in the reference's call order (preprocess, sort, render)."""
+    import subprocess
+    from test_host import _build_gs_hpp_check
+    exe = _build_gs_hpp_check(tmp_path)
+    r = subprocess.run([exe, str(tmp_path), "gpu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "gpu ok" in r.stdout

@@ -157,3 +157,22 @@ def test_product_does_not_import_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert "gs_oracle" not in src and "from oracle" not in src and "import oracle" not in src, fn
+
+
+def _build_gs_hpp_check(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "gs_hpp_check")
+    pkg = os.path.join(ROOT, "wgpu-3dgs-viewer-app_b200")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", os.path.join(ROOT, "tests", "gs_hpp_check.cpp"), "-o", exe,
+                    "-L" + pkg, "-lb200gs", "-Wl,-rpath," + pkg], check=True)
+    return exe
+
+
+def test_cpp_gs_mirror_host_side(G, tmp_path):
+    """host/gs.hpp — the C++ mirror of the reference's gs:: names — compiles against the C ABI and its
+    host half (PLY streaming, Gaussian::from, layout constants, error type) works without a GPU."""
+    import subprocess
+    exe = _build_gs_hpp_check(tmp_path)
+    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "host-only ok" in r.stdout

@@ -202,12 +202,16 @@ class OrbitCamera:
 
 
 def view_batch(n_az=32, n_el=8, radii=(3.0, 4.5, 6.0, 8.0), el_range=(-10.0, 60.0)):
-    """The 1024-view batch of SURVEY.md §8d: 32 azimuths x 8 elevations x 4 radii, fixed order."""
+    """The 1024-view batch of SURVEY.md §8d: 32 azimuths x 8 elevations x 4 radii, fixed order.
+
+    Radius varies fastest, then elevation, then azimuth, so that every run of 32 consecutive views
+    holds all radii and elevations: contiguous per-rank blocks (and the few hundred views a short
+    bench run touches) then carry statistically the same work on every rank."""
     cams = []
-    for r in radii:
+    for a in range(n_az):
         for e in range(n_el):
             el = el_range[0] + (el_range[1] - el_range[0]) * e / max(n_el - 1, 1)
-            for a in range(n_az):
+            for r in radii:
                 cams.append(OrbitCamera.orbit(r, el, 360.0 * a / n_az))
     return cams
 
