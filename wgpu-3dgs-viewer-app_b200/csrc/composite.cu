@@ -32,10 +32,10 @@ __global__ void __launch_bounds__(kThreads) k_composite(const uint32_t* __restri
                                                         size_t pitch, uint32_t W, uint32_t H, uint32_t tiles_x,
                                                         uint32_t n_tiles, float bg0, float bg1, float bg2, float bg3,
                                                         unsigned long long* evals) {
-    __shared__ float4 sA[kThreads];  // mx, my, a', b'   (conic pre-scaled: power in log2 units)
-    __shared__ float4 sB[kThreads];  // c', opacity, red, green
-    __shared__ int4 sD[kThreads];    // x0, x1-x0, y0, y1-y0 (pixel bounds clipped to the viewport)
-    __shared__ float2 sC[kThreads];  // blue, footprint threshold (in the units of the pre-scaled conic)
+    // one 64-byte record per staged splat: {mx, my, a', b'} {c', opacity, red, green}
+    // {cx, hx, cy, hy} {blue, tau', -, -}; conic pre-scaled so that power is in log2 units, extent
+    // square clipped to the viewport stored as centre / half-size (exact: half-integers)
+    __shared__ float4 sS[kThreads * 4];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t* __restrict__ tile_vals = *tile_in_b ? tile_vals_b : tile_vals_a;
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(kThreads) k_composite(const uint32_t* __restri
 
     // warp -> 8x4 sub-tile, lane -> pixel
     const int wx0 = (int)(tx * GS_TILE) + (warp & 1) * 8, wy0 = (int)(ty * GS_TILE) + (warp >> 1) * 4;
-    const int wx1 = wx0 + 7, wy1 = wy0 + 3;
+    const float fwx0 = (float)wx0, fwx1 = (float)(wx0 + 7), fwy0 = (float)wy0, fwy1 = (float)(wy0 + 3);
     const int px = wx0 + (lane & 7), py = wy0 + (lane >> 3);
     const float fpx = (float)px, fpy = (float)py;
     const bool inside = px < (int)W && py < (int)H;
@@ -74,10 +74,11 @@ __global__ void __launch_bounds__(kThreads) k_composite(const uint32_t* __restri
             if (fy0 < 0.0f) fy0 = 0.0f;
             if (fx1 > Wf - 1.0f) fx1 = Wf - 1.0f;
             if (fy1 > Hf - 1.0f) fy1 = Hf - 1.0f;
-            sA[tid] = make_float4(mx, my, -0.5f * kLog2e * ca, -kLog2e * cbq);
-            sB[tid] = make_float4(-0.5f * kLog2e * cc, op, cr, cg);
-            sD[tid] = make_int4((int)fx0, (int)fx1 - (int)fx0, (int)fy0, (int)fy1 - (int)fy0);
-            sC[tid] = make_float2(cb, 0.5f * kLog2e * gs_footprint_tau(op, FLAT));
+            float4* rec = &sS[tid * 4];
+            rec[0] = make_float4(mx, my, -0.5f * kLog2e * ca, -kLog2e * cbq);
+            rec[1] = make_float4(-0.5f * kLog2e * cc, op, cr, cg);
+            rec[2] = make_float4(0.5f * (fx0 + fx1), 0.5f * (fx1 - fx0), 0.5f * (fy0 + fy1), 0.5f * (fy1 - fy0));
+            rec[3] = make_float4(cb, 0.5f * kLog2e * gs_footprint_tau(op, FLAT), r, 0.0f);
         }
         __syncthreads();
 
@@ -86,13 +87,17 @@ __global__ void __launch_bounds__(kThreads) k_composite(const uint32_t* __restri
                 const uint32_t s = g + lane;
                 bool ov = false;
                 if (s < cnt) {
-                    // exact footprint test of splat s against this warp's 8x4 sub-tile (∩ extent square)
-                    const int4 d = sD[s];
-                    const int x0 = max(d.x, wx0), x1 = min(d.x + d.y, wx1), y0 = max(d.z, wy0), y1 = min(d.z + d.w, wy1);
+                    // splat s against this warp's 8x4 sub-tile: extent-square overlap first; the exact
+                    // footprint test (can any pixel of the overlap reach alpha >= 1/255?) only when
+                    // the splat is large enough for it to matter
+                    const float4 C = sS[s * 4 + 2];
+                    const float x0 = fmaxf(C.x - C.y, fwx0), x1 = fminf(C.x + C.y, fwx1);
+                    const float y0 = fmaxf(C.z - C.w, fwy0), y1 = fminf(C.z + C.w, fwy1);
                     if (x0 <= x1 && y0 <= y1) {
-                        const float4 A = sA[s];
-                        const float pa = -A.z, pb = -0.5f * A.w, pc = -sB[s].x;  // 0.5*log2e * (a, b, c)
-                        const float dx0 = (float)x0 - A.x, dx1 = (float)x1 - A.x, dy0 = (float)y0 - A.y, dy1 = (float)y1 - A.y;
+                        const float4 A = sS[s * 4];
+                        const float4 D = sS[s * 4 + 3];
+                        const float pa = -A.z, pb = -0.5f * A.w, pc = -sS[s * 4 + 1].x;  // 0.5*log2e * (a, b, c)
+                        const float dx0 = x0 - A.x, dx1 = x1 - A.x, dy0 = y0 - A.y, dy1 = y1 - A.y;
                         const bool inx = dx0 <= 0.0f && dx1 >= 0.0f, iny = dy0 <= 0.0f && dy1 >= 0.0f;
                         float best = (inx && iny) ? 0.0f : 3.0e38f;
                         if (!inx) {
@@ -105,20 +110,20 @@ __global__ void __launch_bounds__(kThreads) k_composite(const uint32_t* __restri
                             const float dx = fminf(dx1, fmaxf(dx0, __fdividef(-pb * dy, pa)));
                             best = fminf(best, pa * dx * dx + 2.0f * pb * dx * dy + pc * dy * dy);
                         }
-                        ov = best <= sC[s].y;
+                        ov = best <= D.y;
                     }
                 }
                 uint32_t m = __ballot_sync(0xffffffffu, ov);
                 while (m) {
                     const int s2 = (int)g + __ffs((int)m) - 1;
                     m &= m - 1;
-                    const float4 A = sA[s2];
-                    const float4 B = sB[s2];
-                    const int4 D = sD[s2];
-                    const float cb = sC[s2].x;
-                    const bool in = (uint32_t)(px - D.x) <= (uint32_t)D.y && (uint32_t)(py - D.z) <= (uint32_t)D.w;
+                    const float4* rec = &sS[s2 * 4];
+                    const float4 A = rec[0];
+                    const float4 B = rec[1];
+                    const float4 C = rec[2];
                     const float dx = fpx - A.x, dy = fpy - A.y;
-                    const float p2 = A.z * dx * dx + B.x * dy * dy + A.w * dx * dy;
+                    const bool in = fabsf(fpx - C.x) <= C.y && fabsf(fpy - C.z) <= C.w;
+                    const float p2 = __fmaf_rn(__fmaf_rn(A.w, dy, A.z * dx), dx, (B.x * dy) * dy);
                     float al;
                     if (FLAT) al = (p2 >= -0.5f * GS_FLAT_D2 * kLog2e) ? fminf(GS_ALPHA_MAX, B.y) : 0.0f;
                     else al = fminf(GS_ALPHA_MAX, B.y * ex2_approx(p2));
@@ -126,9 +131,9 @@ __global__ void __launch_bounds__(kThreads) k_composite(const uint32_t* __restri
                     if (COUNT) my_evals += (in && !done) ? 1ull : 0ull;
                     if (ok) {
                         const float w = al * T;
-                        Cr += B.z * w;
-                        Cg += B.w * w;
-                        Cb += cb * w;
+                        Cr = __fmaf_rn(B.z, w, Cr);
+                        Cg = __fmaf_rn(B.w, w, Cg);
+                        Cb = __fmaf_rn(rec[3].x, w, Cb);
                         T -= w;
                         done = T < GS_T_EPS;
                     }
