@@ -251,6 +251,13 @@ B200GS_API int b200gs_render_frame(b200gs_viewer* v, b200gs_model* const* far_to
  * `rgba8_host` (width*4 pitch) and waits.  This is the end-to-end call a headless caller makes. */
 B200GS_API int b200gs_render_frame_host(b200gs_viewer* v, b200gs_model* const* far_to_near, uint32_t n_models,
                                         const float view[16], const float proj[16], void* rgba8_host);
+/* pipelined variant: _begin enqueues frame + D2H copy (second stream) and returns; _end waits for
+ * the OLDEST frame in flight (at most two).  rgba8_host should be page-locked (b200gs_host_alloc). */
+B200GS_API int b200gs_render_frame_host_begin(b200gs_viewer* v, b200gs_model* const* far_to_near, uint32_t n_models,
+                                              const float view[16], const float proj[16], void* rgba8_host);
+B200GS_API int b200gs_render_frame_host_end(b200gs_viewer* v);
+/* number of CUDA kernels this viewer has launched so far */
+B200GS_API int b200gs_launch_count(b200gs_viewer* v, uint64_t* out);
 /* sort models by squared distance of `world_center` to the camera, farthest first
  * (scene.rs:533-558).  centers: n x 3 model-space centres; order_out: n indices. */
 B200GS_API int b200gs_order_models(b200gs_viewer* v, b200gs_model* const* models, const float* centers, uint32_t n,

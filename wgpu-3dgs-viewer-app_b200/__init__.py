@@ -509,6 +509,22 @@ class Viewer:
                                            _p(view), _p(proj), C.c_void_p(out.ctypes.data)))
         return out.reshape(self.height, self.width, 4)
 
+    def render_frame_host_begin(self, models_far_to_near, camera, out):
+        """Pipelined end-to-end frame: returns at once; `out` (pinned uint8 array) is valid after the
+        matching render_frame_host_end().  At most two frames in flight."""
+        view = _f(camera.view(), 16)
+        proj = _f(camera.projection(np.float32(self.width) / np.float32(self.height)), 16)
+        _ck(lib().b200gs_render_frame_host_begin(self.h, self._handles(models_far_to_near), C.c_uint32(len(models_far_to_near)),
+                                                 _p(view), _p(proj), C.c_void_p(out.ctypes.data)))
+
+    def render_frame_host_end(self):
+        _ck(lib().b200gs_render_frame_host_end(self.h))
+
+    def launch_count(self):
+        n = C.c_uint64(0)
+        _ck(lib().b200gs_launch_count(self.h, C.byref(n)))
+        return n.value
+
     def last_timings(self):
         t = Timings()
         _ck(lib().b200gs_last_timings(self.h, C.byref(t)))

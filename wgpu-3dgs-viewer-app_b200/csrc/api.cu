@@ -106,8 +106,12 @@ struct b200gs_viewer {
     uint32_t* ranges = nullptr;
     uint32_t ranges_tiles = 0;
     uint32_t* vctrl = nullptr;
-    uint8_t* image = nullptr;  // internal RGBA8 target for render_frame_host
+    uint8_t* image = nullptr;  // internal RGBA8 targets for render_frame_host (2 slots, image + image_bytes)
     size_t image_bytes = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    uint32_t ring_head = 0, ring_pending = 0;
+    uint64_t launches = 0;     // kernels launched by this viewer (b200gs_launch_count)
     uint32_t epoch = 0;
     bool timing = false, count_evals = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -208,7 +212,7 @@ static int ensure_frame_buffers(b200gs_viewer* v) {
     if (v->image_bytes < img) {
         CK(cudaStreamSynchronize(v->stream));
         if (v->image) CK(cudaFree(v->image));
-        TRY(dev_alloc(&v->image, img, true, v->stream));
+        TRY(dev_alloc(&v->image, img * 2, true, v->stream));
         v->image_bytes = img;
     }
     if (!v->layout_dirty) return B200GS_OK;
@@ -304,6 +308,11 @@ extern "C" int b200gs_viewer_create(int device, uint32_t sh, uint32_t cov3d, uin
     if (e == cudaSuccess) e = cudaMalloc((void**)&v->vctrl, VC_WORDS * 4);
     if (e == cudaSuccess) e = cudaMemsetAsync(v->vctrl, 0, VC_WORDS * 4, v->stream);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&v->h_small, 4096);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+        e = cudaEventCreateWithFlags(&v->ev_rendered[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&v->ev_copied[i], cudaEventDisableTiming);
+    }
     for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&v->ev[i]);
     if (e != cudaSuccess) {
         gs_set_error("viewer_create: %s", cudaGetErrorString(e));
@@ -334,6 +343,11 @@ extern "C" int b200gs_viewer_destroy(b200gs_viewer* v) {
     if (v->h_small) cudaFreeHost(v->h_small);
     for (auto& e : v->ev)
         if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 2; i++) {
+        if (v->ev_rendered[i]) cudaEventDestroy(v->ev_rendered[i]);
+        if (v->ev_copied[i]) cudaEventDestroy(v->ev_copied[i]);
+    }
+    if (v->copy_stream) { cudaStreamSynchronize(v->copy_stream); cudaStreamDestroy(v->copy_stream); }
     if (v->stream) cudaStreamDestroy(v->stream);
     delete v;
     return B200GS_OK;
@@ -641,6 +655,7 @@ extern "C" int b200gs_model_preprocess(b200gs_model* m, int use_unedited) {
     a.sort_hist = m->ctrl + MC_SORT_HIST;
     if (v->timing) CK(cudaEventRecord(v->ev[0], v->stream));
     CK(gs_launch_preprocess(a, f, xf, v->num_sms, v->stream));
+    v->launches += 1;
     if (v->timing) CK(cudaEventRecord(v->ev[1], v->stream));
     m->preprocessed = true;
     m->sorted = false;
@@ -660,6 +675,7 @@ extern "C" int b200gs_model_sort(b200gs_model* m) {
     a.tickets = m->ctrl + MC_SORT_TICKET; a.passes = 4; a.hist_prefilled = true; a.vals_identity = true;
     a.result_in_b = m->ctrl + MC_CTRL + GS_CTRL_SORT_IN_B;
     CK(gs_launch_sort(a, v->num_sms, v->stream));
+    v->launches += a.passes;
     if (v->timing) CK(cudaEventRecord(v->ev[2], v->stream));
     m->sorted = true;
     return B200GS_OK;
@@ -705,6 +721,7 @@ extern "C" int b200gs_render(b200gs_viewer* v, b200gs_model* const* far_to_near,
         b.tile_keys = v->tk_a; b.tile_vals = v->tv_a; b.capacity = (uint32_t)v->entry_cap;
         b.tile_hist = v->vctrl + VC_TSORT_HIST;
         CK(gs_launch_bin(b, f, v->num_sms, st));
+        v->launches += 2;
     }
     GsSortArgs s;
     s.keys_a = v->tk_a; s.vals_a = v->tv_a; s.keys_b = v->tk_b; s.vals_b = v->tv_b;
@@ -720,6 +737,7 @@ extern "C" int b200gs_render(b200gs_viewer* v, b200gs_model* const* far_to_near,
     c.out = (uint8_t*)rgba8_out; c.pitch = pitch;
     c.evals = v->count_evals ? (unsigned long long*)(v->vctrl + VC_EVALS) : nullptr;
     CK(gs_launch_composite(c, f, st));
+    v->launches += s.passes + 2;  // tile sort passes, tile ranges, compositor
     if (v->timing) CK(cudaEventRecord(v->ev[4], st));
     return B200GS_OK;
 }
@@ -734,15 +752,51 @@ extern "C" int b200gs_render_frame(b200gs_viewer* v, b200gs_model* const* far_to
     return b200gs_render(v, far_to_near, n_models, rgba8_out, pitch);
 }
 
-extern "C" int b200gs_render_frame_host(b200gs_viewer* v, b200gs_model* const* far_to_near, uint32_t n_models,
-                                        const float view[16], const float proj[16], void* rgba8_host) {
+// Pipelined host frames: _begin enqueues the frame and its D2H copy (on a second stream) into one
+// of two slots and returns; _end waits for the OLDEST outstanding frame.  With begin(i+1) issued
+// before end(i), the copy of frame i overlaps the rendering of frame i+1.
+extern "C" int b200gs_render_frame_host_begin(b200gs_viewer* v, b200gs_model* const* far_to_near, uint32_t n_models,
+                                              const float view[16], const float proj[16], void* rgba8_host) {
     REQUIRE(v && rgba8_host, "null argument");
+    REQUIRE(v->ring_pending < 2, "two frames are already in flight: call b200gs_render_frame_host_end first");
     if (view && proj) TRY(b200gs_set_camera(v, view, proj, nullptr));
     TRY(set_device(v));
     TRY(ensure_frame_buffers(v));
-    TRY(b200gs_render_frame(v, far_to_near, n_models, v->image, (size_t)v->W * 4));
-    CK(cudaMemcpyAsync(rgba8_host, v->image, (size_t)v->W * v->H * 4, cudaMemcpyDeviceToHost, v->stream));
-    CK(cudaStreamSynchronize(v->stream));
+    const uint32_t slot = (v->ring_head + v->ring_pending) & 1u;
+    const size_t img = (size_t)v->W * v->H * 4;
+    uint8_t* dev = v->image + (size_t)slot * v->image_bytes;
+    // this slot's previous image (two frames ago) must have left the device before it is overwritten
+    CK(cudaStreamWaitEvent(v->stream, v->ev_copied[slot], 0));
+    TRY(b200gs_render_frame(v, far_to_near, n_models, dev, (size_t)v->W * 4));
+    CK(cudaEventRecord(v->ev_rendered[slot], v->stream));
+    CK(cudaStreamWaitEvent(v->copy_stream, v->ev_rendered[slot], 0));
+    CK(cudaMemcpyAsync(rgba8_host, dev, img, cudaMemcpyDeviceToHost, v->copy_stream));
+    CK(cudaEventRecord(v->ev_copied[slot], v->copy_stream));
+    v->ring_pending++;
+    return B200GS_OK;
+}
+
+extern "C" int b200gs_render_frame_host_end(b200gs_viewer* v) {
+    REQUIRE(v, "null viewer");
+    REQUIRE(v->ring_pending > 0, "no frame in flight");
+    TRY(set_device(v));
+    CK(cudaEventSynchronize(v->ev_copied[v->ring_head & 1u]));
+    v->ring_head++;
+    v->ring_pending--;
+    return B200GS_OK;
+}
+
+extern "C" int b200gs_render_frame_host(b200gs_viewer* v, b200gs_model* const* far_to_near, uint32_t n_models,
+                                        const float view[16], const float proj[16], void* rgba8_host) {
+    REQUIRE(v && rgba8_host, "null argument");
+    while (v->ring_pending) TRY(b200gs_render_frame_host_end(v));
+    TRY(b200gs_render_frame_host_begin(v, far_to_near, n_models, view, proj, rgba8_host));
+    return b200gs_render_frame_host_end(v);
+}
+
+extern "C" int b200gs_launch_count(b200gs_viewer* v, uint64_t* out) {
+    REQUIRE(v && out, "null argument");
+    *out = v->launches;
     return B200GS_OK;
 }
 
