@@ -114,6 +114,57 @@ __device__ __forceinline__ float byte_to_float(uint32_t x, int k) {
     return __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7440u | (uint32_t)k)) - 8388608.0f;
 }
 
+// SH bands 1..DEG added to rgb (TOLERANCE class: FMA).  Inria computeColorFromSH sign convention.
+template <int SH, int DEG>
+__device__ __forceinline__ void sh_colour(const uint32_t* shw, float dx, float dy, float dz, float rgb[3]) {
+    constexpr int NCOEF = DEG >= 3 ? 15 : (DEG == 2 ? 8 : 3);
+    float bs[NCOEF];
+    bs[0] = -0.4886025119029199f * dy;
+    bs[1] = 0.4886025119029199f * dz;
+    bs[2] = -0.4886025119029199f * dx;
+    if (DEG >= 2) {
+        const float xx = dx * dx, yy = dy * dy, zz = dz * dz, xy = dx * dy, yz = dy * dz, xz = dx * dz;
+        bs[3] = 1.0925484305920792f * xy;
+        bs[4] = -1.0925484305920792f * yz;
+        bs[5] = 0.31539156525252005f * (2.0f * zz - xx - yy);
+        bs[6] = -1.0925484305920792f * xz;
+        bs[7] = 0.5462742152960396f * (xx - yy);
+        if (DEG >= 3) {
+            bs[8] = -0.5900435899266435f * dy * (3.0f * xx - yy);
+            bs[9] = 2.890611442640554f * xy * dz;
+            bs[10] = -0.4570457994644658f * dy * (4.0f * zz - xx - yy);
+            bs[11] = 0.3731763325901154f * dz * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+            bs[12] = -0.4570457994644658f * dx * (4.0f * zz - xx - yy);
+            bs[13] = 1.445305721320277f * dz * (xx - yy);
+            bs[14] = -0.5900435899266435f * dx * (xx - 3.0f * yy);
+        }
+    }
+    float acc[3] = {0.0f, 0.0f, 0.0f};
+    if (SH == 2) {
+        // Σ b_k (q_k·2/255 − 1) = (2/255)·Σ b_k q_k − Σ b_k : one PRMT + FADD + FFMA per coefficient
+        float sum_b = 0.0f;
+#pragma unroll
+        for (int k = 0; k < NCOEF; k++) {
+            sum_b += bs[k];
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                const int e = 3 * k + ch;
+                acc[ch] = __fmaf_rn(bs[k], byte_to_float(shw[e >> 2], e & 3), acc[ch]);
+            }
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) rgb[ch] += __fmaf_rn(acc[ch], 2.0f / 255.0f, -sum_b);
+    } else {
+#pragma unroll
+        for (int k = 0; k < NCOEF; k++) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) acc[ch] = __fmaf_rn(bs[k], sh_coef<SH>(shw, 3 * k + ch), acc[ch]);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) rgb[ch] += acc[ch];
+    }
+}
+
 // EXACT class: model/view/projection chain, frustum cull.  Returns visibility; pw/pv/ndc out.
 __device__ __forceinline__ bool project_and_cull(const uint32_t* w, const GsFrame& f, const GsModelXf& m, float pw[3],
                                                  float pv[3], float& nx, float& ny, float& nz) {
@@ -380,59 +431,12 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
                 float rgb[3];
 #pragma unroll
                 for (int ch = 0; ch < 3; ch++) rgb[ch] = f.no_sh0 ? 0.0f : byte_to_float(colw, ch) * (1.0f / 255.0f);
-                const uint32_t deg = SH == 3 ? 0u : f.sh_deg;
-                if (SH != 3 && deg >= 1) {
-                    float bs[15];
-                    bs[0] = -0.4886025119029199f * dy;
-                    bs[1] = 0.4886025119029199f * dz;
-                    bs[2] = -0.4886025119029199f * dx;
-                    int ncoef = 3;
-                    if (deg >= 2) {
-                        const float xx = dx * dx, yy = dy * dy, zz = dz * dz, xy = dx * dy, yz = dy * dz, xz = dx * dz;
-                        bs[3] = 1.0925484305920792f * xy;
-                        bs[4] = -1.0925484305920792f * yz;
-                        bs[5] = 0.31539156525252005f * (2.0f * zz - xx - yy);
-                        bs[6] = -1.0925484305920792f * xz;
-                        bs[7] = 0.5462742152960396f * (xx - yy);
-                        ncoef = 8;
-                        if (deg >= 3) {
-                            bs[8] = -0.5900435899266435f * dy * (3.0f * xx - yy);
-                            bs[9] = 2.890611442640554f * xy * dz;
-                            bs[10] = -0.4570457994644658f * dy * (4.0f * zz - xx - yy);
-                            bs[11] = 0.3731763325901154f * dz * (2.0f * zz - 3.0f * xx - 3.0f * yy);
-                            bs[12] = -0.4570457994644658f * dx * (4.0f * zz - xx - yy);
-                            bs[13] = 1.445305721320277f * dz * (xx - yy);
-                            bs[14] = -0.5900435899266435f * dx * (xx - 3.0f * yy);
-                            ncoef = 15;
-                        }
-                    }
-                    float acc[3] = {0.0f, 0.0f, 0.0f};
-                    if (SH == 2) {
-                        // Σ b_k (q_k·2/255 − 1) = (2/255)·Σ b_k q_k − Σ b_k : one PRMT + FADD + FFMA per coefficient
-                        float sum_b = 0.0f;
-#pragma unroll
-                        for (int k = 0; k < 15; k++) {
-                            if (k < ncoef) {
-                                sum_b += bs[k];
-#pragma unroll
-                                for (int ch = 0; ch < 3; ch++) {
-                                    const int e = 3 * k + ch;
-                                    acc[ch] = __fmaf_rn(bs[k], byte_to_float(shw[e >> 2], e & 3), acc[ch]);
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int ch = 0; ch < 3; ch++) rgb[ch] += __fmaf_rn(acc[ch], 2.0f / 255.0f, -sum_b);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 15; k++) {
-                            if (k < ncoef) {
-#pragma unroll
-                                for (int ch = 0; ch < 3; ch++) acc[ch] = __fmaf_rn(bs[k], sh_coef<SH>(shw, 3 * k + ch), acc[ch]);
-                            }
-                        }
-#pragma unroll
-                        for (int ch = 0; ch < 3; ch++) rgb[ch] += acc[ch];
+                if (SH != 3) {  // the degree is uniform per frame: one fully unrolled variant per degree
+                    switch (f.sh_deg) {
+                        case 1: sh_colour<SH, 1>(shw, dx, dy, dz, rgb); break;
+                        case 2: sh_colour<SH, 2>(shw, dx, dy, dz, rgb); break;
+                        case 3: sh_colour<SH, 3>(shw, dx, dy, dz, rgb); break;
+                        default: break;
                     }
                 }
 #pragma unroll
@@ -464,13 +468,21 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
 
             // digit histograms of the emitted keys for the depth sort (saves its histogram kernel);
             // warp-aggregated: depth keys share their top bytes
-            if (sort_hist && vis) {
+            if (sort_hist && ballot) {
                 const uint32_t key = __float_as_uint(nz);
+                const int first = __ffs((int)ballot) - 1;
+                const uint32_t key0 = __shfl_sync(0xffffffffu, key, first);
 #pragma unroll
-                for (int p = 0; p < 4; p++) {
+                for (int p = 3; p >= 0; p--) {
                     const uint32_t dgt = (key >> (8 * p)) & 0xffu;
-                    const uint32_t peers = __match_any_sync(ballot, dgt);
-                    if (lane == __ffs((int)peers) - 1) atomicAdd(&s_hist[p * 256 + dgt], (uint32_t)__popc(peers));
+                    // the top bytes are usually the same for the whole warp: one vote instead of a match
+                    const bool uniform = p >= 2 && __all_sync(0xffffffffu, !vis || dgt == ((key0 >> (8 * p)) & 0xffu));
+                    if (uniform) {
+                        if (lane == first) atomicAdd(&s_hist[p * 256 + dgt], (uint32_t)__popc(ballot));
+                    } else if (vis) {
+                        const uint32_t peers = __match_any_sync(ballot, dgt);
+                        if (lane == __ffs((int)peers) - 1) atomicAdd(&s_hist[p * 256 + dgt], (uint32_t)__popc(peers));
+                    }
                 }
             }
 
