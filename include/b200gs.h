@@ -143,6 +143,15 @@ typedef struct b200gs_splat {
     uint16_t flags;      /* bit0 selected                                          */
 } b200gs_splat;
 
+/* One entry of the per-pixel hit list (mirror of gs::QueryHitResultPod, src/tab/scene.rs:650-657):
+ * the splats that contribute to a pixel, front to back. */
+typedef struct b200gs_hit {
+    uint32_t model;   /* position of the model in the far_to_near array passed to the render   */
+    uint32_t index;   /* Gaussian index inside that model                                       */
+    float alpha;      /* the splat's alpha at the pixel (>= 1/255)                              */
+    float depth;      /* ndc.z of the Gaussian (the depth key as a float)                       */
+} b200gs_hit;
+
 /* Per-stage device times of the last b200gs_render_frame / explicit stage calls (ms). */
 typedef struct b200gs_timings {
     float preprocess_ms, sort_ms, bin_ms, composite_ms, total_ms;
@@ -278,6 +287,19 @@ B200GS_API int b200gs_model_download_indices(b200gs_model* m, uint32_t* idx, uin
 /* projected splats in the same order as the indices */
 B200GS_API int b200gs_model_download_splats(b200gs_model* m, b200gs_splat* out, uint64_t cap, uint64_t* n);
 B200GS_API int b200gs_last_timings(b200gs_viewer* v, b200gs_timings* out);
+/* gs::QueryHitPod + gs::query::download (src/tab/scene.rs:617-657): the ordered hit list of pixel
+ * (px, py) of the LAST rendered frame (same models, same camera), nearest first, at most `cap`. */
+B200GS_API int b200gs_query_hits(b200gs_viewer* v, b200gs_model* const* far_to_near, uint32_t n_models, uint32_t px,
+                                 uint32_t py, b200gs_hit* out, uint64_t cap, uint64_t* n);
+/* gs::query::hit_pos_by_closest / hit_pos_by_alpha_range (src/tab/scene.rs:659-676): world position of
+ * the picked surface point on the ray through the pixel.  closest = depth of the first hit;
+ * alpha_range = alpha-weighted mean depth of the hits with alpha >= threshold (0.05 in the app).
+ * Returns B200GS_ERR_INVALID if no hit qualifies. */
+B200GS_API int b200gs_hit_pos_by_closest(const b200gs_hit* hits, uint64_t n, const float view[16], const float proj[16],
+                                         const float size[2], uint32_t px, uint32_t py, float pos_out[3]);
+B200GS_API int b200gs_hit_pos_by_alpha_range(const b200gs_hit* hits, uint64_t n, float alpha_threshold, const float view[16],
+                                             const float proj[16], const float size[2], uint32_t px, uint32_t py,
+                                             float pos_out[3]);
 /* raw sort entry point (keys/values DEVICE arrays of n u32, sorted ascending & stable in place;
  * bits = number of low key bits to sort, multiple of 8).  Used by the sort parity tests. */
 B200GS_API int b200gs_sort_pairs_device(b200gs_viewer* v, uint32_t* keys_dev, uint32_t* values_dev, uint64_t n,

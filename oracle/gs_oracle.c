@@ -404,8 +404,24 @@ static void sh_basis(float x, float y, float z, uint32_t deg, float b[15]) {
     b[14] = -0.5900435899266435f * x * (xx - 3.0f * yy);
 }
 
+/* Selection query in immediate mode (gs::QueryToolset rect / brush, src/tab/scene.rs:758-791,
+ * 1224-1263; ops src/app.rs:1453): splat centre in viewport pixels (top-left origin) inside the
+ * rectangle, or within `radius` of the brush segment. */
+static int query_hit(const b200gs_query_pod* q, float sx, float sy) {
+    if (q->kind == B200GS_QUERY_RECT) return sx >= q->p0[0] && sx <= q->p1[0] && sy >= q->p0[1] && sy <= q->p1[1];
+    float vx = q->p1[0] - q->p0[0], vy = q->p1[1] - q->p0[1];
+    float wx = sx - q->p0[0], wy = sy - q->p0[1];
+    float vv = vx * vx + vy * vy;
+    float t = vv > 0.0f ? (wx * vx + wy * vy) / vv : 0.0f;
+    t = fminf(1.0f, fmaxf(0.0f, t));
+    float dx = wx - t * vx, dy = wy - t * vy;
+    return dx * dx + dy * dy <= q->radius * q->radius;
+}
+
 /* one Gaussian; returns 1 if visible */
-static int pre_one(const orc_frame* f, const orc_model* m, const pre_ctx* c, uint64_t i, uint32_t* key, b200gs_splat* out) {
+static int pre_one(const orc_frame* f, const orc_model* m, const pre_ctx* c, uint64_t i, uint32_t* key, b200gs_splat* out,
+                   int* selected_out) {
+    if (selected_out) *selected_out = m->selection ? (int)((m->selection[i >> 5] >> (i & 31)) & 1u) : 0;
     if (m->mask && !((m->mask[i >> 5] >> (i & 31)) & 1u)) return 0;
     const b200gs_edit_pod* ed = m->edits ? &m->edits[i] : NULL;
     int selected = m->selection ? (int)((m->selection[i >> 5] >> (i & 31)) & 1u) : 0;
@@ -430,6 +446,15 @@ static int pre_one(const orc_frame* f, const orc_model* m, const pre_ctx* c, uin
     if (!(nz > 0.0f && nz < 1.0f && fabsf(nx) <= ORC_CULL_XY && fabsf(ny) <= ORC_CULL_XY)) return 0;
     /* depth key [§8c.6]: bits(ndc.z), ascending = near -> far */
     memcpy(key, &nz, 4);
+    /* selection query: the new selection state is what this frame shows */
+    if (f->query.kind >= B200GS_QUERY_RECT) {
+        float sx = ((nx + 1.0f) * c->W - 1.0f) * 0.5f + 0.5f, sy = ((1.0f - ny) * c->H - 1.0f) * 0.5f + 0.5f;
+        int hit = query_hit(&f->query, sx, sy);
+        if (f->query.op == B200GS_SELECT_SET) selected = hit;
+        else if (f->query.op == B200GS_SELECT_ADD) selected = selected | hit;
+        else selected = selected & !hit;
+        if (selected_out) *selected_out = selected;
+    }
 
     /* Σ' = (R_m S_m) Σ (R_m S_m)^T · size² */
     float S[3][3] = {{cv[0], cv[1], cv[2]}, {cv[1], cv[3], cv[4]}, {cv[2], cv[4], cv[5]}};
@@ -534,7 +559,7 @@ uint64_t orc_preprocess(const orc_frame* f, const orc_model* m, uint32_t* indice
         for (uint64_t i = lo; i < hi; i++) {
             uint32_t key;
             b200gs_splat s;
-            vis[i] = (uint8_t)pre_one(f, m, &c, i, &key, &s);
+            vis[i] = (uint8_t)pre_one(f, m, &c, i, &key, &s, NULL);
             k += vis[i];
         }
         cnt[t + 1] = k;
@@ -549,7 +574,7 @@ uint64_t orc_preprocess(const orc_frame* f, const orc_model* m, uint32_t* indice
             uint32_t key;
             b200gs_splat s;
             memset(&s, 0, sizeof s);
-            pre_one(f, m, &c, i, &key, &s);
+            pre_one(f, m, &c, i, &key, &s, NULL);
             if (indices) indices[k] = (uint32_t)i;
             if (keys) keys[k] = key;
             if (splats) splats[k] = s;
@@ -560,6 +585,23 @@ uint64_t orc_preprocess(const orc_frame* f, const orc_model* m, uint32_t* indice
     free(cnt);
     free(vis);
     return v;
+}
+
+void orc_query_selection(const orc_frame* f, const orc_model* m, uint32_t* words_out) {
+    pre_ctx c;
+    pre_setup(f, m, &c);
+    uint64_t nw = (m->n + 31) / 32;
+    for (uint64_t w = 0; w < nw; w++) words_out[w] = 0;
+    for (uint64_t i = 0; i < m->n; i++) {
+        uint32_t key;
+        b200gs_splat s;
+        int sel = 0;
+        int vis = pre_one(f, m, &c, i, &key, &s, &sel);
+        /* a culled Gaussian is never hit: Set clears it, Add / Remove keep its old state */
+        if (!vis) sel = (f->query.kind >= B200GS_QUERY_RECT && f->query.op == B200GS_SELECT_SET)
+                            ? 0 : (m->selection ? (int)((m->selection[i >> 5] >> (i & 31)) & 1u) : 0);
+        if (sel) words_out[i >> 5] |= 1u << (i & 31);
+    }
 }
 
 /* --------------------------------------------------------------- sort (a2)

@@ -46,6 +46,7 @@ typedef struct orc_frame {
     b200gs_edit_pod selection_edit;
     float highlight[4];
     float background[4];
+    b200gs_query_pod query; /* selection query tested during preprocess (rect / brush) */
 } orc_frame;
 
 typedef struct orc_model {
@@ -88,7 +89,8 @@ uint64_t orc_render_frame(const orc_frame* f, const orc_model* far_to_near, uint
 /* N2: mask evaluation */
 void orc_eval_mask(const orc_model* m, const b200gs_mask_op* postfix, uint32_t n_ops, const b200gs_mask_shape* shapes,
                    uint32_t n_shapes, uint32_t* words);
-/* N2: selection query (rect / brush) applied to a selection bitset */
+/* N2: selection query (rect / brush, Set/Add/Remove) of f->query applied to m->selection -> words_out */
+void orc_query_selection(const orc_frame* f, const orc_model* m, uint32_t* words_out);
 void orc_apply_edit(const b200gs_edit_pod* e, float rgb[3], float* opacity);
 int orc_num_threads(void);
 

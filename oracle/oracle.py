@@ -31,11 +31,16 @@ class EditPod(C.Structure):
                 ("gamma", C.c_float), ("alpha", C.c_float)]
 
 
+class QueryPod(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("op", C.c_uint32), ("p0", C.c_float * 2), ("p1", C.c_float * 2),
+                ("radius", C.c_float), ("_pad", C.c_uint32)]
+
+
 class Frame(C.Structure):
     _fields_ = [("view", C.c_float * 16), ("proj", C.c_float * 16), ("size", C.c_float * 2),
                 ("gaussian_size", C.c_float), ("display_mode", C.c_uint32), ("sh_deg", C.c_uint32),
                 ("no_sh0", C.c_uint32), ("selection_edit", EditPod), ("highlight", C.c_float * 4),
-                ("background", C.c_float * 4)]
+                ("background", C.c_float * 4), ("query", QueryPod)]
 
 
 class Model(C.Structure):
@@ -140,7 +145,7 @@ def quat_from_euler_zyx_deg(rot_deg):
 
 
 def make_frame(view, proj, width, height, gaussian_size=1.0, display_mode=0, sh_deg=3, no_sh0=0,
-               selection_edit=None, highlight=(0, 0, 0, 0), background=(0, 0, 0, 0)):
+               selection_edit=None, highlight=(0, 0, 0, 0), background=(0, 0, 0, 0), query=None):
     f = Frame()
     f.view[:] = [float(x) for x in view]
     f.proj[:] = [float(x) for x in proj]
@@ -150,6 +155,8 @@ def make_frame(view, proj, width, height, gaussian_size=1.0, display_mode=0, sh_
     f.selection_edit = selection_edit if selection_edit is not None else default_edit()
     f.highlight[:] = [float(x) for x in highlight]
     f.background[:] = [float(x) for x in background]
+    if query is not None:
+        f.query = query
     return f
 
 
@@ -232,6 +239,21 @@ def eval_mask(model, ops, shapes):
     shapes = np.ascontiguousarray(shapes, dtype=MASK_SHAPE)
     words = np.zeros((model.n + 31) // 32, np.uint32)
     lib().orc_eval_mask(C.byref(model.c), _p(ops), C.c_uint32(len(ops)), _p(shapes), C.c_uint32(len(shapes)), _p(words))
+    return words
+
+
+def query_pod(kind, op=0, p0=(0, 0), p1=(0, 0), radius=0.0):
+    """kind: 0 none, 1 hit, 2 rect, 3 brush; op: 0 set, 1 add, 2 remove (include/b200gs.h)."""
+    q = QueryPod()
+    q.kind, q.op, q.radius = kind, op, radius
+    q.p0[:] = [float(x) for x in p0]
+    q.p1[:] = [float(x) for x in p1]
+    return q
+
+
+def query_selection(frame, model):
+    words = np.zeros((model.n + 31) // 32, np.uint32)
+    lib().orc_query_selection(C.byref(frame), C.byref(model.c), _p(words))
     return words
 
 

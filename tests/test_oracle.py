@@ -433,3 +433,42 @@ def test_golden_fixture(O):
         assert np.array_equal(keys, z["keys_" + tag])
         assert np.array_equal(img, z["img_" + tag])
         assert psnr(img, O.composite(f, spl, True)[0]) > 50
+
+
+def test_selection_query_rect_and_brush(O):
+    """Immediate-mode selection queries (reference src/tab/scene.rs:758-791, 1224-1263; ops src/app.rs:1453):
+    a Gaussian is hit when its projected centre lies in the shape; Set / Add / Remove on the bitset."""
+    import math
+    W = H = 64
+    D = 5.0
+    fy = (1 / math.tan(math.radians(30))) * H / 2
+    # a 5x5 lattice whose centres project to pixel centres x = 32 + 8*i (i = -2..2), same for y
+    step = 8.0 * D / fy
+    pts = [[i * step, -j * step, 0.0] for j in range(-2, 3) for i in range(-2, 3)]
+    g = make_gaussians(O.GAUSSIAN, pts, scale=0.01)
+    packed = O.pack(0, 0, g)
+    view = O.look_at_rh((0, 0, D))
+    proj = O.perspective_rh(np.float32(np.deg2rad(60)), np.float32(1.0), 0.1, 1e4)
+    sx = np.array([32 + 8 * i for j in range(-2, 3) for i in range(-2, 3)], float)
+    sy = np.array([32 + 8 * j for j in range(-2, 3) for i in range(-2, 3)], float)
+
+    f = O.make_frame(view, proj, W, H, query=O.query_pod(2, 0, (20, 20), (44, 36)))          # rect, Set
+    sel = bits_set(O.query_selection(f, O.ModelRef(0, 0, packed, 25)), 25)
+    assert np.array_equal(sel, (sx >= 20) & (sx <= 44) & (sy >= 20) & (sy <= 36)) and sel.sum() == 6
+    old = pack_bits(np.arange(25) % 2 == 0)
+    f = O.make_frame(view, proj, W, H, query=O.query_pod(2, 1, (20, 20), (44, 36)))          # Add
+    got = bits_set(O.query_selection(f, O.ModelRef(0, 0, packed, 25, selection=old)), 25)
+    assert np.array_equal(got, sel | (np.arange(25) % 2 == 0))
+    f = O.make_frame(view, proj, W, H, query=O.query_pod(2, 2, (20, 20), (44, 36)))          # Remove
+    got = bits_set(O.query_selection(f, O.ModelRef(0, 0, packed, 25, selection=old)), 25)
+    assert np.array_equal(got, ~sel & (np.arange(25) % 2 == 0))
+    # brush: capsule of radius 9 around the diagonal segment (16,16)-(48,48)
+    f = O.make_frame(view, proj, W, H, query=O.query_pod(3, 0, (16, 16), (48, 48), 9.0))
+    got = bits_set(O.query_selection(f, O.ModelRef(0, 0, packed, 25)), 25)
+    t = np.clip(((sx - 16) * 32 + (sy - 16) * 32) / (2 * 32 * 32), 0, 1)
+    d2 = (sx - 16 - 32 * t) ** 2 + (sy - 16 - 32 * t) ** 2
+    assert np.array_equal(got, d2 <= 81) and 5 <= got.sum() <= 15
+    # the frame shows the NEW selection: highlighted splats carry the flag
+    f = O.make_frame(view, proj, W, H, query=O.query_pod(2, 0, (20, 20), (44, 36)), highlight=(1, 0, 1, 0.5))
+    idx, _, spl = O.preprocess(f, O.ModelRef(0, 0, packed, 25))
+    assert np.array_equal(spl["flags"].astype(bool), sel[idx])

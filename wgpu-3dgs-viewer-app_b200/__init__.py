@@ -31,6 +31,7 @@ SPLAT = np.dtype([("mx", "<f4"), ("my", "<f4"), ("radius", "<u2"), ("opacity_h",
                   ("g_h", "<f2"), ("ca", "<f4"), ("cb", "<f4"), ("cc", "<f4"), ("b_h", "<f2"), ("flags", "<u2")])
 MASK_SHAPE = np.dtype([("kind", "<u4"), ("pos", "<f4", 3), ("quat", "<f4", 4), ("scale", "<f4", 3)])
 MASK_OP = np.dtype([("kind", "<u4"), ("arg", "<u4")])
+HIT = np.dtype([("model", "<u4"), ("index", "<u4"), ("alpha", "<f4"), ("depth", "<f4")])
 
 
 class EditPod(C.Structure):
@@ -54,6 +55,20 @@ class EditPod(C.Structure):
 class QueryPod(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("op", C.c_uint32), ("p0", C.c_float * 2), ("p1", C.c_float * 2),
                 ("radius", C.c_float), ("_pad", C.c_uint32)]
+
+
+QUERY_NONE, QUERY_HIT, QUERY_RECT, QUERY_BRUSH = 0, 1, 2, 3
+SELECT_SET, SELECT_ADD, SELECT_REMOVE = 0, 1, 2
+
+
+def query_pod(kind=QUERY_NONE, op=SELECT_SET, p0=(0, 0), p1=(0, 0), radius=0.0):
+    """gs::Query*Pod / QueryToolset in immediate mode (reference src/tab/scene.rs:758-791, 1224-1263):
+    rect = [p0, p1] in viewport pixels (top-left origin), brush = segment p0->p1 with `radius`."""
+    q = QueryPod()
+    q.kind, q.op, q.radius = kind, op, radius
+    q.p0[:] = [float(x) for x in p0]
+    q.p1[:] = [float(x) for x in p1]
+    return q
 
 
 class Timings(C.Structure):
@@ -266,6 +281,24 @@ def read_ply_bytes(data):
 def write_ply(path, verts):
     verts = np.ascontiguousarray(verts, dtype=PLY)
     _ck(lib().b200gs_ply_write(path.encode(), _p(verts), C.c_uint64(len(verts))))
+
+
+def hit_pos_by_closest(hits, view, proj, size, px, py):
+    """gs::query::hit_pos_by_closest (reference src/tab/scene.rs:668-672)."""
+    hits = np.ascontiguousarray(hits, dtype=HIT)
+    out = np.zeros(3, np.float32)
+    _ck(lib().b200gs_hit_pos_by_closest(_p(hits), C.c_uint64(len(hits)), _p(_f(view, 16)), _p(_f(proj, 16)), _p(_f(size, 2)),
+                                        C.c_uint32(px), C.c_uint32(py), _p(out)))
+    return out
+
+
+def hit_pos_by_alpha_range(hits, alpha_threshold, view, proj, size, px, py):
+    """gs::query::hit_pos_by_alpha_range(.., 0.05) (reference src/tab/scene.rs:659-667)."""
+    hits = np.ascontiguousarray(hits, dtype=HIT)
+    out = np.zeros(3, np.float32)
+    _ck(lib().b200gs_hit_pos_by_alpha_range(_p(hits), C.c_uint64(len(hits)), C.c_float(alpha_threshold), _p(_f(view, 16)),
+                                            _p(_f(proj, 16)), _p(_f(size, 2)), C.c_uint32(px), C.c_uint32(py), _p(out)))
+    return out
 
 
 # ------------------------------------------------------------------ pinned host memory
@@ -524,6 +557,15 @@ class Viewer:
         n = C.c_uint64(0)
         _ck(lib().b200gs_launch_count(self.h, C.byref(n)))
         return n.value
+
+    def query_hits(self, models_far_to_near, px, py, cap=4096):
+        """gs::QueryHitPod + query::download (reference src/tab/scene.rs:617-657): ordered hit list of a pixel
+        of the last rendered frame."""
+        out = np.zeros(cap, dtype=HIT)
+        n = C.c_uint64(0)
+        _ck(lib().b200gs_query_hits(self.h, self._handles(models_far_to_near), C.c_uint32(len(models_far_to_near)),
+                                    C.c_uint32(px), C.c_uint32(py), _p(out), C.c_uint64(cap), C.byref(n)))
+        return out[:min(n.value, cap)]
 
     def last_timings(self):
         t = Timings()

@@ -113,7 +113,7 @@ struct b200gs_viewer {
     uint32_t ring_head = 0, ring_pending = 0;
     uint64_t launches = 0;     // kernels launched by this viewer (b200gs_launch_count)
     uint32_t epoch = 0;
-    bool timing = false, count_evals = false;
+    bool timing = false, count_evals = false, rendered = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     b200gs_timings last = {};
     uint32_t* h_small = nullptr;  // pinned scratch
@@ -158,6 +158,7 @@ static GsFrame make_frame(const b200gs_viewer* v) {
     memcpy(f.bg, v->bg, 16);
     f.tiles_x = (v->W + GS_TILE - 1) / GS_TILE;
     f.tiles_y = (v->H + GS_TILE - 1) / GS_TILE;
+    f.query = v->query;
     const float (*P)[4] = f.P;
     f.std_proj = (P[0][1] == 0.0f && P[0][2] == 0.0f && P[0][3] == 0.0f && P[1][0] == 0.0f && P[1][2] == 0.0f &&
                   P[1][3] == 0.0f && P[2][0] == 0.0f && P[2][1] == 0.0f && P[3][0] == 0.0f && P[3][1] == 0.0f &&
@@ -645,6 +646,8 @@ extern "C" int b200gs_model_preprocess(b200gs_model* m, int use_unedited) {
     TRY(ensure_frame_buffers(v));
     CK(cudaMemsetAsync(m->ctrl, 0, MC_WORDS * 4, v->stream));
     GsFrame f = make_frame(v);
+    if (f.query.kind >= B200GS_QUERY_RECT && !m->selection)  // a selection query writes the selection bitset
+        TRY(dev_alloc(&m->selection, (m->cap + 31) / 32, true, v->stream));
     if (use_unedited) f.sel_edit = b200gs_edit_pod{0, {0.0f, 1.0f, 1.0f}, 0.0f, 0.0f, 1.0f, 1.0f};
     GsModelXf xf = make_xf(m);
     GsPreprocessArgs a;
@@ -738,6 +741,7 @@ extern "C" int b200gs_render(b200gs_viewer* v, b200gs_model* const* far_to_near,
     c.evals = v->count_evals ? (unsigned long long*)(v->vctrl + VC_EVALS) : nullptr;
     CK(gs_launch_composite(c, f, st));
     v->launches += s.passes + 2;  // tile sort passes, tile ranges, compositor
+    v->rendered = true;
     if (v->timing) CK(cudaEventRecord(v->ev[4], st));
     return B200GS_OK;
 }
@@ -969,6 +973,71 @@ extern "C" int b200gs_last_timings(b200gs_viewer* v, b200gs_timings* out) {
     memcpy(&ev, &v->h_small[VC_EVALS], 8);
     out->evals = ev;
     out->overflow = v->h_small[VC_OVERFLOW];
+    return B200GS_OK;
+}
+
+// ---------------------------------------------------------------------------- hit query (row N3)
+extern "C" int b200gs_query_hits(b200gs_viewer* v, b200gs_model* const* far_to_near, uint32_t n_models, uint32_t px,
+                                 uint32_t py, b200gs_hit* out, uint64_t cap, uint64_t* n) {
+    REQUIRE(v && n && (out || cap == 0) && (far_to_near || n_models == 0), "null argument");
+    REQUIRE(px < v->W && py < v->H, "pixel outside the viewport");
+    REQUIRE(v->rendered, "query_hits needs a rendered frame");
+    for (uint32_t i = 0; i < n_models; i++) REQUIRE(far_to_near[i] && far_to_near[i]->v == v && far_to_near[i]->sorted, "model not rendered");
+    TRY(set_device(v));
+    cudaStream_t st = v->stream;
+    const uint32_t c32 = (uint32_t)std::min<uint64_t>(cap, 1u << 20);
+    uint2* d_out = nullptr;
+    uint32_t* d_cnt = nullptr;
+    TRY(dev_alloc(&d_out, c32, false, st));
+    TRY(dev_alloc(&d_cnt, 1, true, st));
+    GsFrame f = make_frame(v);
+    GsCompositeArgs c;
+    c.tile_vals = v->tv_a; c.tile_vals_b = v->tv_b; c.tile_in_b = v->vctrl + VC_TSORT_IN_B; c.ranges = v->ranges;
+    c.splats = v->arena; c.out = nullptr; c.pitch = 0; c.evals = nullptr;
+    CK(gs_launch_query_hits(c, f, px, py, d_out, c32, d_cnt, st));
+    std::vector<uint2> raw(c32);
+    uint32_t cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, st));
+    if (c32) CK(cudaMemcpyAsync(raw.data(), d_out, (size_t)c32 * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d_out); cudaFree(d_cnt);
+    *n = cnt;
+    const uint64_t take = std::min<uint64_t>(cnt, c32);
+    // splat id -> (model, Gaussian index, depth): the arena slot is the compaction slot of its model
+    struct MInfo { uint64_t lo, vc; std::vector<uint32_t> idx, key_sorted, slot_sorted; };
+    std::vector<MInfo> info(n_models);
+    for (uint32_t k = 0; k < n_models; k++) {
+        b200gs_model* m = far_to_near[k];
+        info[k].lo = m->arena_offset;
+        TRY(visible_count(m, &info[k].vc));
+    }
+    for (uint64_t h = 0; h < take; h++) {
+        const uint32_t id = raw[h].x;
+        out[h].model = 0xffffffffu; out[h].index = 0xffffffffu; out[h].depth = 0.0f;
+        memcpy(&out[h].alpha, &raw[h].y, 4);
+        for (uint32_t k = 0; k < n_models; k++) {
+            if (id < info[k].lo || id >= info[k].lo + info[k].vc) continue;
+            MInfo& mi = info[k];
+            b200gs_model* m = far_to_near[k];
+            if (mi.idx.empty() && mi.vc) {  // lazily fetch the model's index / key tables
+                bool in_b;
+                TRY(sorted_in_b(m, &in_b));
+                mi.idx.resize(mi.vc); mi.key_sorted.resize(mi.vc); mi.slot_sorted.resize(mi.vc);
+                TRY(download_u32(m, m->idx, mi.idx.data(), mi.vc));
+                TRY(download_u32(m, in_b ? m->keys_b : m->keys_a, mi.key_sorted.data(), mi.vc));
+                TRY(download_u32(m, in_b ? m->vals_b : m->vals_a, mi.slot_sorted.data(), mi.vc));
+                std::vector<uint32_t> key_by_slot(mi.vc);
+                for (uint64_t r = 0; r < mi.vc; r++)
+                    if (mi.slot_sorted[r] < mi.vc) key_by_slot[mi.slot_sorted[r]] = mi.key_sorted[r];
+                mi.key_sorted.swap(key_by_slot);  // now indexed by slot
+            }
+            const uint32_t slot = id - (uint32_t)mi.lo;
+            out[h].model = k;
+            out[h].index = mi.idx[slot];
+            memcpy(&out[h].depth, &mi.key_sorted[slot], 4);
+            break;
+        }
+    }
     return B200GS_OK;
 }
 

@@ -40,6 +40,7 @@ struct GsFrame {
     float bg[4];
     uint32_t tiles_x, tiles_y;
     uint32_t std_proj;  // 1: only P00,P11,P22,P23,P32 are non-zero (glam perspective_rh): kernels skip the zero terms
+    b200gs_query_pod query;  // selection query tested in the preprocess kernel (rect / brush)
 };
 
 // Per-model uniforms (ModelTransformPod, scene.rs:796-802)
@@ -66,7 +67,7 @@ enum {
 // ------------------------------------------------------------- launch API (csrc/*.cu)
 struct GsPreprocessArgs {
     const uint8_t* recs; uint32_t n; uint32_t sh, cov;
-    const uint32_t* mask; const uint32_t* selection; const b200gs_edit_pod* edits;
+    const uint32_t* mask; uint32_t* selection; const b200gs_edit_pod* edits;  // selection is rewritten by a rect/brush query
     uint32_t* ctrl;      // GS_CTRL_WORDS, zeroed before launch
     uint64_t* lookback;  // one status word per 256-Gaussian chunk (epoch-tagged, never cleared)
     uint32_t epoch;
@@ -132,6 +133,8 @@ struct GsCompositeArgs {
     unsigned long long* evals;      // optional work counter (may be null)
 };
 cudaError_t gs_launch_composite(const GsCompositeArgs& a, const GsFrame& f, cudaStream_t st);
+cudaError_t gs_launch_query_hits(const GsCompositeArgs& a, const GsFrame& f, uint32_t px, uint32_t py, uint2* out,
+                                 uint32_t cap, uint32_t* count, cudaStream_t st);
 
 // Mask evaluation / postprocess (row N2)
 cudaError_t gs_launch_eval_mask(const uint8_t* recs, uint32_t n, uint32_t record_bytes, const GsModelXf& m,

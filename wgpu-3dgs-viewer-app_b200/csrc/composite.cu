@@ -160,7 +160,58 @@ __global__ void __launch_bounds__(kThreads) k_composite(const uint32_t* __restri
     }
 }
 
+// Hit query (row N3): the ordered list of splats contributing to ONE pixel — a single-warp walk of
+// the pixel's tile list with the compositor's own alpha rule.  Replaces the query_results buffer
+// the reference renderer appends to (src/tab/scene.rs:635-657).
+__global__ void __launch_bounds__(32) k_query_hits(const uint32_t* __restrict__ tile_vals_a,
+                                                   const uint32_t* __restrict__ tile_vals_b, const uint32_t* tile_in_b,
+                                                   const uint32_t* __restrict__ ranges,
+                                                   const b200gs_splat* __restrict__ splats, uint32_t W, uint32_t H,
+                                                   uint32_t tiles_x, uint32_t n_tiles, uint32_t px, uint32_t py,
+                                                   uint32_t flat, uint2* out, uint32_t cap, uint32_t* count) {
+    const uint32_t* __restrict__ tile_vals = *tile_in_b ? tile_vals_b : tile_vals_a;
+    const uint32_t tile = (py / GS_TILE) * tiles_x + px / GS_TILE;
+    const uint32_t start = ranges[tile], end = ranges[n_tiles + tile];
+    const int lane = threadIdx.x;
+    const float fpx = (float)px, fpy = (float)py, Wf = (float)W, Hf = (float)H;
+    uint32_t n_out = 0;
+    for (uint32_t base = start; base < end; base += 32) {
+        const uint32_t e = base + lane;
+        bool ok = false;
+        uint32_t id = 0;
+        float al = 0.0f;
+        if (e < end) {
+            id = tile_vals[e];
+            const uint4* sp = reinterpret_cast<const uint4*>(splats + id);
+            const uint4 q0 = __ldg(sp), q1 = __ldg(sp + 1);
+            const float mx = __uint_as_float(q0.x), my = __uint_as_float(q0.y);
+            const float r = (float)(q0.z & 0xffffu);
+            const float op = __half2float(__ushort_as_half((unsigned short)(q0.z >> 16)));
+            float fx0 = ceilf(mx - r), fx1 = floorf(mx + r), fy0 = ceilf(my - r), fy1 = floorf(my + r);
+            fx0 = fmaxf(fx0, 0.0f); fy0 = fmaxf(fy0, 0.0f); fx1 = fminf(fx1, Wf - 1.0f); fy1 = fminf(fy1, Hf - 1.0f);
+            const float dx = fpx - mx, dy = fpy - my;
+            const float power = -0.5f * (__uint_as_float(q1.x) * dx * dx + __uint_as_float(q1.z) * dy * dy) - __uint_as_float(q1.y) * dx * dy;
+            if (flat) al = power >= -0.5f * GS_FLAT_D2 ? fminf(GS_ALPHA_MAX, op) : 0.0f;
+            else al = fminf(GS_ALPHA_MAX, op * __expf(power));
+            ok = fpx >= fx0 && fpx <= fx1 && fpy >= fy0 && fpy <= fy1 && power <= 0.0f && al >= GS_ALPHA_MIN;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+        const uint32_t o = n_out + __popc(bal & ((1u << lane) - 1u));
+        if (ok && o < cap) out[o] = make_uint2(id, __float_as_uint(al));
+        n_out += __popc(bal);
+    }
+    if (lane == 0) *count = n_out;
+}
+
 }  // namespace
+
+cudaError_t gs_launch_query_hits(const GsCompositeArgs& a, const GsFrame& f, uint32_t px, uint32_t py, uint2* out,
+                                 uint32_t cap, uint32_t* count, cudaStream_t st) {
+    k_query_hits<<<1, 32, 0, st>>>(a.tile_vals, a.tile_vals_b, a.tile_in_b, a.ranges, a.splats, (uint32_t)f.W, (uint32_t)f.H,
+                                   f.tiles_x, f.tiles_x * f.tiles_y, px, py, f.display_mode != B200GS_DISPLAY_SPLAT ? 1u : 0u,
+                                   out, cap, count);
+    return cudaGetLastError();
+}
 
 cudaError_t gs_launch_composite(const GsCompositeArgs& a, const GsFrame& f, cudaStream_t st) {
     const uint32_t n_tiles = f.tiles_x * f.tiles_y;

@@ -195,10 +195,24 @@ __device__ __forceinline__ bool project_and_cull(const uint32_t* w, const GsFram
     return nz > 0.0f && nz < 1.0f && fabsf(nx) <= GS_CULL_XY && fabsf(ny) <= GS_CULL_XY;
 }
 
+// Selection query (gs::QueryToolset rect / brush in immediate mode, reference src/tab/scene.rs:758-791,
+// 1224-1263): does the splat centre, in viewport pixels (top-left origin), fall inside the shape?
+// EXACT class: same float operations as the oracle.
+__device__ __forceinline__ bool query_hit(const b200gs_query_pod& q, float sx, float sy) {
+    if (q.kind == B200GS_QUERY_RECT) return sx >= q.p0[0] && sx <= q.p1[0] && sy >= q.p0[1] && sy <= q.p1[1];
+    const float vx = q.p1[0] - q.p0[0], vy = q.p1[1] - q.p0[1];
+    const float wx = sx - q.p0[0], wy = sy - q.p0[1];
+    const float vv = vx * vx + vy * vy;
+    float t = vv > 0.0f ? (wx * vx + wy * vy) / vv : 0.0f;
+    t = fminf(1.0f, fmaxf(0.0f, t));
+    const float dx = wx - t * vx, dy = wy - t * vy;
+    return dx * dx + dy * dy <= q.radius * q.radius;
+}
+
 // mask / hidden-edit / selection tests that precede the frustum cull (reference preprocess bindings,
 // src/tab/scene.rs:1835-1852; flags src/app.rs:1548-1551)
 __device__ __forceinline__ bool pre_tests(uint32_t i, uint32_t n, const uint32_t* __restrict__ mask,
-                                          const uint32_t* __restrict__ selection,
+                                          const uint32_t* selection,
                                           const b200gs_edit_pod* __restrict__ edits, const GsFrame& f, bool& selected,
                                           b200gs_edit_pod& ed) {
     bool vis = i < n;
@@ -220,8 +234,7 @@ __device__ __forceinline__ bool pre_tests(uint32_t i, uint32_t n, const uint32_t
 
 template <int SH, int COV>
 __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restrict__ recs, uint32_t n,
-                                                         const uint32_t* __restrict__ mask,
-                                                         const uint32_t* __restrict__ selection,
+                                                         const uint32_t* __restrict__ mask, uint32_t* selection,
                                                          const b200gs_edit_pod* __restrict__ edits,
                                                          const __grid_constant__ GsFrame f,
                                                          const __grid_constant__ GsModelXf m, uint32_t* ctrl,
@@ -345,6 +358,21 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
             float pw[3], pv[3], nx = 0.0f, ny = 0.0f, nz = 0.0f;
             if (vis) vis = project_and_cull(w, f, m, pw, pv, nx, ny, nz);
             const uint32_t ballot = __ballot_sync(0xffffffffu, vis);
+
+            // ---------------- selection query: rewrites this warp's selection word (32 Gaussians) -------
+            if (f.query.kind >= B200GS_QUERY_RECT && selection) {
+                const float sx = ((nx + 1.0f) * f.W - 1.0f) * 0.5f + 0.5f, sy = ((1.0f - ny) * f.H - 1.0f) * 0.5f + 0.5f;
+                const bool hit = vis && query_hit(f.query, sx, sy);
+                const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+                if (i - lane < n) {  // warp-uniform: the word exists
+                    uint32_t word = lane == 0 ? selection[i >> 5] : 0u;
+                    word = __shfl_sync(0xffffffffu, word, 0);
+                    const uint32_t neww = f.query.op == B200GS_SELECT_SET ? hits
+                                          : (f.query.op == B200GS_SELECT_ADD ? (word | hits) : (word & ~hits));
+                    if (lane == 0 && neww != word) selection[i >> 5] = neww;
+                    selected = (neww >> lane) & 1u;   // shown (highlight / edit) with the new selection
+                }
+            }
 
             // ---------------- phase 2: projected splat for the visible ones ----------------
             uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);

@@ -279,6 +279,42 @@ extern "C" void b200gs_quat_from_euler_zyx_deg(const float rot_deg[3], float qua
     quat_xyzw[3] = cz * cy * cx + sz * sy * sx;
 }
 
+// ------------------------------------------------------------------ hit positions (row N3)
+// gs::query::hit_pos_by_closest / hit_pos_by_alpha_range (src/tab/scene.rs:659-676): unproject the
+// pixel centre at the chosen depth.  The crate's exact selection rule is not visible from the app;
+// ours: closest = first hit; alpha_range = alpha-weighted mean ndc depth of the hits whose alpha is
+// >= threshold.
+static int unproject_pixel(const float view[16], const float proj[16], const float size[2], uint32_t px, uint32_t py,
+                           float ndc_z, float out[3]) {
+    // ndc of the pixel centre (row 0 = top)
+    const double nx = (2.0 * ((double)px + 0.5)) / size[0] - 1.0, ny = 1.0 - (2.0 * ((double)py + 0.5)) / size[1];
+    // perspective_rh-shaped projection: clip = (P00 x, P11 y, P22 z + P23, P32 z); solve for view-space point
+    const double P00 = proj[0], P11 = proj[5], P22 = proj[10], P23 = proj[14], P32 = proj[11];
+    const double den = (double)ndc_z * P32 - P22;
+    if (den == 0.0 || P00 == 0.0 || P11 == 0.0) return B200GS_ERR_INVALID;
+    const double zv = P23 / den, w = P32 * zv;
+    const double xv = nx * w / P00, yv = ny * w / P11;
+    // world = R^T (p_view - t) for a rigid view matrix (column-major)
+    const double px_ = xv - view[12], py_ = yv - view[13], pz_ = zv - view[14];
+    for (int a = 0; a < 3; a++) out[a] = (float)(view[4 * a + 0] * px_ + view[4 * a + 1] * py_ + view[4 * a + 2] * pz_);
+    return B200GS_OK;
+}
+extern "C" int b200gs_hit_pos_by_closest(const b200gs_hit* hits, uint64_t n, const float view[16], const float proj[16],
+                                         const float size[2], uint32_t px, uint32_t py, float pos_out[3]) {
+    if (!hits || !n || !view || !proj || !size || !pos_out) { gs_set_error("hit_pos_by_closest: no hit"); return B200GS_ERR_INVALID; }
+    return unproject_pixel(view, proj, size, px, py, hits[0].depth, pos_out);
+}
+extern "C" int b200gs_hit_pos_by_alpha_range(const b200gs_hit* hits, uint64_t n, float alpha_threshold, const float view[16],
+                                             const float proj[16], const float size[2], uint32_t px, uint32_t py,
+                                             float pos_out[3]) {
+    if (!hits || !view || !proj || !size || !pos_out) { gs_set_error("hit_pos_by_alpha_range: null argument"); return B200GS_ERR_INVALID; }
+    double wsum = 0.0, zsum = 0.0;
+    for (uint64_t i = 0; i < n; i++)
+        if (hits[i].alpha >= alpha_threshold) { wsum += hits[i].alpha; zsum += (double)hits[i].alpha * hits[i].depth; }
+    if (wsum == 0.0) { gs_set_error("hit_pos_by_alpha_range: no hit above the threshold"); return B200GS_ERR_INVALID; }
+    return unproject_pixel(view, proj, size, px, py, (float)(zsum / wsum), pos_out);
+}
+
 // ------------------------------------------------------------------ synthetic scene (§8d)
 // Counter-based: value = f(seed, Gaussian index, stream), so any sub-range can be generated
 // independently (and on any number of threads) with identical bytes.
