@@ -158,6 +158,7 @@ typedef struct b200gs_timings {
     uint64_t visible;      /* sum over models of V                                  */
     uint64_t tile_entries; /* duplicated (tile, splat) entries binned               */
     uint64_t evals;        /* splat-pixel evaluations (only when counting is enabled) */
+    uint64_t staged_entries; /* tile entries the compositor read before its tiles finished (counting only) */
     uint32_t overflow;     /* 1 = tile-entry capacity was exceeded (entries dropped)  */
     uint32_t _pad;
 } b200gs_timings;
@@ -193,6 +194,11 @@ B200GS_API int b200gs_set_selection_highlight(b200gs_viewer* v, const float rgba
 B200GS_API int b200gs_set_query(b200gs_viewer* v, const b200gs_query_pod* pod);
 /* headless clear colour (premultiplied RGBA in 0..1); default transparent black */
 B200GS_API int b200gs_set_background(b200gs_viewer* v, const float rgba[4]);
+/* depth slabs: the frame is binned + composited in n+1 slabs of depth ranks split at these
+ * increasing fractions of the nearest model's visible count; tiles finished by a nearer slab take no
+ * entries from farther ones.  Default n = 0 (single slab: on the benchmark scene too few tiles finish
+ * early for the extra passes to pay off).  The image does not depend on the setting. */
+B200GS_API int b200gs_set_depth_slabs(b200gs_viewer* v, const float* fractions, uint32_t n);
 /* capacity of the (tile, splat) entry list per frame; default 8 x total Gaussian capacity */
 B200GS_API int b200gs_set_tile_entry_capacity(b200gs_viewer* v, uint64_t entries);
 /* record per-stage CUDA-event times (and optionally count splat evaluations) for

@@ -550,3 +550,30 @@ def test_hit_query_list_and_positions(G, O):
             for h in got:
                 if int(h["index"]) in d:
                     assert abs(h["alpha"] - d[int(h["index"])][1]) < 2e-3 and h["depth"] == np.float32(d[int(h["index"])][2])
+
+
+def test_depth_slabs_do_not_change_the_image(G, O):
+    """b200gs_set_depth_slabs: binning + compositing in depth slabs with finished-tile skipping is an
+    execution strategy only — same bytes as the single-slab frame, for one and for several models."""
+    W, H, n = 640, 360, 120_000
+    cam = G.OrbitCamera.orbit(3.0, 10.0, 40.0)
+    with G.Viewer(W, H) as v:
+        ms = []
+        for k, seed in enumerate((0xB2000082, 0xB2000083)):
+            m = v.add_model("m%d" % k, n)
+            m.upload_packed(0, G.pack_gaussians(2, 1, G.gaussian_from_ply(G.synth_scene(seed, n))))
+            m.set_transform((0.5 * k, 0, 0), G.quat_from_euler_zyx_deg([0, 20 * k, 0]), (1, 1, 1))
+            ms.append(m)
+        v.update_camera(cam)
+        v.enable_timings(True, True)
+        for models in ([ms[0]], ms):
+            v.set_depth_slabs([])
+            ref = v.render_frame_host(models).copy()
+            e0 = v.last_timings().tile_entries
+            for fr in ([0.125], [0.05, 0.3], [0.02, 0.1, 0.5]):
+                v.set_depth_slabs(fr)
+                img = v.render_frame_host(models).copy()
+                assert np.array_equal(img, ref), fr
+                assert v.last_timings().tile_entries <= e0
+        with pytest.raises(G.GsError):
+            v.set_depth_slabs([0.5, 0.25])

@@ -74,7 +74,8 @@ def query_pod(kind=QUERY_NONE, op=SELECT_SET, p0=(0, 0), p1=(0, 0), radius=0.0):
 class Timings(C.Structure):
     _fields_ = [("preprocess_ms", C.c_float), ("sort_ms", C.c_float), ("bin_ms", C.c_float),
                 ("composite_ms", C.c_float), ("total_ms", C.c_float), ("visible", C.c_uint64),
-                ("tile_entries", C.c_uint64), ("evals", C.c_uint64), ("overflow", C.c_uint32), ("_pad", C.c_uint32)]
+                ("tile_entries", C.c_uint64), ("evals", C.c_uint64), ("staged_entries", C.c_uint64),
+                ("overflow", C.c_uint32), ("_pad", C.c_uint32)]
 
 
 class GsError(RuntimeError):
@@ -473,6 +474,10 @@ class Viewer:
 
     def set_background(self, rgba):
         _ck(lib().b200gs_set_background(self.h, _p(_f(rgba, 4))))
+
+    def set_depth_slabs(self, fractions):
+        fr = np.ascontiguousarray(fractions, dtype=np.float32)
+        _ck(lib().b200gs_set_depth_slabs(self.h, _p(fr) if len(fr) else None, C.c_uint32(len(fr))))
 
     def set_tile_entry_capacity(self, entries):
         _ck(lib().b200gs_set_tile_entry_capacity(self.h, C.c_uint64(entries)))

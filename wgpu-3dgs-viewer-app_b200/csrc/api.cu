@@ -105,6 +105,12 @@ struct b200gs_viewer {
     uint64_t cand_off_words = 0, block_cap = 0;
     uint32_t* ranges = nullptr;
     uint32_t ranges_tiles = 0;
+    uint8_t* tile_done = nullptr;          // per tile: finished by a nearer depth slab
+    float4* pix_state = nullptr;           // per pixel (Cr, Cg, Cb, T) between depth slabs
+    size_t pix_state_px = 0;
+    unsigned long long* stats = nullptr;   // [0] evals, [1] staged entries, [2] tile entries (per frame)
+    std::vector<uint32_t> slab_q;          // depth-slab boundaries as 16.16 fractions of V (default: none = one slab)
+    cudaEvent_t ev_slab[4][3] = {};        // per slab: start, after binning, after compositing
     uint32_t* vctrl = nullptr;
     uint8_t* image = nullptr;  // internal RGBA8 targets for render_frame_host (2 slots, image + image_bytes)
     size_t image_bytes = 0;
@@ -114,6 +120,7 @@ struct b200gs_viewer {
     uint64_t launches = 0;     // kernels launched by this viewer (b200gs_launch_count)
     uint32_t epoch = 0;
     bool timing = false, count_evals = false, rendered = false;
+    uint32_t last_slabs = 1;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     b200gs_timings last = {};
     uint32_t* h_small = nullptr;  // pinned scratch
@@ -207,7 +214,15 @@ static int ensure_frame_buffers(b200gs_viewer* v) {
         CK(cudaStreamSynchronize(v->stream));
         if (v->ranges) CK(cudaFree(v->ranges));
         TRY(dev_alloc(&v->ranges, (size_t)n_tiles * 2, true, v->stream));
+        if (v->tile_done) CK(cudaFree(v->tile_done));
+        TRY(dev_alloc(&v->tile_done, (size_t)n_tiles, true, v->stream));
         v->ranges_tiles = n_tiles;
+    }
+    if (v->pix_state_px < (size_t)v->W * v->H) {
+        CK(cudaStreamSynchronize(v->stream));
+        if (v->pix_state) CK(cudaFree(v->pix_state));
+        TRY(dev_alloc(&v->pix_state, (size_t)v->W * v->H, false, v->stream));
+        v->pix_state_px = (size_t)v->W * v->H;
     }
     const size_t img = (size_t)v->W * v->H * 4;
     if (v->image_bytes < img) {
@@ -309,6 +324,10 @@ extern "C" int b200gs_viewer_create(int device, uint32_t sh, uint32_t cov3d, uin
     if (e == cudaSuccess) e = cudaMalloc((void**)&v->vctrl, VC_WORDS * 4);
     if (e == cudaSuccess) e = cudaMemsetAsync(v->vctrl, 0, VC_WORDS * 4, v->stream);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&v->h_small, 4096);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&v->stats, 64);
+    if (e == cudaSuccess) e = cudaMemsetAsync(v->stats, 0, 64, v->stream);
+    for (int k = 0; k < 4 && e == cudaSuccess; k++)
+        for (int j = 0; j < 3 && e == cudaSuccess; j++) e = cudaEventCreate(&v->ev_slab[k][j]);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) {
         e = cudaEventCreateWithFlags(&v->ev_rendered[i], cudaEventDisableTiming);
@@ -338,12 +357,15 @@ extern "C" int b200gs_viewer_destroy(b200gs_viewer* v) {
     if (v->stream) cudaStreamSynchronize(v->stream);
     for (auto* m : v->models) free_model(m);
     void* ps[] = {v->arena, v->tk_a, v->tv_a, v->tk_b, v->tv_b, v->lb_bin, v->lb_tsort, v->lb_emit, v->cand_off, v->block_rank,
-                  v->ranges, v->vctrl, v->image};
+                  v->ranges, v->vctrl, v->image, v->tile_done, v->pix_state, v->stats};
     for (void* p : ps)
         if (p) cudaFree(p);
     if (v->h_small) cudaFreeHost(v->h_small);
     for (auto& e : v->ev)
         if (e) cudaEventDestroy(e);
+    for (auto& row : v->ev_slab)
+        for (auto& e : row)
+            if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) {
         if (v->ev_rendered[i]) cudaEventDestroy(v->ev_rendered[i]);
         if (v->ev_copied[i]) cudaEventDestroy(v->ev_copied[i]);
@@ -401,6 +423,19 @@ extern "C" int b200gs_set_query(b200gs_viewer* v, const b200gs_query_pod* pod) {
 extern "C" int b200gs_set_background(b200gs_viewer* v, const float rgba[4]) {
     REQUIRE(v && rgba, "null argument");
     memcpy(v->bg, rgba, 16);
+    return B200GS_OK;
+}
+extern "C" int b200gs_set_depth_slabs(b200gs_viewer* v, const float* fractions, uint32_t n) {
+    REQUIRE(v && (fractions || n == 0), "null argument");
+    REQUIRE(n <= 3, "at most 3 slab boundaries (4 slabs)");
+    std::vector<uint32_t> q;
+    for (uint32_t i = 0; i < n; i++) {
+        REQUIRE(fractions[i] > 0.0f && fractions[i] < 1.0f, "fractions must lie in (0, 1)");
+        const uint32_t x = (uint32_t)(fractions[i] * 65536.0f);
+        REQUIRE(x > (q.empty() ? 0u : q.back()), "fractions must increase");
+        q.push_back(x);
+    }
+    v->slab_q = q;
     return B200GS_OK;
 }
 extern "C" int b200gs_set_tile_entry_capacity(b200gs_viewer* v, uint64_t entries) {
@@ -684,6 +719,86 @@ extern "C" int b200gs_model_sort(b200gs_model* m) {
     return B200GS_OK;
 }
 
+// One frame = one or more DEPTH SLABS.  Slab 0 holds the nearest ranks of the nearest model; each
+// slab is binned, tile-sorted and composited on its own, and tiles whose pixels all reached
+// T < eps are marked done so that later (farther) slabs emit no entries for them — most of a tile
+// list is occluded, so most of the binning work disappears.  Pixel state is carried between slabs,
+// the arithmetic per pixel is unchanged (same splats, same order): the image is bit-identical to
+// the single-slab one.
+static int render_slabs(b200gs_viewer* v, b200gs_model* const* far_to_near, uint32_t n_models, void* rgba8_out,
+                        size_t pitch, const std::vector<uint32_t>& slab_q) {
+    cudaStream_t st = v->stream;
+    GsFrame f = make_frame(v);
+    const uint32_t n_tiles = f.tiles_x * f.tiles_y;
+    std::vector<uint32_t> bounds = {0};
+    if (n_models > 0)
+        for (uint32_t q : slab_q)
+            if (q > bounds.back() && q < 65536 && bounds.size() < 4) bounds.push_back(q);
+    bounds.push_back(65536);
+    const uint32_t n_slabs = (uint32_t)bounds.size() - 1;
+    CK(cudaMemsetAsync(v->stats, 0, 64, st));
+    if (n_slabs > 1) CK(cudaMemsetAsync(v->tile_done, 0, n_tiles, st));
+    v->last_slabs = n_slabs;
+    for (uint32_t sl = 0; sl < n_slabs; sl++) {
+        const bool last = sl + 1 == n_slabs;
+        if (v->timing) CK(cudaEventRecord(v->ev_slab[sl][0], st));
+        CK(cudaMemsetAsync(v->vctrl, 0, VC_WORDS * 4, st));
+        // nearest model first: its splats come first in every tile's front-to-back list; the
+        // models behind it are expanded whole in the last slab
+        const uint32_t n_seg = last ? n_models : std::min<uint32_t>(n_models, 1);
+        for (uint32_t k = 0; k < n_seg; k++) {
+            b200gs_model* m = far_to_near[n_models - 1 - k];
+            GsBinArgs b;
+            b.sorted_slot = m->vals_a;
+            b.sorted_slot_b = m->vals_b;
+            b.sorted_in_b = m->ctrl + MC_CTRL + GS_CTRL_SORT_IN_B;
+            b.splats = v->arena + m->arena_offset;
+            b.d_v = m->ctrl + MC_CTRL + GS_CTRL_VISIBLE;
+            b.v_max = (uint32_t)m->cap;
+            b.splat_base = (uint32_t)m->arena_offset;
+            b.lookback = v->lb_bin + (size_t)k * v->lb_bin_words;
+            b.lookback_emit = v->lb_emit;   // reused across launches: every launch has its own epoch
+            b.epoch = ++v->epoch;
+            b.ticket = v->vctrl + VC_BIN_TICKET + 2 * k;
+            b.cand_off = v->cand_off;       // models are expanded one after the other on the stream
+            b.block_rank = v->block_rank;
+            b.block_cap = (uint32_t)v->block_cap;
+            b.cand_total = v->vctrl + VC_CAND_TOTAL + k;
+            b.entry_base_in = v->vctrl + VC_ENTRY_TOTAL + k;
+            b.entry_total_out = v->vctrl + VC_ENTRY_TOTAL + k + 1;
+            b.overflow = (uint32_t*)(v->stats + 3);
+            b.tile_keys = v->tk_a; b.tile_vals = v->tv_a; b.capacity = (uint32_t)v->entry_cap;
+            b.tile_hist = v->vctrl + VC_TSORT_HIST;
+            b.q_lo = k == 0 ? bounds[sl] : 0;
+            b.q_hi = k == 0 ? bounds[sl + 1] : 65536;
+            b.tile_done = sl > 0 ? v->tile_done : nullptr;
+            CK(gs_launch_bin(b, f, v->num_sms, st));
+            v->launches += 2;
+        }
+        GsSortArgs s;
+        s.keys_a = v->tk_a; s.vals_a = v->tv_a; s.keys_b = v->tk_b; s.vals_b = v->tv_b;
+        s.d_n = v->vctrl + VC_ENTRY_TOTAL + n_seg; s.n_max = (uint32_t)v->entry_cap;
+        s.hist = v->vctrl + VC_TSORT_HIST; s.lookback = v->lb_tsort; s.epoch = ++v->epoch;
+        s.tickets = v->vctrl + VC_TSORT_TICKET; s.passes = 2; s.hist_prefilled = true; s.vals_identity = false;
+        s.result_in_b = v->vctrl + VC_TSORT_IN_B;
+        CK(gs_launch_sort(s, v->num_sms, st));
+        CK(gs_launch_tile_ranges(v->tk_a, v->tk_b, s.result_in_b, s.d_n, (uint32_t)v->entry_cap, v->ranges, n_tiles,
+                                 v->stats + 2, v->num_sms, st));
+        if (v->timing) CK(cudaEventRecord(v->ev_slab[sl][1], st));
+        GsCompositeArgs c;
+        c.tile_vals = v->tv_a; c.tile_vals_b = v->tv_b; c.tile_in_b = s.result_in_b; c.ranges = v->ranges; c.splats = v->arena;
+        c.out = (uint8_t*)rgba8_out; c.pitch = pitch;
+        c.evals = v->count_evals ? v->stats : nullptr;
+        c.state = v->pix_state; c.tile_done = v->tile_done; c.resume = sl > 0; c.last = last;
+        CK(gs_launch_composite(c, f, st));
+        if (v->timing) CK(cudaEventRecord(v->ev_slab[sl][2], st));
+        v->launches += s.passes + 2;  // tile sort passes, tile ranges, compositor
+    }
+    if (v->timing) CK(cudaEventRecord(v->ev[4], st));
+    v->rendered = true;
+    return B200GS_OK;
+}
+
 extern "C" int b200gs_render(b200gs_viewer* v, b200gs_model* const* far_to_near, uint32_t n_models, void* rgba8_out, size_t pitch) {
     REQUIRE(v && rgba8_out && (far_to_near || n_models == 0), "null argument");
     REQUIRE(n_models <= kMaxModelsPerFrame, "too many models");
@@ -695,55 +810,7 @@ extern "C" int b200gs_render(b200gs_viewer* v, b200gs_model* const* far_to_near,
     TRY(set_device(v));
     TRY(ensure_frame_buffers(v));
     for (uint32_t i = 0; i < n_models; i++) REQUIRE(far_to_near[i]->sorted, "model layout changed; preprocess + sort again");
-    cudaStream_t st = v->stream;
-    GsFrame f = make_frame(v);
-    const uint32_t n_tiles = f.tiles_x * f.tiles_y;
-    CK(cudaMemsetAsync(v->vctrl, 0, VC_WORDS * 4, st));
-    // nearest model first: its splats come first in every tile's front-to-back list
-    for (uint32_t k = 0; k < n_models; k++) {
-        b200gs_model* m = far_to_near[n_models - 1 - k];
-        GsBinArgs b;
-        b.sorted_slot = m->vals_a;
-        b.sorted_slot_b = m->vals_b;
-        b.sorted_in_b = m->ctrl + MC_CTRL + GS_CTRL_SORT_IN_B;
-        b.splats = v->arena + m->arena_offset;
-        b.d_v = m->ctrl + MC_CTRL + GS_CTRL_VISIBLE;
-        b.v_max = (uint32_t)m->cap;
-        b.splat_base = (uint32_t)m->arena_offset;
-        b.lookback = v->lb_bin + (size_t)k * v->lb_bin_words;
-        b.lookback_emit = v->lb_emit;   // reused across models: every launch has its own epoch
-        b.epoch = ++v->epoch;
-        b.ticket = v->vctrl + VC_BIN_TICKET + 2 * k;
-        b.cand_off = v->cand_off;       // models are expanded one after the other on the stream
-        b.block_rank = v->block_rank;
-        b.block_cap = (uint32_t)v->block_cap;
-        b.cand_total = v->vctrl + VC_CAND_TOTAL + k;
-        b.entry_base_in = v->vctrl + VC_ENTRY_TOTAL + k;
-        b.entry_total_out = v->vctrl + VC_ENTRY_TOTAL + k + 1;
-        b.overflow = v->vctrl + VC_OVERFLOW;
-        b.tile_keys = v->tk_a; b.tile_vals = v->tv_a; b.capacity = (uint32_t)v->entry_cap;
-        b.tile_hist = v->vctrl + VC_TSORT_HIST;
-        CK(gs_launch_bin(b, f, v->num_sms, st));
-        v->launches += 2;
-    }
-    GsSortArgs s;
-    s.keys_a = v->tk_a; s.vals_a = v->tv_a; s.keys_b = v->tk_b; s.vals_b = v->tv_b;
-    s.d_n = v->vctrl + VC_ENTRY_TOTAL + n_models; s.n_max = (uint32_t)v->entry_cap;
-    s.hist = v->vctrl + VC_TSORT_HIST; s.lookback = v->lb_tsort; s.epoch = ++v->epoch;
-    s.tickets = v->vctrl + VC_TSORT_TICKET; s.passes = 2; s.hist_prefilled = true; s.vals_identity = false;
-    s.result_in_b = v->vctrl + VC_TSORT_IN_B;
-    CK(gs_launch_sort(s, v->num_sms, st));
-    CK(gs_launch_tile_ranges(v->tk_a, v->tk_b, s.result_in_b, s.d_n, (uint32_t)v->entry_cap, v->ranges, n_tiles, v->num_sms, st));
-    if (v->timing) CK(cudaEventRecord(v->ev[3], st));
-    GsCompositeArgs c;
-    c.tile_vals = v->tv_a; c.tile_vals_b = v->tv_b; c.tile_in_b = s.result_in_b; c.ranges = v->ranges; c.splats = v->arena;
-    c.out = (uint8_t*)rgba8_out; c.pitch = pitch;
-    c.evals = v->count_evals ? (unsigned long long*)(v->vctrl + VC_EVALS) : nullptr;
-    CK(gs_launch_composite(c, f, st));
-    v->launches += s.passes + 2;  // tile sort passes, tile ranges, compositor
-    v->rendered = true;
-    if (v->timing) CK(cudaEventRecord(v->ev[4], st));
-    return B200GS_OK;
+    return render_slabs(v, far_to_near, n_models, rgba8_out, pitch, v->slab_q);
 }
 
 extern "C" int b200gs_render_frame(b200gs_viewer* v, b200gs_model* const* far_to_near, uint32_t n_models, void* rgba8_out, size_t pitch) {
@@ -952,8 +1019,10 @@ extern "C" int b200gs_last_timings(b200gs_viewer* v, b200gs_timings* out) {
         float t;
         if (cudaEventElapsedTime(&t, v->ev[0], v->ev[1]) == cudaSuccess) out->preprocess_ms = t;
         if (cudaEventElapsedTime(&t, v->ev[1], v->ev[2]) == cudaSuccess) out->sort_ms = t;
-        if (cudaEventElapsedTime(&t, v->ev[2], v->ev[3]) == cudaSuccess) out->bin_ms = t;
-        if (cudaEventElapsedTime(&t, v->ev[3], v->ev[4]) == cudaSuccess) out->composite_ms = t;
+        for (uint32_t sl = 0; sl < v->last_slabs && sl < 4; sl++) {
+            if (cudaEventElapsedTime(&t, v->ev_slab[sl][0], v->ev_slab[sl][1]) == cudaSuccess) out->bin_ms += t;
+            if (cudaEventElapsedTime(&t, v->ev_slab[sl][1], v->ev_slab[sl][2]) == cudaSuccess) out->composite_ms += t;
+        }
         if (cudaEventElapsedTime(&t, v->ev[0], v->ev[4]) == cudaSuccess) out->total_ms = t;
         (void)cudaGetLastError();
     }
@@ -964,15 +1033,14 @@ extern "C" int b200gs_last_timings(b200gs_viewer* v, b200gs_timings* out) {
         vis += c;
     }
     out->visible = vis;
-    CK(cudaMemcpyAsync(v->h_small, v->vctrl, VC_WORDS * 4, cudaMemcpyDeviceToHost, v->stream));
+    CK(cudaMemcpyAsync(v->h_small, v->stats, 64, cudaMemcpyDeviceToHost, v->stream));
     CK(cudaStreamSynchronize(v->stream));
-    uint32_t last = 0;
-    for (uint32_t k = 0; k <= kMaxModelsPerFrame; k++) last = std::max(last, v->h_small[VC_ENTRY_TOTAL + k]);
-    out->tile_entries = last;
-    uint64_t ev;
-    memcpy(&ev, &v->h_small[VC_EVALS], 8);
-    out->evals = ev;
-    out->overflow = v->h_small[VC_OVERFLOW];
+    uint64_t st64[4];
+    memcpy(st64, v->h_small, 32);
+    out->evals = st64[0];
+    out->staged_entries = st64[1];
+    out->tile_entries = st64[2];
+    out->overflow = (uint32_t)st64[3];
     return B200GS_OK;
 }
 
@@ -985,6 +1053,9 @@ extern "C" int b200gs_query_hits(b200gs_viewer* v, b200gs_model* const* far_to_n
     for (uint32_t i = 0; i < n_models; i++) REQUIRE(far_to_near[i] && far_to_near[i]->v == v && far_to_near[i]->sorted, "model not rendered");
     TRY(set_device(v));
     cudaStream_t st = v->stream;
+    // the hit list needs the complete per-tile lists: re-bin the frame as a single slab (event-driven call)
+    TRY(ensure_frame_buffers(v));
+    TRY(render_slabs(v, far_to_near, n_models, v->image + v->image_bytes, (size_t)v->W * 4, std::vector<uint32_t>()));
     const uint32_t c32 = (uint32_t)std::min<uint64_t>(cap, 1u << 20);
     uint2* d_out = nullptr;
     uint32_t* d_cnt = nullptr;

@@ -91,15 +91,18 @@ __global__ void __launch_bounds__(kThreads) k_bin_count(const uint32_t* __restri
                                                         const uint32_t* d_v, uint32_t v_max, uint64_t* lookback,
                                                         uint32_t epoch, uint32_t* ticket, uint2* __restrict__ cand_off,
                                                         uint32_t* __restrict__ block_rank, uint32_t block_cap,
-                                                        uint32_t* cand_total, float W, float H, uint32_t flat) {
+                                                        uint32_t* cand_total, float W, float H, uint32_t flat,
+                                                        uint32_t q_lo, uint32_t q_hi) {
     __shared__ uint32_t s_wsum[kThreads / 32];
     __shared__ uint32_t s_chunk, s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t* __restrict__ sorted_slot = (sorted_in_b && *sorted_in_b) ? sorted_b : sorted_a;
-    uint32_t v = *d_v;
-    if (v > v_max) v = v_max;
-    const uint32_t nchunks = (v + kChunk - 1) / kChunk;
-    if (v == 0) {
+    uint32_t vis = *d_v;
+    if (vis > v_max) vis = v_max;
+    // depth slab: ranks [lo, v) of this model, as 16.16 fractions of the visible count
+    const uint32_t lo = (uint32_t)(((uint64_t)vis * q_lo) >> 16), v = (uint32_t)(((uint64_t)vis * q_hi) >> 16);
+    const uint32_t nchunks = (v - lo + kChunk - 1) / kChunk;
+    if (v == lo) {
         if (blockIdx.x == 0 && tid == 0) *cand_total = 0;
         return;
     }
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(kThreads) k_bin_count(const uint32_t* __restri
         const uint32_t c = s_chunk;
         const bool valid = c < nchunks;
         uint32_t cnt[kIpt], slot[kIpt], sum = 0, chunk_total = 0, local = 0;
-        const uint32_t r0 = c * kChunk + tid * kIpt;
+        const uint32_t r0 = lo + c * kChunk + tid * kIpt;
 #pragma unroll
         for (int k = 0; k < kIpt; k++) cnt[k] = slot[k] = 0;
         if (valid) {
@@ -193,7 +196,8 @@ __global__ void __launch_bounds__(kThreads) k_bin_emit(const b200gs_splat* __res
                                                        uint32_t* entry_total_out, uint32_t* overflow,
                                                        uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ tile_vals,
                                                        uint32_t capacity, uint32_t* tile_hist, float W, float H,
-                                                       uint32_t tiles_x, uint32_t flat) {
+                                                       uint32_t tiles_x, uint32_t flat, uint32_t q_lo, uint32_t q_hi,
+                                                       const uint8_t* __restrict__ tile_done) {
     __shared__ int32_t s_owner[kBlock];       // rank owning each candidate (after the max-scan)
     __shared__ uint32_t s_keys[2][kBlock];    // kept entries of the block, double-buffered:
     __shared__ uint32_t s_vals[2][kBlock];    // block b+1 is staged before block b is written out
@@ -202,9 +206,10 @@ __global__ void __launch_bounds__(kThreads) k_bin_emit(const b200gs_splat* __res
     __shared__ int32_t s_wmax[kThreads / 32];
     __shared__ uint32_t s_blk, s_base, s_kept;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t v = *d_v;
-    if (v > v_max) v = v_max;
-    const uint32_t total = v ? *cand_total_p : 0u;
+    uint32_t vis = *d_v;
+    if (vis > v_max) vis = v_max;
+    const uint32_t lo = (uint32_t)(((uint64_t)vis * q_lo) >> 16), v = (uint32_t)(((uint64_t)vis * q_hi) >> 16);
+    const uint32_t total = v > lo ? *cand_total_p : 0u;
     uint32_t nblocks = (total + kBlock - 1) / kBlock;
     if (nblocks > block_cap - 1) {  // candidate space larger than the scratch: drop the tail, flag it
         nblocks = block_cap - 1;
@@ -287,8 +292,9 @@ __global__ void __launch_bounds__(kThreads) k_bin_emit(const b200gs_splat* __res
                     cd.nbc = __fdividef(-cd.b, cd.c); cd.nba = __fdividef(-cd.b, cd.a);  // tau carries the slack
                     const uint32_t e = cbase + p - os.x;
                     const uint32_t y = e / cd.nx, x = e - y * cd.nx;
-                    keep[k] = tile_hit(cd, x, y);
                     key[k] = (cd.ty0 + y) * tiles_x + cd.tx0 + x;
+                    // tiles already finished by a nearer depth slab take no more entries
+                    keep[k] = !(tile_done && tile_done[key[k]]) && tile_hit(cd, x, y);
                     val[k] = splat_base + slot;
                 }
             }
@@ -376,10 +382,12 @@ __global__ void __launch_bounds__(kThreads) k_bin_emit(const b200gs_splat* __res
 // ranges[tile] = first entry, ranges[n_tiles + tile] = one past the last entry (both 0 if none)
 __global__ void __launch_bounds__(256) k_tile_ranges(const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b,
                                                      const uint32_t* in_b, const uint32_t* d_entries,
-                                                     uint32_t capacity, uint32_t* ranges, uint32_t n_tiles) {
+                                                     uint32_t capacity, uint32_t* ranges, uint32_t n_tiles,
+                                                     unsigned long long* entry_stat) {
     const uint32_t* __restrict__ tile_keys = *in_b ? keys_b : keys_a;
     uint32_t n = *d_entries;
     if (n > capacity) n = capacity;
+    if (entry_stat && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(entry_stat, (unsigned long long)n);
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
         uint32_t k = tile_keys[e];
         if (k >= n_tiles) continue;
@@ -408,20 +416,20 @@ cudaError_t gs_launch_bin(const GsBinArgs& a, const GsFrame& f, int num_sms, cud
     if (grid > nchunks) grid = nchunks;
     if (grid < 1) grid = 1;
     k_bin_count<<<grid, kThreads, 0, st>>>(a.sorted_slot, a.sorted_slot_b, a.sorted_in_b, a.splats, a.d_v, a.v_max, a.lookback, a.epoch, a.ticket,
-                                           a.cand_off, a.block_rank, a.block_cap, a.cand_total, f.W, f.H, flat);
+                                           a.cand_off, a.block_rank, a.block_cap, a.cand_total, f.W, f.H, flat, a.q_lo, a.q_hi);
     k_bin_emit<<<(uint32_t)(bps_emit * num_sms), kThreads, 0, st>>>(
         a.splats, a.d_v, a.v_max, a.splat_base, a.cand_off, a.block_rank, a.block_cap, a.cand_total,
         a.lookback_emit,
         a.epoch, a.ticket + 1, a.entry_base_in, a.entry_total_out, a.overflow, a.tile_keys, a.tile_vals, a.capacity,
-        a.tile_hist, f.W, f.H, f.tiles_x, flat);
+        a.tile_hist, f.W, f.H, f.tiles_x, flat, a.q_lo, a.q_hi, a.tile_done);
     return cudaGetLastError();
 }
 
 cudaError_t gs_launch_tile_ranges(const uint32_t* keys_a, const uint32_t* keys_b, const uint32_t* in_b,
                                   const uint32_t* d_entries, uint32_t capacity, uint32_t* ranges, uint32_t n_tiles,
-                                  int num_sms, cudaStream_t st) {
+                                  unsigned long long* entry_stat, int num_sms, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(ranges, 0, (size_t)n_tiles * 2 * sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
-    k_tile_ranges<<<num_sms * 8, 256, 0, st>>>(keys_a, keys_b, in_b, d_entries, capacity, ranges, n_tiles);
+    k_tile_ranges<<<num_sms * 8, 256, 0, st>>>(keys_a, keys_b, in_b, d_entries, capacity, ranges, n_tiles, entry_stat);
     return cudaGetLastError();
 }

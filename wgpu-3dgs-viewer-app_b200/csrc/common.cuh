@@ -115,13 +115,15 @@ struct GsBinArgs {
     uint32_t* entry_total_out;     // entry_base_in + this model's entries (a different word)
     uint32_t* overflow;            // set to 1 when the capacity is exceeded
     uint32_t* tile_keys; uint32_t* tile_vals; uint32_t capacity;
-    uint32_t* tile_hist;           // 2 x 256 digit histogram of the emitted tile ids (zeroed before the frame)
+    uint32_t* tile_hist;           // 2 x 256 digit histogram of the emitted tile ids (zeroed before the slab)
+    uint32_t q_lo, q_hi;           // depth slab: ranks [V*q_lo >> 16, V*q_hi >> 16) of this model
+    const uint8_t* tile_done;      // tiles finished by nearer slabs (null in the first slab)
 };
 size_t gs_bin_block_words(uint32_t capacity_candidates);
 cudaError_t gs_launch_bin(const GsBinArgs& a, const GsFrame& f, int num_sms, cudaStream_t st);
 cudaError_t gs_launch_tile_ranges(const uint32_t* keys_a, const uint32_t* keys_b, const uint32_t* in_b,
                                   const uint32_t* d_entries, uint32_t capacity, uint32_t* ranges /* 2 x tiles */,
-                                  uint32_t n_tiles, int num_sms, cudaStream_t st);
+                                  uint32_t n_tiles, unsigned long long* entry_stat, int num_sms, cudaStream_t st);
 
 struct GsCompositeArgs {
     const uint32_t* tile_vals;      // entries sorted by tile, depth order inside a tile
@@ -130,7 +132,10 @@ struct GsCompositeArgs {
     const uint32_t* ranges;         // [tile] = start, [n_tiles + tile] = end
     const b200gs_splat* splats;     // frame arena
     uint8_t* out; size_t pitch;     // RGBA8
-    unsigned long long* evals;      // optional work counter (may be null)
+    unsigned long long* evals;      // optional work counters: [0] evaluations, [1] entries staged (may be null)
+    float4* state;                  // per-pixel (Cr, Cg, Cb, T) carried between depth slabs
+    uint8_t* tile_done;             // per-tile: every pixel reached T < eps in an earlier slab
+    bool resume, last;              // not the first slab / the last slab of the frame
 };
 cudaError_t gs_launch_composite(const GsCompositeArgs& a, const GsFrame& f, cudaStream_t st);
 cudaError_t gs_launch_query_hits(const GsCompositeArgs& a, const GsFrame& f, uint32_t px, uint32_t py, uint2* out,

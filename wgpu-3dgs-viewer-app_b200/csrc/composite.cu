@@ -24,7 +24,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 template <bool FLAT, bool COUNT>
-__global__ void __launch_bounds__(kThreads) k_composite(const uint32_t* __restrict__ tile_vals_a,
+__global__ void __launch_bounds__(kThreads) k_composite(float4* __restrict__ state, uint8_t* tile_done, uint32_t resume,
+                                                        uint32_t last,
+                                                        const uint32_t* __restrict__ tile_vals_a,
                                                         const uint32_t* __restrict__ tile_vals_b,
                                                         const uint32_t* tile_in_b,
                                                         const uint32_t* __restrict__ ranges,
@@ -34,8 +36,9 @@ __global__ void __launch_bounds__(kThreads) k_composite(const uint32_t* __restri
                                                         unsigned long long* evals) {
     // one 64-byte record per staged splat: {mx, my, a', b'} {c', opacity, red, green}
     // {cx, hx, cy, hy} {blue, tau', -, -}; conic pre-scaled so that power is in log2 units, extent
-    // square clipped to the viewport stored as centre / half-size (exact: half-integers)
-    __shared__ float4 sS[kThreads * 4];
+    // square clipped to the viewport stored as centre / half-size (exact: half-integers).
+    // Double-buffered: the next round's splats are in flight while this round is blended.
+    __shared__ float4 sS[2][kThreads * 4];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t* __restrict__ tile_vals = *tile_in_b ? tile_vals_b : tile_vals_a;
@@ -54,13 +57,32 @@ __global__ void __launch_bounds__(kThreads) k_composite(const uint32_t* __restri
     bool done = !inside;
     unsigned long long my_evals = 0;
     const float Wf = (float)W, Hf = (float)H;
+    // depth slabs: a tile finished by a nearer slab has its final pixels already; otherwise pick up
+    // the accumulated colour / transmittance where the previous slab left them
+    if (resume) {
+        if (tile_done[tile]) return;
+        if (inside) {
+            const float4 st = state[(size_t)py * W + px];
+            Cr = st.x; Cg = st.y; Cb = st.z; T = st.w;
+            done = T < GS_T_EPS;
+        }
+    }
 
-    for (uint32_t base = start; base < end; base += kThreads) {
+    // software pipeline of the staging loads: splat records one round ahead, entry ids two rounds ahead
+    uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
+    uint32_t id_next = 0;
+    if (start + tid < end) {
+        const uint4* sp = reinterpret_cast<const uint4*>(splats + tile_vals[start + tid]);
+        q0 = __ldg(sp); q1 = __ldg(sp + 1);
+    }
+    if (start + kThreads + tid < end) id_next = tile_vals[start + kThreads + tid];
+
+    uint32_t buf = 0;
+    for (uint32_t base = start; base < end; base += kThreads, buf ^= 1u) {
         const uint32_t cnt = min((uint32_t)kThreads, end - base);
+        if (COUNT && tid == 0) atomicAdd(evals + 1, (unsigned long long)cnt);  // entries staged before the tile finished
+        float4* sSb = sS[buf];
         if ((uint32_t)tid < cnt) {
-            const uint32_t id = tile_vals[base + tid];
-            const uint4* sp = reinterpret_cast<const uint4*>(splats + id);
-            const uint4 q0 = __ldg(sp), q1 = __ldg(sp + 1);
             const float mx = __uint_as_float(q0.x), my = __uint_as_float(q0.y);
             const float r = (float)(q0.z & 0xffffu);
             const float op = __half2float(__ushort_as_half((unsigned short)(q0.z >> 16)));
@@ -74,29 +96,34 @@ __global__ void __launch_bounds__(kThreads) k_composite(const uint32_t* __restri
             if (fy0 < 0.0f) fy0 = 0.0f;
             if (fx1 > Wf - 1.0f) fx1 = Wf - 1.0f;
             if (fy1 > Hf - 1.0f) fy1 = Hf - 1.0f;
-            float4* rec = &sS[tid * 4];
+            float4* rec = &sSb[tid * 4];
             rec[0] = make_float4(mx, my, -0.5f * kLog2e * ca, -kLog2e * cbq);
             rec[1] = make_float4(-0.5f * kLog2e * cc, op, cr, cg);
             rec[2] = make_float4(0.5f * (fx0 + fx1), 0.5f * (fx1 - fx0), 0.5f * (fy0 + fy1), 0.5f * (fy1 - fy0));
             rec[3] = make_float4(cb, 0.5f * kLog2e * gs_footprint_tau(op, FLAT), r, 0.0f);
         }
         __syncthreads();
+        // issue the next round's loads now; they land while this round is blended
+        if (base + kThreads + tid < end) {
+            const uint4* sp = reinterpret_cast<const uint4*>(splats + id_next);
+            q0 = __ldg(sp); q1 = __ldg(sp + 1);
+        }
+        if (base + 2 * kThreads + tid < end) id_next = tile_vals[base + 2 * kThreads + tid];
 
         if (!__all_sync(0xffffffffu, done)) {
             for (uint32_t g = 0; g < cnt; g += 32) {
                 const uint32_t s = g + lane;
                 bool ov = false;
                 if (s < cnt) {
-                    // splat s against this warp's 8x4 sub-tile: extent-square overlap first; the exact
-                    // footprint test (can any pixel of the overlap reach alpha >= 1/255?) only when
-                    // the splat is large enough for it to matter
-                    const float4 C = sS[s * 4 + 2];
+                    // splat s against this warp's 8x4 sub-tile: extent-square overlap first, then the exact
+                    // footprint test (can any pixel of the overlap reach alpha >= 1/255?)
+                    const float4 C = sSb[s * 4 + 2];
                     const float x0 = fmaxf(C.x - C.y, fwx0), x1 = fminf(C.x + C.y, fwx1);
                     const float y0 = fmaxf(C.z - C.w, fwy0), y1 = fminf(C.z + C.w, fwy1);
                     if (x0 <= x1 && y0 <= y1) {
-                        const float4 A = sS[s * 4];
-                        const float4 D = sS[s * 4 + 3];
-                        const float pa = -A.z, pb = -0.5f * A.w, pc = -sS[s * 4 + 1].x;  // 0.5*log2e * (a, b, c)
+                        const float4 A = sSb[s * 4];
+                        const float4 D = sSb[s * 4 + 3];
+                        const float pa = -A.z, pb = -0.5f * A.w, pc = -sSb[s * 4 + 1].x;  // 0.5*log2e * (a, b, c)
                         const float dx0 = x0 - A.x, dx1 = x1 - A.x, dy0 = y0 - A.y, dy1 = y1 - A.y;
                         const bool inx = dx0 <= 0.0f && dx1 >= 0.0f, iny = dy0 <= 0.0f && dy1 >= 0.0f;
                         float best = (inx && iny) ? 0.0f : 3.0e38f;
@@ -114,26 +141,46 @@ __global__ void __launch_bounds__(kThreads) k_composite(const uint32_t* __restri
                     }
                 }
                 uint32_t m = __ballot_sync(0xffffffffu, ov);
+                // two splats per trip: their alpha evaluations are independent (ILP), the blends are
+                // applied in order
                 while (m) {
-                    const int s2 = (int)g + __ffs((int)m) - 1;
+                    const int sa = (int)g + __ffs((int)m) - 1;
                     m &= m - 1;
-                    const float4* rec = &sS[s2 * 4];
-                    const float4 A = rec[0];
-                    const float4 B = rec[1];
-                    const float4 C = rec[2];
-                    const float dx = fpx - A.x, dy = fpy - A.y;
-                    const bool in = fabsf(fpx - C.x) <= C.y && fabsf(fpy - C.z) <= C.w;
-                    const float p2 = __fmaf_rn(__fmaf_rn(A.w, dy, A.z * dx), dx, (B.x * dy) * dy);
-                    float al;
-                    if (FLAT) al = (p2 >= -0.5f * GS_FLAT_D2 * kLog2e) ? fminf(GS_ALPHA_MAX, B.y) : 0.0f;
-                    else al = fminf(GS_ALPHA_MAX, B.y * ex2_approx(p2));
-                    const bool ok = in && !done && p2 <= 0.0f && al >= GS_ALPHA_MIN;
-                    if (COUNT) my_evals += (in && !done) ? 1ull : 0ull;
-                    if (ok) {
-                        const float w = al * T;
-                        Cr = __fmaf_rn(B.z, w, Cr);
-                        Cg = __fmaf_rn(B.w, w, Cg);
-                        Cb = __fmaf_rn(rec[3].x, w, Cb);
+                    const bool has_b = m != 0;
+                    const int sb = has_b ? (int)g + __ffs((int)m) - 1 : sa;
+                    m &= m - 1;  // no-op when m == 0
+                    const float4* ra = &sSb[sa * 4];
+                    const float4* rb = &sSb[sb * 4];
+                    const float4 Aa = ra[0], Ba = ra[1], Ca = ra[2];
+                    const float4 Ab = rb[0], Bb = rb[1], Cbb = rb[2];
+                    const float dxa = fpx - Aa.x, dya = fpy - Aa.y, dxb = fpx - Ab.x, dyb = fpy - Ab.y;
+                    const bool ina = fabsf(fpx - Ca.x) <= Ca.y && fabsf(fpy - Ca.z) <= Ca.w;
+                    const bool inb = has_b && fabsf(fpx - Cbb.x) <= Cbb.y && fabsf(fpy - Cbb.z) <= Cbb.w;
+                    const float pa2 = __fmaf_rn(__fmaf_rn(Aa.w, dya, Aa.z * dxa), dxa, (Ba.x * dya) * dya);
+                    const float pb2 = __fmaf_rn(__fmaf_rn(Ab.w, dyb, Ab.z * dxb), dxb, (Bb.x * dyb) * dyb);
+                    float ala, alb;
+                    if (FLAT) {
+                        ala = (pa2 >= -0.5f * GS_FLAT_D2 * kLog2e) ? fminf(GS_ALPHA_MAX, Ba.y) : 0.0f;
+                        alb = (pb2 >= -0.5f * GS_FLAT_D2 * kLog2e) ? fminf(GS_ALPHA_MAX, Bb.y) : 0.0f;
+                    } else {
+                        ala = fminf(GS_ALPHA_MAX, Ba.y * ex2_approx(pa2));
+                        alb = fminf(GS_ALPHA_MAX, Bb.y * ex2_approx(pb2));
+                    }
+                    if (COUNT) my_evals += (ina && !done) ? 1ull : 0ull;
+                    if (ina && !done && pa2 <= 0.0f && ala >= GS_ALPHA_MIN) {
+                        const float w = ala * T;
+                        Cr = __fmaf_rn(Ba.z, w, Cr);
+                        Cg = __fmaf_rn(Ba.w, w, Cg);
+                        Cb = __fmaf_rn(ra[3].x, w, Cb);
+                        T -= w;
+                        done = T < GS_T_EPS;
+                    }
+                    if (COUNT) my_evals += (inb && !done) ? 1ull : 0ull;
+                    if (inb && !done && pb2 <= 0.0f && alb >= GS_ALPHA_MIN) {
+                        const float w = alb * T;
+                        Cr = __fmaf_rn(Bb.z, w, Cr);
+                        Cg = __fmaf_rn(Bb.w, w, Cg);
+                        Cb = __fmaf_rn(rb[3].x, w, Cb);
                         T -= w;
                         done = T < GS_T_EPS;
                     }
@@ -144,7 +191,17 @@ __global__ void __launch_bounds__(kThreads) k_composite(const uint32_t* __restri
         if (__syncthreads_and(done)) break;
     }
 
-    if (inside) {
+    bool final_write = true;
+    if (!last) {
+        // not the last slab: only finished tiles write pixels now, the others park their state
+        const bool all_done = __syncthreads_and(done) != 0;
+        if (all_done) { if (tid == 0) tile_done[tile] = 1; }
+        else {
+            final_write = false;
+            if (inside) state[(size_t)py * W + px] = make_float4(Cr, Cg, Cb, T);
+        }
+    }
+    if (inside && final_write) {
         const float r = Cr + bg0 * T, g = Cg + bg1 * T, b = Cb + bg2 * T, a = (1.0f - T) + bg3 * T;
         auto q = [](float v) -> uint32_t {
             v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
@@ -218,7 +275,7 @@ cudaError_t gs_launch_composite(const GsCompositeArgs& a, const GsFrame& f, cuda
     const bool flat = f.display_mode != B200GS_DISPLAY_SPLAT;
     const uint32_t W = (uint32_t)f.W, H = (uint32_t)f.H;
 #define GS_LAUNCH_COMPOSITE(FLAT, COUNT)                                                                              \
-    k_composite<FLAT, COUNT><<<n_tiles, kThreads, 0, st>>>(a.tile_vals, a.tile_vals_b, a.tile_in_b, a.ranges, a.splats, a.out, a.pitch, W, H,      \
+    k_composite<FLAT, COUNT><<<n_tiles, kThreads, 0, st>>>(a.state, a.tile_done, a.resume ? 1u : 0u, a.last ? 1u : 0u, a.tile_vals, a.tile_vals_b, a.tile_in_b, a.ranges, a.splats, a.out, a.pitch, W, H,      \
                                                            f.tiles_x, n_tiles, f.bg[0], f.bg[1], f.bg[2], f.bg[3],     \
                                                            a.evals)
     if (flat) {
