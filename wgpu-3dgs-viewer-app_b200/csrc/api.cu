@@ -213,7 +213,7 @@ static int ensure_frame_buffers(b200gs_viewer* v) {
     if (v->ranges_tiles < n_tiles) {
         CK(cudaStreamSynchronize(v->stream));
         if (v->ranges) CK(cudaFree(v->ranges));
-        TRY(dev_alloc(&v->ranges, (size_t)n_tiles * 2, true, v->stream));
+        TRY(dev_alloc(&v->ranges, (size_t)n_tiles * 3, true, v->stream));
         if (v->tile_done) CK(cudaFree(v->tile_done));
         TRY(dev_alloc(&v->tile_done, (size_t)n_tiles, true, v->stream));
         v->ranges_tiles = n_tiles;
@@ -792,7 +792,7 @@ static int render_slabs(b200gs_viewer* v, b200gs_model* const* far_to_near, uint
         c.state = v->pix_state; c.tile_done = v->tile_done; c.resume = sl > 0; c.last = last;
         CK(gs_launch_composite(c, f, st));
         if (v->timing) CK(cudaEventRecord(v->ev_slab[sl][2], st));
-        v->launches += s.passes + 2;  // tile sort passes, tile ranges, compositor
+        v->launches += s.passes + 3;  // tile sort passes, tile ranges, tile order, compositor
     }
     if (v->timing) CK(cudaEventRecord(v->ev[4], st));
     v->rendered = true;

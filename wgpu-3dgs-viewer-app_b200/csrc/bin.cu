@@ -396,6 +396,41 @@ __global__ void __launch_bounds__(256) k_tile_ranges(const uint32_t* __restrict_
     }
 }
 
+// Launch order of the compositor's tiles: longest list first (LPT), so that the few very long tiles
+// of a frame start at once instead of wherever their index falls.  Counting sort on the number of
+// 256-entry rounds, one CTA.
+__global__ void __launch_bounds__(1024) k_tile_order(const uint32_t* __restrict__ ranges, uint32_t n_tiles,
+                                                     uint32_t* __restrict__ order) {
+    __shared__ uint32_t s_cnt[256];
+    const int tid = threadIdx.x;
+    if (tid < 256) s_cnt[tid] = 0;
+    __syncthreads();
+    for (uint32_t t = tid; t < n_tiles; t += 1024) {
+        const uint32_t len = ranges[n_tiles + t] - ranges[t];
+        atomicAdd(&s_cnt[255u - min(255u, (len + 255u) >> 8)], 1u);   // bucket 0 = longest
+    }
+    __syncthreads();
+    if (tid < 32) {  // exclusive scan of 256 buckets by one warp (8 per lane)
+        uint32_t loc[8], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { loc[k] = sum; sum += s_cnt[tid * 8 + k]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+            if (tid >= o) incl += x;
+        }
+        const uint32_t base = incl - sum;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s_cnt[tid * 8 + k] = base + loc[k];
+    }
+    __syncthreads();
+    for (uint32_t t = tid; t < n_tiles; t += 1024) {
+        const uint32_t len = ranges[n_tiles + t] - ranges[t];
+        order[atomicAdd(&s_cnt[255u - min(255u, (len + 255u) >> 8)], 1u)] = t;
+    }
+}
+
 }  // namespace
 
 size_t gs_bin_block_words(uint32_t capacity_candidates) { return (size_t)capacity_candidates / kBlock + 2; }
@@ -431,5 +466,6 @@ cudaError_t gs_launch_tile_ranges(const uint32_t* keys_a, const uint32_t* keys_b
     cudaError_t e = cudaMemsetAsync(ranges, 0, (size_t)n_tiles * 2 * sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
     k_tile_ranges<<<num_sms * 8, 256, 0, st>>>(keys_a, keys_b, in_b, d_entries, capacity, ranges, n_tiles, entry_stat);
+    k_tile_order<<<1, 1024, 0, st>>>(ranges, n_tiles, ranges + 2 * (size_t)n_tiles);
     return cudaGetLastError();
 }

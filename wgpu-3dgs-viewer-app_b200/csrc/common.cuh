@@ -122,14 +122,14 @@ struct GsBinArgs {
 size_t gs_bin_block_words(uint32_t capacity_candidates);
 cudaError_t gs_launch_bin(const GsBinArgs& a, const GsFrame& f, int num_sms, cudaStream_t st);
 cudaError_t gs_launch_tile_ranges(const uint32_t* keys_a, const uint32_t* keys_b, const uint32_t* in_b,
-                                  const uint32_t* d_entries, uint32_t capacity, uint32_t* ranges /* 2 x tiles */,
+                                  const uint32_t* d_entries, uint32_t capacity, uint32_t* ranges /* 3 x tiles: start, end, launch order */,
                                   uint32_t n_tiles, unsigned long long* entry_stat, int num_sms, cudaStream_t st);
 
 struct GsCompositeArgs {
     const uint32_t* tile_vals;      // entries sorted by tile, depth order inside a tile
     const uint32_t* tile_vals_b;    // the tile sort's other buffer, selected when *tile_in_b != 0
     const uint32_t* tile_in_b;
-    const uint32_t* ranges;         // [tile] = start, [n_tiles + tile] = end
+    const uint32_t* ranges;         // [tile] = start, [n_tiles + tile] = end, [2 n_tiles + i] = i-th tile to launch
     const b200gs_splat* splats;     // frame arena
     uint8_t* out; size_t pitch;     // RGBA8
     unsigned long long* evals;      // optional work counters: [0] evaluations, [1] entries staged (may be null)

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(kThreads) k_composite(float4* __restrict__ sta
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t* __restrict__ tile_vals = *tile_in_b ? tile_vals_b : tile_vals_a;
-    const uint32_t tile = blockIdx.x;
+    const uint32_t tile = ranges[2 * n_tiles + blockIdx.x];  // longest lists first
     const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
     const uint32_t start = ranges[tile], end = ranges[n_tiles + tile];
 
