@@ -74,7 +74,7 @@ struct b200gs_model {
     b200gs_edit_pod* edits = nullptr;
     float pos[3] = {0, 0, 0}, quat[4] = {0, 0, 0, 1}, scale[3] = {1, 1, 1};
     uint32_t* ctrl = nullptr;
-    uint32_t *keys_a = nullptr, *vals_a = nullptr, *keys_b = nullptr, *vals_b = nullptr, *idx = nullptr;
+    uint32_t *keys_a = nullptr, *vals_a = nullptr, *keys_b = nullptr, *vals_b = nullptr, *idx = nullptr, *ncand = nullptr;
     uint64_t *lb_pre = nullptr, *lb_sort = nullptr;
     uint64_t arena_offset = 0;
     bool preprocessed = false, sorted = false;
@@ -344,7 +344,7 @@ extern "C" int b200gs_viewer_create(int device, uint32_t sh, uint32_t cov3d, uin
 }
 
 static void free_model(b200gs_model* m) {
-    void* ps[] = {m->recs, m->mask, m->selection, m->edits, m->ctrl, m->keys_a, m->vals_a, m->keys_b, m->vals_b, m->idx,
+    void* ps[] = {m->recs, m->mask, m->selection, m->edits, m->ctrl, m->keys_a, m->vals_a, m->keys_b, m->vals_b, m->idx, m->ncand,
                   m->lb_pre, m->lb_sort};
     for (void* p : ps)
         if (p) cudaFree(p);
@@ -376,9 +376,17 @@ extern "C" int b200gs_viewer_destroy(b200gs_viewer* v) {
     return B200GS_OK;
 }
 
+// the projected splats (and their candidate-tile counts) are computed for one viewport / display mode:
+// changing either makes the preprocessed state stale
+static void invalidate_models(b200gs_viewer* v) {
+    for (auto* m : v->models) m->preprocessed = m->sorted = false;
+    v->rendered = false;
+}
+
 extern "C" int b200gs_resize(b200gs_viewer* v, uint32_t width, uint32_t height) {
     REQUIRE(v, "null viewer");
     REQUIRE(width >= 1 && height >= 1 && width <= 16384 && height <= 16384, "invalid size");
+    if (v->W != width || v->H != height) invalidate_models(v);
     v->W = width; v->H = height;
     v->size[0] = (float)width; v->size[1] = (float)height;
     return B200GS_OK;
@@ -390,6 +398,7 @@ extern "C" int b200gs_set_camera(b200gs_viewer* v, const float view[16], const f
     memcpy(v->proj, proj, 64);
     if (size) {
         REQUIRE(size[0] >= 1.0f && size[1] >= 1.0f, "invalid size");
+        if (v->W != (uint32_t)size[0] || v->H != (uint32_t)size[1]) invalidate_models(v);
         v->size[0] = size[0]; v->size[1] = size[1];
         v->W = (uint32_t)size[0]; v->H = (uint32_t)size[1];
     }
@@ -401,6 +410,7 @@ extern "C" int b200gs_set_gaussian_transform(b200gs_viewer* v, float size, uint3
     REQUIRE(v, "null viewer");
     REQUIRE(display_mode <= 2, "display_mode out of range");
     REQUIRE(sh_deg <= 3, "sh_deg out of range (gs::GaussianShDegree::new)");
+    if (v->display_mode != display_mode) invalidate_models(v);
     v->gsize = size; v->display_mode = display_mode; v->sh_deg = sh_deg; v->no_sh0 = no_sh0 ? 1 : 0;
     return B200GS_OK;
 }
@@ -492,6 +502,7 @@ extern "C" int b200gs_model_create(b200gs_viewer* v, const char* key, uint64_t c
     if (rc == B200GS_OK) rc = dev_alloc(&m->keys_b, capacity, false, st);
     if (rc == B200GS_OK) rc = dev_alloc(&m->vals_b, capacity, false, st);
     if (rc == B200GS_OK) rc = dev_alloc(&m->idx, capacity, false, st);
+    if (rc == B200GS_OK) rc = dev_alloc(&m->ncand, capacity, false, st);
     if (rc == B200GS_OK) rc = dev_alloc(&m->lb_pre, (capacity + 255) / 256 + 1, true, st);
     if (rc == B200GS_OK) rc = dev_alloc(&m->lb_sort, gs_sort_lookback_words((uint32_t)capacity, 4), true, st);
     if (rc != B200GS_OK) { free_model(m); return rc; }
@@ -691,6 +702,7 @@ extern "C" int b200gs_model_preprocess(b200gs_model* m, int use_unedited) {
     a.ctrl = m->ctrl + MC_CTRL; a.lookback = m->lb_pre; a.epoch = ++v->epoch;
     a.keys = m->keys_a; a.idx = m->idx; a.splats = v->arena + m->arena_offset;
     a.sort_hist = m->ctrl + MC_SORT_HIST;
+    a.ncand = m->ncand;
     if (v->timing) CK(cudaEventRecord(v->ev[0], v->stream));
     CK(gs_launch_preprocess(a, f, xf, v->num_sms, v->stream));
     v->launches += 1;
@@ -753,6 +765,7 @@ static int render_slabs(b200gs_viewer* v, b200gs_model* const* far_to_near, uint
             b.sorted_slot_b = m->vals_b;
             b.sorted_in_b = m->ctrl + MC_CTRL + GS_CTRL_SORT_IN_B;
             b.splats = v->arena + m->arena_offset;
+            b.ncand = m->ncand;
             b.d_v = m->ctrl + MC_CTRL + GS_CTRL_VISIBLE;
             b.v_max = (uint32_t)m->cap;
             b.splat_base = (uint32_t)m->arena_offset;

@@ -31,36 +31,8 @@ constexpr int kChunk = kThreads * kIpt;      // 1024 ranks per chunk
 constexpr int kCpt = 8;                      // candidates per thread in k_bin_emit
 constexpr uint32_t kBlock = kThreads * kCpt; // 2048 candidates per block
 
-struct Cand {
-    float mx, my, a, b, c, tau;   // ellipse
-    float nbc, nba;               // -b/c, -b/a
-    float fx0, fx1, fy0, fy1;     // pixel bounds of the extent square clipped to the viewport
-    uint32_t tx0, ty0, nx, ny;    // candidate tile rectangle
-};
-
-// candidate tile rectangle of a projected splat (first 16 bytes); false if it cannot touch anything
-__device__ __forceinline__ bool make_rect(const uint4& q0, float W, float H, bool flat, Cand& c) {
-    const uint32_t radius = q0.z & 0xffffu;
-    if (radius == 0) return false;
-    c.mx = __uint_as_float(q0.x);
-    c.my = __uint_as_float(q0.y);
-    const float op = __half2float(__ushort_as_half((unsigned short)(q0.z >> 16)));
-    c.tau = gs_footprint_tau(op, flat);
-    if (c.tau < 0.0f) return false;
-    // same bounds expression as the compositor / the oracle (exact in float)
-    const float r = (float)radius;
-    c.fx0 = ceilf(c.mx - r); c.fx1 = floorf(c.mx + r); c.fy0 = ceilf(c.my - r); c.fy1 = floorf(c.my + r);
-    if (c.fx0 < 0.0f) c.fx0 = 0.0f;
-    if (c.fy0 < 0.0f) c.fy0 = 0.0f;
-    if (c.fx1 > W - 1.0f) c.fx1 = W - 1.0f;
-    if (c.fy1 > H - 1.0f) c.fy1 = H - 1.0f;
-    if (!(c.fx0 <= c.fx1 && c.fy0 <= c.fy1)) return false;
-    c.tx0 = (uint32_t)c.fx0 / GS_TILE;
-    c.ty0 = (uint32_t)c.fy0 / GS_TILE;
-    c.nx = (uint32_t)c.fx1 / GS_TILE - c.tx0 + 1;
-    c.ny = (uint32_t)c.fy1 / GS_TILE - c.ty0 + 1;
-    return true;
-}
+using Cand = GsCand;
+__device__ __forceinline__ bool make_rect(const uint4& q0, float W, float H, bool flat, Cand& c) { return gs_make_rect(q0, W, H, flat, c); }
 
 // can candidate tile (x, y) of the rectangle be touched?  (gs_min_q_rect with the divisions hoisted)
 __device__ __forceinline__ bool tile_hit(const Cand& c, uint32_t x, uint32_t y) {
@@ -87,12 +59,11 @@ __device__ __forceinline__ bool tile_hit(const Cand& c, uint32_t x, uint32_t y) 
 __global__ void __launch_bounds__(kThreads) k_bin_count(const uint32_t* __restrict__ sorted_a,
                                                         const uint32_t* __restrict__ sorted_b,
                                                         const uint32_t* sorted_in_b,
-                                                        const b200gs_splat* __restrict__ splats,
+                                                        const uint32_t* __restrict__ ncand,
                                                         const uint32_t* d_v, uint32_t v_max, uint64_t* lookback,
                                                         uint32_t epoch, uint32_t* ticket, uint2* __restrict__ cand_off,
                                                         uint32_t* __restrict__ block_rank, uint32_t block_cap,
-                                                        uint32_t* cand_total, float W, float H, uint32_t flat,
-                                                        uint32_t q_lo, uint32_t q_hi) {
+                                                        uint32_t* cand_total, uint32_t q_lo, uint32_t q_hi) {
     __shared__ uint32_t s_wsum[kThreads / 32];
     __shared__ uint32_t s_chunk, s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -123,18 +94,13 @@ __global__ void __launch_bounds__(kThreads) k_bin_count(const uint32_t* __restri
 #pragma unroll
         for (int k = 0; k < kIpt; k++) cnt[k] = slot[k] = 0;
         if (valid) {
-            uint4 q0[kIpt];
 #pragma unroll
             for (int k = 0; k < kIpt; k++) slot[k] = (r0 + k < v) ? (sorted_slot ? sorted_slot[r0 + k] : r0 + k) : 0u;
+            // candidate-tile counts were stored per compaction slot by the preprocess kernel (a 4-byte
+            // gather from an L2-resident array instead of a 32-byte splat gather from HBM)
 #pragma unroll
             for (int k = 0; k < kIpt; k++) {
-                q0[k] = make_uint4(0, 0, 0, 0);
-                if (r0 + k < v) q0[k] = __ldg(reinterpret_cast<const uint4*>(splats + slot[k]));
-            }
-#pragma unroll
-            for (int k = 0; k < kIpt; k++) {
-                Cand cd;
-                cnt[k] = (r0 + k < v && make_rect(q0[k], W, H, flat != 0, cd)) ? cd.nx * cd.ny : 0u;
+                cnt[k] = (r0 + k < v) ? __ldg(&ncand[slot[k]]) : 0u;
                 sum += cnt[k];
             }
             uint32_t incl = sum;
@@ -388,11 +354,24 @@ __global__ void __launch_bounds__(256) k_tile_ranges(const uint32_t* __restrict_
     uint32_t n = *d_entries;
     if (n > capacity) n = capacity;
     if (entry_stat && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(entry_stat, (unsigned long long)n);
-    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-        uint32_t k = tile_keys[e];
-        if (k >= n_tiles) continue;
-        if (e == 0 || tile_keys[e - 1] != k) ranges[k] = e;
-        if (e == n - 1 || tile_keys[e + 1] != k) ranges[n_tiles + k] = e + 1;
+    // 4 consecutive entries per thread (one 128-bit load) + the two neighbours
+    for (uint32_t e0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4; e0 < n; e0 += gridDim.x * blockDim.x * 4) {
+        uint32_t k[6];
+        if (e0 + 4 <= n) {
+            const uint4 q = *reinterpret_cast<const uint4*>(tile_keys + e0);
+            k[1] = q.x; k[2] = q.y; k[3] = q.z; k[4] = q.w;
+        } else {
+            for (int j = 0; j < 4; j++) k[1 + j] = e0 + j < n ? tile_keys[e0 + j] : 0xffffffffu;
+        }
+        k[0] = e0 > 0 ? tile_keys[e0 - 1] : 0xffffffffu;
+        k[5] = e0 + 4 < n ? tile_keys[e0 + 4] : 0xffffffffu;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t e = e0 + j, kk = k[1 + j];
+            if (e >= n || kk >= n_tiles) continue;
+            if (k[j] != kk) ranges[kk] = e;
+            if (e == n - 1 || k[j + 2] != kk) ranges[n_tiles + kk] = e + 1;
+        }
     }
 }
 
@@ -450,8 +429,8 @@ cudaError_t gs_launch_bin(const GsBinArgs& a, const GsFrame& f, int num_sms, cud
     uint32_t grid = (uint32_t)(bps_count * num_sms);
     if (grid > nchunks) grid = nchunks;
     if (grid < 1) grid = 1;
-    k_bin_count<<<grid, kThreads, 0, st>>>(a.sorted_slot, a.sorted_slot_b, a.sorted_in_b, a.splats, a.d_v, a.v_max, a.lookback, a.epoch, a.ticket,
-                                           a.cand_off, a.block_rank, a.block_cap, a.cand_total, f.W, f.H, flat, a.q_lo, a.q_hi);
+    k_bin_count<<<grid, kThreads, 0, st>>>(a.sorted_slot, a.sorted_slot_b, a.sorted_in_b, a.ncand, a.d_v, a.v_max, a.lookback, a.epoch, a.ticket,
+                                           a.cand_off, a.block_rank, a.block_cap, a.cand_total, a.q_lo, a.q_hi);
     k_bin_emit<<<(uint32_t)(bps_emit * num_sms), kThreads, 0, st>>>(
         a.splats, a.d_v, a.v_max, a.splat_base, a.cand_off, a.block_rank, a.block_cap, a.cand_total,
         a.lookback_emit,

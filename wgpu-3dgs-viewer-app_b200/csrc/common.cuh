@@ -72,6 +72,7 @@ struct GsPreprocessArgs {
     uint64_t* lookback;  // one status word per 256-Gaussian chunk (epoch-tagged, never cleared)
     uint32_t epoch;
     uint32_t* keys; uint32_t* idx; b200gs_splat* splats;
+    uint32_t* ncand;      // per compaction slot: candidate tiles of the splat (consumed by k_bin_count)
     uint32_t* sort_hist;  // 4 x 256 digit histogram of the emitted keys (zeroed before launch), or null
 };
 cudaError_t gs_launch_preprocess(const GsPreprocessArgs& a, const GsFrame& f, const GsModelXf& m, int num_sms,
@@ -100,6 +101,7 @@ struct GsBinArgs {
     const uint32_t* sorted_slot_b; // the sort's other buffer, selected when *sorted_in_b != 0
     const uint32_t* sorted_in_b;   // device flag written by the sort (GsSortArgs::result_in_b)
     const b200gs_splat* splats;    // this model's splats (compaction order)
+    const uint32_t* ncand;         // this model's per-slot candidate tile counts (from the preprocess kernel)
     const uint32_t* d_v;           // visible count of this model on device
     uint32_t v_max;
     uint32_t splat_base;           // global id of this model's splat 0 in the frame arena
@@ -281,4 +283,37 @@ __device__ __forceinline__ float gs_footprint_tau(float opacity, bool flat) {
     const float t = flat ? GS_FLAT_D2 : 2.0f * __logf(opacity * 255.0f);
     return t * 1.001f + 0.01f;
 }
+// ---- candidate tile rectangle of a projected splat (shared by preprocess and binning) --------
+struct GsCand {
+    float mx, my, a, b, c, tau;   // ellipse
+    float nbc, nba;               // -b/c, -b/a
+    float fx0, fx1, fy0, fy1;     // pixel bounds of the extent square clipped to the viewport
+    uint32_t tx0, ty0, nx, ny;    // candidate tile rectangle
+};
+
+// candidate tile rectangle of a projected splat (first 16 bytes); false if it cannot touch anything
+__device__ __forceinline__ bool gs_make_rect(const uint4& q0, float W, float H, bool flat, GsCand& c) {
+    const uint32_t radius = q0.z & 0xffffu;
+    if (radius == 0) return false;
+    c.mx = __uint_as_float(q0.x);
+    c.my = __uint_as_float(q0.y);
+    const float op = __half2float(__ushort_as_half((unsigned short)(q0.z >> 16)));
+    c.tau = gs_footprint_tau(op, flat);
+    if (c.tau < 0.0f) return false;
+    // same bounds expression as the compositor / the oracle (exact in float)
+    const float r = (float)radius;
+    c.fx0 = ceilf(c.mx - r); c.fx1 = floorf(c.mx + r); c.fy0 = ceilf(c.my - r); c.fy1 = floorf(c.my + r);
+    if (c.fx0 < 0.0f) c.fx0 = 0.0f;
+    if (c.fy0 < 0.0f) c.fy0 = 0.0f;
+    if (c.fx1 > W - 1.0f) c.fx1 = W - 1.0f;
+    if (c.fy1 > H - 1.0f) c.fy1 = H - 1.0f;
+    if (!(c.fx0 <= c.fx1 && c.fy0 <= c.fy1)) return false;
+    c.tx0 = (uint32_t)c.fx0 / GS_TILE;
+    c.ty0 = (uint32_t)c.fy0 / GS_TILE;
+    c.nx = (uint32_t)c.fx1 / GS_TILE - c.tx0 + 1;
+    c.ny = (uint32_t)c.fy1 / GS_TILE - c.ty0 + 1;
+    return true;
+}
+
+
 #endif

@@ -240,7 +240,8 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
                                                          const __grid_constant__ GsModelXf m, uint32_t* ctrl,
                                                          uint64_t* lookback, uint32_t epoch,
                                                          uint32_t* __restrict__ keys, uint32_t* __restrict__ idx,
-                                                         b200gs_splat* __restrict__ splats, uint32_t* sort_hist) {
+                                                         b200gs_splat* __restrict__ splats, uint32_t* __restrict__ ncand,
+                                                         uint32_t* sort_hist) {
     constexpr int RB = 16 + ShBytes<SH>::v + CovBytes<COV>::v;  // record bytes
     constexpr int RW = RB / 4;                                  // record words
     constexpr int NSTAGE = 3;                                   // chunk j, chunk j+1 (counted ahead), one in flight
@@ -524,6 +525,9 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
                 uint4* sp = reinterpret_cast<uint4*>(splats + off);
                 sp[0] = q0;
                 sp[1] = q1;
+                // candidate tiles of this splat (from the STORED record, exactly as the binning kernels decode it)
+                GsCand cd;
+                ncand[off] = gs_make_rect(q0, f.W, f.H, f.display_mode != B200GS_DISPLAY_SPLAT, cd) ? cd.nx * cd.ny : 0u;
             }
         }
     }
@@ -556,7 +560,7 @@ cudaError_t launch_t(const GsPreprocessArgs& a, const GsFrame& f, const GsModelX
     if (grid > nchunks) grid = nchunks;
     if (grid < 1) grid = 1;
     kern<<<grid, kThreads, smem, st>>>(a.recs, a.n, a.mask, a.selection, a.edits, f, m, a.ctrl, a.lookback, a.epoch,
-                                       a.keys, a.idx, a.splats, a.sort_hist);
+                                       a.keys, a.idx, a.splats, a.ncand, a.sort_hist);
     return cudaGetLastError();
 }
 
