@@ -257,7 +257,11 @@ __global__ void __launch_bounds__(kThreads) k_bin_emit(const b200gs_splat* __res
                     cd.a = __uint_as_float(q1.x); cd.b = __uint_as_float(q1.y); cd.c = __uint_as_float(q1.z);
                     cd.nbc = __fdividef(-cd.b, cd.c); cd.nba = __fdividef(-cd.b, cd.a);  // tau carries the slack
                     const uint32_t e = cbase + p - os.x;
-                    const uint32_t y = e / cd.nx, x = e - y * cd.nx;
+                    // e / nx without the integer-division sequence (e < 2^24, nx <= 1024: exact after one fix-up)
+                    uint32_t y = (uint32_t)(__fdividef((float)e + 0.5f, (float)cd.nx));
+                    if (y * cd.nx > e) y--;
+                    else if ((y + 1) * cd.nx <= e) y++;
+                    const uint32_t x = e - y * cd.nx;
                     key[k] = (cd.ty0 + y) * tiles_x + cd.tx0 + x;
                     // tiles already finished by a nearer depth slab take no more entries
                     keep[k] = !(tile_done && tile_done[key[k]]) && tile_hit(cd, x, y);

@@ -68,47 +68,45 @@ __global__ void __launch_bounds__(kThreads) k_composite(float4* __restrict__ sta
         }
     }
 
-    // software pipeline of the staging loads: splat records one round ahead, entry ids two rounds ahead
+    // software pipeline of the staging: entry ids two rounds ahead, splat records one round ahead in
+    // registers, converted into the other shared-memory buffer at the end of the current round, so a
+    // round costs ONE barrier (which also carries the early-exit vote)
     uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
     uint32_t id_next = 0;
-    if (start + tid < end) {
-        const uint4* sp = reinterpret_cast<const uint4*>(splats + tile_vals[start + tid]);
+    auto stage = [&](float4* dst) {
+        const float mx = __uint_as_float(q0.x), my = __uint_as_float(q0.y);
+        const float r = (float)(q0.z & 0xffffu);
+        const float op = __half2float(__ushort_as_half((unsigned short)(q0.z >> 16)));
+        const float cr = __half2float(__ushort_as_half((unsigned short)(q0.w & 0xffffu)));
+        const float cg = __half2float(__ushort_as_half((unsigned short)(q0.w >> 16)));
+        const float cb = __half2float(__ushort_as_half((unsigned short)(q1.w & 0xffffu)));
+        const float ca = __uint_as_float(q1.x), cbq = __uint_as_float(q1.y), cc = __uint_as_float(q1.z);
+        // same bounds expression as bin.cu / the oracle (exact in float)
+        float fx0 = ceilf(mx - r), fx1 = floorf(mx + r), fy0 = ceilf(my - r), fy1 = floorf(my + r);
+        if (fx0 < 0.0f) fx0 = 0.0f;
+        if (fy0 < 0.0f) fy0 = 0.0f;
+        if (fx1 > Wf - 1.0f) fx1 = Wf - 1.0f;
+        if (fy1 > Hf - 1.0f) fy1 = Hf - 1.0f;
+        float4* rec = &dst[tid * 4];
+        rec[0] = make_float4(mx, my, -0.5f * kLog2e * ca, -kLog2e * cbq);
+        rec[1] = make_float4(-0.5f * kLog2e * cc, op, cr, cg);
+        rec[2] = make_float4(0.5f * (fx0 + fx1), 0.5f * (fx1 - fx0), 0.5f * (fy0 + fy1), 0.5f * (fy1 - fy0));
+        rec[3] = make_float4(cb, 0.5f * kLog2e * gs_footprint_tau(op, FLAT), r, 0.0f);
+    };
+    auto load_splat = [&](uint32_t id) {
+        const uint4* sp = reinterpret_cast<const uint4*>(splats + id);
         q0 = __ldg(sp); q1 = __ldg(sp + 1);
-    }
-    if (start + kThreads + tid < end) id_next = tile_vals[start + kThreads + tid];
+    };
+    if (start + tid < end) { load_splat(tile_vals[start + tid]); stage(sS[0]); }              // round 0 -> buffer 0
+    if (start + kThreads + tid < end) load_splat(tile_vals[start + kThreads + tid]);            // round 1 -> registers
+    if (start + 2 * kThreads + tid < end) id_next = tile_vals[start + 2 * kThreads + tid];      // round 2 ids
+    __syncthreads();
 
     uint32_t buf = 0;
     for (uint32_t base = start; base < end; base += kThreads, buf ^= 1u) {
         const uint32_t cnt = min((uint32_t)kThreads, end - base);
         if (COUNT && tid == 0) atomicAdd(evals + 1, (unsigned long long)cnt);  // entries staged before the tile finished
-        float4* sSb = sS[buf];
-        if ((uint32_t)tid < cnt) {
-            const float mx = __uint_as_float(q0.x), my = __uint_as_float(q0.y);
-            const float r = (float)(q0.z & 0xffffu);
-            const float op = __half2float(__ushort_as_half((unsigned short)(q0.z >> 16)));
-            const float cr = __half2float(__ushort_as_half((unsigned short)(q0.w & 0xffffu)));
-            const float cg = __half2float(__ushort_as_half((unsigned short)(q0.w >> 16)));
-            const float cb = __half2float(__ushort_as_half((unsigned short)(q1.w & 0xffffu)));
-            const float ca = __uint_as_float(q1.x), cbq = __uint_as_float(q1.y), cc = __uint_as_float(q1.z);
-            // same bounds expression as bin.cu / the oracle (exact in float)
-            float fx0 = ceilf(mx - r), fx1 = floorf(mx + r), fy0 = ceilf(my - r), fy1 = floorf(my + r);
-            if (fx0 < 0.0f) fx0 = 0.0f;
-            if (fy0 < 0.0f) fy0 = 0.0f;
-            if (fx1 > Wf - 1.0f) fx1 = Wf - 1.0f;
-            if (fy1 > Hf - 1.0f) fy1 = Hf - 1.0f;
-            float4* rec = &sSb[tid * 4];
-            rec[0] = make_float4(mx, my, -0.5f * kLog2e * ca, -kLog2e * cbq);
-            rec[1] = make_float4(-0.5f * kLog2e * cc, op, cr, cg);
-            rec[2] = make_float4(0.5f * (fx0 + fx1), 0.5f * (fx1 - fx0), 0.5f * (fy0 + fy1), 0.5f * (fy1 - fy0));
-            rec[3] = make_float4(cb, 0.5f * kLog2e * gs_footprint_tau(op, FLAT), r, 0.0f);
-        }
-        __syncthreads();
-        // issue the next round's loads now; they land while this round is blended
-        if (base + kThreads + tid < end) {
-            const uint4* sp = reinterpret_cast<const uint4*>(splats + id_next);
-            q0 = __ldg(sp); q1 = __ldg(sp + 1);
-        }
-        if (base + 2 * kThreads + tid < end) id_next = tile_vals[base + 2 * kThreads + tid];
+        const float4* sSb = sS[buf];
 
         if (!__all_sync(0xffffffffu, done)) {
             for (uint32_t g = 0; g < cnt; g += 32) {
@@ -188,6 +186,10 @@ __global__ void __launch_bounds__(kThreads) k_composite(float4* __restrict__ sta
                 if (__all_sync(0xffffffffu, done)) break;
             }
         }
+        // next round: registers -> the other buffer, then fetch the round after it
+        if (base + kThreads + tid < end) stage(sS[buf ^ 1u]);
+        if (base + 2 * kThreads + tid < end) load_splat(id_next);
+        if (base + 3 * kThreads + tid < end) id_next = tile_vals[base + 3 * kThreads + tid];
         if (__syncthreads_and(done)) break;
     }
 
