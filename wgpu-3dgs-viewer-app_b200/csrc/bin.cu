@@ -32,7 +32,6 @@ constexpr int kCpt = 8;                      // candidates per thread in k_bin_e
 constexpr uint32_t kBlock = kThreads * kCpt; // 2048 candidates per block
 
 using Cand = GsCand;
-__device__ __forceinline__ bool make_rect(const uint4& q0, float W, float H, bool flat, Cand& c) { return gs_make_rect(q0, W, H, flat, c); }
 
 // can candidate tile (x, y) of the rectangle be touched?  (gs_min_q_rect with the divisions hoisted)
 __device__ __forceinline__ bool tile_hit(const Cand& c, uint32_t x, uint32_t y) {
@@ -253,8 +252,7 @@ __global__ void __launch_bounds__(kThreads) k_bin_emit(const b200gs_splat* __res
                 const uint4* sp = reinterpret_cast<const uint4*>(splats + slot);
                 const uint4 q0 = __ldg(sp), q1 = __ldg(sp + 1);
                 Cand cd;
-                if (make_rect(q0, W, H, flat != 0, cd)) {
-                    cd.a = __uint_as_float(q1.x); cd.b = __uint_as_float(q1.y); cd.c = __uint_as_float(q1.z);
+                if (gs_make_rect(q0, q1, W, H, flat != 0, cd)) {
                     cd.nbc = __fdividef(-cd.b, cd.c); cd.nba = __fdividef(-cd.b, cd.a);  // tau carries the slack
                     const uint32_t e = cbase + p - os.x;
                     // e / nx without the integer-division sequence (e < 2^24, nx <= 1024: exact after one fix-up)

@@ -280,8 +280,10 @@ __device__ __forceinline__ float gs_min_q_rect(float mx, float my, float a, floa
 // footprint threshold (with slack so that rounding can never cull a contributing pixel)
 __device__ __forceinline__ float gs_footprint_tau(float opacity, bool flat) {
     if (!(opacity * 255.0f >= 1.0f)) return -1.0f;  // alpha < 1/255 everywhere
-    const float t = flat ? GS_FLAT_D2 : 2.0f * __logf(opacity * 255.0f);
-    return t * 1.001f + 0.01f;
+    // explicit single-rounding ops: this value feeds the candidate tile rectangle, which must come out
+    // identical in translation units compiled with and without -fmad
+    const float t = flat ? GS_FLAT_D2 : __fmul_rn(2.0f, __logf(__fmul_rn(opacity, 255.0f)));
+    return __fadd_rn(__fmul_rn(t, 1.001f), 0.01f);
 }
 // ---- candidate tile rectangle of a projected splat (shared by preprocess and binning) --------
 struct GsCand {
@@ -291,8 +293,13 @@ struct GsCand {
     uint32_t tx0, ty0, nx, ny;    // candidate tile rectangle
 };
 
-// candidate tile rectangle of a projected splat (first 16 bytes); false if it cannot touch anything
-__device__ __forceinline__ bool gs_make_rect(const uint4& q0, float W, float H, bool flat, GsCand& c) {
+// candidate tile rectangle of a projected splat; false if it cannot touch anything.  The pixel
+// range is the extent square (same expression as the compositor / the oracle, exact in float)
+// intersected with a conservative axis-aligned box of the footprint ellipse q <= tau (half-widths
+// sqrt(tau * cov_xx), sqrt(tau * cov_yy), inflated): tiles outside it cannot be touched.
+// Deterministic function of the STORED record, so the preprocess kernel (candidate counts) and
+// the binning kernels (enumeration) agree exactly.
+__device__ __forceinline__ bool gs_make_rect(const uint4& q0, const uint4& q1, float W, float H, bool flat, GsCand& c) {
     const uint32_t radius = q0.z & 0xffffu;
     if (radius == 0) return false;
     c.mx = __uint_as_float(q0.x);
@@ -300,9 +307,23 @@ __device__ __forceinline__ bool gs_make_rect(const uint4& q0, float W, float H, 
     const float op = __half2float(__ushort_as_half((unsigned short)(q0.z >> 16)));
     c.tau = gs_footprint_tau(op, flat);
     if (c.tau < 0.0f) return false;
-    // same bounds expression as the compositor / the oracle (exact in float)
+    c.a = __uint_as_float(q1.x);
+    c.b = __uint_as_float(q1.y);
+    c.c = __uint_as_float(q1.z);
     const float r = (float)radius;
-    c.fx0 = ceilf(c.mx - r); c.fx1 = floorf(c.mx + r); c.fy0 = ceilf(c.my - r); c.fy1 = floorf(c.my + r);
+    float rx = r, ry = r;
+    // (explicit single-rounding ops, see gs_footprint_tau)
+    const float det = __fsub_rn(__fmul_rn(c.a, c.c), __fmul_rn(c.b, c.b));
+    if (det > 0.0f) {
+        const float k = __fdividef(c.tau, det);
+        rx = fminf(r, __fadd_rn(__fmul_rn(__fsqrt_rn(__fmul_rn(k, c.c)), 1.002f), 0.02f));
+        ry = fminf(r, __fadd_rn(__fmul_rn(__fsqrt_rn(__fmul_rn(k, c.a)), 1.002f), 0.02f));
+    }
+    c.fx0 = ceilf(__fsub_rn(c.mx, rx)); c.fx1 = floorf(__fadd_rn(c.mx, rx));
+    c.fy0 = ceilf(__fsub_rn(c.my, ry)); c.fy1 = floorf(__fadd_rn(c.my, ry));
+    // never beyond the extent square itself
+    c.fx0 = fmaxf(c.fx0, ceilf(c.mx - r)); c.fx1 = fminf(c.fx1, floorf(c.mx + r));
+    c.fy0 = fmaxf(c.fy0, ceilf(c.my - r)); c.fy1 = fminf(c.fy1, floorf(c.my + r));
     if (c.fx0 < 0.0f) c.fx0 = 0.0f;
     if (c.fy0 < 0.0f) c.fy0 = 0.0f;
     if (c.fx1 > W - 1.0f) c.fx1 = W - 1.0f;

@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
                 sp[1] = q1;
                 // candidate tiles of this splat (from the STORED record, exactly as the binning kernels decode it)
                 GsCand cd;
-                ncand[off] = gs_make_rect(q0, f.W, f.H, f.display_mode != B200GS_DISPLAY_SPLAT, cd) ? cd.nx * cd.ny : 0u;
+                ncand[off] = gs_make_rect(q0, q1, f.W, f.H, f.display_mode != B200GS_DISPLAY_SPLAT, cd) ? cd.nx * cd.ny : 0u;
             }
         }
     }
