@@ -46,14 +46,11 @@ extern "C" const char* b200gs_version(void) { return "b200gs 0.1 (sm_100a)"; }
 
 // ---------------------------------------------------------------------------- handles
 enum {  // viewer control block (u32 words), zeroed at the start of every render
-    VC_BIN_TICKET = 0,     // 2 x 64 words: (count, emit) tickets per model in the frame
+    VC_BIN_TICKET = 0,     // 64 words: chunk ticket per model in the frame
     VC_ENTRY_TOTAL = 128,  // 65 words: running (tile, splat) entry count after each model
-    VC_OVERFLOW = 194,
-    VC_TSORT_TICKET = 196, // 2 words
-    VC_TSORT_IN_B = 198,   // 1 = tile-sorted entries are in the *_b buffers
-    VC_EVALS = 200,        // u64
-    VC_CAND_TOTAL = 208,   // 64 words: candidate tiles per model
-    VC_TSORT_HIST = 512,   // 2 x 256
+    VC_TSORT_TICKET = 196, // 3 words
+    VC_TSORT_IN_B = 200,   // 1 = tile-sorted entries are in the *_b buffers
+    VC_TSORT_HIST = 256,   // 3 x 256 (written by the tile scan)
     VC_WORDS = 1024
 };
 enum {  // model control block layout
@@ -74,7 +71,7 @@ struct b200gs_model {
     b200gs_edit_pod* edits = nullptr;
     float pos[3] = {0, 0, 0}, quat[4] = {0, 0, 0, 1}, scale[3] = {1, 1, 1};
     uint32_t* ctrl = nullptr;
-    uint32_t *keys_a = nullptr, *vals_a = nullptr, *keys_b = nullptr, *vals_b = nullptr, *idx = nullptr, *ncand = nullptr;
+    uint32_t *keys_a = nullptr, *vals_a = nullptr, *keys_b = nullptr, *vals_b = nullptr, *idx = nullptr, *binword = nullptr;
     uint64_t *lb_pre = nullptr, *lb_sort = nullptr;
     uint64_t arena_offset = 0;
     bool preprocessed = false, sorted = false;
@@ -98,12 +95,10 @@ struct b200gs_viewer {
     bool layout_dirty = true;
     uint32_t *tk_a = nullptr, *tv_a = nullptr, *tk_b = nullptr, *tv_b = nullptr;
     uint64_t entry_cap = 0, entry_cap_user = 0;
-    uint64_t *lb_bin = nullptr, *lb_tsort = nullptr, *lb_emit = nullptr;
+    uint64_t *lb_bin = nullptr, *lb_tsort = nullptr;
     uint64_t lb_bin_words = 0;
-    uint2* cand_off = nullptr;
-    uint32_t* block_rank = nullptr;
-    uint64_t cand_off_words = 0, block_cap = 0;
     uint32_t* ranges = nullptr;
+    uint32_t* tile_count = nullptr;        // per tile: entries written by the binning kernel (cleared by the tile scan)
     uint32_t ranges_tiles = 0;
     uint8_t* tile_done = nullptr;          // per tile: finished by a nearer depth slab
     float4* pix_state = nullptr;           // per pixel (Cr, Cg, Cb, T) between depth slabs
@@ -216,6 +211,8 @@ static int ensure_frame_buffers(b200gs_viewer* v) {
         TRY(dev_alloc(&v->ranges, (size_t)n_tiles * 3, true, v->stream));
         if (v->tile_done) CK(cudaFree(v->tile_done));
         TRY(dev_alloc(&v->tile_done, (size_t)n_tiles, true, v->stream));
+        if (v->tile_count) CK(cudaFree(v->tile_count));
+        TRY(dev_alloc(&v->tile_count, gs_tile_count_words(n_tiles), true, v->stream));
         v->ranges_tiles = n_tiles;
     }
     if (v->pix_state_px < (size_t)v->W * v->H) {
@@ -253,13 +250,7 @@ static int ensure_frame_buffers(b200gs_viewer* v) {
             TRY(dev_alloc(p, want, false, v->stream));
         }
         if (v->lb_tsort) CK(cudaFree(v->lb_tsort));
-        TRY(dev_alloc(&v->lb_tsort, gs_sort_lookback_words((uint32_t)want, 2), true, v->stream));
-        // candidate space of the binning stage: up to 2 candidates per kept entry before the tail is dropped
-        v->block_cap = gs_bin_block_words((uint32_t)std::min<uint64_t>(want * 2, 0x7fffffffull));
-        if (v->block_rank) CK(cudaFree(v->block_rank));
-        TRY(dev_alloc(&v->block_rank, v->block_cap, true, v->stream));
-        if (v->lb_emit) CK(cudaFree(v->lb_emit));
-        TRY(dev_alloc(&v->lb_emit, v->block_cap * kMaxModelsPerFrame / 8 + v->block_cap, true, v->stream));
+        TRY(dev_alloc(&v->lb_tsort, gs_sort_lookback_words((uint32_t)want, 3), true, v->stream));
         v->entry_cap = want;
     }
     uint64_t lbw = (maxcap + 1023) / 1024 + 1;
@@ -267,11 +258,6 @@ static int ensure_frame_buffers(b200gs_viewer* v) {
         if (v->lb_bin) CK(cudaFree(v->lb_bin));
         TRY(dev_alloc(&v->lb_bin, lbw * kMaxModelsPerFrame, true, v->stream));
         v->lb_bin_words = lbw;
-    }
-    if (maxcap + 1 > v->cand_off_words) {
-        if (v->cand_off) CK(cudaFree(v->cand_off));
-        TRY(dev_alloc(&v->cand_off, maxcap + 1, true, v->stream));
-        v->cand_off_words = maxcap + 1;
     }
     v->layout_dirty = false;
     return B200GS_OK;
@@ -344,7 +330,7 @@ extern "C" int b200gs_viewer_create(int device, uint32_t sh, uint32_t cov3d, uin
 }
 
 static void free_model(b200gs_model* m) {
-    void* ps[] = {m->recs, m->mask, m->selection, m->edits, m->ctrl, m->keys_a, m->vals_a, m->keys_b, m->vals_b, m->idx, m->ncand,
+    void* ps[] = {m->recs, m->mask, m->selection, m->edits, m->ctrl, m->keys_a, m->vals_a, m->keys_b, m->vals_b, m->idx, m->binword,
                   m->lb_pre, m->lb_sort};
     for (void* p : ps)
         if (p) cudaFree(p);
@@ -356,7 +342,7 @@ extern "C" int b200gs_viewer_destroy(b200gs_viewer* v) {
     cudaSetDevice(v->device);
     if (v->stream) cudaStreamSynchronize(v->stream);
     for (auto* m : v->models) free_model(m);
-    void* ps[] = {v->arena, v->tk_a, v->tv_a, v->tk_b, v->tv_b, v->lb_bin, v->lb_tsort, v->lb_emit, v->cand_off, v->block_rank,
+    void* ps[] = {v->arena, v->tk_a, v->tv_a, v->tk_b, v->tv_b, v->lb_bin, v->lb_tsort, v->tile_count,
                   v->ranges, v->vctrl, v->image, v->tile_done, v->pix_state, v->stats};
     for (void* p : ps)
         if (p) cudaFree(p);
@@ -502,7 +488,7 @@ extern "C" int b200gs_model_create(b200gs_viewer* v, const char* key, uint64_t c
     if (rc == B200GS_OK) rc = dev_alloc(&m->keys_b, capacity, false, st);
     if (rc == B200GS_OK) rc = dev_alloc(&m->vals_b, capacity, false, st);
     if (rc == B200GS_OK) rc = dev_alloc(&m->idx, capacity, false, st);
-    if (rc == B200GS_OK) rc = dev_alloc(&m->ncand, capacity, false, st);
+    if (rc == B200GS_OK) rc = dev_alloc(&m->binword, capacity, false, st);
     if (rc == B200GS_OK) rc = dev_alloc(&m->lb_pre, (capacity + 255) / 256 + 1, true, st);
     if (rc == B200GS_OK) rc = dev_alloc(&m->lb_sort, gs_sort_lookback_words((uint32_t)capacity, 4), true, st);
     if (rc != B200GS_OK) { free_model(m); return rc; }
@@ -702,7 +688,7 @@ extern "C" int b200gs_model_preprocess(b200gs_model* m, int use_unedited) {
     a.ctrl = m->ctrl + MC_CTRL; a.lookback = m->lb_pre; a.epoch = ++v->epoch;
     a.keys = m->keys_a; a.idx = m->idx; a.splats = v->arena + m->arena_offset;
     a.sort_hist = m->ctrl + MC_SORT_HIST;
-    a.ncand = m->ncand;
+    a.binword = m->binword;
     if (v->timing) CK(cudaEventRecord(v->ev[0], v->stream));
     CK(gs_launch_preprocess(a, f, xf, v->num_sms, v->stream));
     v->launches += 1;
@@ -765,38 +751,34 @@ static int render_slabs(b200gs_viewer* v, b200gs_model* const* far_to_near, uint
             b.sorted_slot_b = m->vals_b;
             b.sorted_in_b = m->ctrl + MC_CTRL + GS_CTRL_SORT_IN_B;
             b.splats = v->arena + m->arena_offset;
-            b.ncand = m->ncand;
+            b.binword = m->binword;
             b.d_v = m->ctrl + MC_CTRL + GS_CTRL_VISIBLE;
             b.v_max = (uint32_t)m->cap;
             b.splat_base = (uint32_t)m->arena_offset;
             b.lookback = v->lb_bin + (size_t)k * v->lb_bin_words;
-            b.lookback_emit = v->lb_emit;   // reused across launches: every launch has its own epoch
             b.epoch = ++v->epoch;
-            b.ticket = v->vctrl + VC_BIN_TICKET + 2 * k;
-            b.cand_off = v->cand_off;       // models are expanded one after the other on the stream
-            b.block_rank = v->block_rank;
-            b.block_cap = (uint32_t)v->block_cap;
-            b.cand_total = v->vctrl + VC_CAND_TOTAL + k;
+            b.ticket = v->vctrl + VC_BIN_TICKET + k;
             b.entry_base_in = v->vctrl + VC_ENTRY_TOTAL + k;
             b.entry_total_out = v->vctrl + VC_ENTRY_TOTAL + k + 1;
             b.overflow = (uint32_t*)(v->stats + 3);
             b.tile_keys = v->tk_a; b.tile_vals = v->tv_a; b.capacity = (uint32_t)v->entry_cap;
-            b.tile_hist = v->vctrl + VC_TSORT_HIST;
+            b.tile_count = v->tile_count;
             b.q_lo = k == 0 ? bounds[sl] : 0;
             b.q_hi = k == 0 ? bounds[sl + 1] : 65536;
             b.tile_done = sl > 0 ? v->tile_done : nullptr;
             CK(gs_launch_bin(b, f, v->num_sms, st));
-            v->launches += 2;
+            v->launches += 1;
         }
+        // tile ids are sorted on 16 bits (2 onesweep passes); viewports with more than 65536 tiles take a third
+        const uint32_t tpasses = n_tiles > 65536u ? 3u : 2u;
+        CK(gs_launch_tile_ranges(v->tile_count, v->ranges, n_tiles, v->vctrl + VC_TSORT_HIST, tpasses, v->stats + 2, st));
         GsSortArgs s;
         s.keys_a = v->tk_a; s.vals_a = v->tv_a; s.keys_b = v->tk_b; s.vals_b = v->tv_b;
         s.d_n = v->vctrl + VC_ENTRY_TOTAL + n_seg; s.n_max = (uint32_t)v->entry_cap;
         s.hist = v->vctrl + VC_TSORT_HIST; s.lookback = v->lb_tsort; s.epoch = ++v->epoch;
-        s.tickets = v->vctrl + VC_TSORT_TICKET; s.passes = 2; s.hist_prefilled = true; s.vals_identity = false;
+        s.tickets = v->vctrl + VC_TSORT_TICKET; s.passes = tpasses; s.hist_prefilled = true; s.vals_identity = false;
         s.result_in_b = v->vctrl + VC_TSORT_IN_B;
         CK(gs_launch_sort(s, v->num_sms, st));
-        CK(gs_launch_tile_ranges(v->tk_a, v->tk_b, s.result_in_b, s.d_n, (uint32_t)v->entry_cap, v->ranges, n_tiles,
-                                 v->stats + 2, v->num_sms, st));
         if (v->timing) CK(cudaEventRecord(v->ev_slab[sl][1], st));
         GsCompositeArgs c;
         c.tile_vals = v->tv_a; c.tile_vals_b = v->tv_b; c.tile_in_b = s.result_in_b; c.ranges = v->ranges; c.splats = v->arena;
@@ -805,7 +787,7 @@ static int render_slabs(b200gs_viewer* v, b200gs_model* const* far_to_near, uint
         c.state = v->pix_state; c.tile_done = v->tile_done; c.resume = sl > 0; c.last = last;
         CK(gs_launch_composite(c, f, st));
         if (v->timing) CK(cudaEventRecord(v->ev_slab[sl][2], st));
-        v->launches += s.passes + 3;  // tile sort passes, tile ranges, tile order, compositor
+        v->launches += s.passes + 4;  // tile sort passes, tile sum, tile scan, tile order, compositor
     }
     if (v->timing) CK(cudaEventRecord(v->ev[4], st));
     v->rendered = true;

@@ -72,7 +72,7 @@ struct GsPreprocessArgs {
     uint64_t* lookback;  // one status word per 256-Gaussian chunk (epoch-tagged, never cleared)
     uint32_t epoch;
     uint32_t* keys; uint32_t* idx; b200gs_splat* splats;
-    uint32_t* ncand;      // per compaction slot: candidate tiles of the splat (consumed by k_bin_count)
+    uint32_t* binword;    // per compaction slot: bin word of the splat (gs_make_bin_word; consumed by k_bin)
     uint32_t* sort_hist;  // 4 x 256 digit histogram of the emitted keys (zeroed before launch), or null
 };
 cudaError_t gs_launch_preprocess(const GsPreprocessArgs& a, const GsFrame& f, const GsModelXf& m, int num_sms,
@@ -101,31 +101,27 @@ struct GsBinArgs {
     const uint32_t* sorted_slot_b; // the sort's other buffer, selected when *sorted_in_b != 0
     const uint32_t* sorted_in_b;   // device flag written by the sort (GsSortArgs::result_in_b)
     const b200gs_splat* splats;    // this model's splats (compaction order)
-    const uint32_t* ncand;         // this model's per-slot candidate tile counts (from the preprocess kernel)
+    const uint32_t* binword;       // this model's per-slot bin words (from the preprocess kernel)
     const uint32_t* d_v;           // visible count of this model on device
     uint32_t v_max;
     uint32_t splat_base;           // global id of this model's splat 0 in the frame arena
-    uint64_t* lookback;            // k_bin_count: per-1024-rank-chunk status words (epoch-tagged, never cleared)
-    uint64_t* lookback_emit;       // k_bin_emit: per-2048-candidate-block status words
+    uint64_t* lookback;            // per-1024-rank-chunk status words (epoch-tagged, never cleared)
     uint32_t epoch;
-    uint32_t* ticket;              // 2 words (count, emit), zeroed before launch
-    uint2* cand_off;               // v_max x {exclusive prefix of the candidate counts, splat slot}
-    uint32_t* block_rank;          // block_cap words: first owning rank of every 2048-candidate block
-    uint32_t block_cap;
-    uint32_t* cand_total;          // 1 word
+    uint32_t* ticket;              // 1 word, zeroed before launch
     const uint32_t* entry_base_in; // entries already emitted by nearer models
     uint32_t* entry_total_out;     // entry_base_in + this model's entries (a different word)
     uint32_t* overflow;            // set to 1 when the capacity is exceeded
     uint32_t* tile_keys; uint32_t* tile_vals; uint32_t capacity;
-    uint32_t* tile_hist;           // 2 x 256 digit histogram of the emitted tile ids (zeroed before the slab)
+    uint32_t* tile_count;          // gs_tile_count_words(n_tiles) words: replicated per-tile entry counters (all zero between frames)
     uint32_t q_lo, q_hi;           // depth slab: ranks [V*q_lo >> 16, V*q_hi >> 16) of this model
     const uint8_t* tile_done;      // tiles finished by nearer slabs (null in the first slab)
 };
-size_t gs_bin_block_words(uint32_t capacity_candidates);
 cudaError_t gs_launch_bin(const GsBinArgs& a, const GsFrame& f, int num_sms, cudaStream_t st);
-cudaError_t gs_launch_tile_ranges(const uint32_t* keys_a, const uint32_t* keys_b, const uint32_t* in_b,
-                                  const uint32_t* d_entries, uint32_t capacity, uint32_t* ranges /* 3 x tiles: start, end, launch order */,
-                                  uint32_t n_tiles, unsigned long long* entry_stat, int num_sms, cudaStream_t st);
+size_t gs_tile_count_words(uint32_t n_tiles);
+// per-tile list boundaries + launch order + the tile sort's digit histograms, from the per-tile counters
+cudaError_t gs_launch_tile_ranges(uint32_t* tile_count, uint32_t* ranges /* 3 x tiles: start, end, launch order */,
+                                  uint32_t n_tiles, uint32_t* hist, uint32_t passes, unsigned long long* entry_stat,
+                                  cudaStream_t st);
 
 struct GsCompositeArgs {
     const uint32_t* tile_vals;      // entries sorted by tile, depth order inside a tile
@@ -336,5 +332,51 @@ __device__ __forceinline__ bool gs_make_rect(const uint4& q0, const uint4& q1, f
     return true;
 }
 
+// can candidate tile (x, y) of the rectangle be touched?  (gs_min_q_rect with the divisions hoisted into
+// nbc = -b/c, nba = -b/a; tau carries the rounding slack, so the answer is conservative)
+__device__ __forceinline__ bool gs_tile_hit(const GsCand& c, uint32_t x, uint32_t y) {
+    const float tx = (float)((c.tx0 + x) * GS_TILE), ty = (float)((c.ty0 + y) * GS_TILE);
+    const float dx0 = fmaxf(tx, c.fx0) - c.mx, dx1 = fminf(tx + (float)(GS_TILE - 1), c.fx1) - c.mx;
+    const float dy0 = fmaxf(ty, c.fy0) - c.my, dy1 = fminf(ty + (float)(GS_TILE - 1), c.fy1) - c.my;
+    const bool inx = dx0 <= 0.0f && dx1 >= 0.0f, iny = dy0 <= 0.0f && dy1 >= 0.0f;
+    if (inx && iny) return true;
+    float best = 3.0e38f;
+    if (!inx) {
+        const float dx = dx0 > 0.0f ? dx0 : dx1;
+        const float dy = fminf(dy1, fmaxf(dy0, c.nbc * dx));
+        best = c.a * dx * dx + 2.0f * c.b * dx * dy + c.c * dy * dy;
+    }
+    if (!iny) {
+        const float dy = dy0 > 0.0f ? dy0 : dy1;
+        const float dx = fminf(dx1, fmaxf(dx0, c.nba * dy));
+        best = fminf(best, c.a * dx * dx + 2.0f * c.b * dx * dy + c.c * dy * dy);
+    }
+    return best <= c.tau;
+}
+
+// ---- bin word: what the binning kernel needs to know about a splat, one u32 per compaction slot ----
+// Written by the preprocess kernel (which has the projected splat in registers), so that the binning
+// kernel expands splats from a 4-byte L2-resident gather instead of a 32-byte one.  The candidate tile
+// rectangle (gs_make_rect: extent square ∩ bounding box of the alpha >= 1/255 footprint) is kept whole:
+// measured on the garden-scale scenes an exact per-tile footprint test would drop only 4-9 % of the
+// entries, less than it costs, and the compositor culls every staged splat exactly anyway.
+//   0                         : touches no tile
+//   bit 31 clear (small)      : bits 0..19 first tile id (ty0 * tiles_x + tx0), bits 20..21 nx - 1,
+//                               bits 22..25 kept mask over the nx * ny <= 4 candidates (row-major)
+//   bits 31..30 = 10 (medium) : bits 0..19 first tile id, bits 20..24 nx - 1, bits 25..29 ny - 1 (nx, ny <= 32)
+//   bits 31..30 = 11 (huge)   : bits 0..29 number of candidate tiles; the binning kernel rebuilds the
+//                               rectangle from the stored splat
+#define GS_BIN_INLINE 4u
+#define GS_BIN_BIG 0x80000000u
+#define GS_BIN_HUGE 0x40000000u
+__device__ __forceinline__ uint32_t gs_make_bin_word(const uint4& q0, const uint4& q1, float W, float H, bool flat,
+                                                     uint32_t tiles_x) {
+    GsCand cd;
+    if (!gs_make_rect(q0, q1, W, H, flat, cd)) return 0u;
+    const uint32_t cand = cd.nx * cd.ny, origin = cd.ty0 * tiles_x + cd.tx0;
+    if (cand <= GS_BIN_INLINE) return origin | ((cd.nx - 1u) << 20) | (((1u << cand) - 1u) << 22);
+    if (cd.nx <= 32u && cd.ny <= 32u) return GS_BIN_BIG | origin | ((cd.nx - 1u) << 20) | ((cd.ny - 1u) << 25);
+    return GS_BIN_BIG | GS_BIN_HUGE | cand;
+}
 
 #endif

@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
                                                          const __grid_constant__ GsModelXf m, uint32_t* ctrl,
                                                          uint64_t* lookback, uint32_t epoch,
                                                          uint32_t* __restrict__ keys, uint32_t* __restrict__ idx,
-                                                         b200gs_splat* __restrict__ splats, uint32_t* __restrict__ ncand,
+                                                         b200gs_splat* __restrict__ splats, uint32_t* __restrict__ binword,
                                                          uint32_t* sort_hist) {
     constexpr int RB = 16 + ShBytes<SH>::v + CovBytes<COV>::v;  // record bytes
     constexpr int RW = RB / 4;                                  // record words
@@ -377,6 +377,7 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
 
             // ---------------- phase 2: projected splat for the visible ones ----------------
             uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
+            uint32_t bw = 0;
             if (vis) {
                 const uint32_t* shw = w + 4;
                 const uint32_t* cw = w + 4 + ShBytes<SH>::v / 4;
@@ -492,6 +493,9 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
                 q1.y = __float_as_uint(cb);
                 q1.z = __float_as_uint(cc);
                 q1.w = (uint32_t)__half_as_ushort(__float2half_rn(rgb[2])) | ((selected ? 1u : 0u) << 16);
+                // bin word (from the STORED record, exactly as the binning kernel decodes big splats): the tile
+                // tests of the common small splats are done here, where the splat is in registers
+                bw = gs_make_bin_word(q0, q1, f.W, f.H, f.display_mode != B200GS_DISPLAY_SPLAT, f.tiles_x);
             }
             bar_arrive(kBarFree + (int)(it & 3u));  // every read of this stage's shared memory is done
 
@@ -525,9 +529,7 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
                 uint4* sp = reinterpret_cast<uint4*>(splats + off);
                 sp[0] = q0;
                 sp[1] = q1;
-                // candidate tiles of this splat (from the STORED record, exactly as the binning kernels decode it)
-                GsCand cd;
-                ncand[off] = gs_make_rect(q0, q1, f.W, f.H, f.display_mode != B200GS_DISPLAY_SPLAT, cd) ? cd.nx * cd.ny : 0u;
+                binword[off] = bw;
             }
         }
     }
@@ -560,7 +562,7 @@ cudaError_t launch_t(const GsPreprocessArgs& a, const GsFrame& f, const GsModelX
     if (grid > nchunks) grid = nchunks;
     if (grid < 1) grid = 1;
     kern<<<grid, kThreads, smem, st>>>(a.recs, a.n, a.mask, a.selection, a.edits, f, m, a.ctrl, a.lookback, a.epoch,
-                                       a.keys, a.idx, a.splats, a.ncand, a.sort_hist);
+                                       a.keys, a.idx, a.splats, a.binword, a.sort_hist);
     return cudaGetLastError();
 }
 
