@@ -709,6 +709,7 @@ extern "C" int b200gs_model_sort(b200gs_model* m) {
     a.d_n = m->ctrl + MC_CTRL + GS_CTRL_VISIBLE; a.n_max = (uint32_t)m->cap;
     a.hist = m->ctrl + MC_SORT_HIST; a.lookback = m->lb_sort; a.epoch = ++v->epoch;
     a.tickets = m->ctrl + MC_SORT_TICKET; a.passes = 4; a.hist_prefilled = true; a.vals_identity = true;
+    a.vote_mask = 0x3;  // depth keys: the two low bytes are spread, the two high bytes concentrated
     a.result_in_b = m->ctrl + MC_CTRL + GS_CTRL_SORT_IN_B;
     CK(gs_launch_sort(a, v->num_sms, v->stream));
     v->launches += a.passes;
@@ -777,6 +778,7 @@ static int render_slabs(b200gs_viewer* v, b200gs_model* const* far_to_near, uint
         s.d_n = v->vctrl + VC_ENTRY_TOTAL + n_seg; s.n_max = (uint32_t)v->entry_cap;
         s.hist = v->vctrl + VC_TSORT_HIST; s.lookback = v->lb_tsort; s.epoch = ++v->epoch;
         s.tickets = v->vctrl + VC_TSORT_TICKET; s.passes = tpasses; s.hist_prefilled = true; s.vals_identity = false;
+        s.vote_mask = 0x1;  // tile ids: the low byte is spread, the row-band bytes concentrated
         s.result_in_b = v->vctrl + VC_TSORT_IN_B;
         CK(gs_launch_sort(s, v->num_sms, st));
         if (v->timing) CK(cudaEventRecord(v->ev_slab[sl][1], st));
@@ -1128,6 +1130,7 @@ extern "C" int b200gs_sort_pairs_device(b200gs_viewer* v, uint32_t* keys_dev, ui
     a.keys_a = keys_dev; a.vals_a = values_dev; a.keys_b = kb; a.vals_b = vb;
     a.d_n = ctl; a.n_max = nn; a.hist = ctl + 1024; a.lookback = lb; a.epoch = ++v->epoch;
     a.tickets = ctl + 8; a.passes = passes; a.hist_prefilled = false; a.vals_identity = false;
+    a.vote_mask = 0xf;  // arbitrary keys: assume spread digits
     a.result_in_b = ctl + 16;
     CK(gs_launch_sort(a, v->num_sms, st));
     CK(cudaMemcpyAsync(v->h_small, ctl + 16, 4, cudaMemcpyDeviceToHost, st));

@@ -91,6 +91,7 @@ struct GsSortArgs {
     uint32_t* result_in_b; // device flag written by the last pass: 1 = the sorted data is in keys_b/vals_b
     bool hist_prefilled; // histogram already accumulated by the producer
     bool vals_identity;  // pass 0 synthesises value = input position instead of reading vals_a
+    uint32_t vote_mask;  // bit p: pass p finds same-digit peers with ballots (spread digits) instead of MATCH.ANY (concentrated)
 };
 size_t gs_sort_lookback_words(uint32_t n_max, uint32_t passes);
 cudaError_t gs_launch_sort(const GsSortArgs& a, int num_sms, cudaStream_t st);

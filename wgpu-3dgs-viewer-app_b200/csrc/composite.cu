@@ -34,11 +34,12 @@ __global__ void __launch_bounds__(kThreads) k_composite(float4* __restrict__ sta
                                                         size_t pitch, uint32_t W, uint32_t H, uint32_t tiles_x,
                                                         uint32_t n_tiles, float bg0, float bg1, float bg2, float bg3,
                                                         unsigned long long* evals) {
-    // one 64-byte record per staged splat: {mx, my, a', b'} {c', opacity, red, green}
+    // 64 bytes per staged splat as four float4 planes [j][splat] (a lane reading its own splat in the cull
+    // loop touches consecutive 16-byte words: no bank conflicts): {mx, my, a', b'} {c', opacity, red, green}
     // {cx, hx, cy, hy} {blue, tau', -, -}; conic pre-scaled so that power is in log2 units, extent
     // square clipped to the viewport stored as centre / half-size (exact: half-integers).
     // Double-buffered: the next round's splats are in flight while this round is blended.
-    __shared__ float4 sS[2][kThreads * 4];
+    __shared__ float4 sS[2][4 * kThreads];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t* __restrict__ tile_vals = *tile_in_b ? tile_vals_b : tile_vals_a;
@@ -87,11 +88,10 @@ __global__ void __launch_bounds__(kThreads) k_composite(float4* __restrict__ sta
         if (fy0 < 0.0f) fy0 = 0.0f;
         if (fx1 > Wf - 1.0f) fx1 = Wf - 1.0f;
         if (fy1 > Hf - 1.0f) fy1 = Hf - 1.0f;
-        float4* rec = &dst[tid * 4];
-        rec[0] = make_float4(mx, my, -0.5f * kLog2e * ca, -kLog2e * cbq);
-        rec[1] = make_float4(-0.5f * kLog2e * cc, op, cr, cg);
-        rec[2] = make_float4(0.5f * (fx0 + fx1), 0.5f * (fx1 - fx0), 0.5f * (fy0 + fy1), 0.5f * (fy1 - fy0));
-        rec[3] = make_float4(cb, 0.5f * kLog2e * gs_footprint_tau(op, FLAT), r, 0.0f);
+        dst[tid] = make_float4(mx, my, -0.5f * kLog2e * ca, -kLog2e * cbq);
+        dst[kThreads + tid] = make_float4(-0.5f * kLog2e * cc, op, cr, cg);
+        dst[2 * kThreads + tid] = make_float4(0.5f * (fx0 + fx1), 0.5f * (fx1 - fx0), 0.5f * (fy0 + fy1), 0.5f * (fy1 - fy0));
+        dst[3 * kThreads + tid] = make_float4(cb, 0.5f * kLog2e * gs_footprint_tau(op, FLAT), r, 0.0f);
     };
     auto load_splat = [&](uint32_t id) {
         const uint4* sp = reinterpret_cast<const uint4*>(splats + id);
@@ -115,13 +115,13 @@ __global__ void __launch_bounds__(kThreads) k_composite(float4* __restrict__ sta
                 if (s < cnt) {
                     // splat s against this warp's 8x4 sub-tile: extent-square overlap first, then the exact
                     // footprint test (can any pixel of the overlap reach alpha >= 1/255?)
-                    const float4 C = sSb[s * 4 + 2];
+                    const float4 C = sSb[2 * kThreads + s];
                     const float x0 = fmaxf(C.x - C.y, fwx0), x1 = fminf(C.x + C.y, fwx1);
                     const float y0 = fmaxf(C.z - C.w, fwy0), y1 = fminf(C.z + C.w, fwy1);
                     if (x0 <= x1 && y0 <= y1) {
-                        const float4 A = sSb[s * 4];
-                        const float4 D = sSb[s * 4 + 3];
-                        const float pa = -A.z, pb = -0.5f * A.w, pc = -sSb[s * 4 + 1].x;  // 0.5*log2e * (a, b, c)
+                        const float4 A = sSb[s];
+                        const float4 D = sSb[3 * kThreads + s];
+                        const float pa = -A.z, pb = -0.5f * A.w, pc = -sSb[kThreads + s].x;  // 0.5*log2e * (a, b, c)
                         const float dx0 = x0 - A.x, dx1 = x1 - A.x, dy0 = y0 - A.y, dy1 = y1 - A.y;
                         const bool inx = dx0 <= 0.0f && dx1 >= 0.0f, iny = dy0 <= 0.0f && dy1 >= 0.0f;
                         float best = (inx && iny) ? 0.0f : 3.0e38f;
@@ -147,10 +147,8 @@ __global__ void __launch_bounds__(kThreads) k_composite(float4* __restrict__ sta
                     const bool has_b = m != 0;
                     const int sb = has_b ? (int)g + __ffs((int)m) - 1 : sa;
                     m &= m - 1;  // no-op when m == 0
-                    const float4* ra = &sSb[sa * 4];
-                    const float4* rb = &sSb[sb * 4];
-                    const float4 Aa = ra[0], Ba = ra[1], Ca = ra[2];
-                    const float4 Ab = rb[0], Bb = rb[1], Cbb = rb[2];
+                    const float4 Aa = sSb[sa], Ba = sSb[kThreads + sa], Ca = sSb[2 * kThreads + sa];
+                    const float4 Ab = sSb[sb], Bb = sSb[kThreads + sb], Cbb = sSb[2 * kThreads + sb];
                     const float dxa = fpx - Aa.x, dya = fpy - Aa.y, dxb = fpx - Ab.x, dyb = fpy - Ab.y;
                     const bool ina = fabsf(fpx - Ca.x) <= Ca.y && fabsf(fpy - Ca.z) <= Ca.w;
                     const bool inb = has_b && fabsf(fpx - Cbb.x) <= Cbb.y && fabsf(fpy - Cbb.z) <= Cbb.w;
@@ -169,7 +167,7 @@ __global__ void __launch_bounds__(kThreads) k_composite(float4* __restrict__ sta
                         const float w = ala * T;
                         Cr = __fmaf_rn(Ba.z, w, Cr);
                         Cg = __fmaf_rn(Ba.w, w, Cg);
-                        Cb = __fmaf_rn(ra[3].x, w, Cb);
+                        Cb = __fmaf_rn(sSb[3 * kThreads + sa].x, w, Cb);
                         T -= w;
                         done = T < GS_T_EPS;
                     }
@@ -178,7 +176,7 @@ __global__ void __launch_bounds__(kThreads) k_composite(float4* __restrict__ sta
                         const float w = alb * T;
                         Cr = __fmaf_rn(Bb.z, w, Cr);
                         Cg = __fmaf_rn(Bb.w, w, Cg);
-                        Cb = __fmaf_rn(rb[3].x, w, Cb);
+                        Cb = __fmaf_rn(sSb[3 * kThreads + sb].x, w, Cb);
                         T -= w;
                         done = T < GS_T_EPS;
                     }

@@ -7,7 +7,7 @@
 //
 // Design: one histogram kernel (all digit histograms in one read of the keys), then one
 // kernel per 8-bit digit.  A digit pass is a single sweep: each 3072-key tile ranks its keys
-// with warp-level __match_any_sync histograms, publishes its per-digit counts and resolves
+// with warp-level same-digit peer masks (ballots or MATCH.ANY), publishes its per-digit counts and resolves
 // its global offsets by decoupled look-back over epoch-tagged status words (chained scan, no
 // separate scan kernel, no second read of the keys), then scatters keys and values through
 // shared memory so that global writes are runs of consecutive addresses.  Tiles are handed
@@ -73,6 +73,12 @@ struct PassSmem {
     uint32_t tile_id;
 };
 
+// kVote: how the lanes of a warp find their same-digit peers.  MATCH.ANY costs ADU cycles per DISTINCT
+// value among the 32 lanes (measured: ~2 cycles each; a pass over uniformly spread digits is ADU-bound),
+// one ballot per digit bit costs the same whatever the digits are.  The host picks per pass: ballots for
+// spread digits (the low bytes of depth keys, the low byte of tile ids), MATCH.ANY for concentrated ones
+// (the top bytes of depth keys, the row-band byte of tile ids).
+template <bool kVote>
 __global__ void __launch_bounds__(kThreads, 3) k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a,
                                                            uint32_t* __restrict__ keys_b, uint32_t* __restrict__ vals_b,
                                                            const uint32_t* d_n, uint32_t n_max,
@@ -185,7 +191,18 @@ __global__ void __launch_bounds__(kThreads, 3) k_sort_pass(uint32_t* __restrict_
 #pragma unroll
             for (int k = 0; k < kKpt; k++) {
                 const uint32_t d = (key[k] >> shift) & 0xffu;
-                const uint32_t peers = __match_any_sync(0xffffffffu, d);
+                uint32_t peers;
+                if (kVote) {
+                    peers = 0xffffffffu;
+#pragma unroll
+                    for (int b = 0; b < 8; b++) {
+                        const bool bit = (d >> b) & 1u;
+                        const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+                        peers &= bit ? bal : ~bal;
+                    }
+                } else {
+                    peers = __match_any_sync(0xffffffffu, d);
+                }
                 const int leader = __ffs((int)peers) - 1;
                 uint32_t old = 0;
                 if (lane == leader) {
@@ -271,16 +288,19 @@ cudaError_t gs_launch_sort(const GsSortArgs& a, int num_sms, cudaStream_t st) {
     }
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
-        cudaError_t e = cudaFuncSetAttribute(k_sort_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
+        cudaError_t e = cudaFuncSetAttribute(k_sort_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_sort_pass, kThreads, sizeof(PassSmem));
+        e = cudaFuncSetAttribute(k_sort_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_sort_pass<false>, kThreads, sizeof(PassSmem));
         if (e != cudaSuccess) return e;
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
     uint32_t grid = (uint32_t)(blocks_per_sm * num_sms);
     if (grid > tiles) grid = (uint32_t)tiles;
     for (uint32_t p = 0; p < a.passes; p++) {
-        k_sort_pass<<<grid, kThreads, sizeof(PassSmem), st>>>(a.keys_a, a.vals_a, a.keys_b, a.vals_b, a.d_n, a.n_max, a.hist, p, a.passes,
+        auto kern = ((a.vote_mask >> p) & 1u) ? k_sort_pass<true> : k_sort_pass<false>;
+        kern<<<grid, kThreads, sizeof(PassSmem), st>>>(a.keys_a, a.vals_a, a.keys_b, a.vals_b, a.d_n, a.n_max, a.hist, p, a.passes,
                                                a.lookback + (size_t)p * tiles * kRadix, a.epoch, a.tickets + p,
                                                a.result_in_b, a.vals_identity ? 1u : 0u);
     }
