@@ -323,42 +323,59 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
         }
     } else {
         // ------------------------------------------------------------ compute warps
-        // count-ahead of chunk j: cull only, publish the warp's visible count
-        auto count_ahead = [&](uint32_t j) {
+        // phase 1 of chunk j (cheap, exact class): mask / edit / selection tests, projection, frustum cull;
+        // publishes the warp's visible count and keeps the results in registers for the heavy phase
+        struct Phase1 { bool vis; uint32_t ballot; float pv[3], nx, ny, nz; };
+        auto phase1 = [&](uint32_t j) -> Phase1 {
+            Phase1 r;
+            r.vis = false; r.ballot = 0u; r.pv[0] = r.pv[1] = r.pv[2] = r.nx = r.ny = r.nz = 0.0f;
             const int stage = j % NSTAGE;
             const uint32_t c = s_chunk[stage];
-            if (c >= nchunks) return;
+            if (c >= nchunks) return r;
             gs_mbar_wait(&bars[stage], (j / NSTAGE) & 1u);
             const uint32_t i = c * kChunk + tid;
             const uint32_t* w = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)stage * STAGE_BYTES) + tid * RW;
             bool selected;
             b200gs_edit_pod ed;
-            bool vis = pre_tests(i, n, mask, selection, edits, f, selected, ed);
-            if (vis) {
-                float pw[3], pv[3], nx, ny, nz;
-                vis = project_and_cull(w, f, m, pw, pv, nx, ny, nz);
+            r.vis = pre_tests(i, n, mask, selection, edits, f, selected, ed);
+            if (r.vis) {
+                float pw[3];
+                r.vis = project_and_cull(w, f, m, pw, r.pv, r.nx, r.ny, r.nz);
             }
-            const uint32_t ballot = __ballot_sync(0xffffffffu, vis);
-            if (lane == 0) s_wcount_all[(j & 3u) * 8 + warp] = __popc(ballot);
+            r.ballot = __ballot_sync(0xffffffffu, r.vis);
+            if (lane == 0) s_wcount_all[(j & 3u) * 8 + warp] = __popc(r.ballot);
             bar_arrive(kBarCounts + (int)(j & 3u));
+            return r;
         };
-        count_ahead(0);
+        Phase1 cur = phase1(0);
         for (uint32_t it = 0;; it++) {
             const int stage = it % NSTAGE;
             const uint32_t c = s_chunk[stage];
             if (c >= nchunks) break;
-            count_ahead(it + 1);
+            // chunk it+1 is culled and counted BEFORE the heavy phase of chunk it (see above)
+            const Phase1 nxt = phase1(it + 1);
 
             const uint32_t i = c * kChunk + tid;
             const uint32_t* w = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)stage * STAGE_BYTES) + tid * RW;
-
-            // ---------------- phase 1 again (cheap, exact class): same decisions as the count-ahead
-            bool selected;
+            const bool vis = cur.vis;
+            const uint32_t ballot = cur.ballot;
+            const float nx = cur.nx, ny = cur.ny, nz = cur.nz;
+            float pv[3] = {cur.pv[0], cur.pv[1], cur.pv[2]};
+            // per-Gaussian inputs of the heavy phase that phase 1 did not keep
+            bool selected = false;
             b200gs_edit_pod ed;
-            bool vis = pre_tests(i, n, mask, selection, edits, f, selected, ed);
-            float pw[3], pv[3], nx = 0.0f, ny = 0.0f, nz = 0.0f;
-            if (vis) vis = project_and_cull(w, f, m, pw, pv, nx, ny, nz);
-            const uint32_t ballot = __ballot_sync(0xffffffffu, vis);
+            ed.flag = 0;
+            if (mask || selection || edits) (void)pre_tests(i, n, mask, selection, edits, f, selected, ed);
+            float pw[3];
+            {
+                const float p0 = __uint_as_float(w[0]), p1 = __uint_as_float(w[1]), p2 = __uint_as_float(w[2]);
+                if (m.identity) { pw[0] = p0; pw[1] = p1; pw[2] = p2; }
+                else {
+                    const float ps0 = m.s[0] * p0, ps1 = m.s[1] * p1, ps2 = m.s[2] * p2;
+#pragma unroll
+                    for (int r = 0; r < 3; r++) pw[r] = m.R[r][0] * ps0 + m.R[r][1] * ps1 + m.R[r][2] * ps2 + m.t[r];
+                }
+            }
 
             // ---------------- selection query: rewrites this warp's selection word (32 Gaussians) -------
             if (f.query.kind >= B200GS_QUERY_RECT && selection) {
@@ -506,16 +523,22 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
                 const int first = __ffs((int)ballot) - 1;
                 const uint32_t key0 = __shfl_sync(0xffffffffu, key, first);
 #pragma unroll
-                for (int p = 3; p >= 0; p--) {
+                for (int p = 3; p >= 2; p--) {
                     const uint32_t dgt = (key >> (8 * p)) & 0xffu;
                     // the top bytes are usually the same for the whole warp: one vote instead of a match
-                    const bool uniform = p >= 2 && __all_sync(0xffffffffu, !vis || dgt == ((key0 >> (8 * p)) & 0xffu));
+                    const bool uniform = __all_sync(0xffffffffu, !vis || dgt == ((key0 >> (8 * p)) & 0xffu));
                     if (uniform) {
                         if (lane == first) atomicAdd(&s_hist[p * 256 + dgt], (uint32_t)__popc(ballot));
                     } else if (vis) {
                         const uint32_t peers = __match_any_sync(ballot, dgt);
                         if (lane == __ffs((int)peers) - 1) atomicAdd(&s_hist[p * 256 + dgt], (uint32_t)__popc(peers));
                     }
+                }
+                // the low bytes are spread: ~30 distinct values among 32 lanes, where MATCH.ANY costs more ADU
+                // cycles than 32 fire-and-forget shared-memory atomics cost the (idle) LSU
+                if (vis) {
+                    atomicAdd(&s_hist[256 + ((key >> 8) & 0xffu)], 1u);
+                    atomicAdd(&s_hist[key & 0xffu], 1u);
                 }
             }
 
@@ -531,6 +554,7 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
                 sp[1] = q1;
                 binword[off] = bw;
             }
+            cur = nxt;
         }
     }
     if (sort_hist) {
