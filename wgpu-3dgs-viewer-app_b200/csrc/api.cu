@@ -50,8 +50,11 @@ enum {  // viewer control block (u32 words), zeroed at the start of every render
     VC_ENTRY_TOTAL = 128,  // 65 words: running (tile, splat) entry count after each model
     VC_TSORT_TICKET = 196, // 3 words
     VC_TSORT_IN_B = 200,   // 1 = tile-sorted entries are in the *_b buffers
-    VC_TSORT_HIST = 256,   // 3 x 256 (written by the tile scan)
-    VC_WORDS = 1024
+    VC_TILE_TICKET = 201,  // tile-finish kernel: chunk ticket, finished-CTA counter
+    VC_TILE_DONE = 202,
+    VC_TSORT_HIST = 256,   // 3 x 256 (accumulated by the tile-finish kernel)
+    VC_TILE_BUCKETS = 1024, // 256: tiles per list-length bucket (launch order)
+    VC_WORDS = 1280
 };
 enum {  // model control block layout
     MC_CTRL = 0,               // GS_CTRL_WORDS
@@ -95,7 +98,7 @@ struct b200gs_viewer {
     bool layout_dirty = true;
     uint32_t *tk_a = nullptr, *tv_a = nullptr, *tk_b = nullptr, *tv_b = nullptr;
     uint64_t entry_cap = 0, entry_cap_user = 0;
-    uint64_t *lb_bin = nullptr, *lb_tsort = nullptr;
+    uint64_t *lb_bin = nullptr, *lb_tsort = nullptr, *lb_tiles = nullptr;
     uint64_t lb_bin_words = 0;
     uint32_t* ranges = nullptr;
     uint32_t* tile_count = nullptr;        // per tile: entries written by the binning kernel (cleared by the tile scan)
@@ -208,7 +211,9 @@ static int ensure_frame_buffers(b200gs_viewer* v) {
     if (v->ranges_tiles < n_tiles) {
         CK(cudaStreamSynchronize(v->stream));
         if (v->ranges) CK(cudaFree(v->ranges));
-        TRY(dev_alloc(&v->ranges, (size_t)n_tiles * 3, true, v->stream));
+        TRY(dev_alloc(&v->ranges, (size_t)n_tiles * 4, true, v->stream));
+        if (v->lb_tiles) CK(cudaFree(v->lb_tiles));
+        TRY(dev_alloc(&v->lb_tiles, gs_tile_lookback_words(n_tiles), true, v->stream));
         if (v->tile_done) CK(cudaFree(v->tile_done));
         TRY(dev_alloc(&v->tile_done, (size_t)n_tiles, true, v->stream));
         if (v->tile_count) CK(cudaFree(v->tile_count));
@@ -342,7 +347,7 @@ extern "C" int b200gs_viewer_destroy(b200gs_viewer* v) {
     cudaSetDevice(v->device);
     if (v->stream) cudaStreamSynchronize(v->stream);
     for (auto* m : v->models) free_model(m);
-    void* ps[] = {v->arena, v->tk_a, v->tv_a, v->tk_b, v->tv_b, v->lb_bin, v->lb_tsort, v->tile_count,
+    void* ps[] = {v->arena, v->tk_a, v->tv_a, v->tk_b, v->tv_b, v->lb_bin, v->lb_tsort, v->lb_tiles, v->tile_count,
                   v->ranges, v->vctrl, v->image, v->tile_done, v->pix_state, v->stats};
     for (void* p : ps)
         if (p) cudaFree(p);
@@ -772,7 +777,12 @@ static int render_slabs(b200gs_viewer* v, b200gs_model* const* far_to_near, uint
         }
         // tile ids are sorted on 16 bits (2 onesweep passes); viewports with more than 65536 tiles take a third
         const uint32_t tpasses = n_tiles > 65536u ? 3u : 2u;
-        CK(gs_launch_tile_ranges(v->tile_count, v->ranges, n_tiles, v->vctrl + VC_TSORT_HIST, tpasses, v->stats + 2, st));
+        GsTileRangesArgs tr;
+        tr.tile_count = v->tile_count; tr.ranges = v->ranges; tr.n_tiles = n_tiles;
+        tr.hist = v->vctrl + VC_TSORT_HIST; tr.passes = tpasses; tr.entry_stat = v->stats + 2;
+        tr.lookback = v->lb_tiles; tr.epoch = ++v->epoch;
+        tr.ticket = v->vctrl + VC_TILE_TICKET; tr.done_ctr = v->vctrl + VC_TILE_DONE; tr.buckets = v->vctrl + VC_TILE_BUCKETS;
+        CK(gs_launch_tile_ranges(tr, st));
         GsSortArgs s;
         s.keys_a = v->tk_a; s.vals_a = v->tv_a; s.keys_b = v->tk_b; s.vals_b = v->tv_b;
         s.d_n = v->vctrl + VC_ENTRY_TOTAL + n_seg; s.n_max = (uint32_t)v->entry_cap;
@@ -789,7 +799,7 @@ static int render_slabs(b200gs_viewer* v, b200gs_model* const* far_to_near, uint
         c.state = v->pix_state; c.tile_done = v->tile_done; c.resume = sl > 0; c.last = last;
         CK(gs_launch_composite(c, f, st));
         if (v->timing) CK(cudaEventRecord(v->ev_slab[sl][2], st));
-        v->launches += s.passes + 4;  // tile sort passes, tile sum, tile scan, tile order, compositor
+        v->launches += s.passes + 2;  // tile sort passes, tile finish, compositor
     }
     if (v->timing) CK(cudaEventRecord(v->ev[4], st));
     v->rendered = true;

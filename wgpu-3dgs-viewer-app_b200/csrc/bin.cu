@@ -19,7 +19,7 @@
 //   * order-preserving compaction: per-rank counts -> block scan -> decoupled look-back over the chunks
 //     (pipelined by one chunk: chunk c+1 is counted and published before chunk c is resolved and
 //     written), entries written at their final depth-ordered position;
-//   * every written entry bumps its tile's counter (RED), from which k_tile_scan derives the per-tile
+//   * every written entry bumps its tile's counter (RED), from which k_tile_finish derives the per-tile
 //     list boundaries, the digit histograms of the tile sort and the compositor's launch order — no pass
 //     over the entries is needed for any of them.
 // The candidate rectangle is kept whole (see common.cuh): the compositor culls every staged splat against
@@ -280,117 +280,107 @@ __global__ void __launch_bounds__(kThreads) k_bin(const uint32_t* __restrict__ s
     }
 }
 
-// Sum of the replicated per-tile counters (cleared on the way for the next frame): sums[t] = Σ copies.
-__global__ void __launch_bounds__(256) k_tile_sum(uint32_t* __restrict__ replicas, uint32_t copies, uint32_t stride,
-                                                  uint32_t n_tiles, uint32_t* __restrict__ sums) {
-    const uint32_t t = blockIdx.x * 256 + threadIdx.x;
-    if (t >= n_tiles) return;
-    uint32_t s = 0;
-    for (uint32_t c0 = 0; c0 < copies; c0 += 8) {
-        uint32_t x[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) x[j] = c0 + j < copies ? replicas[(size_t)(c0 + j) * stride + t] : 0u;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            s += x[j];
-            if (x[j]) replicas[(size_t)(c0 + j) * stride + t] = 0u;
-        }
-    }
-    sums[t] = s;
-}
-
-// Per-tile list boundaries, tile-sort digit histograms and total from the per-tile entry counts.  One CTA
-// (n_tiles is a few thousand; a 16K x 16K viewport has 2^20).  ranges[tile] = first entry,
-// ranges[n_tiles + tile] = one past the last entry (on entry: the tile's count).
-__global__ void __launch_bounds__(1024) k_tile_scan(uint32_t n_tiles, uint32_t* ranges, uint32_t* __restrict__ hist,
-                                                    uint32_t passes, unsigned long long* entry_stat) {
-    const uint32_t* tile_count = ranges + n_tiles;   // k_tile_sum left the counts in the `end` slots
-    __shared__ uint32_t s_hist[3 * 256];
-    __shared__ uint32_t s_wsum[32];
+// Everything the tile sort and the compositor need from the replicated per-tile counters, in one kernel:
+// per-tile sums (counters cleared on the way for the next frame), exclusive scan -> per-tile list
+// boundaries (ranges[tile] = first entry, ranges[n_tiles + tile] = one past the last), the digit
+// histograms of the tile sort, the total, and the compositor's launch order: longest list first (LPT), so
+// that the few very long tiles of a frame start at once instead of wherever their index falls — a counting
+// sort on the number of 256-entry rounds.  Chunks of 64 tiles per CTA, chained by decoupled look-back; the
+// last CTA to finish turns the bucket ranks into the launch order.
+constexpr int kTfTiles = 64;
+__global__ void __launch_bounds__(256) k_tile_finish(uint32_t* __restrict__ replicas, uint32_t copies, uint32_t stride,
+                                                     uint32_t n_tiles, uint32_t n_chunks, uint32_t* __restrict__ ranges,
+                                                     uint32_t* __restrict__ hist, uint32_t passes,
+                                                     unsigned long long* entry_stat, uint64_t* lookback, uint32_t epoch,
+                                                     uint32_t* ticket, uint32_t* done_ctr, uint32_t* buckets) {
+    __shared__ uint32_t s_part[4][kTfTiles];
+    __shared__ uint32_t s_bk[256];
+    __shared__ uint32_t s_chunk, s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 3 * 256; i += 1024) s_hist[i] = 0;
-    const uint32_t per = (n_tiles + 1023u) / 1024u;
-    const uint32_t t0 = min(n_tiles, tid * per), t1 = min(n_tiles, t0 + per);
-    uint32_t sum = 0;
-    for (uint32_t t = t0; t < t1; t += 8) {
-        uint32_t x[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) x[j] = t + j < t1 ? tile_count[t + j] : 0u;
-#pragma unroll
-        for (int j = 0; j < 8; j++) sum += x[j];
-    }
-    uint32_t incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += x;
-    }
-    if (lane == 31) s_wsum[warp] = incl;
+    uint32_t* __restrict__ tmp = ranges + 3 * (size_t)n_tiles;     // per tile: bucket << 24 | rank inside the bucket
+    uint32_t* __restrict__ order = ranges + 2 * (size_t)n_tiles;
+    if (tid == 0) s_chunk = atomicAdd(ticket, 1u);
     __syncthreads();
-    if (warp == 0) {
-        const uint32_t a = s_wsum[lane];
-        uint32_t i2 = a;
+    const uint32_t c = s_chunk;
+    {
+        // 4 groups of threads share the copies of the chunk's 64 tiles
+        const uint32_t q = tid >> 6, t = c * kTfTiles + (tid & 63);
+        const uint32_t per = (copies + 3u) / 4u, c0 = min(copies, q * per), c1 = min(copies, c0 + per);
+        uint32_t sum = 0;
+        if (t < n_tiles) {
+            for (uint32_t cc = c0; cc < c1; cc += 8) {
+                uint32_t x[8];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t x = __shfl_up_sync(0xffffffffu, i2, o);
-            if (lane >= o) i2 += x;
-        }
-        s_wsum[lane] = i2 - a;
-        if (lane == 31 && entry_stat) atomicAdd(entry_stat, (unsigned long long)i2);
-    }
-    __syncthreads();
-    uint32_t run = s_wsum[warp] + incl - sum;
-    for (uint32_t t = t0; t < t1; t += 8) {
-        uint32_t x[8];
+                for (int j = 0; j < 8; j++) x[j] = cc + j < c1 ? replicas[(size_t)(cc + j) * stride + t] : 0u;
 #pragma unroll
-        for (int j = 0; j < 8; j++) x[j] = t + j < t1 ? tile_count[t + j] : 0u;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            if (t + j < t1) {
-                ranges[t + j] = run;
-                ranges[n_tiles + t + j] = run + x[j];
-                run += x[j];
-                if (x[j])
-                    for (uint32_t p = 0; p < passes; p++) atomicAdd(&s_hist[p * 256 + (((t + j) >> (8 * p)) & 0xffu)], x[j]);
+                for (int j = 0; j < 8; j++) {
+                    sum += x[j];
+                    if (x[j]) replicas[(size_t)(cc + j) * stride + t] = 0u;
+                }
             }
         }
+        s_part[q][tid & 63] = sum;
     }
     __syncthreads();
-    for (int i = tid; i < (int)passes * 256; i += 1024) hist[i] = s_hist[i];
-}
-
-// Launch order of the compositor's tiles: longest list first (LPT), so that the few very long tiles
-// of a frame start at once instead of wherever their index falls.  Counting sort on the number of
-// 256-entry rounds, one CTA.
-__global__ void __launch_bounds__(1024) k_tile_order(const uint32_t* __restrict__ ranges, uint32_t n_tiles,
-                                                     uint32_t* __restrict__ order) {
-    __shared__ uint32_t s_cnt[256];
-    const int tid = threadIdx.x;
-    if (tid < 256) s_cnt[tid] = 0;
-    __syncthreads();
-    for (uint32_t t = tid; t < n_tiles; t += 1024) {
-        const uint32_t len = ranges[n_tiles + t] - ranges[t];
-        atomicAdd(&s_cnt[255u - min(255u, (len + 255u) >> 8)], 1u);   // bucket 0 = longest
+    if (warp == 0) {
+        // lane l owns tiles 2l and 2l + 1 of the chunk
+        const uint32_t a0 = s_part[0][2 * lane] + s_part[1][2 * lane] + s_part[2][2 * lane] + s_part[3][2 * lane];
+        const uint32_t a1 = s_part[0][2 * lane + 1] + s_part[1][2 * lane + 1] + s_part[2][2 * lane + 1] + s_part[3][2 * lane + 1];
+        uint32_t incl = a0 + a1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += x;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t base = gs_lookback_warp(lookback, epoch, c, total, lane);
+        if (c == n_chunks - 1 && lane == 0 && entry_stat) atomicAdd(entry_stat, (unsigned long long)(base + total));
+        uint32_t run = base + incl - (a0 + a1);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t t = c * kTfTiles + 2 * lane + h, cnt = h ? a1 : a0;
+            if (t < n_tiles) {
+                ranges[t] = run;
+                ranges[n_tiles + t] = run + cnt;
+                if (cnt)
+                    for (uint32_t p = 0; p < passes; p++) atomicAdd(&hist[p * 256 + ((t >> (8 * p)) & 0xffu)], cnt);
+                const uint32_t bk = 255u - min(255u, (cnt + 255u) >> 8);   // bucket 0 = longest
+                tmp[t] = (bk << 24) | atomicAdd(&buckets[bk], 1u);
+            }
+            run += cnt;
+        }
     }
+    // ---- the last CTA to get here turns (bucket, rank) into the launch order
+    __threadfence();
     __syncthreads();
-    if (tid < 32) {  // exclusive scan of 256 buckets by one warp (8 per lane)
+    if (tid == 0) s_last = atomicAdd(done_ctr, 1u) == n_chunks - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    s_bk[tid] = __ldcg(&buckets[tid]);
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan of 256 buckets by one warp (8 per lane)
         uint32_t loc[8], sum = 0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) { loc[k] = sum; sum += s_cnt[tid * 8 + k]; }
+        for (int k = 0; k < 8; k++) { loc[k] = sum; sum += s_bk[lane * 8 + k]; }
         uint32_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
-            if (tid >= o) incl += x;
+            if (lane >= o) incl += x;
         }
         const uint32_t base = incl - sum;
 #pragma unroll
-        for (int k = 0; k < 8; k++) s_cnt[tid * 8 + k] = base + loc[k];
+        for (int k = 0; k < 8; k++) s_bk[lane * 8 + k] = base + loc[k];
     }
     __syncthreads();
-    for (uint32_t t = tid; t < n_tiles; t += 1024) {
-        const uint32_t len = ranges[n_tiles + t] - ranges[t];
-        order[atomicAdd(&s_cnt[255u - min(255u, (len + 255u) >> 8)], 1u)] = t;
+    for (uint32_t t0 = tid; t0 < n_tiles; t0 += 256 * 8) {
+        uint32_t x[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) x[j] = t0 + j * 256 < n_tiles ? __ldcg(&tmp[t0 + j * 256]) : 0u;
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (t0 + j * 256 < n_tiles) order[s_bk[x[j] >> 24] + (x[j] & 0xffffffu)] = t0 + j * 256;
     }
 }
 
@@ -426,12 +416,12 @@ cudaError_t gs_launch_bin(const GsBinArgs& a, const GsFrame& f, int num_sms, cud
     return cudaGetLastError();
 }
 
-cudaError_t gs_launch_tile_ranges(uint32_t* tile_count, uint32_t* ranges /* 3 x tiles: start, end, launch order */,
-                                  uint32_t n_tiles, uint32_t* hist, uint32_t passes, unsigned long long* entry_stat,
-                                  cudaStream_t st) {
-    k_tile_sum<<<(n_tiles + 255) / 256, 256, 0, st>>>(tile_count, gs_tile_count_copies(n_tiles), n_tiles, n_tiles,
-                                                      ranges + n_tiles);
-    k_tile_scan<<<1, 1024, 0, st>>>(n_tiles, ranges, hist, passes, entry_stat);
-    k_tile_order<<<1, 1024, 0, st>>>(ranges, n_tiles, ranges + 2 * (size_t)n_tiles);
+size_t gs_tile_lookback_words(uint32_t n_tiles) { return (size_t)(n_tiles + kTfTiles - 1) / kTfTiles + 1; }
+
+cudaError_t gs_launch_tile_ranges(const GsTileRangesArgs& a, cudaStream_t st) {
+    const uint32_t n_chunks = (a.n_tiles + kTfTiles - 1) / kTfTiles;
+    k_tile_finish<<<n_chunks, 256, 0, st>>>(a.tile_count, gs_tile_count_copies(a.n_tiles), a.n_tiles, a.n_tiles, n_chunks,
+                                            a.ranges, a.hist, a.passes, a.entry_stat, a.lookback, a.epoch, a.ticket,
+                                            a.done_ctr, a.buckets);
     return cudaGetLastError();
 }

@@ -120,9 +120,17 @@ struct GsBinArgs {
 cudaError_t gs_launch_bin(const GsBinArgs& a, const GsFrame& f, int num_sms, cudaStream_t st);
 size_t gs_tile_count_words(uint32_t n_tiles);
 // per-tile list boundaries + launch order + the tile sort's digit histograms, from the per-tile counters
-cudaError_t gs_launch_tile_ranges(uint32_t* tile_count, uint32_t* ranges /* 3 x tiles: start, end, launch order */,
-                                  uint32_t n_tiles, uint32_t* hist, uint32_t passes, unsigned long long* entry_stat,
-                                  cudaStream_t st);
+struct GsTileRangesArgs {
+    uint32_t* tile_count;          // replicated per-tile counters (cleared on the way)
+    uint32_t* ranges;              // 4 x n_tiles: start, end, launch order, scratch
+    uint32_t n_tiles;
+    uint32_t* hist; uint32_t passes;   // passes x 256 digit histogram of the tile ids (zeroed before launch)
+    unsigned long long* entry_stat;    // += total entries (may be null)
+    uint64_t* lookback; uint32_t epoch;   // gs_tile_lookback_words(n_tiles) status words (epoch-tagged, never cleared)
+    uint32_t* ticket; uint32_t* done_ctr; uint32_t* buckets;   // 1 + 1 + 256 words, zeroed before launch
+};
+size_t gs_tile_lookback_words(uint32_t n_tiles);
+cudaError_t gs_launch_tile_ranges(const GsTileRangesArgs& a, cudaStream_t st);
 
 struct GsCompositeArgs {
     const uint32_t* tile_vals;      // entries sorted by tile, depth order inside a tile
@@ -313,8 +321,11 @@ __device__ __forceinline__ bool gs_make_rect(const uint4& q0, const uint4& q1, f
     const float det = __fsub_rn(__fmul_rn(c.a, c.c), __fmul_rn(c.b, c.b));
     if (det > 0.0f) {
         const float k = __fdividef(c.tau, det);
-        rx = fminf(r, __fadd_rn(__fmul_rn(__fsqrt_rn(__fmul_rn(k, c.c)), 1.002f), 0.02f));
-        ry = fminf(r, __fadd_rn(__fmul_rn(__fsqrt_rn(__fmul_rn(k, c.a)), 1.002f), 0.02f));
+        // sqrt(x) as x * rsqrt(x) (MUFU.RSQ: ~1 ulp, covered by the inflation; a NaN from x = 0 or inf
+        // leaves the extent radius in place)
+        const float vx = __fmul_rn(k, c.c), vy = __fmul_rn(k, c.a);
+        rx = fminf(r, __fadd_rn(__fmul_rn(__fmul_rn(vx, rsqrtf(vx)), 1.002f), 0.02f));
+        ry = fminf(r, __fadd_rn(__fmul_rn(__fmul_rn(vy, rsqrtf(vy)), 1.002f), 0.02f));
     }
     c.fx0 = ceilf(__fsub_rn(c.mx, rx)); c.fx1 = floorf(__fadd_rn(c.mx, rx));
     c.fy0 = ceilf(__fsub_rn(c.my, ry)); c.fy1 = floorf(__fadd_rn(c.my, ry));
