@@ -24,6 +24,8 @@
 //     over the entries is needed for any of them.
 // The candidate rectangle is kept whole (see common.cuh): the compositor culls every staged splat against
 // its sub-tiles exactly, so a kept tile the splat cannot reach costs one staged record, not pixels.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -32,6 +34,7 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kIpt = 4;                      // depth ranks per thread
 constexpr int kChunk = kThreads * kIpt;      // 1024 ranks per chunk; rank = chunk base + k * 256 + tid
+constexpr uint32_t kStage = 4096;            // entries of one chunk staged in shared memory for a coalesced write-out
 
 using Cand = GsCand;
 
@@ -68,8 +71,8 @@ __device__ __forceinline__ void big_rect(uint32_t w, const b200gs_splat* __restr
 template <bool WRITE>
 __device__ __forceinline__ uint32_t big_rounds(uint32_t origin, uint32_t nx, uint32_t total, uint32_t tiles_x,
                                                const uint8_t* __restrict__ tile_done, int lane, uint32_t o, uint32_t val,
-                                               uint32_t capacity, uint32_t* __restrict__ tile_keys,
-                                               uint32_t* __restrict__ tile_vals, uint32_t* __restrict__ tile_count) {
+                                               uint32_t capacity, uint32_t* tile_keys, uint32_t* tile_vals,
+                                               uint32_t* __restrict__ tile_count) {
     const uint32_t lane_lt = (1u << lane) - 1u;
     const float inv_nx = __frcp_rn((float)nx);
     uint32_t kept = 0;
@@ -108,6 +111,7 @@ __global__ void __launch_bounds__(kThreads) k_bin(const uint32_t* __restrict__ s
                                                   uint32_t tiles_x, uint32_t flat, uint32_t q_lo, uint32_t q_hi,
                                                   const uint8_t* __restrict__ tile_done) {
     __shared__ uint32_t s_cnt[kIpt][kWarps];   // per (k, warp) kept counts -> exclusive offsets
+    __shared__ uint32_t s_keys[kStage], s_vals[kStage];   // the chunk's entries, in order, before the write-out
     __shared__ uint32_t s_total;
     __shared__ uint32_t s_chunk, s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -236,21 +240,34 @@ __global__ void __launch_bounds__(kThreads) k_bin(const uint32_t* __restrict__ s
             }
             __syncthreads();
             const uint32_t gbase = ebase + s_base;
+            // Entries go through shared memory (the usual chunk holds ~2 K of them) so that the global writes
+            // are whole lines; a chunk that does not fit (the nearest, hugest splats) writes directly.  Either
+            // way an entry past the capacity is dropped together with its count.
+            const bool staged = p_total <= kStage;
+            uint32_t* const dst_k = staged ? s_keys : tile_keys;
+            uint32_t* const dst_v = staged ? s_vals : tile_vals;
+            const uint32_t room = capacity > gbase ? capacity - gbase : 0u;
+            const uint32_t cap = staged ? min(room, kStage) : capacity;
+            const uint32_t obase = staged ? 0u : gbase;
 #pragma unroll
             for (int k = 0; k < kIpt; k++) {
                 const uint32_t wk = p_w[k];
-                uint32_t o = gbase + p_loc[k];
+                uint32_t o = obase + p_loc[k];
                 const uint32_t val = splat_base + p_slot[k];
                 if (!(wk & GS_BIN_BIG)) {
-                    const uint32_t m = (wk >> 22) & 15u;
+                    // the <= 4 candidate tiles of a small splat form a 1xN / Nx1 run or a 2x2 block: their
+                    // ids follow from two strides
+                    const uint32_t m = (wk >> 22) & 15u, nx = ((wk >> 20) & 3u) + 1u, k0 = wk & 0xfffffu;
+                    const uint32_t d1 = nx > 1u ? 1u : tiles_x;
+                    const uint32_t k2 = nx == 2u ? k0 + tiles_x : k0 + 2u * d1;
+                    const uint32_t keys[4] = {k0, k0 + d1, k2, k2 + d1};
 #pragma unroll
                     for (uint32_t e = 0; e < GS_BIN_INLINE; e++) {
                         if ((m >> e) & 1u) {
-                            if (o < capacity) {
-                                const uint32_t key = small_key(wk, e, tiles_x);
-                                tile_keys[o] = key;
-                                tile_vals[o] = val;
-                                atomicAdd(&tile_count[key], 1u);
+                            if (o < cap) {
+                                dst_k[o] = keys[e];
+                                dst_v[o] = val;
+                                atomicAdd(&tile_count[keys[e]], 1u);
                             }
                             o++;
                         }
@@ -265,9 +282,17 @@ __global__ void __launch_bounds__(kThreads) k_bin(const uint32_t* __restrict__ s
                         big &= big - 1;
                         big_rounds<true>(__shfl_sync(0xffffffffu, b_origin, src), __shfl_sync(0xffffffffu, b_nx, src),
                                          __shfl_sync(0xffffffffu, b_total, src), tiles_x, tile_done, lane,
-                                         __shfl_sync(0xffffffffu, o, src), __shfl_sync(0xffffffffu, val, src), capacity,
-                                         tile_keys, tile_vals, tile_count);
+                                         __shfl_sync(0xffffffffu, o, src), __shfl_sync(0xffffffffu, val, src), cap,
+                                         dst_k, dst_v, tile_count);
                     }
+                }
+            }
+            if (staged) {
+                __syncthreads();
+                const uint32_t nw = min(p_total, cap);
+                for (uint32_t i = tid; i < nw; i += kThreads) {
+                    tile_keys[gbase + i] = s_keys[i];
+                    tile_vals[gbase + i] = s_vals[i];
                 }
             }
         }
@@ -388,7 +413,9 @@ __global__ void __launch_bounds__(256) k_tile_finish(uint32_t* __restrict__ repl
 
 // replicas of the per-tile counters: a power of two <= 128, at most 2M words in total
 uint32_t gs_tile_count_copies(uint32_t n_tiles) {
-    uint32_t c = 128;
+    static uint32_t cmax = 0;
+    if (!cmax) { const char* e = getenv("B200GS_BIN_COPIES"); cmax = e ? (uint32_t)atoi(e) : 128u; }
+    uint32_t c = cmax;
     while (c > 1 && (uint64_t)c * n_tiles > (2u << 20)) c >>= 1;
     return c;
 }
