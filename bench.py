@@ -39,6 +39,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--views", type=int, default=8, help="views rendered per step per GPU")
+    ap.add_argument("--viewers", type=int, default=2,
+                    help="viewer handles (one CUDA stream + one scene replica each) per GPU; the views of a step are "
+                         "dealt round-robin, so independent frames overlap on the device")
     ap.add_argument("--gaussians", type=int, default=6_000_000)
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
@@ -155,9 +158,14 @@ def run_ours(a, rank, world, local_rank):
     W, H, B, N = a.width, a.height, a.views, a.gaussians
     rb = G.record_bytes(G.SH_NORM8, G.COV3D_HALF)
 
-    v = G.Viewer(W, H, G.SH_NORM8, G.COV3D_HALF, device=local_rank)
-    m = v.add_model("scene", N)
-    stream = torch.cuda.ExternalStream(v.stream(), device=dev)
+    # K viewer handles per GPU: frames of a view batch are independent, so they are dealt round-robin to K
+    # viewers (one stream each) and the latency-bound kernels of one frame overlap the issue-bound kernels
+    # of another.  Viewer 0 doubles as the single-stream viewer of the per-stage measurements.
+    K = max(1, a.viewers)
+    viewers = [G.Viewer(W, H, G.SH_NORM8, G.COV3D_HALF, device=local_rank) for _ in range(K)]
+    models = [vv.add_model("scene", N) for vv in viewers]
+    streams = [torch.cuda.ExternalStream(vv.stream(), device=dev) for vv in viewers]
+    v, m, stream = viewers[0], models[0], streams[0]
 
     # ---- scene: generated on rank 0, broadcast once over NCCL/NVLink, replicated on every GPU
     t0 = time.perf_counter()
@@ -178,12 +186,14 @@ def run_ours(a, rank, world, local_rank):
         e1.record()
         torch.cuda.synchronize()
         bcast_ms = e0.elapsed_time(e1)
-        m.upload_packed_device(0, buf.data_ptr(), N)
-        v.sync()
+        for vv, mm in zip(viewers, models):
+            mm.upload_packed_device(0, buf.data_ptr(), N)
+            vv.sync()
         del buf
     else:
         t1 = time.perf_counter()
-        m.upload_packed(0, packed)
+        for mm in models:
+            mm.upload_packed(0, packed)
         bcast_ms = (time.perf_counter() - t1) * 1e3
 
     # ---- this rank's contiguous block of the 1024-view batch
@@ -205,12 +215,17 @@ def run_ours(a, rank, world, local_rank):
         if pending[slot] is not None:
             pending[slot].wait()
             pending[slot] = None
+            for st in streams[1:]:
+                st.wait_stream(stream)          # the gather that read this slot ran behind viewer 0's stream
         base = ring[slot].data_ptr()
         for j in range(B):
             view, proj = mats[(s * B + j) % len(mats)]
-            v.update_camera_matrices(view, proj, (W, H))
-            v.render_frame([m], base + j * img_bytes, W * 4)
+            k = j % K
+            viewers[k].update_camera_matrices(view, proj, (W, H))
+            viewers[k].render_frame([models[k]], base + j * img_bytes, W * 4)
         if world > 1 and not a.no_gather:
+            for st in streams[1:]:
+                stream.wait_stream(st)          # every image of the slot is complete before it is gathered
             pending[slot] = dist.gather(ring[slot], gathered[slot] if rank == 0 else None, dst=0, async_op=True)
 
     def barrier():
@@ -228,17 +243,19 @@ def run_ours(a, rank, world, local_rank):
             time.sleep(0.15)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
-        launches_before = v.launch_count()
-        e0.record(stream)
+        launches_before = sum(vv.launch_count() for vv in viewers)
+        e0.record(stream)                       # every stream is idle here (barrier above)
         for s in range(a.warmup, a.warmup + a.steps):
             step(s)
         for p in pending:
             if p is not None:
                 p.wait()
         pending[0] = pending[1] = None
+        for st in streams[1:]:
+            stream.wait_stream(st)              # e1 is behind the last frame of every viewer
         e1.record(stream)
         barrier()
-        launches_timed = v.launch_count() - launches_before
+        launches_timed = sum(vv.launch_count() for vv in viewers) - launches_before
         elapsed_ms = e0.elapsed_time(e1)
         clocks = sampler.finish() if sampler else None
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
@@ -251,24 +268,30 @@ def run_ours(a, rank, world, local_rank):
     # ---- end to end: host camera in, host image out (pinned), D2H inside the timed region.
     # Two frames in flight (b200gs_render_frame_host_begin/_end): the D2H copy of frame i overlaps the
     # rendering of frame i+1; every frame's image still lands in host memory inside the timed region.
-    host_img = [G.PinnedBuffer(img_bytes) for _ in range(2)]
-    launches0 = v.launch_count()
+    host_img = [[G.PinnedBuffer(img_bytes) for _ in range(2)] for _ in range(K)]
 
     def e2e_loop(n_frames, first):
+        inflight = [0] * K
         for s in range(n_frames):
-            v.render_frame_host_begin([m], block[(first + s) % len(block)], host_img[s & 1].array)
-            if s > 0:
-                v.render_frame_host_end()
-        v.render_frame_host_end()
+            k = s % K
+            if inflight[k] == 2:                # at most two frames in flight per viewer: retire the oldest
+                viewers[k].render_frame_host_end()
+                inflight[k] -= 1
+            viewers[k].render_frame_host_begin([models[k]], block[(first + s) % len(block)], host_img[k][(s // K) & 1].array)
+            inflight[k] += 1
+        for k in range(K):
+            while inflight[k]:
+                viewers[k].render_frame_host_end()
+                inflight[k] -= 1
 
     e2e_loop(max(3, a.warmup) * 2, 0)
     barrier()
-    launches1 = v.launch_count()
+    launches1 = sum(vv.launch_count() for vv in viewers)
     t0 = time.perf_counter()
     e2e_loop(a.steps * B, 0)
     barrier()
     e2e_s = time.perf_counter() - t0
-    launches_e2e = v.launch_count() - launches1
+    launches_e2e = sum(vv.launch_count() for vv in viewers) - launches1
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -306,14 +329,14 @@ def run_ours(a, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "views_per_step_per_gpu": B, "gaussians": N,
+            "config": {"workload": workload_name(a), "views_per_step_per_gpu": B, "viewers_per_gpu": K, "gaussians": N,
                        "record_bytes": rb, "parallelism": "views partitioned over %d GPU(s), scene replicated; "
                        "images gathered to rank 0 with NCCL off the critical path" % world,
                        "l2": "inputs larger than L2: the %.0f MB packed scene is re-streamed every frame (L2 = 126 MB); "
                              "camera changes every frame" % (N * rb / 1e6)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 136, "d2h_bytes_per_step": B * img_bytes,
-                    "call": "b200gs_render_frame_host_begin/_end, 2 frames in flight (camera pod in, RGBA8 image out to "
-                            "pinned host memory)", "gpu_launches": int(launches_e2e)},
+                    "call": "b200gs_render_frame_host_begin/_end, %d viewer(s) x 2 frames in flight (camera pod in, RGBA8 "
+                            "image out to pinned host memory)" % K, "gpu_launches": int(launches_e2e)},
             "gpu_launches": int(launches_timed),
             "roofline": {"bound": "hbm", "kernel": "k_preprocess", "achieved": ach_pre, "peak": peak, "unit": "GB/s",
                          "frac": ach_pre / peak, "traffic": traffic, "peak_source": peak_src,
@@ -333,7 +356,8 @@ def run_ours(a, rank, world, local_rank):
         if world == 1 and not a.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(a, packed, block)
         print(json.dumps(out))
-    v.close()
+    for vv in viewers:
+        vv.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
