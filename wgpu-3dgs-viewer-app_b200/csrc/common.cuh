@@ -327,11 +327,9 @@ __device__ __forceinline__ bool gs_make_rect(const uint4& q0, const uint4& q1, f
         rx = fminf(r, __fadd_rn(__fmul_rn(__fmul_rn(vx, rsqrtf(vx)), 1.002f), 0.02f));
         ry = fminf(r, __fadd_rn(__fmul_rn(__fmul_rn(vy, rsqrtf(vy)), 1.002f), 0.02f));
     }
+    // (rx, ry <= r and rounding is monotonic, so this box never reaches beyond the extent square itself)
     c.fx0 = ceilf(__fsub_rn(c.mx, rx)); c.fx1 = floorf(__fadd_rn(c.mx, rx));
     c.fy0 = ceilf(__fsub_rn(c.my, ry)); c.fy1 = floorf(__fadd_rn(c.my, ry));
-    // never beyond the extent square itself
-    c.fx0 = fmaxf(c.fx0, ceilf(c.mx - r)); c.fx1 = fminf(c.fx1, floorf(c.mx + r));
-    c.fy0 = fmaxf(c.fy0, ceilf(c.my - r)); c.fy1 = fminf(c.fy1, floorf(c.my + r));
     if (c.fx0 < 0.0f) c.fx0 = 0.0f;
     if (c.fy0 < 0.0f) c.fy0 = 0.0f;
     if (c.fx1 > W - 1.0f) c.fx1 = W - 1.0f;
