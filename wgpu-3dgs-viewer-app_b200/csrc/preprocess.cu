@@ -141,7 +141,9 @@ __device__ __forceinline__ void sh_colour(const uint32_t* shw, float dx, float d
     }
     float acc[3] = {0.0f, 0.0f, 0.0f};
     if (SH == 2) {
-        // Σ b_k (q_k·2/255 − 1) = (2/255)·Σ b_k q_k − Σ b_k : one PRMT + FADD + FFMA per coefficient
+        // unorm8 coefficient q -> x = 1 + q·2^-15 by ONE PRMT (the byte dropped into mantissa bits 8..15 of
+        // 1.0f), so a coefficient costs PRMT + FFMA:  Σ b_k x_k = Σ b_k + 2^-15 Σ b_k q_k,  and
+        // Σ b_k (q_k·2/255 − 1) = (2^16/255)·(Σ b_k x_k − Σ b_k) − Σ b_k   (error ~3e-4, tolerance class)
         float sum_b = 0.0f;
 #pragma unroll
         for (int k = 0; k < NCOEF; k++) {
@@ -149,11 +151,12 @@ __device__ __forceinline__ void sh_colour(const uint32_t* shw, float dx, float d
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) {
                 const int e = 3 * k + ch;
-                acc[ch] = __fmaf_rn(bs[k], byte_to_float(shw[e >> 2], e & 3), acc[ch]);
+                const float x = __uint_as_float(__byte_perm(shw[e >> 2], 0x3F800000u, 0x7604u | ((uint32_t)(e & 3) << 4)));
+                acc[ch] = __fmaf_rn(bs[k], x, acc[ch]);
             }
         }
 #pragma unroll
-        for (int ch = 0; ch < 3; ch++) rgb[ch] += __fmaf_rn(acc[ch], 2.0f / 255.0f, -sum_b);
+        for (int ch = 0; ch < 3; ch++) rgb[ch] += __fmaf_rn(acc[ch] - sum_b, 65536.0f / 255.0f, -sum_b);
     } else {
 #pragma unroll
         for (int k = 0; k < NCOEF; k++) {
