@@ -1,4 +1,4 @@
-"""One row per kernel from an `ncu --page raw --csv` export: python tools/ncu_summary.py raw.csv [--md]"""
+"""One row per kernel from an `ncu --page raw --csv` export: python tools/ncu_summary.py raw.csv [summary.json]"""
 import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, units, data = rows[0], rows[1], rows[2:]
@@ -32,9 +32,15 @@ for r in data:
                     l2_pct=g(r, "lts__throughput.avg.pct_of_peak_sustained_elapsed"),
                     warps=g(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
                     inst=g(r, "smsp__inst_executed.sum"), issue=g(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                    adu_pct=g(r, "sm__inst_executed_pipe_adu.avg.pct_of_peak_sustained_active"),
+                    fma_pct=g(r, "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+                    alu_pct=g(r, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
                     stalls=", ".join("%s %.0f%%" % (n, 100 * v / ssum) for v, n in st[:4])))
-print("| kernel | µs (share) | grid×block | regs | DRAM rd/wr MB | DRAM % | L2 % | LSU % | SM % | warps % | warp-inst | issue % | top stalls |")
-print("|---|---|---|---|---|---|---|---|---|---|---|---|---|")
+print("| kernel | µs (share) | grid×block | regs | DRAM rd/wr MB | DRAM % | L2 % | LSU % | SM % | warps % | warp-inst | issue % | pipes fma/alu/adu % | top stalls |")
+print("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
 for o in out:
-    print("| %(kernel)s | %(us).1f (%(share).0f%%) | %(grid)s×%(block)s | %(regs).0f | %(dram_rd).0f / %(dram_wr).0f | %(dram_pct).0f | %(l2_pct).0f | %(lsu_pct).0f | %(sm_pct).0f | %(warps).0f | %(inst).3g | %(issue).0f | %(stalls)s |" % o)
+    print("| %(kernel)s | %(us).1f (%(share).0f%%) | %(grid)s×%(block)s | %(regs).0f | %(dram_rd).0f / %(dram_wr).0f | %(dram_pct).0f | %(l2_pct).0f | %(lsu_pct).0f | %(sm_pct).0f | %(warps).0f | %(inst).3g | %(issue).0f | %(fma_pct).0f / %(alu_pct).0f / %(adu_pct).0f | %(stalls)s |" % o)
 print("\nTotal: %.1f µs" % tot)
+if len(sys.argv) > 2:
+    import json
+    json.dump({"kernels": out, "total_us": tot}, open(sys.argv[2], "w"), indent=1)

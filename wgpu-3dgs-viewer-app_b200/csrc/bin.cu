@@ -24,8 +24,6 @@
 //     over the entries is needed for any of them.
 // The candidate rectangle is kept whole (see common.cuh): the compositor culls every staged splat against
 // its sub-tiles exactly, so a kept tile the splat cannot reach costs one staged record, not pixels.
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace {
@@ -413,9 +411,7 @@ __global__ void __launch_bounds__(256) k_tile_finish(uint32_t* __restrict__ repl
 
 // replicas of the per-tile counters: a power of two <= 128, at most 2M words in total
 uint32_t gs_tile_count_copies(uint32_t n_tiles) {
-    static uint32_t cmax = 0;
-    if (!cmax) { const char* e = getenv("B200GS_BIN_COPIES"); cmax = e ? (uint32_t)atoi(e) : 128u; }
-    uint32_t c = cmax;
+    uint32_t c = 128;   // measured on a 6M-splat frame: 8 copies 186 us, 32 copies 152 us, 128 copies 144 us
     while (c > 1 && (uint64_t)c * n_tiles > (2u << 20)) c >>= 1;
     return c;
 }

@@ -257,31 +257,9 @@ __device__ __forceinline__ uint32_t gs_lookback_warp(uint64_t* status, uint32_t 
     return gs_lookback_resolve(status, epoch, tile, aggregate, lane);
 }
 
-// ---- exact footprint test ---------------------------------------------------------------
+// ---- footprint threshold ------------------------------------------------------------------
 // A splat contributes to a pixel only if alpha = o*exp(-q/2) >= 1/255, i.e. q <= tau with
 // q = a dx^2 + 2 b dx dy + c dy^2 and tau = 2 ln(255 o) (flat display modes: tau = GS_FLAT_D2).
-// gs_min_q_rect returns the minimum of q over a pixel rectangle (inclusive float bounds): if it
-// exceeds tau (plus slack for rounding) no pixel of the rectangle can be touched, so skipping
-// the rectangle leaves the image unchanged.  Convex q: when the centre is outside the rectangle
-// the minimum lies on an edge facing the centre.
-__device__ __forceinline__ float gs_min_q_rect(float mx, float my, float a, float b, float c, float x0, float x1,
-                                               float y0, float y1) {
-    const float dx0 = x0 - mx, dx1 = x1 - mx, dy0 = y0 - my, dy1 = y1 - my;
-    const bool inx = dx0 <= 0.0f && dx1 >= 0.0f, iny = dy0 <= 0.0f && dy1 >= 0.0f;
-    if (inx && iny) return 0.0f;
-    float best = 3.0e38f;
-    if (!inx) {
-        const float dx = dx0 > 0.0f ? dx0 : dx1;
-        const float dy = fminf(dy1, fmaxf(dy0, -b * dx / c));
-        best = a * dx * dx + 2.0f * b * dx * dy + c * dy * dy;
-    }
-    if (!iny) {
-        const float dy = dy0 > 0.0f ? dy0 : dy1;
-        const float dx = fminf(dx1, fmaxf(dx0, -b * dy / a));
-        best = fminf(best, a * dx * dx + 2.0f * b * dx * dy + c * dy * dy);
-    }
-    return best;
-}
 // footprint threshold (with slack so that rounding can never cull a contributing pixel)
 __device__ __forceinline__ float gs_footprint_tau(float opacity, bool flat) {
     if (!(opacity * 255.0f >= 1.0f)) return -1.0f;  // alpha < 1/255 everywhere
@@ -293,7 +271,6 @@ __device__ __forceinline__ float gs_footprint_tau(float opacity, bool flat) {
 // ---- candidate tile rectangle of a projected splat (shared by preprocess and binning) --------
 struct GsCand {
     float mx, my, a, b, c, tau;   // ellipse
-    float nbc, nba;               // -b/c, -b/a
     float fx0, fx1, fy0, fy1;     // pixel bounds of the extent square clipped to the viewport
     uint32_t tx0, ty0, nx, ny;    // candidate tile rectangle
 };
@@ -302,8 +279,8 @@ struct GsCand {
 // range is the extent square (same expression as the compositor / the oracle, exact in float)
 // intersected with a conservative axis-aligned box of the footprint ellipse q <= tau (half-widths
 // sqrt(tau * cov_xx), sqrt(tau * cov_yy), inflated): tiles outside it cannot be touched.
-// Deterministic function of the STORED record, so the preprocess kernel (candidate counts) and
-// the binning kernels (enumeration) agree exactly.
+// Deterministic function of the STORED record, so the preprocess kernel (bin word: candidate count of a
+// huge splat) and the binning kernel (its enumeration) agree exactly.
 __device__ __forceinline__ bool gs_make_rect(const uint4& q0, const uint4& q1, float W, float H, bool flat, GsCand& c) {
     const uint32_t radius = q0.z & 0xffffu;
     if (radius == 0) return false;
@@ -340,28 +317,6 @@ __device__ __forceinline__ bool gs_make_rect(const uint4& q0, const uint4& q1, f
     c.nx = (uint32_t)c.fx1 / GS_TILE - c.tx0 + 1;
     c.ny = (uint32_t)c.fy1 / GS_TILE - c.ty0 + 1;
     return true;
-}
-
-// can candidate tile (x, y) of the rectangle be touched?  (gs_min_q_rect with the divisions hoisted into
-// nbc = -b/c, nba = -b/a; tau carries the rounding slack, so the answer is conservative)
-__device__ __forceinline__ bool gs_tile_hit(const GsCand& c, uint32_t x, uint32_t y) {
-    const float tx = (float)((c.tx0 + x) * GS_TILE), ty = (float)((c.ty0 + y) * GS_TILE);
-    const float dx0 = fmaxf(tx, c.fx0) - c.mx, dx1 = fminf(tx + (float)(GS_TILE - 1), c.fx1) - c.mx;
-    const float dy0 = fmaxf(ty, c.fy0) - c.my, dy1 = fminf(ty + (float)(GS_TILE - 1), c.fy1) - c.my;
-    const bool inx = dx0 <= 0.0f && dx1 >= 0.0f, iny = dy0 <= 0.0f && dy1 >= 0.0f;
-    if (inx && iny) return true;
-    float best = 3.0e38f;
-    if (!inx) {
-        const float dx = dx0 > 0.0f ? dx0 : dx1;
-        const float dy = fminf(dy1, fmaxf(dy0, c.nbc * dx));
-        best = c.a * dx * dx + 2.0f * c.b * dx * dy + c.c * dy * dy;
-    }
-    if (!iny) {
-        const float dy = dy0 > 0.0f ? dy0 : dy1;
-        const float dx = fminf(dx1, fmaxf(dx0, c.nba * dy));
-        best = fminf(best, c.a * dx * dx + 2.0f * c.b * dx * dy + c.c * dy * dy);
-    }
-    return best <= c.tau;
 }
 
 // ---- bin word: what the binning kernel needs to know about a splat, one u32 per compaction slot ----
