@@ -9,9 +9,11 @@ Workload (BASELINE.json `metric`, configs[2] + configs[4]): the synthetic 6M-Gau
 orbit batch of SURVEY.md §8d.  One step = every rank renders `--views` consecutive views of ITS
 contiguous block of the batch (weak scaling: per-GPU work is fixed); the scene is replicated
 (broadcast once with NCCL), no collective runs inside a frame, finished images are gathered to
-rank 0 with NCCL on the side.  `value` = frames/s over all ranks with the scene resident in HBM;
-`e2e` = the same through b200gs_render_frame_host (host camera in, RGBA8 image out to pinned host
-memory, D2H inside the timed region).  `--impl reference` times the CPU restatement of the
+rank 0 with NCCL on the side.  Every GPU runs `--viewers` viewer handles (one CUDA stream + one
+scene replica each, default 2) and deals the views of a step round-robin, so independent frames
+overlap on the device.  `value` = frames/s over all ranks with the scene resident in HBM;
+`e2e` = the same through b200gs_render_frame_host_begin/_end (host camera in, RGBA8 image out to
+pinned host memory, D2H inside the timed region).  `--impl reference` times the CPU restatement of the
 reference path (oracle/, all host threads) on a bounded sample of the same workload.
 """
 import argparse
@@ -312,10 +314,10 @@ def run_ours(a, rank, world, local_rank):
 
     if rank == 0:
         peak, peak_src = peaks()
-        # algorithmic bytes: preprocess = N*R + 8*V (key+index) + 32*V (projected splat);
-        # sort = 68*V (histogram read + 4 x (read 8 + write 8))
+        # algorithmic bytes: preprocess = N*R + 8*V (key+index) + 32*V (projected splat) + 4*V (bin
+        # word); sort = 68*V (histogram read + 4 x (read 8 + write 8))
         b_pre_survey = N * rb + 8 * vis
-        b_pre = b_pre_survey + 32 * vis
+        b_pre = b_pre_survey + 36 * vis
         b_sort = 68 * vis
         ach_pre = b_pre / (pre_ms * 1e-3) / 1e9
         traffic = None
