@@ -389,6 +389,29 @@ def test_huge_splat_and_tile_capacity_overflow(G, O):
         assert v.last_timings().overflow == 1
 
 
+def test_viewport_with_more_than_65536_tiles(G, O):
+    """4112 x 4112 pixels = 257 x 257 = 66049 tiles: tile ids need 17 bits, so the tile sort takes a third
+    onesweep pass and bin words carry 20-bit tile ids; a screen-filling splat exercises the huge class (rows
+    of more than 32 tiles), the scene the small / medium classes."""
+    W = H = 4112
+    n = 20_000
+    g = G.gaussian_from_ply(G.synth_scene(SEED_100K, n))
+    big = make_gaussians(G.GAUSSIAN, [[0, 0, 0.2]], scale=2.0, color=(40, 160, 220, 90))
+    allg = np.concatenate([g, big])
+    packed = G.pack_gaussians(2, 1, allg)
+    cam = G.OrbitCamera.orbit()
+    with G.Viewer(W, H) as v:
+        m = v.add_model("m", len(allg))
+        m.upload_packed(0, packed)
+        v.update_camera(cam)
+        img = v.render_frame_host([m]).copy()
+        t = v.last_timings()
+        assert t.overflow == 0 and t.tile_entries >= 257 * 257
+        f = O.make_frame(cam.view(), cam.projection(np.float32(W) / np.float32(H)), W, H)
+        ref, _, _ = O.render_frame(f, [O.ModelRef(2, 1, packed, len(allg))])
+        assert_image_close(img, ref)
+
+
 def test_call_order_errors(G):
     with G.Viewer(64, 64) as v:
         m = v.add_model("m", 10)

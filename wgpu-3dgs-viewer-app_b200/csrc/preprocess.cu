@@ -396,9 +396,11 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
             }
 
             // ---------------- phase 2: projected splat for the visible ones ----------------
+            // (warp-uniform branch: the culled lanes of a warp with any visible Gaussian run the arithmetic on
+            // whatever their record holds and store nothing — no divergence bookkeeping inside)
             uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
             uint32_t bw = 0;
-            if (vis) {
+            if (ballot != 0u) {
                 const uint32_t* shw = w + 4;
                 const uint32_t* cw = w + 4 + ShBytes<SH>::v / 4;
                 float cv[6];
