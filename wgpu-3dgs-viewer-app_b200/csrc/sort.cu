@@ -13,6 +13,8 @@
 // shared memory so that global writes are runs of consecutive addresses.  Tiles are handed
 // out by an atomic ticket so that every predecessor a tile waits on is owned by a running CTA.
 // The same kernels sort the (tile id, splat) entries of the binning stage with 2 passes.
+#include <initializer_list>
+
 #include "common.cuh"
 
 namespace {
@@ -75,10 +77,13 @@ struct PassSmem {
 
 // kVote: how the lanes of a warp find their same-digit peers.  MATCH.ANY costs ADU cycles per DISTINCT
 // value among the 32 lanes (measured: ~2 cycles each; a pass over uniformly spread digits is ADU-bound),
-// one ballot per digit bit costs the same whatever the digits are.  The host picks per pass: ballots for
-// spread digits (the low bytes of depth keys, the low byte of tile ids), MATCH.ANY for concentrated ones
-// (the top bytes of depth keys, the row-band byte of tile ids).
-template <bool kVote>
+// one ballot per digit bit costs ~4 ALU instructions whatever the digits are.  kVote = number of low digit
+// bits resolved by ballots, the remaining high bits (<= 2^(8 - kVote) distinct values) by MATCH.ANY; measured
+// on 5.9 M spread keys: 0 bits 63 us, 3: 60, 4: 53, 5: 47, 6: 48, 8: 51.  The host picks per pass: kVoteBits
+// for spread digits (the low bytes of depth keys, the low byte of tile ids), pure MATCH.ANY for concentrated
+// ones (the top bytes of depth keys, the row-band byte of tile ids).
+constexpr int kVoteBits = 5;
+template <int kVote>
 __global__ void __launch_bounds__(kThreads, 3) k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a,
                                                            uint32_t* __restrict__ keys_b, uint32_t* __restrict__ vals_b,
                                                            const uint32_t* d_n, uint32_t n_max,
@@ -192,10 +197,11 @@ __global__ void __launch_bounds__(kThreads, 3) k_sort_pass(uint32_t* __restrict_
             for (int k = 0; k < kKpt; k++) {
                 const uint32_t d = (key[k] >> shift) & 0xffu;
                 uint32_t peers;
-                if (kVote) {
-                    peers = 0xffffffffu;
+                if (kVote > 0) {
+                    // the low kVote bits by ballots, the remaining high bits (few distinct values) by MATCH.ANY
+                    peers = kVote < 8 ? __match_any_sync(0xffffffffu, d >> kVote) : 0xffffffffu;
 #pragma unroll
-                    for (int b = 0; b < 8; b++) {
+                    for (int b = 0; b < kVote; b++) {
                         const bool bit = (d >> b) & 1u;
                         const uint32_t bal = __ballot_sync(0xffffffffu, bit);
                         peers &= bit ? bal : ~bal;
@@ -288,18 +294,19 @@ cudaError_t gs_launch_sort(const GsSortArgs& a, int num_sms, cudaStream_t st) {
     }
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
-        cudaError_t e = cudaFuncSetAttribute(k_sort_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_sort_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_sort_pass<false>, kThreads, sizeof(PassSmem));
+        cudaError_t e = cudaSuccess;
+        for (auto k : {k_sort_pass<0>, k_sort_pass<kVoteBits>}) {
+            e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
+            if (e != cudaSuccess) return e;
+        }
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_sort_pass<0>, kThreads, sizeof(PassSmem));
         if (e != cudaSuccess) return e;
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
     uint32_t grid = (uint32_t)(blocks_per_sm * num_sms);
     if (grid > tiles) grid = (uint32_t)tiles;
     for (uint32_t p = 0; p < a.passes; p++) {
-        auto kern = ((a.vote_mask >> p) & 1u) ? k_sort_pass<true> : k_sort_pass<false>;
+        auto kern = ((a.vote_mask >> p) & 1u) ? k_sort_pass<kVoteBits> : k_sort_pass<0>;
         kern<<<grid, kThreads, sizeof(PassSmem), st>>>(a.keys_a, a.vals_a, a.keys_b, a.vals_b, a.d_n, a.n_max, a.hist, p, a.passes,
                                                a.lookback + (size_t)p * tiles * kRadix, a.epoch, a.tickets + p,
                                                a.result_in_b, a.vals_identity ? 1u : 0u);
