@@ -1,4 +1,4 @@
-"""Median per-stage device times for the bench workload: python tools/time_stages.py [N] [frames]"""
+"""Median per-stage device times for the bench workload: python tools/time_stages.py [N] [frames] [W] [H]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -6,7 +6,8 @@ import ctypes as C
 import b200gs as G
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 6_000_000
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else 24
-W, H = 1920, 1080
+W = int(sys.argv[3]) if len(sys.argv) > 3 else 1920
+H = int(sys.argv[4]) if len(sys.argv) > 4 else 1080
 packed = G.pack_gaussians(G.SH_NORM8, G.COV3D_HALF, G.gaussian_from_ply(G.synth_scene(0xB2000006, N)))
 cams = G.view_batch()
 with G.Viewer(W, H) as v:
