@@ -202,9 +202,22 @@ __global__ void __launch_bounds__(kThreads, 3) k_sort_pass(uint32_t* __restrict_
                     peers = kVote < 8 ? __match_any_sync(0xffffffffu, d >> kVote) : 0xffffffffu;
 #pragma unroll
                     for (int b = 0; b < kVote; b++) {
-                        const bool bit = (d >> b) & 1u;
-                        const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-                        peers &= bit ? bal : ~bal;
+                        // peers &= lanes whose bit equals mine: test the key bit (LOP3 -> predicate), ballot, flip
+                        // the ballot if my bit is clear (SEL), and (LOP3) — four instructions; the C++ form
+                        // compiles to six (shift, and, two predicates, select, vote, and)
+                        asm volatile(
+                            "{\n"
+                            ".reg .pred p;\n"
+                            ".reg .b32 t, bal, sx;\n"
+                            "and.b32 t, %1, %2;\n"
+                            "setp.ne.u32 p, t, 0;\n"
+                            "vote.sync.ballot.b32 bal, p, 0xffffffff;\n"
+                            "selp.b32 sx, 0, -1, p;\n"
+                            "xor.b32 bal, bal, sx;\n"
+                            "and.b32 %0, %0, bal;\n"
+                            "}\n"
+                            : "+r"(peers)
+                            : "r"(key[k]), "r"(1u << (shift + b)));
                     }
                 } else {
                     peers = __match_any_sync(0xffffffffu, d);
