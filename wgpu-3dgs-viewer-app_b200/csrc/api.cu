@@ -367,7 +367,7 @@ extern "C" int b200gs_viewer_destroy(b200gs_viewer* v) {
     return B200GS_OK;
 }
 
-// the projected splats (and their candidate-tile counts) are computed for one viewport / display mode:
+// the projected splats (and their bin words) are computed for one viewport / display mode:
 // changing either makes the preprocessed state stale
 static void invalidate_models(b200gs_viewer* v) {
     for (auto* m : v->models) m->preprocessed = m->sorted = false;

@@ -6,7 +6,8 @@
 // frustum cull, mask + hidden-edit + selection test, 3D->2D covariance projection, conic and
 // extent, SH colour up to degree 3, edits and highlight.  Emits, for the V visible Gaussians in
 // ASCENDING INDEX ORDER (order-preserving compaction by decoupled look-back, so that the later
-// stable sort is deterministic): depth key, Gaussian index, and a 32-byte projected splat.
+// stable sort is deterministic): depth key, Gaussian index, a 32-byte projected splat and a 4-byte
+// bin word (the splat's candidate tile rectangle, consumed by the binning kernel, common.cuh).
 //
 // Data movement: persistent CTAs of 8 compute warps + 1 control warp; each 256-Gaussian chunk
 // (256*R contiguous bytes, 16-byte aligned because 256*R is a multiple of 1024) is pulled into
