@@ -346,6 +346,7 @@ def run_ours(a, rank, world, local_rank):
                          "frac_survey_formula": (b_pre_survey / (pre_ms * 1e-3) / 1e9) / peak},
             "stages": {
                 "preprocess_ms": pre_ms, "sort_ms": sort_ms, "bin_ms": bin_ms, "composite_ms": comp_ms, "frame_ms": tot_ms,
+                "frames_per_s_one_stream": 1e3 / tot_ms,   # one viewer, frames back to back on its stream
                 "visible": int(vis), "tile_entries": int(entries), "splat_evals": int(evals),
                 "sort_gkeys_per_s": vis / (sort_ms * 1e-3) / 1e9,
                 "sort_hbm_frac": (b_sort / (sort_ms * 1e-3) / 1e9) / peak,
