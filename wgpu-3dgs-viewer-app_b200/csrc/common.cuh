@@ -217,7 +217,7 @@ __device__ __forceinline__ uint32_t gs_lookback_resolve(uint64_t* status, uint32
     // costs a handful of L2 round trips instead of one per 32 tiles.
     if (tile == 0) return 0;
     constexpr int kGroups = 4;
-    uint32_t excl = 0;
+    uint32_t part = 0;   // this lane's share of the sum: ONE warp reduction at the end, none per group
     int64_t p = (int64_t)tile - 1;
     while (true) {
         uint64_t v[kGroups];
@@ -237,10 +237,7 @@ __device__ __forceinline__ uint32_t gs_lookback_resolve(uint64_t* status, uint32
                 const uint32_t needed = first >= 31u ? 0xffffffffu : ((2u << first) - 1u);
                 if (m_inv & needed) stalled = true;  // a needed predecessor has not published yet: retry from here
                 else {
-                    uint32_t contrib = ((needed >> lane) & 1u) ? ((uint32_t)v[j] & GS_LOOKBACK_VALUE_MASK) : 0u;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-                    excl += contrib;
+                    if ((needed >> lane) & 1u) part += (uint32_t)v[j] & GS_LOOKBACK_VALUE_MASK;
                     if (first < 32u) done = true;
                     else p -= 32;
                 }
@@ -248,6 +245,9 @@ __device__ __forceinline__ uint32_t gs_lookback_resolve(uint64_t* status, uint32
         }
         if (done) break;
     }
+    uint32_t excl = part;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) excl += __shfl_xor_sync(0xffffffffu, excl, o);
     if (lane == 0) gs_st_status(&status[tile], epoch, GS_LOOKBACK_FLAG_INCL | (excl + aggregate));
     return excl;
 }
