@@ -212,11 +212,13 @@ __device__ __forceinline__ void gs_lookback_publish(uint64_t* status, uint32_t e
 }
 __device__ __forceinline__ uint32_t gs_lookback_resolve(uint64_t* status, uint32_t epoch, uint32_t tile,
                                                         uint32_t aggregate, int lane) {
-    // Each round inspects the 128 predecessors p .. p-127 with 4 independent loads per lane
-    // (group j holds p-32j-lane), so a walk over the few hundred tiles that are in flight at once
-    // costs a handful of L2 round trips instead of one per 32 tiles.
+    // Each round inspects the 64 predecessors p .. p-63 with 2 independent loads per lane (group j holds
+    // p-32j-lane).  Measured on the preprocess kernel (444 CTAs in flight): 1 or 2 groups per round 206 us,
+    // 4 groups 212 us, 8 groups 227 us — the pipelined callers publish a whole iteration before they resolve,
+    // so an inclusive prefix is usually within the first few dozen predecessors and wider rounds only add
+    // L2 traffic on the status words.
     if (tile == 0) return 0;
-    constexpr int kGroups = 4;
+    constexpr int kGroups = 2;
     uint32_t part = 0;   // this lane's share of the sum: ONE warp reduction at the end, none per group
     int64_t p = (int64_t)tile - 1;
     while (true) {
