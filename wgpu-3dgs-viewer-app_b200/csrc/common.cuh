@@ -167,6 +167,9 @@ __device__ __forceinline__ void gs_fence_mbar_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void gs_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gs_smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void gs_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gs_smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void gs_mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"

@@ -263,7 +263,11 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
     const uint32_t nchunks = (n + kChunk - 1) / kChunk;
     const bool is_control = warp == kChunk / 32;
 
+    // fill `stage` with chunk c; a chunk past the end completes the stage's barrier with no data, so that the
+    // compute warps can always wait on the barrier BEFORE they read which chunk the stage holds (they run
+    // ahead of the refill: the barrier is what orders their read of s_chunk behind it)
     auto issue = [&](int stage, uint32_t c) {
+        if (c >= nchunks) { gs_mbar_arrive(&bars[stage]); return; }
         uint32_t cnt = min((uint32_t)kChunk, n - c * kChunk);
         uint32_t bytes = (cnt * RB + 15u) & ~15u;  // buffer is padded, see api.cu
         gs_mbar_expect_tx(&bars[stage], bytes);
@@ -276,7 +280,7 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
         for (int s = 0; s < NSTAGE; s++) {
             uint32_t c = atomicAdd(&ctrl[GS_CTRL_TICKET], 1u);
             s_chunk[s] = c;
-            if (c < nchunks) issue(s, c);
+            issue(s, c);
         }
     }
     if (sort_hist)
@@ -312,7 +316,7 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
                 if (lane == 0) {
                     const uint32_t c2 = atomicAdd(&ctrl[GS_CTRL_TICKET], 1u);
                     s_chunk[(j - 1) % NSTAGE] = c2;
-                    if (c2 < nchunks) issue((int)((j - 1) % NSTAGE), c2);
+                    issue((int)((j - 1) % NSTAGE), c2);
                 }
                 __syncwarp();
             }
@@ -334,9 +338,9 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
             Phase1 r;
             r.vis = false; r.ballot = 0u; r.pv[0] = r.pv[1] = r.pv[2] = r.nx = r.ny = r.nz = 0.0f;
             const int stage = j % NSTAGE;
+            gs_mbar_wait(&bars[stage], (j / NSTAGE) & 1u);   // also orders the read of s_chunk behind the refill
             const uint32_t c = s_chunk[stage];
             if (c >= nchunks) return r;
-            gs_mbar_wait(&bars[stage], (j / NSTAGE) & 1u);
             const uint32_t i = c * kChunk + tid;
             const uint32_t* w = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)stage * STAGE_BYTES) + tid * RW;
             bool selected;
@@ -351,6 +355,29 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
             bar_arrive(kBarCounts + (int)(j & 3u));
             return r;
         };
+        // The outputs of chunk it are written one phase 1 LATER (after phase 1 of chunk it+2, at the start of
+        // iteration it+1): the chunk's output base needs the counts of all 8 warps and the control warp's
+        // look-back, and a warp that runs ahead of its CTA would otherwise sit at the base barrier.
+        struct Pending { bool valid, vis; uint32_t seq, ballot, key, index, bw; uint4 q0, q1; };
+        Pending pend;
+        pend.valid = false; pend.vis = false; pend.seq = pend.ballot = pend.key = pend.index = pend.bw = 0;
+        pend.q0 = pend.q1 = make_uint4(0, 0, 0, 0);
+        auto flush = [&]() {
+            if (!pend.valid) return;   // (CTA-uniform)
+            bar_sync(kBarBase + (int)(pend.seq & 3u));
+            if (pend.vis) {
+                uint32_t off = s_base_all[pend.seq & 3u];
+                for (int k = 0; k < warp; k++) off += s_wcount_all[(pend.seq & 3u) * 8 + k];
+                off += __popc(pend.ballot & ((1u << lane) - 1u));
+                keys[off] = pend.key;
+                idx[off] = pend.index;
+                uint4* sp = reinterpret_cast<uint4*>(splats + off);
+                sp[0] = pend.q0;
+                sp[1] = pend.q1;
+                binword[off] = pend.bw;
+            }
+            pend.valid = false;
+        };
         Phase1 cur = phase1(0);
         for (uint32_t it = 0;; it++) {
             const int stage = it % NSTAGE;
@@ -358,6 +385,7 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
             if (c >= nchunks) break;
             // chunk it+1 is culled and counted BEFORE the heavy phase of chunk it (see above)
             const Phase1 nxt = phase1(it + 1);
+            flush();   // chunk it-1
 
             const uint32_t i = c * kChunk + tid;
             const uint32_t* w = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)stage * STAGE_BYTES) + tid * RW;
@@ -548,20 +576,11 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
                 }
             }
 
-            bar_sync(kBarBase + (int)(it & 3u));
-            if (vis) {
-                uint32_t off = s_base_all[it & 3u];
-                for (int k = 0; k < warp; k++) off += s_wcount_all[(it & 3u) * 8 + k];
-                off += __popc(ballot & ((1u << lane) - 1u));
-                keys[off] = __float_as_uint(nz);
-                idx[off] = i;
-                uint4* sp = reinterpret_cast<uint4*>(splats + off);
-                sp[0] = q0;
-                sp[1] = q1;
-                binword[off] = bw;
-            }
+            pend.valid = true; pend.vis = vis; pend.seq = it; pend.ballot = ballot;
+            pend.key = __float_as_uint(nz); pend.index = i; pend.bw = bw; pend.q0 = q0; pend.q1 = q1;
             cur = nxt;
         }
+        flush();
     }
     if (sort_hist) {
         __syncthreads();
