@@ -24,6 +24,8 @@
 //     over the entries is needed for any of them.
 // The candidate rectangle is kept whole (see common.cuh): the compositor culls every staged splat against
 // its sub-tiles exactly, so a kept tile the splat cannot reach costs one staged record, not pixels.
+#include <mutex>
+
 #include "common.cuh"
 
 namespace {
@@ -313,7 +315,7 @@ __global__ void __launch_bounds__(kThreads) k_bin(const uint32_t* __restrict__ s
 constexpr int kTfTiles = 64;
 __global__ void __launch_bounds__(256) k_tile_finish(uint32_t* __restrict__ replicas, uint32_t copies, uint32_t stride,
                                                      uint32_t n_tiles, uint32_t n_chunks, uint32_t* __restrict__ ranges,
-                                                     uint32_t* __restrict__ hist, uint32_t passes,
+                                                     uint32_t* __restrict__ hist, uint32_t key_bits,
                                                      unsigned long long* entry_stat, uint64_t* lookback, uint32_t epoch,
                                                      uint32_t* ticket, uint32_t* done_ctr, uint32_t* buckets) {
     __shared__ uint32_t s_part[4][kTfTiles];
@@ -366,7 +368,8 @@ __global__ void __launch_bounds__(256) k_tile_finish(uint32_t* __restrict__ repl
                 ranges[t] = run;
                 ranges[n_tiles + t] = run + cnt;
                 if (cnt)
-                    for (uint32_t p = 0; p < passes; p++) atomicAdd(&hist[p * 256 + ((t >> (8 * p)) & 0xffu)], cnt);
+                    for (uint32_t p = 0; p * GS_SORT_DIGIT_BITS < key_bits; p++)
+                        atomicAdd(&hist[p * GS_SORT_BINS + ((t >> (GS_SORT_DIGIT_BITS * p)) & (GS_SORT_BINS - 1u))], cnt);
                 const uint32_t bk = 255u - min(255u, (cnt + 255u) >> 8);   // bucket 0 = longest
                 tmp[t] = (bk << 24) | atomicAdd(&buckets[bk], 1u);
             }
@@ -419,11 +422,21 @@ uint32_t gs_tile_count_copies(uint32_t n_tiles) {
 size_t gs_tile_count_words(uint32_t n_tiles) { return (size_t)(2u << 20) + (size_t)n_tiles; }
 
 cudaError_t gs_launch_bin(const GsBinArgs& a, const GsFrame& f, int num_sms, cudaStream_t st) {
-    static int bps = 0;
-    if (bps == 0) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_bin, kThreads, 0);
-        if (e != cudaSuccess) return e;
-        if (bps < 1) bps = 1;
+    static std::mutex mu;
+    static int bps_dev[64] = {0};   // per device
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    int bps;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (bps_dev[dev] == 0) {
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_dev[dev], k_bin, kThreads, 0);
+            if (e != cudaSuccess) { bps_dev[dev] = 0; return e; }
+            if (bps_dev[dev] < 1) bps_dev[dev] = 1;
+        }
+        bps = bps_dev[dev];
     }
     const uint32_t flat = f.display_mode != B200GS_DISPLAY_SPLAT ? 1u : 0u;
     const uint32_t n_tiles = f.tiles_x * f.tiles_y;
@@ -444,7 +457,7 @@ size_t gs_tile_lookback_words(uint32_t n_tiles) { return (size_t)(n_tiles + kTfT
 cudaError_t gs_launch_tile_ranges(const GsTileRangesArgs& a, cudaStream_t st) {
     const uint32_t n_chunks = (a.n_tiles + kTfTiles - 1) / kTfTiles;
     k_tile_finish<<<n_chunks, 256, 0, st>>>(a.tile_count, gs_tile_count_copies(a.n_tiles), a.n_tiles, a.n_tiles, n_chunks,
-                                            a.ranges, a.hist, a.passes, a.entry_stat, a.lookback, a.epoch, a.ticket,
+                                            a.ranges, a.hist, a.key_bits, a.entry_stat, a.lookback, a.epoch, a.ticket,
                                             a.done_ctr, a.buckets);
     return cudaGetLastError();
 }

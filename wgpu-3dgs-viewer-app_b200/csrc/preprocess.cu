@@ -22,11 +22,20 @@
 // order, so that those results are bit-identical to the CPU oracle's (built with
 // -ffp-contract=off).  Do not re-associate that arithmetic.  The TOLERANCE class (SH colour,
 // edits) uses explicit __fmaf_rn / rsqrtf and is compared within the RGBA tolerance.
+#include <mutex>
+
 #include "common.cuh"
 
 namespace {
 
 constexpr int kChunk = 256;
+// Digit histograms of the emitted depth keys for the sort (11-bit digits: bits 0..10, 11..21, 22..31 -> 2048 + 2048 +
+// 1024 counters), kept per CTA as u16 counters packed two per shared-memory word (one 32-bit atomic adds 1 or 1 << 16).
+// A CTA therefore stops drawing chunks after kMaxChunksPerCta (65280 Gaussians: no counter can wrap); the launcher
+// falls back to the sort's own histogram kernel when the grid could not cover the model under that cap.
+constexpr int kHistCounters = 2048 + 2048 + 1024;
+constexpr int kHistWords = kHistCounters / 2;
+constexpr uint32_t kMaxChunksPerCta = 255;
 
 template <int SH> struct ShBytes { static constexpr int v = SH == 0 ? 180 : SH == 1 ? 92 : SH == 2 ? 48 : 0; };
 template <int COV> struct CovBytes { static constexpr int v = COV == 0 ? 24 : 12; };
@@ -257,7 +266,7 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
     uint32_t* s_chunk = reinterpret_cast<uint32_t*>(bars + NSTAGE);  // NSTAGE
     uint32_t* s_wcount_all = s_chunk + NSTAGE + 1;                   // 4 x 8 warp counts (by sequence number & 3)
     uint32_t* s_base_all = s_wcount_all + 32;                        // 4
-    uint32_t* s_hist = s_base_all + 4;                               // 4 x 256 (only if sort_hist)
+    uint32_t* s_hist = s_base_all + 4;                               // kHistWords (only if sort_hist): u16 counters, two per word
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t nchunks = (n + kChunk - 1) / kChunk;
@@ -284,7 +293,7 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
         }
     }
     if (sort_hist)
-        for (int i = tid; i < 1024; i += kThreads) s_hist[i] = 0;
+        for (int i = tid; i < kHistWords; i += kThreads) s_hist[i] = 0;
     __syncthreads();
 
     // The CTA works through the chunks it drew, j = 0, 1, 2, ... (stage j % 3).  The cull/count of
@@ -304,6 +313,7 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
             if (lane == 0) gs_lookback_publish(lookback, epoch, c, total);
             return total;
         };
+        uint32_t drawn = NSTAGE;   // chunks drawn by this CTA so far (see kMaxChunksPerCta)
         uint32_t c = s_chunk[0];
         uint32_t total = c < nchunks ? publish(0, c) : 0u;
         for (uint32_t j = 0; c < nchunks; j++) {
@@ -314,7 +324,8 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
                 // chunk j-1's stage was read for the last time in its heavy phase: refill it
                 bar_sync(kBarFree + (int)((j - 1) & 3u));
                 if (lane == 0) {
-                    const uint32_t c2 = atomicAdd(&ctrl[GS_CTRL_TICKET], 1u);
+                    const uint32_t c2 = (!sort_hist || drawn < kMaxChunksPerCta) ? atomicAdd(&ctrl[GS_CTRL_TICKET], 1u) : 0xffffffffu;
+                    drawn++;
                     s_chunk[(j - 1) % NSTAGE] = c2;
                     issue((int)((j - 1) % NSTAGE), c2);
                 }
@@ -550,29 +561,25 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
             }
             bar_arrive(kBarFree + (int)(it & 3u));  // every read of this stage's shared memory is done
 
-            // digit histograms of the emitted keys for the depth sort (saves its histogram kernel);
-            // warp-aggregated: depth keys share their top bytes
+            // digit histograms of the emitted keys for the depth sort (saves its histogram kernel)
             if (sort_hist && ballot) {
                 const uint32_t key = __float_as_uint(nz);
+                // the top digit is usually the same for the whole warp: one vote and one atomic instead of a match
                 const int first = __ffs((int)ballot) - 1;
-                const uint32_t key0 = __shfl_sync(0xffffffffu, key, first);
-#pragma unroll
-                for (int p = 3; p >= 2; p--) {
-                    const uint32_t dgt = (key >> (8 * p)) & 0xffu;
-                    // the top bytes are usually the same for the whole warp: one vote instead of a match
-                    const bool uniform = __all_sync(0xffffffffu, !vis || dgt == ((key0 >> (8 * p)) & 0xffu));
-                    if (uniform) {
-                        if (lane == first) atomicAdd(&s_hist[p * 256 + dgt], (uint32_t)__popc(ballot));
-                    } else if (vis) {
-                        const uint32_t peers = __match_any_sync(ballot, dgt);
-                        if (lane == __ffs((int)peers) - 1) atomicAdd(&s_hist[p * 256 + dgt], (uint32_t)__popc(peers));
-                    }
+                const uint32_t d2 = key >> 22;
+                const bool uniform = __all_sync(0xffffffffu, !vis || d2 == __shfl_sync(0xffffffffu, d2, first));
+                if (uniform) {
+                    if (lane == first) atomicAdd(&s_hist[2048 + (d2 >> 1)], (uint32_t)__popc(ballot) << (16u * (d2 & 1u)));
+                } else if (vis) {
+                    const uint32_t peers = __match_any_sync(ballot, d2);
+                    if (lane == __ffs((int)peers) - 1) atomicAdd(&s_hist[2048 + (d2 >> 1)], (uint32_t)__popc(peers) << (16u * (d2 & 1u)));
                 }
-                // the low bytes are spread: ~30 distinct values among 32 lanes, where MATCH.ANY costs more ADU
-                // cycles than 32 fire-and-forget shared-memory atomics cost the (idle) LSU
+                // the two low digits are spread: ~32 distinct values among 32 lanes, where MATCH.ANY costs more ADU
+                // cycles than 32 fire-and-forget shared-memory atomics cost the LSU
                 if (vis) {
-                    atomicAdd(&s_hist[256 + ((key >> 8) & 0xffu)], 1u);
-                    atomicAdd(&s_hist[key & 0xffu], 1u);
+                    const uint32_t d1 = (key >> 11) & 2047u, d0 = key & 2047u;
+                    atomicAdd(&s_hist[1024 + (d1 >> 1)], 1u << (16u * (d1 & 1u)));
+                    atomicAdd(&s_hist[d0 >> 1], 1u << (16u * (d0 & 1u)));
                 }
             }
 
@@ -584,34 +591,52 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
     }
     if (sort_hist) {
         __syncthreads();
-        for (int i = tid; i < 1024; i += kThreads) {
-            const uint32_t cnt = s_hist[i];
-            if (cnt) atomicAdd(&sort_hist[i], cnt);
+        for (int i = tid; i < kHistWords; i += kThreads) {
+            const uint32_t w = s_hist[i];
+            if (w & 0xffffu) atomicAdd(&sort_hist[2 * i], w & 0xffffu);
+            if (w >> 16) atomicAdd(&sort_hist[2 * i + 1], w >> 16);
         }
     }
     if (n == 0 && blockIdx.x == 0 && tid == 0) ctrl[GS_CTRL_VISIBLE] = 0;
 }
 
+struct DevInfo { int blocks_per_sm[8] = {0, 0, 0, 0, 0, 0, 0, 0}; };   // per layout
+std::mutex g_mu;
+DevInfo g_dev[64];   // attributes and occupancy are per device: a process may hold viewers on several GPUs
+
 template <int SH, int COV>
 cudaError_t launch_t(const GsPreprocessArgs& a, const GsFrame& f, const GsModelXf& m, int num_sms, cudaStream_t st) {
     constexpr int RB = 16 + ShBytes<SH>::v + CovBytes<COV>::v;
     constexpr int NSTAGE = 3;
-    constexpr size_t smem = (size_t)NSTAGE * kChunk * RB + NSTAGE * 8 + (NSTAGE + 1) * 4 + 32 * 4 + 4 * 4 + 1024 * 4 + 16;
+    constexpr size_t smem = (size_t)NSTAGE * kChunk * RB + NSTAGE * 8 + (NSTAGE + 1) * 4 + 32 * 4 + 4 * 4 + kHistWords * 4 + 16;
     auto kern = k_preprocess<SH, COV>;
-    static int blocks_per_sm = 0;
-    if (blocks_per_sm == 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kThreads, smem);
-        if (e != cudaSuccess) return e;
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    int blocks_per_sm;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        int& b = g_dev[dev].blocks_per_sm[SH * 2 + COV];
+        if (b == 0) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kThreads, smem);
+            if (e != cudaSuccess) { b = 0; return e; }
+            if (b < 1) b = 1;
+        }
+        blocks_per_sm = b;
     }
     uint32_t nchunks = (a.n + kChunk - 1) / kChunk;
     uint32_t grid = (uint32_t)(blocks_per_sm * num_sms);
     if (grid > nchunks) grid = nchunks;
     if (grid < 1) grid = 1;
+    // the per-CTA u16 histogram counters cap a CTA at kMaxChunksPerCta chunks: a model the grid cannot cover under
+    // that cap is preprocessed without histograms (the sort then runs its own histogram kernel)
+    const bool fill_hist = a.sort_hist != nullptr && (uint64_t)nchunks <= (uint64_t)grid * kMaxChunksPerCta;
+    if (a.hist_filled) *a.hist_filled = fill_hist;
     kern<<<grid, kThreads, smem, st>>>(a.recs, a.n, a.mask, a.selection, a.edits, f, m, a.ctrl, a.lookback, a.epoch,
-                                       a.keys, a.idx, a.splats, a.binword, a.sort_hist);
+                                       a.keys, a.idx, a.splats, a.binword, fill_hist ? a.sort_hist : nullptr);
     return cudaGetLastError();
 }
 

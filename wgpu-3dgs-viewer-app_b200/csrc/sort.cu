@@ -1,19 +1,28 @@
-// sort.cu — K2: onesweep-style LSD radix sort of (u32 key, u32 value) pairs.
+// sort.cu — K2: onesweep-style LSD radix sort of (u32 key, u32 value) pairs, 11-bit digits.
 //
 // Replaces viewer.radix_sorter.sort(encoder, bind_group, radix_sort_indirect_args)
 // (reference src/tab/scene.rs:865-869): stable ascending sort of the depth keys (f32 bits as
 // u32) with the Gaussian indices as payload; the element count lives on the device (the
 // reference sizes an indirect dispatch from it), here `*d_n`.
 //
-// Design: one histogram kernel (all digit histograms in one read of the keys), then one
-// kernel per 8-bit digit.  A digit pass is a single sweep: each 3072-key tile ranks its keys
-// with warp-level same-digit peer masks (ballots or MATCH.ANY), publishes its per-digit counts and resolves
-// its global offsets by decoupled look-back over epoch-tagged status words (chained scan, no
-// separate scan kernel, no second read of the keys), then scatters keys and values through
-// shared memory so that global writes are runs of consecutive addresses.  Tiles are handed
-// out by an atomic ticket so that every predecessor a tile waits on is owned by a running CTA.
-// The same kernels sort the (tile id, splat) entries of the binning stage with 2 passes.
-#include <initializer_list>
+// Design.  A digit pass is a single sweep over the keys (one read, one write): tiles rank their keys
+// with warp-level same-digit peer masks, publish per-digit counts, resolve global offsets by decoupled
+// look-back over epoch-tagged status words (no scan kernel, no second read), and scatter through shared
+// memory so that global writes are runs of consecutive addresses.  Round 1 used 8-bit digits: 3 executed
+// passes for the ~23 live bits of a depth key, each bound by its per-pass overhead (and by 2-cycle-per-lane
+// shared-memory atomics in the counting step), not by HBM.  This version sorts 11 bits per pass — depth keys
+// in [0.5, 1) take TWO passes (bits 0..10, 11..21; the 10-bit top digit is degenerate and skipped) and the
+// tile ids of a 1080p frame ONE — which needs 2048 status words per look-back step instead of 256.  To keep
+// that affordable the unit of look-back is a THREAD-BLOCK CLUSTER of 8 CTAs: each CTA ranks 4096 keys in
+// shared memory, the cluster's 32768 keys form one super-tile, and CTA r of the cluster owns digits
+// [256 r, 256 r + 256): one digit per thread.  The owner reads the 8 CTAs' counts of its digit through
+// distributed shared memory (DSMEM), publishes the super-tile's count, walks the look-back, and writes every
+// CTA's global base for the digit back into that CTA's shared memory.  Status traffic per key drops 8x
+// (16 KB per 32768 keys) and only ~50 super-tiles are in flight, so look-back walks stay short.
+// Ranking uses no shared-memory atomics: per-warp u16 histograms are updated by one leader lane per digit.
+// Super-tiles are handed out by an atomic ticket (drawn by CTA 0 of the cluster, distributed through DSMEM),
+// so that every predecessor a super-tile waits on is owned by a running cluster.
+#include <mutex>
 
 #include "common.cuh"
 
@@ -21,160 +30,235 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kKpt = 12;                       // keys per thread
-constexpr int kTile = kThreads * kKpt;         // 3072 keys per tile
-constexpr int kRadix = 256;
+constexpr int kKpt = 16;                         // keys per thread
+constexpr int kTile = kThreads * kKpt;           // 4096 keys per CTA
+constexpr int kCluster = 8;                      // CTAs per cluster
+constexpr int kSuper = kTile * kCluster;         // 32768 keys per super-tile
+constexpr int kBins = GS_SORT_BINS;              // 2048
+constexpr int kWarpSpan = 32 * kKpt;             // 512 consecutive keys per warp
+static_assert(kBins == kCluster * kThreads, "one owned digit per thread");
 
-// ------------------------------------------------------------------ histogram kernel
-// hist[pass][digit] += count, for `passes` digits.  Warp-aggregated (match_any) shared-memory
-// atomics: depth keys share their top bytes, so naive atomics would serialise on one bin.
+// ------------------------------------------------------------------ histogram kernel (raw sort API only)
+// hist[pass][digit] += count.  The frame path never runs it: the preprocess kernel and the tile-finish
+// kernel accumulate the histograms of the keys they produce.
 __global__ void __launch_bounds__(kThreads) k_sort_hist(const uint32_t* __restrict__ keys, const uint32_t* d_n,
-                                                        uint32_t n_max, uint32_t* hist, uint32_t passes) {
-    __shared__ uint32_t s_hist[4 * kRadix];
-    for (int i = threadIdx.x; i < 4 * kRadix; i += kThreads) s_hist[i] = 0;
+                                                        uint32_t n_max, uint32_t* hist, uint32_t key_bits) {
+    extern __shared__ uint32_t s_hist[];   // passes x kBins
+    const uint32_t passes = gs_sort_passes(key_bits);
+    for (uint32_t i = threadIdx.x; i < passes * kBins; i += kThreads) s_hist[i] = 0;
     __syncthreads();
     uint32_t n = *d_n;
     if (n > n_max) n = n_max;
-    const int lane = threadIdx.x & 31;
-    // each warp walks 32-key groups, grid-stride
-    const uint32_t warps_total = gridDim.x * kWarps;
-    const uint32_t gw = blockIdx.x * kWarps + (threadIdx.x >> 5);
-    const uint32_t ngroups = (n + 31) / 32;
-    for (uint32_t g = gw; g < ngroups; g += warps_total) {
-        uint32_t i = g * 32 + lane;
-        bool ok = i < n;
-        uint32_t k = ok ? keys[i] : 0u;
-        uint32_t act = __ballot_sync(0xffffffffu, ok);
-        if (ok) {
-            for (uint32_t p = 0; p < passes; p++) {
-                uint32_t d = (k >> (8 * p)) & 0xffu;
-                uint32_t peers = __match_any_sync(act, d);
-                if ((uint32_t)lane == (uint32_t)(__ffs((int)peers) - 1)) atomicAdd(&s_hist[p * kRadix + d], __popc(peers));
-            }
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+        const uint32_t k = keys[i];
+        for (uint32_t p = 0; p < passes; p++) {
+            const uint32_t bits = min((uint32_t)GS_SORT_DIGIT_BITS, key_bits - GS_SORT_DIGIT_BITS * p);
+            atomicAdd(&s_hist[p * kBins + ((k >> (GS_SORT_DIGIT_BITS * p)) & ((1u << bits) - 1u))], 1u);
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < (int)passes * kRadix; i += kThreads) {
-        uint32_t c = s_hist[i];
+    for (uint32_t i = threadIdx.x; i < passes * kBins; i += kThreads) {
+        const uint32_t c = s_hist[i];
         if (c) atomicAdd(&hist[i], c);
     }
 }
 
+// ---------------------------------------------------------------------- cluster / DSMEM helpers
+__device__ __forceinline__ uint32_t cl_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cl_map(const void* p, uint32_t rank) {  // my shared address -> the same variable in CTA `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(gs_smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ uint32_t cl_ld_u16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared::cluster.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cl_st_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cl_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---------------------------------------------------------------------- digit pass
-// Software-pipelined by one tile with double-buffered shared memory: tile t+1 is loaded, counted
-// (its per-digit aggregates PUBLISHED), ranked and scattered into its exchange buffer BEFORE tile
-// t's look-back is resolved and tile t is written out, so a look-back only ever waits for
-// aggregates that were published a whole tile-time earlier.
-struct PassSmem {
-    uint32_t warp_hist[kWarps][kRadix];  // per-warp digit counts -> running per-warp offsets
-    uint32_t exch_k[2][kTile];           // keys / values in tile-sorted order, double-buffered
-    uint32_t exch_v[2][kTile];
-    uint32_t tile_start[2][kRadix];      // first position of each digit inside the sorted tile
-    int32_t global_off[kRadix];          // global index = global_off[digit] + position in sorted tile
+struct __align__(16) PassSmem {
+    union {
+        uint16_t whist[kWarps][kBins];   // per-warp digit counts -> exclusive offsets of the warp inside the CTA's digit run
+        uint32_t gpos[kBins];            // (after the scatter) global index of this CTA's first key of each digit, written by the digit's owner
+    };
+    uint32_t exch_k[kTile];              // keys / values of the CTA in digit order
+    uint32_t exch_v[kTile];
+    uint16_t cta_count[kBins];           // this CTA's count per digit (read by the owner CTA through DSMEM)
+    uint16_t tile_start[kBins];          // first position of each digit inside the sorted tile
     uint32_t scan_tmp[kWarps];
-    uint32_t tile_id;
+    uint32_t tile_id[2];                 // super-tile of this / the next iteration (written by CTA 0 of the cluster)
 };
 
-// kVote: how the lanes of a warp find their same-digit peers.  MATCH.ANY costs ADU cycles per DISTINCT
-// value among the 32 lanes (measured: ~2 cycles each; a pass over uniformly spread digits is ADU-bound),
-// one ballot per digit bit costs ~4 ALU instructions whatever the digits are.  kVote = number of low digit
-// bits resolved by ballots, the remaining high bits (<= 2^(8 - kVote) distinct values) by MATCH.ANY; measured
-// on 5.9 M spread keys: 0 bits 63 us, 3: 60, 4: 53, 5: 47, 6: 48, 8: 51.  The host picks per pass: kVoteBits
-// for spread digits (the low bytes of depth keys, the low byte of tile ids), pure MATCH.ANY for concentrated
-// ones (the top bytes of depth keys, the row-band byte of tile ids).
-constexpr int kVoteBits = 5;
-template <int kVote>
-__global__ void __launch_bounds__(kThreads, 3) k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a,
-                                                           uint32_t* __restrict__ keys_b, uint32_t* __restrict__ vals_b,
-                                                           const uint32_t* d_n, uint32_t n_max,
-                                                           const uint32_t* __restrict__ hist_all, uint32_t pass,
-                                                           uint32_t passes, uint64_t* lookback, uint32_t epoch,
-                                                           uint32_t* ticket, uint32_t* result_in_b, uint32_t vals_identity) {
+// peers of this lane = lanes of the warp whose digit equals mine.  One ballot per digit bit (4 instructions:
+// bit test -> predicate, vote, flip by my own bit, and); MATCH.ANY costs ADU cycles per DISTINCT value and 11-bit
+// digits are spread (measured in round 1: a MATCH.ANY pass over spread digits was ADU-bound).
+template <int BITS>
+__device__ __forceinline__ uint32_t digit_peers(uint32_t key, uint32_t shift) {
+    uint32_t peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < BITS; b++) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            ".reg .b32 t, bal, sx;\n"
+            "and.b32 t, %1, %2;\n"
+            "setp.ne.u32 p, t, 0;\n"
+            "vote.sync.ballot.b32 bal, p, 0xffffffff;\n"
+            "selp.b32 sx, 0, -1, p;\n"
+            "xor.b32 bal, bal, sx;\n"
+            "and.b32 %0, %0, bal;\n"
+            "}\n"
+            : "+r"(peers)
+            : "r"(key), "r"(1u << (shift + b)));
+    }
+    return peers;
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(kThreads, 3)
+k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, uint32_t* __restrict__ keys_b,
+            uint32_t* __restrict__ vals_b, const uint32_t* d_n, uint32_t n_max, const uint32_t* __restrict__ hist_all,
+            uint32_t pass, uint32_t key_bits, uint64_t* lookback, uint32_t epoch, uint32_t* ticket, uint32_t* result_in_b,
+            uint32_t vals_identity) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     PassSmem& sm = *reinterpret_cast<PassSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t rank = cl_rank();
     uint32_t n = *d_n;
     if (n > n_max) n = n_max;
-    const uint32_t ntiles = (n + kTile - 1) / kTile;
-    const uint32_t shift = 8 * pass;
+    const uint32_t nsuper = (n + kSuper - 1) / kSuper;
+    const uint32_t passes = gs_sort_passes(key_bits);
+    const uint32_t shift = GS_SORT_DIGIT_BITS * pass;
+    const uint32_t dmask = (1u << BITS) - 1u;
 
-    // A digit whose histogram has a single non-empty bin leaves the order unchanged: the pass is
-    // skipped (depth keys share their top byte).  Every CTA derives the same plan from the global
+    // A digit whose histogram has a single non-empty bin leaves the order unchanged: the pass is skipped
+    // (depth keys in [0.5, 1) share their top 10 bits).  Every CTA derives the same plan from the global
     // histograms: which passes run, hence which buffer holds this pass's input.
     uint32_t executed_before = 0;
     bool skip_me = false;
     for (uint32_t q = 0; q < passes; q++) {
-        const int degenerate = __syncthreads_or(n > 0 && hist_all[q * kRadix + tid] == n);
+        const uint4* h4 = reinterpret_cast<const uint4*>(hist_all + q * kBins) + 2 * tid;
+        const uint4 x = h4[0], y = h4[1];
+        const bool hit = n > 0 && (x.x == n || x.y == n || x.z == n || x.w == n || y.x == n || y.y == n || y.z == n || y.w == n);
+        const int degenerate = __syncthreads_or(hit);
         if (q < pass) executed_before += degenerate ? 0u : 1u;
         if (q == pass) skip_me = degenerate != 0;
     }
     const bool src_b = (executed_before & 1u) != 0;
-    if (pass == passes - 1 && blockIdx.x == 0 && tid == 0)
-        *result_in_b = ((executed_before + (skip_me ? 0u : 1u)) & 1u);
-    if (skip_me || n == 0) return;
+    if (pass == passes - 1 && blockIdx.x == 0 && tid == 0) *result_in_b = ((executed_before + (skip_me ? 0u : 1u)) & 1u);
+    if (skip_me || n == 0) return;   // (uniform over the grid)
     const uint32_t* __restrict__ keys_in = src_b ? keys_b : keys_a;
     const uint32_t* __restrict__ vals_in = src_b ? vals_b : vals_a;
     uint32_t* __restrict__ keys_out = src_b ? keys_a : keys_b;
     uint32_t* __restrict__ vals_out = src_b ? vals_a : vals_b;
     const bool synth_vals = vals_identity && executed_before == 0;  // first executed pass: value = input position
-    const uint32_t* __restrict__ hist = hist_all + pass * kRadix;
 
-    // exclusive prefix of the global histogram of this digit (thread d owns digit d)
+    // global base of the digit this thread owns: exclusive prefix of the pass's histogram
+    const uint32_t own = rank * kThreads + tid;
     uint32_t gbase;
     {
-        uint32_t c = hist[tid];
-        uint32_t incl = c;
+        const uint4* h4 = reinterpret_cast<const uint4*>(hist_all + pass * kBins) + 2 * tid;
+        const uint4 x = h4[0], y = h4[1];
+        const uint32_t c[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+        uint32_t sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) sum += c[j];
+        uint32_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
         }
         if (lane == 31) sm.scan_tmp[warp] = incl;
         __syncthreads();
-        uint32_t wbase = 0;
-        for (int k = 0; k < warp; k++) wbase += sm.scan_tmp[k];
-        gbase = wbase + incl - c;
-    }
-    uint64_t* lb = lookback + (size_t)tid;
-
-    bool have_prev = false;
-    uint32_t p_tile = 0, p_count = 0, p_valid = 0;
-    for (uint32_t iter = 0;; iter++) {
-        const uint32_t buf = iter & 1u;
-        __syncthreads();  // previous iteration's ranking / write-out are done
-        if (tid == 0) sm.tile_id = atomicAdd(ticket, 1u);
+        uint32_t run = incl - sum;
+        for (int k = 0; k < warp; k++) run += sm.scan_tmp[k];
 #pragma unroll
-        for (int k = 0; k < kRadix / 32; k++) sm.warp_hist[warp][k * 32 + lane] = 0;
+        for (int j = 0; j < 8; j++) { sm.exch_k[8 * tid + j] = run; run += c[j]; }
         __syncthreads();
-        const uint32_t tile = sm.tile_id;
-        const bool valid_tile = tile < ntiles;
-        uint32_t count = 0, valid = 0;
-        if (valid_tile) {
-            const uint32_t tile_base = tile * kTile;
-            valid = min((uint32_t)kTile, n - tile_base);
-            // ---- load keys (warp-striped: slot = warp*32*KPT + k*32 + lane keeps index order inside a warp)
-            uint32_t key[kKpt];
-            const uint32_t wbase_idx = warp * (32 * kKpt);
+        gbase = sm.exch_k[own];
+    }
+    uint64_t* lb = lookback + own;
+
+    // first ticket
+    if (rank == 0 && tid == 0) {
+        const uint32_t t = atomicAdd(ticket, 1u);
 #pragma unroll
-            for (int k = 0; k < kKpt; k++) {
-                const uint32_t s = wbase_idx + k * 32 + lane;
-                key[k] = s < valid ? keys_in[tile_base + s] : 0xffffffffu;
-            }
-            // ---- early counts (per-warp histograms), so the aggregates can be published at once
+        for (int r = 0; r < kCluster; r++) cl_st_u32(cl_map(&sm.tile_id[0], r), t);
+    }
+    cl_sync();
+
+    for (uint32_t it = 0;; it++) {
+        const uint32_t super = sm.tile_id[it & 1u];
+        if (super >= nsuper) break;   // (uniform over the cluster)
+        // ---- clear the per-warp histograms (the previous write-out, which read gpos = the same memory, is done:
+        // barrier at the end of the loop body)
+        {
+            uint4* z = reinterpret_cast<uint4*>(&sm.whist[0][0]);
 #pragma unroll
-            for (int k = 0; k < kKpt; k++) atomicAdd(&sm.warp_hist[warp][(key[k] >> shift) & 0xffu], 1u);
-            __syncthreads();
-            // per digit (thread d): exclusive scan over warps, tile total
+            for (int k = 0; k < (int)(sizeof(sm.whist) / 16 / kThreads); k++) z[k * kThreads + tid] = make_uint4(0, 0, 0, 0);
+        }
+        // ---- load keys (warp-striped: slot = warp*512 + k*32 + lane keeps index order inside a warp); slots past
+        // the end hold 0xffffffff: they carry the largest digit and the highest positions, so they rank behind
+        // every real key of that digit and fall off the end of the sorted tile
+        const uint32_t tile_base = super * kSuper + rank * kTile;
+        const uint32_t valid = tile_base < n ? min((uint32_t)kTile, n - tile_base) : 0u;
+        const uint32_t wslot = warp * kWarpSpan + lane;
+        uint32_t key[kKpt];
+#pragma unroll
+        for (int k = 0; k < kKpt; k++) {
+            const uint32_t s = wslot + k * 32;
+            key[k] = s < valid ? keys_in[tile_base + s] : 0xffffffffu;
+        }
+        __syncthreads();
+        // ---- rank inside the warp: position among the warp's earlier keys of the same digit
+        uint32_t rk[kKpt / 2];   // two u16 ranks per register
+        uint16_t* wh = sm.whist[warp];
+        const uint32_t lane_lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int k = 0; k < kKpt; k++) {
+            const uint32_t d = (key[k] >> shift) & dmask;
+            const uint32_t peers = digit_peers<BITS>(key[k], shift);
+            const uint32_t before = wh[d];                    // every peer reads the same counter ...
+            const uint32_t mine = __popc(peers & lane_lt);
+            __syncwarp();
+            if (mine == 0) wh[d] = (uint16_t)(before + __popc(peers));   // ... and the first peer advances it
+            __syncwarp();
+            const uint32_t r = before + mine;
+            if (k & 1) rk[k >> 1] |= r << 16;
+            else rk[k >> 1] = r;
+        }
+        __syncthreads();
+        // ---- per digit: exclusive scan over the warps (thread t owns digits 8t .. 8t+7 = one 16-byte word per warp
+        // row; two u16 counters per u32 add, no carry: a CTA holds 4096 keys), the CTA's count, and the exclusive
+        // scan of the counts over all digits -> start of each digit's run in the sorted tile
+        {
+            uint4 run = make_uint4(0, 0, 0, 0);
 #pragma unroll
             for (int w2 = 0; w2 < kWarps; w2++) {
-                const uint32_t t = sm.warp_hist[w2][tid];
-                sm.warp_hist[w2][tid] = count;
-                count += t;
+                uint4* p = reinterpret_cast<uint4*>(&sm.whist[w2][0]) + tid;
+                const uint4 v = *p;
+                *p = run;
+                run.x += v.x; run.y += v.y; run.z += v.z; run.w += v.w;
             }
-            // publish this tile's aggregate for digit `tid`
-            gs_st_status(&lb[(size_t)tile * kRadix], epoch, (tile == 0 ? GS_LOOKBACK_FLAG_INCL : GS_LOOKBACK_FLAG_AGG) | count);
-            // exclusive scan of the tile totals over digits
-            uint32_t incl = count;
+            reinterpret_cast<uint4*>(sm.cta_count)[tid] = run;
+            const uint32_t c[8] = {run.x & 0xffffu, run.x >> 16, run.y & 0xffffu, run.y >> 16,
+                                   run.z & 0xffffu, run.z >> 16, run.w & 0xffffu, run.w >> 16};
+            uint32_t sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) sum += c[j];
+            uint32_t incl = sum;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -182,73 +266,57 @@ __global__ void __launch_bounds__(kThreads, 3) k_sort_pass(uint32_t* __restrict_
             }
             if (lane == 31) sm.scan_tmp[warp] = incl;
             __syncthreads();
-            uint32_t wb = 0;
-            for (int k = 0; k < warp; k++) wb += sm.scan_tmp[k];
-            sm.tile_start[buf][tid] = wb + incl - count;
-            __syncthreads();
-            // ---- values (loaded late to keep registers low), then rank + scatter into the exchange buffer
+            uint32_t s0 = incl - sum;
+            for (int k = 0; k < warp; k++) s0 += sm.scan_tmp[k];
+            uint32_t st[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) { st[j] = s0; s0 += c[j]; }
+            reinterpret_cast<uint4*>(sm.tile_start)[tid] =
+                make_uint4(st[0] | (st[1] << 16), st[2] | (st[3] << 16), st[4] | (st[5] << 16), st[6] | (st[7] << 16));
+        }
+        __syncthreads();
+        // ---- values, then scatter keys and values into digit order
+        {
             uint32_t val[kKpt];
 #pragma unroll
             for (int k = 0; k < kKpt; k++) {
-                const uint32_t s = wbase_idx + k * 32 + lane;
+                const uint32_t s = wslot + k * 32;
                 val[k] = s < valid ? (synth_vals ? tile_base + s : vals_in[tile_base + s]) : 0u;
             }
 #pragma unroll
             for (int k = 0; k < kKpt; k++) {
-                const uint32_t d = (key[k] >> shift) & 0xffu;
-                uint32_t peers;
-                if (kVote > 0) {
-                    // the low kVote bits by ballots, the remaining high bits (few distinct values) by MATCH.ANY
-                    peers = kVote < 8 ? __match_any_sync(0xffffffffu, d >> kVote) : 0xffffffffu;
-#pragma unroll
-                    for (int b = 0; b < kVote; b++) {
-                        // peers &= lanes whose bit equals mine: test the key bit (LOP3 -> predicate), ballot, flip
-                        // the ballot if my bit is clear (SEL), and (LOP3) — four instructions; the C++ form
-                        // compiles to six (shift, and, two predicates, select, vote, and)
-                        asm volatile(
-                            "{\n"
-                            ".reg .pred p;\n"
-                            ".reg .b32 t, bal, sx;\n"
-                            "and.b32 t, %1, %2;\n"
-                            "setp.ne.u32 p, t, 0;\n"
-                            "vote.sync.ballot.b32 bal, p, 0xffffffff;\n"
-                            "selp.b32 sx, 0, -1, p;\n"
-                            "xor.b32 bal, bal, sx;\n"
-                            "and.b32 %0, %0, bal;\n"
-                            "}\n"
-                            : "+r"(peers)
-                            : "r"(key[k]), "r"(1u << (shift + b)));
-                    }
-                } else {
-                    peers = __match_any_sync(0xffffffffu, d);
-                }
-                const int leader = __ffs((int)peers) - 1;
-                uint32_t old = 0;
-                if (lane == leader) {
-                    old = sm.warp_hist[warp][d];
-                    sm.warp_hist[warp][d] = old + __popc(peers);
-                }
-                old = __shfl_sync(0xffffffffu, old, leader);
-                const uint32_t pos = sm.tile_start[buf][d] + old + __popc(peers & ((1u << lane) - 1u));
-                sm.exch_k[buf][pos] = key[k];
-                sm.exch_v[buf][pos] = val[k];
-                __syncwarp();
+                const uint32_t d = (key[k] >> shift) & dmask;
+                const uint32_t r = (k & 1) ? (rk[k >> 1] >> 16) : (rk[k >> 1] & 0xffffu);
+                const uint32_t pos = (uint32_t)sm.tile_start[d] + (uint32_t)wh[d] + r;
+                sm.exch_k[pos] = key[k];
+                sm.exch_v[pos] = val[k];
             }
         }
-        if (have_prev) {
-            // ---- resolve the previous tile's look-back for digit `tid`, kLb status words per round trip
-            const uint32_t pbuf = buf ^ 1u;
+        cl_sync();   // A: every CTA's counts are final, nobody reads whist any more (gpos may be written)
+        // ---- the next super-tile's ticket travels under barrier B
+        if (rank == 0 && tid == 0) {
+            const uint32_t t = atomicAdd(ticket, 1u);
+#pragma unroll
+            for (int r = 0; r < kCluster; r++) cl_st_u32(cl_map(&sm.tile_id[(it + 1) & 1u], r), t);
+        }
+        // ---- owner of digit `own`: counts of the 8 CTAs, the super-tile's total, look-back, global bases
+        {
+            uint32_t c[kCluster], total = 0;
+#pragma unroll
+            for (int r = 0; r < kCluster; r++) { c[r] = cl_ld_u16(cl_map(&sm.cta_count[own], r)); total += c[r]; }
+            uint64_t* my = lb + (size_t)super * kBins;
             uint32_t excl = 0;
-            if (p_tile > 0) {
-                constexpr int kLb = 4;
-                int64_t p = (int64_t)p_tile - 1;
+            if (super == 0) gs_st_status(my, epoch, GS_LOOKBACK_FLAG_INCL | total);
+            else {
+                gs_st_status(my, epoch, GS_LOOKBACK_FLAG_AGG | total);
+                constexpr int kLb = 4;   // status words per round trip
+                int64_t p = (int64_t)super - 1;
                 bool done = false;
                 while (!done) {
                     uint64_t v[kLb];
 #pragma unroll
                     for (int j = 0; j < kLb; j++)
-                        v[j] = (p - j >= 0) ? gs_ld_status(&lb[(size_t)(p - j) * kRadix])
-                                            : (((uint64_t)epoch << 32) | GS_LOOKBACK_FLAG_INCL);
+                        v[j] = (p - j >= 0) ? gs_ld_status(lb + (size_t)(p - j) * kBins) : (((uint64_t)epoch << 32) | GS_LOOKBACK_FLAG_INCL);
                     int used = 0;
 #pragma unroll
                     for (int j = 0; j < kLb; j++) {
@@ -263,66 +331,120 @@ __global__ void __launch_bounds__(kThreads, 3) k_sort_pass(uint32_t* __restrict_
                     }
                     p -= used;
                 }
-                gs_st_status(&lb[(size_t)p_tile * kRadix], epoch, GS_LOOKBACK_FLAG_INCL | (excl + p_count));
+                gs_st_status(my, epoch, GS_LOOKBACK_FLAG_INCL | (excl + total));
             }
-            sm.global_off[tid] = (int32_t)(gbase + excl) - (int32_t)sm.tile_start[pbuf][tid];
-            __syncthreads();
-            // ---- write out the previous tile: consecutive positions of one digit are consecutive addresses
+            uint32_t g = gbase + excl;
 #pragma unroll
-            for (int k = 0; k < kKpt; k++) {
-                const uint32_t p = k * kThreads + tid;
-                if (p < p_valid) {
-                    const uint32_t kk = sm.exch_k[pbuf][p];
-                    const uint32_t g = (uint32_t)(sm.global_off[(kk >> shift) & 0xffu] + (int32_t)p);
-                    keys_out[g] = kk;
-                    vals_out[g] = sm.exch_v[pbuf][p];
-                }
+            for (int r = 0; r < kCluster; r++) { cl_st_u32(cl_map(&sm.gpos[own], r), g); g += c[r]; }
+        }
+        cl_sync();   // B: gpos of every digit has arrived from its owner
+        // ---- write out: consecutive positions of one digit are consecutive addresses
+#pragma unroll
+        for (int k = 0; k < kKpt; k++) {
+            const uint32_t p = k * kThreads + tid;
+            if (p < valid) {
+                const uint32_t kk = sm.exch_k[p];
+                const uint32_t d = (kk >> shift) & dmask;
+                const uint32_t g = sm.gpos[d] + p - (uint32_t)sm.tile_start[d];
+                keys_out[g] = kk;
+                vals_out[g] = sm.exch_v[p];
             }
         }
-        if (!valid_tile) break;
-        have_prev = true;
-        p_tile = tile;
-        p_count = count;
-        p_valid = valid;
+        __syncthreads();
     }
+}
+
+struct DevInfo { int clusters = 0; };   // co-resident clusters of the pass kernel
+std::mutex g_mu;
+DevInfo g_dev[64];
+
+template <int BITS>
+cudaError_t setup_kernel(int* clusters) {
+    auto kern = k_sort_pass<BITS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kCluster, 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = sizeof(PassSmem);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = kCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int nc = 0;
+    e = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
+    if (e != cudaSuccess) return e;
+    if (*clusters == 0 || nc < *clusters) *clusters = nc < 1 ? 1 : nc;
+    return cudaSuccess;
 }
 
 }  // namespace
 
-size_t gs_sort_lookback_words(uint32_t n_max, uint32_t passes) {
-    size_t tiles = ((size_t)n_max + kTile - 1) / kTile;
-    if (tiles < 1) tiles = 1;
-    return tiles * kRadix * passes;
+size_t gs_sort_lookback_words(uint32_t n_max, uint32_t key_bits) {
+    size_t supers = ((size_t)n_max + kSuper - 1) / kSuper;
+    if (supers < 1) supers = 1;
+    return supers * kBins * gs_sort_passes(key_bits);
 }
 
 cudaError_t gs_launch_sort(const GsSortArgs& a, int num_sms, cudaStream_t st) {
-    if (a.passes < 1 || a.passes > 4 || !a.result_in_b) return cudaErrorInvalidValue;
-    size_t tiles = ((size_t)a.n_max + kTile - 1) / kTile;
-    if (tiles < 1) tiles = 1;
-    if (!a.hist_prefilled) {
-        uint32_t grid = (uint32_t)(num_sms * 4);
-        uint32_t need = (uint32_t)((a.n_max + kThreads - 1) / kThreads);
-        if (grid > need) grid = need < 1 ? 1 : need;
-        k_sort_hist<<<grid, kThreads, 0, st>>>(a.keys_a, a.d_n, a.n_max, a.hist, a.passes);
-    }
-    static int blocks_per_sm = 0;
-    if (blocks_per_sm == 0) {
-        cudaError_t e = cudaSuccess;
-        for (auto k : {k_sort_pass<0>, k_sort_pass<kVoteBits>}) {
-            e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
+    (void)num_sms;
+    if (a.key_bits < 1 || a.key_bits > 32 || !a.result_in_b) return cudaErrorInvalidValue;
+    const uint32_t passes = gs_sort_passes(a.key_bits);
+    size_t supers = ((size_t)a.n_max + kSuper - 1) / kSuper;
+    if (supers < 1) supers = 1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    int clusters;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        if (g_dev[dev].clusters == 0) {
+            int nc = 0;
+            e = setup_kernel<11>(&nc);
+            if (e == cudaSuccess) e = setup_kernel<10>(&nc);
+            if (e == cudaSuccess) e = setup_kernel<8>(&nc);
+            if (e == cudaSuccess) e = setup_kernel<5>(&nc);
+            if (e == cudaSuccess) e = setup_kernel<2>(&nc);
             if (e != cudaSuccess) return e;
+            g_dev[dev].clusters = nc;
         }
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_sort_pass<0>, kThreads, sizeof(PassSmem));
-        if (e != cudaSuccess) return e;
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
+        clusters = g_dev[dev].clusters;
     }
-    uint32_t grid = (uint32_t)(blocks_per_sm * num_sms);
-    if (grid > tiles) grid = (uint32_t)tiles;
-    for (uint32_t p = 0; p < a.passes; p++) {
-        auto kern = ((a.vote_mask >> p) & 1u) ? k_sort_pass<kVoteBits> : k_sort_pass<0>;
-        kern<<<grid, kThreads, sizeof(PassSmem), st>>>(a.keys_a, a.vals_a, a.keys_b, a.vals_b, a.d_n, a.n_max, a.hist, p, a.passes,
-                                               a.lookback + (size_t)p * tiles * kRadix, a.epoch, a.tickets + p,
-                                               a.result_in_b, a.vals_identity ? 1u : 0u);
+    if (!a.hist_prefilled) {
+        uint32_t grid = 296;
+        const uint32_t need = (uint32_t)((a.n_max + kThreads - 1) / kThreads);
+        if (grid > need) grid = need < 1 ? 1 : need;
+        k_sort_hist<<<grid, kThreads, passes * kBins * 4, st>>>(a.keys_a, a.d_n, a.n_max, a.hist, a.key_bits);
+    }
+    uint32_t grid_clusters = (uint32_t)clusters;
+    if (grid_clusters > supers) grid_clusters = (uint32_t)supers;
+    for (uint32_t p = 0; p < passes; p++) {
+        // the kernel is instantiated for a few ballot counts; a narrower digit is ranked on the next wider
+        // instantiation that still fits below bit 32: the extra bits lie above key_bits, are zero in every real
+        // key and set only in the 0xffffffff padding, so real digits are unchanged and padding still sorts last
+        const uint32_t shift = GS_SORT_DIGIT_BITS * p;
+        const uint32_t bits = a.key_bits - shift < GS_SORT_DIGIT_BITS ? a.key_bits - shift : GS_SORT_DIGIT_BITS;
+        void (*kern)(uint32_t*, uint32_t*, uint32_t*, uint32_t*, const uint32_t*, uint32_t, const uint32_t*, uint32_t, uint32_t,
+                     uint64_t*, uint32_t, uint32_t*, uint32_t*, uint32_t) = nullptr;
+        if (bits <= 2) kern = k_sort_pass<2>;
+        else if (bits <= 5) kern = k_sort_pass<5>;
+        else if (bits <= 8) kern = k_sort_pass<8>;
+        else if (bits <= 10) kern = k_sort_pass<10>;
+        else kern = k_sort_pass<11>;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid_clusters * kCluster, 1, 1);
+        cfg.blockDim = dim3(kThreads, 1, 1);
+        cfg.dynamicSmemBytes = sizeof(PassSmem);
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = kCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, a.keys_a, a.vals_a, a.keys_b, a.vals_b, a.d_n, a.n_max, (const uint32_t*)a.hist, p, a.key_bits,
+                               a.lookback + (size_t)p * supers * kBins, a.epoch, a.tickets + p, a.result_in_b,
+                               a.vals_identity ? 1u : 0u);
+        if (e != cudaSuccess) return e;
     }
     return cudaGetLastError();
 }
