@@ -25,6 +25,16 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* the thread count is set explicitly by callers that time the oracle (bench.py), because launchers such as
+ * torch.distributed.run export OMP_NUM_THREADS=1 to their children */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 static double now_s(void) {
     struct timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -419,7 +429,7 @@ static int query_hit(const b200gs_query_pod* q, float sx, float sy) {
 }
 
 /* one Gaussian; returns 1 if visible */
-static int pre_one(const orc_frame* f, const orc_model* m, const pre_ctx* c, uint64_t i, uint32_t* key, b200gs_splat* out,
+static int pre_one(const orc_frame* f, const orc_model* m, const pre_ctx* c, uint64_t i, uint32_t* key, orc_splat_f32* out,
                    int* selected_out) {
     if (selected_out) *selected_out = m->selection ? (int)((m->selection[i >> 5] >> (i & 31)) & 1u) : 0;
     if (m->mask && !((m->mask[i >> 5] >> (i & 31)) & 1u)) return 0;
@@ -534,17 +544,39 @@ static int pre_one(const orc_frame* f, const orc_model* m, const pre_ctx* c, uin
 
     out->mx = ((nx + 1.0f) * c->W - 1.0f) * 0.5f;
     out->my = ((1.0f - ny) * c->H - 1.0f) * 0.5f;
-    out->radius = (uint16_t)radf;
-    out->opacity_h = orc_f32_to_f16(op);
-    out->r_h = orc_f32_to_f16(rgb[0]);
-    out->g_h = orc_f32_to_f16(rgb[1]);
-    out->b_h = orc_f32_to_f16(rgb[2]);
+    out->radius = radf;
+    out->opacity = op;
+    out->r = rgb[0]; out->g = rgb[1]; out->b = rgb[2];
     out->ca = ca; out->cb = cb; out->cc = cc;
-    out->flags = (uint16_t)(selected ? 1 : 0);
+    out->flags = (uint32_t)(selected ? 1 : 0);
     return 1;
 }
 
-uint64_t orc_preprocess(const orc_frame* f, const orc_model* m, uint32_t* indices, uint32_t* keys, b200gs_splat* splats) {
+/* the product's 32-byte record of a projected splat: colour and opacity rounded to f16 (RN-even) */
+static void to_record(const orc_splat_f32* s, b200gs_splat* out) {
+    memset(out, 0, sizeof *out);
+    out->mx = s->mx; out->my = s->my;
+    out->radius = (uint16_t)s->radius;
+    out->opacity_h = orc_f32_to_f16(s->opacity);
+    out->r_h = orc_f32_to_f16(s->r);
+    out->g_h = orc_f32_to_f16(s->g);
+    out->b_h = orc_f32_to_f16(s->b);
+    out->ca = s->ca; out->cb = s->cb; out->cc = s->cc;
+    out->flags = (uint16_t)s->flags;
+}
+static void from_record(const b200gs_splat* s, orc_splat_f32* out) {
+    out->mx = s->mx; out->my = s->my;
+    out->radius = (float)s->radius;
+    out->opacity = orc_f16_to_f32(s->opacity_h);
+    out->r = orc_f16_to_f32(s->r_h); out->g = orc_f16_to_f32(s->g_h); out->b = orc_f16_to_f32(s->b_h);
+    out->ca = s->ca; out->cb = s->cb; out->cc = s->cc;
+    out->flags = s->flags;
+}
+
+/* Outputs in ascending Gaussian index order.  `splats` (the product's record, f16 colour / opacity) and
+ * `splats_f32` (the oracle's own fp32 splat, nothing rounded) may each be NULL. */
+static uint64_t preprocess_any(const orc_frame* f, const orc_model* m, uint32_t* indices, uint32_t* keys, b200gs_splat* splats,
+                               orc_splat_f32* splats_f32) {
     pre_ctx c;
     pre_setup(f, m, &c);
     /* two-pass so that the output keeps ascending-index order under threads */
@@ -558,7 +590,7 @@ uint64_t orc_preprocess(const orc_frame* f, const orc_model* m, uint32_t* indice
         uint64_t k = 0;
         for (uint64_t i = lo; i < hi; i++) {
             uint32_t key;
-            b200gs_splat s;
+            orc_splat_f32 s;
             vis[i] = (uint8_t)pre_one(f, m, &c, i, &key, &s, NULL);
             k += vis[i];
         }
@@ -572,12 +604,13 @@ uint64_t orc_preprocess(const orc_frame* f, const orc_model* m, uint32_t* indice
         for (uint64_t i = lo; i < hi; i++) {
             if (!vis[i]) continue;
             uint32_t key;
-            b200gs_splat s;
+            orc_splat_f32 s;
             memset(&s, 0, sizeof s);
             pre_one(f, m, &c, i, &key, &s, NULL);
             if (indices) indices[k] = (uint32_t)i;
             if (keys) keys[k] = key;
-            if (splats) splats[k] = s;
+            if (splats) to_record(&s, &splats[k]);
+            if (splats_f32) splats_f32[k] = s;
             k++;
         }
     }
@@ -585,6 +618,12 @@ uint64_t orc_preprocess(const orc_frame* f, const orc_model* m, uint32_t* indice
     free(cnt);
     free(vis);
     return v;
+}
+uint64_t orc_preprocess(const orc_frame* f, const orc_model* m, uint32_t* indices, uint32_t* keys, b200gs_splat* splats) {
+    return preprocess_any(f, m, indices, keys, splats, NULL);
+}
+uint64_t orc_preprocess_f32(const orc_frame* f, const orc_model* m, uint32_t* indices, uint32_t* keys, orc_splat_f32* splats) {
+    return preprocess_any(f, m, indices, keys, NULL, splats);
 }
 
 void orc_query_selection(const orc_frame* f, const orc_model* m, uint32_t* words_out) {
@@ -594,7 +633,7 @@ void orc_query_selection(const orc_frame* f, const orc_model* m, uint32_t* words
     for (uint64_t w = 0; w < nw; w++) words_out[w] = 0;
     for (uint64_t i = 0; i < m->n; i++) {
         uint32_t key;
-        b200gs_splat s;
+        orc_splat_f32 s;
         int sel = 0;
         int vis = pre_one(f, m, &c, i, &key, &s, &sel);
         /* a culled Gaussian is never hit: Set clears it, Add / Remove keep its old state */
@@ -668,7 +707,7 @@ void orc_sort_pairs(uint64_t n, uint32_t* keys, uint32_t* values, uint32_t bits)
     if (values) memcpy(values, v2, n * 4);
     free(k2); free(v2); free(a);
 }
-void orc_sort(uint64_t v, uint32_t* keys, uint32_t* indices, b200gs_splat* splats) {
+static void sort_any(uint64_t v, uint32_t* keys, uint32_t* indices, void* splats, size_t splat_bytes) {
     kv* a = (kv*)malloc((v ? v : 1) * sizeof(kv));
     sort_perm(v, keys, 0xffffffffu, a);
     uint32_t* k2 = (uint32_t*)malloc((v ? v : 1) * 4);
@@ -678,13 +717,15 @@ void orc_sort(uint64_t v, uint32_t* keys, uint32_t* indices, b200gs_splat* splat
     memcpy(indices, i2, v * 4);
     free(k2); free(i2);
     if (splats) {
-        b200gs_splat* s2 = (b200gs_splat*)malloc((v ? v : 1) * sizeof(b200gs_splat));
-        for (uint64_t i = 0; i < v; i++) s2[i] = splats[a[i].pos];
-        memcpy(splats, s2, v * sizeof(b200gs_splat));
+        uint8_t* s2 = (uint8_t*)malloc((v ? v : 1) * splat_bytes);
+        for (uint64_t i = 0; i < v; i++) memcpy(s2 + i * splat_bytes, (const uint8_t*)splats + (size_t)a[i].pos * splat_bytes, splat_bytes);
+        memcpy(splats, s2, v * splat_bytes);
         free(s2);
     }
     free(a);
 }
+void orc_sort(uint64_t v, uint32_t* keys, uint32_t* indices, b200gs_splat* splats) { sort_any(v, keys, indices, splats, sizeof(b200gs_splat)); }
+void orc_sort_f32(uint64_t v, uint32_t* keys, uint32_t* indices, orc_splat_f32* splats) { sort_any(v, keys, indices, splats, sizeof(orc_splat_f32)); }
 
 /* ---------------------------------------------------------- compositing (a3)
  * Fragment rule [CANON §8c.7]: a splat covers the pixels of the screen-aligned square of
@@ -692,7 +733,7 @@ void orc_sort(uint64_t v, uint32_t* keys, uint32_t* indices, b200gs_splat* splat
  * power = -½(a dx² + c dy²) - b dx dy; dropped if power > 0 or alpha < 1/255.
  * Ellipse/Point display (src/tab/transform.rs:129-131): flat alpha min(0.99, o) inside
  * d² <= ORC_FLAT_D2 [our definition; the crate's is unknown]. */
-static inline int splat_alpha(const orc_frame* f, const b200gs_splat* s, float op, float px, float py, float* alpha) {
+static inline int splat_alpha(const orc_frame* f, const orc_splat_f32* s, float op, float px, float py, float* alpha) {
     float dx = px - s->mx, dy = py - s->my;
     float power = -0.5f * (s->ca * dx * dx + s->cc * dy * dy) - s->cb * dx * dy;
     if (power > 0.0f) return 0;
@@ -703,9 +744,9 @@ static inline int splat_alpha(const orc_frame* f, const b200gs_splat* s, float o
     *alpha = al;
     return 1;
 }
-static inline int splat_bounds(const orc_frame* f, const b200gs_splat* s, int* x0, int* x1, int* y0, int* y1) {
-    if (s->radius == 0) return 0;
-    float r = (float)s->radius;
+static inline int splat_bounds(const orc_frame* f, const orc_splat_f32* s, int* x0, int* x1, int* y0, int* y1) {
+    if (!(s->radius > 0.0f)) return 0;
+    float r = s->radius;
     float fx0 = ceilf(s->mx - r), fx1 = floorf(s->mx + r), fy0 = ceilf(s->my - r), fy1 = floorf(s->my + r);
     float W = f->size[0], H = f->size[1];
     if (fx0 < 0.0f) fx0 = 0.0f;
@@ -728,7 +769,7 @@ static void finish_image(const orc_frame* f, const float* acc, uint64_t npx, flo
 
 /* reference-style: hardware "over" blending, back to front, premultiplied [§8c.8]:
  * C = c·α + C·(1-α), A = α + A·(1-α), starting from the clear colour. */
-void orc_composite_b2f(const orc_frame* f, const b200gs_splat* splats, uint64_t n_total, float* rgba_f, uint8_t* rgba8) {
+void orc_composite_b2f_f32(const orc_frame* f, const orc_splat_f32* splats, uint64_t n_total, float* rgba_f, uint8_t* rgba8) {
     int W = (int)f->size[0], H = (int)f->size[1];
     float* acc = (float*)malloc((size_t)W * H * 16);
     int nt = orc_num_threads();
@@ -742,14 +783,14 @@ void orc_composite_b2f(const orc_frame* f, const b200gs_splat* splats, uint64_t 
             for (int x = 0; x < W; x++)
                 for (int c = 0; c < 4; c++) acc[4 * ((size_t)y * W + x) + c] = f->background[c];
         for (uint64_t k = n_total; k-- > 0;) {
-            const b200gs_splat* s = &splats[k];
+            const orc_splat_f32* s = &splats[k];
             int x0, x1, y0, y1;
             if (!splat_bounds(f, s, &x0, &x1, &y0, &y1)) continue;
             if (y0 < by0) y0 = by0;
             if (y1 > by1) y1 = by1;
             if (y0 > y1) continue;
-            float op = orc_f16_to_f32(s->opacity_h);
-            float col[3] = {orc_f16_to_f32(s->r_h), orc_f16_to_f32(s->g_h), orc_f16_to_f32(s->b_h)};
+            float op = s->opacity;
+            float col[3] = {s->r, s->g, s->b};
             for (int y = y0; y <= y1; y++)
                 for (int x = x0; x <= x1; x++) {
                     float al;
@@ -768,7 +809,7 @@ void orc_composite_b2f(const orc_frame* f, const b200gs_splat* splats, uint64_t 
 }
 
 /* the new design's order: front to back, C += c·α·T, T *= (1-α), stop when T < ORC_T_EPS */
-uint64_t orc_composite_f2b(const orc_frame* f, const b200gs_splat* splats, uint64_t n_total, float* rgba_f, uint8_t* rgba8) {
+uint64_t orc_composite_f2b_f32(const orc_frame* f, const orc_splat_f32* splats, uint64_t n_total, float* rgba_f, uint8_t* rgba8) {
     int W = (int)f->size[0], H = (int)f->size[1];
     float* acc = (float*)malloc((size_t)W * H * 16);
     float* Tr = (float*)malloc((size_t)W * H * 4);
@@ -787,14 +828,14 @@ uint64_t orc_composite_f2b(const orc_frame* f, const b200gs_splat* splats, uint6
                 Tr[p] = 1.0f;
             }
         for (uint64_t k = 0; k < n_total; k++) {
-            const b200gs_splat* s = &splats[k];
+            const orc_splat_f32* s = &splats[k];
             int x0, x1, y0, y1;
             if (!splat_bounds(f, s, &x0, &x1, &y0, &y1)) continue;
             if (y0 < by0) y0 = by0;
             if (y1 > by1) y1 = by1;
             if (y0 > y1) continue;
-            float op = orc_f16_to_f32(s->opacity_h);
-            float col[3] = {orc_f16_to_f32(s->r_h), orc_f16_to_f32(s->g_h), orc_f16_to_f32(s->b_h)};
+            float op = s->opacity;
+            float col[3] = {s->r, s->g, s->b};
             for (int y = y0; y <= y1; y++)
                 for (int x = x0; x <= x1; x++) {
                     size_t p = (size_t)y * W + x;
@@ -824,6 +865,25 @@ uint64_t orc_composite_f2b(const orc_frame* f, const b200gs_splat* splats, uint6
     free(acc);
     free(Tr);
     return evals;
+}
+
+/* the same two compositors over the product's 32-byte records (f16 colour / opacity read back exactly) */
+static orc_splat_f32* records_to_f32(const b200gs_splat* splats, uint64_t n) {
+    orc_splat_f32* t = (orc_splat_f32*)malloc((n ? n : 1) * sizeof(orc_splat_f32));
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; i++) from_record(&splats[i], &t[i]);
+    return t;
+}
+void orc_composite_b2f(const orc_frame* f, const b200gs_splat* splats, uint64_t n_total, float* rgba_f, uint8_t* rgba8) {
+    orc_splat_f32* t = records_to_f32(splats, n_total);
+    orc_composite_b2f_f32(f, t, n_total, rgba_f, rgba8);
+    free(t);
+}
+uint64_t orc_composite_f2b(const orc_frame* f, const b200gs_splat* splats, uint64_t n_total, float* rgba_f, uint8_t* rgba8) {
+    orc_splat_f32* t = records_to_f32(splats, n_total);
+    uint64_t e = orc_composite_f2b_f32(f, t, n_total, rgba_f, rgba8);
+    free(t);
+    return e;
 }
 
 /* ----------------------------------------------------------- model order (a4)
@@ -861,11 +921,12 @@ void orc_order_models(const orc_frame* f, const orc_model* models, const float* 
 }
 
 /* ------------------------------------------------------------- whole frame */
-uint64_t orc_render_frame(const orc_frame* f, const orc_model* far_to_near, uint32_t n_models, int front_to_back,
-                          uint8_t* rgba8, double stage_seconds[3]) {
+static uint64_t render_frame_any(const orc_frame* f, const orc_model* far_to_near, uint32_t n_models, int front_to_back, int fp32,
+                                 uint8_t* rgba8, double stage_seconds[3]) {
     uint64_t cap = 0;
     for (uint32_t i = 0; i < n_models; i++) cap += far_to_near[i].n;
-    b200gs_splat* all = (b200gs_splat*)malloc((cap ? cap : 1) * sizeof(b200gs_splat));
+    b200gs_splat* all = fp32 ? NULL : (b200gs_splat*)malloc((cap ? cap : 1) * sizeof(b200gs_splat));
+    orc_splat_f32* all32 = fp32 ? (orc_splat_f32*)malloc((cap ? cap : 1) * sizeof(orc_splat_f32)) : NULL;
     uint32_t* keys = (uint32_t*)malloc((cap ? cap : 1) * 4);
     uint32_t* idx = (uint32_t*)malloc((cap ? cap : 1) * 4);
     uint64_t total = 0;
@@ -874,21 +935,36 @@ uint64_t orc_render_frame(const orc_frame* f, const orc_model* far_to_near, uint
     for (uint32_t mi = n_models; mi-- > 0;) {
         const orc_model* m = &far_to_near[mi];
         double t0 = now_s();
-        uint64_t v = orc_preprocess(f, m, idx + total, keys + total, all + total);
+        uint64_t v = preprocess_any(f, m, idx + total, keys + total, all ? all + total : NULL, all32 ? all32 + total : NULL);
         double t1 = now_s();
-        orc_sort(v, keys + total, idx + total, all + total);
+        if (fp32) orc_sort_f32(v, keys + total, idx + total, all32 + total);
+        else orc_sort(v, keys + total, idx + total, all + total);
         double t2 = now_s();
         t_pre += t1 - t0;
         t_sort += t2 - t1;
         total += v;
     }
     double t3 = now_s();
-    if (front_to_back) orc_composite_f2b(f, all, total, NULL, rgba8);
-    else orc_composite_b2f(f, all, total, NULL, rgba8);
+    if (fp32) {
+        if (front_to_back) orc_composite_f2b_f32(f, all32, total, NULL, rgba8);
+        else orc_composite_b2f_f32(f, all32, total, NULL, rgba8);
+    } else {
+        if (front_to_back) orc_composite_f2b(f, all, total, NULL, rgba8);
+        else orc_composite_b2f(f, all, total, NULL, rgba8);
+    }
     t_comp = now_s() - t3;
     if (stage_seconds) { stage_seconds[0] = t_pre; stage_seconds[1] = t_sort; stage_seconds[2] = t_comp; }
-    free(all); free(keys); free(idx);
+    free(all); free(all32); free(keys); free(idx);
     return total;
+}
+uint64_t orc_render_frame(const orc_frame* f, const orc_model* far_to_near, uint32_t n_models, int front_to_back,
+                          uint8_t* rgba8, double stage_seconds[3]) {
+    return render_frame_any(f, far_to_near, n_models, front_to_back, 0, rgba8, stage_seconds);
+}
+/* the whole path in fp32 end to end: the projected splat is never rounded to the product's f16 record */
+uint64_t orc_render_frame_f32(const orc_frame* f, const orc_model* far_to_near, uint32_t n_models, int front_to_back,
+                              uint8_t* rgba8, double stage_seconds[3]) {
+    return render_frame_any(f, far_to_near, n_models, front_to_back, 1, rgba8, stage_seconds);
 }
 
 /* ------------------------------------------------------------ mask eval (N2)

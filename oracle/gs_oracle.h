@@ -59,6 +59,16 @@ typedef struct orc_model {
     const b200gs_edit_pod* edits; /* may be NULL = no edits */
 } orc_model;
 
+/* The oracle's OWN projected splat: fp32 throughout, nothing rounded to f16.  (The product stores a 32-byte
+ * record with f16 colour and opacity, `b200gs_splat`; the *_f32 entry points below never touch that format, so
+ * the image tolerance measured against them includes the product's quantisation.) */
+typedef struct orc_splat_f32 {
+    float mx, my, radius; /* pixel centre, extent-square half-size */
+    float opacity, r, g, b;
+    float ca, cb, cc;     /* conic */
+    uint32_t flags;       /* bit 0: selected */
+} orc_splat_f32;
+
 /* host-side conversions */
 uint32_t orc_record_bytes(uint32_t sh, uint32_t cov3d);
 uint16_t orc_f32_to_f16(float f);
@@ -72,6 +82,12 @@ void orc_quat_from_euler_zyx_deg(const float rot_deg[3], float quat[4]);
 
 /* a1: preprocess.  Outputs in ascending Gaussian index order; returns V. */
 uint64_t orc_preprocess(const orc_frame* f, const orc_model* m, uint32_t* indices, uint32_t* keys, b200gs_splat* splats);
+uint64_t orc_preprocess_f32(const orc_frame* f, const orc_model* m, uint32_t* indices, uint32_t* keys, orc_splat_f32* splats);
+void orc_sort_f32(uint64_t v, uint32_t* keys, uint32_t* indices, orc_splat_f32* splats);
+void orc_composite_b2f_f32(const orc_frame* f, const orc_splat_f32* splats, uint64_t n_total, float* rgba_f, uint8_t* rgba8);
+uint64_t orc_composite_f2b_f32(const orc_frame* f, const orc_splat_f32* splats, uint64_t n_total, float* rgba_f, uint8_t* rgba8);
+uint64_t orc_render_frame_f32(const orc_frame* f, const orc_model* far_to_near, uint32_t n_models, int front_to_back,
+                              uint8_t* rgba8, double stage_seconds[3]);
 /* a2: stable ascending sort of (key, index) with the splats carried along */
 void orc_sort(uint64_t v, uint32_t* keys, uint32_t* indices, b200gs_splat* splats);
 void orc_sort_pairs(uint64_t n, uint32_t* keys, uint32_t* values, uint32_t bits);
@@ -93,6 +109,7 @@ void orc_eval_mask(const orc_model* m, const b200gs_mask_op* postfix, uint32_t n
 void orc_query_selection(const orc_frame* f, const orc_model* m, uint32_t* words_out);
 void orc_apply_edit(const b200gs_edit_pod* e, float rgb[3], float* opacity);
 int orc_num_threads(void);
+void orc_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -18,12 +18,14 @@ PLY = np.dtype([("pos", "<f4", 3), ("normal", "<f4", 3), ("f_dc", "<f4", 3), ("f
                 ("opacity", "<f4"), ("scale", "<f4", 3), ("rot", "<f4", 4)])
 EDIT = np.dtype([("flag", "<u4"), ("color", "<f4", 3), ("contrast", "<f4"), ("exposure", "<f4"),
                  ("gamma", "<f4"), ("alpha", "<f4")])
+SPLAT_F32 = np.dtype([("mx", "<f4"), ("my", "<f4"), ("radius", "<f4"), ("opacity", "<f4"), ("r", "<f4"), ("g", "<f4"),
+                      ("b", "<f4"), ("ca", "<f4"), ("cb", "<f4"), ("cc", "<f4"), ("flags", "<u4")])
 SPLAT = np.dtype([("mx", "<f4"), ("my", "<f4"), ("radius", "<u2"), ("opacity_h", "<f2"), ("r_h", "<f2"),
                   ("g_h", "<f2"), ("ca", "<f4"), ("cb", "<f4"), ("cc", "<f4"), ("b_h", "<f2"), ("flags", "<u2")])
 MASK_SHAPE = np.dtype([("kind", "<u4"), ("pos", "<f4", 3), ("quat", "<f4", 4), ("scale", "<f4", 3)])
 MASK_OP = np.dtype([("kind", "<u4"), ("arg", "<u4")])
 assert GAUSSIAN.itemsize == 224 and PLY.itemsize == 248 and EDIT.itemsize == 32 and SPLAT.itemsize == 32
-assert MASK_SHAPE.itemsize == 44
+assert MASK_SHAPE.itemsize == 44 and SPLAT_F32.itemsize == 44
 
 
 class EditPod(C.Structure):
@@ -73,8 +75,11 @@ def lib():
         L.orc_f16_to_f32.restype = C.c_float
         L.orc_f16_to_f32.argtypes = [C.c_uint16]
         L.orc_preprocess.restype = C.c_uint64
+        L.orc_preprocess_f32.restype = C.c_uint64
         L.orc_composite_f2b.restype = C.c_uint64
+        L.orc_composite_f2b_f32.restype = C.c_uint64
         L.orc_render_frame.restype = C.c_uint64
+        L.orc_render_frame_f32.restype = C.c_uint64
         L.orc_num_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -190,10 +195,22 @@ def preprocess(frame, model):
     return idx[:v].copy(), keys[:v].copy(), spl[:v].copy()
 
 
+def preprocess_f32(frame, model):
+    """The oracle's own fp32 projected splats (nothing rounded to the product's f16 record)."""
+    idx = np.zeros(model.n, np.uint32)
+    keys = np.zeros(model.n, np.uint32)
+    spl = np.zeros(model.n, SPLAT_F32)
+    v = int(lib().orc_preprocess_f32(C.byref(frame), C.byref(model.c), _p(idx), _p(keys), _p(spl)))
+    return idx[:v].copy(), keys[:v].copy(), spl[:v].copy()
+
+
 def sort(keys, idx, splats=None):
     keys, idx = keys.copy(), idx.copy()
     splats = None if splats is None else splats.copy()
-    lib().orc_sort(C.c_uint64(len(keys)), _p(keys), _p(idx), _p(splats))
+    if splats is not None and splats.dtype == SPLAT_F32:
+        lib().orc_sort_f32(C.c_uint64(len(keys)), _p(keys), _p(idx), _p(splats))
+    else:
+        lib().orc_sort(C.c_uint64(len(keys)), _p(keys), _p(idx), _p(splats))
     return keys, idx, splats
 
 
@@ -205,14 +222,17 @@ def sort_pairs(keys, values, bits=32):
 
 def composite(frame, splats, front_to_back=False, want_float=False):
     w, h = int(frame.size[0]), int(frame.size[1])
-    splats = np.ascontiguousarray(splats, dtype=SPLAT)
+    fp32 = splats.dtype == SPLAT_F32
+    splats = np.ascontiguousarray(splats, dtype=SPLAT_F32 if fp32 else SPLAT)
     img = np.zeros((h, w, 4), np.uint8)
     imf = np.zeros((h, w, 4), np.float32) if want_float else None
     evals = 0
+    f2b = lib().orc_composite_f2b_f32 if fp32 else lib().orc_composite_f2b
+    b2f = lib().orc_composite_b2f_f32 if fp32 else lib().orc_composite_b2f
     if front_to_back:
-        evals = int(lib().orc_composite_f2b(C.byref(frame), _p(splats), C.c_uint64(len(splats)), _p(imf), _p(img)))
+        evals = int(f2b(C.byref(frame), _p(splats), C.c_uint64(len(splats)), _p(imf), _p(img)))
     else:
-        lib().orc_composite_b2f(C.byref(frame), _p(splats), C.c_uint64(len(splats)), _p(imf), _p(img))
+        b2f(C.byref(frame), _p(splats), C.c_uint64(len(splats)), _p(imf), _p(img))
     return (img, imf, evals) if want_float else (img, evals)
 
 
@@ -224,13 +244,15 @@ def order_models(frame, models, centers):
     return order
 
 
-def render_frame(frame, models_far_to_near, front_to_back=False):
+def render_frame(frame, models_far_to_near, front_to_back=False, fp32=False):
+    """Whole frame; fp32=True keeps the projected splats in fp32 end to end (orc_render_frame_f32)."""
     n = len(models_far_to_near)
     arr = (Model * n)(*[m.c for m in models_far_to_near])
     w, h = int(frame.size[0]), int(frame.size[1])
     img = np.zeros((h, w, 4), np.uint8)
     st = (C.c_double * 3)()
-    v = int(lib().orc_render_frame(C.byref(frame), arr, C.c_uint32(n), C.c_int(1 if front_to_back else 0), _p(img), st))
+    fn = lib().orc_render_frame_f32 if fp32 else lib().orc_render_frame
+    v = int(fn(C.byref(frame), arr, C.c_uint32(n), C.c_int(1 if front_to_back else 0), _p(img), st))
     return img, v, list(st)
 
 
@@ -266,6 +288,12 @@ def apply_edit(edit, rgb, opacity):
 
 def num_threads():
     return int(lib().orc_num_threads())
+
+
+def set_num_threads(n=None):
+    """Use n OpenMP threads (default: every host core), whatever OMP_NUM_THREADS the launcher exported."""
+    lib().orc_set_num_threads(C.c_int(int(n or os.cpu_count() or 1)))
+    return num_threads()
 
 
 def orbit_camera(radius=4.5, elev_deg=20.0, azim_deg=35.0, width=1920, height=1080, vfov_deg=60.0,

@@ -69,6 +69,13 @@ def _full_parity(G, O, n, seed, W, H, sh=2, cov=1, cam=None, check_image=True, *
         if check_image:
             ref, _ = O.composite(f, osp2, front_to_back=False)    # reference-style back-to-front
             assert_image_close(img, ref)
+            # ... and against the oracle's OWN fp32 splats (colour / opacity never rounded to the product's f16
+            # record), so that the 2/255 / 50 dB bar includes the product's quantisation
+            fi, fk, fsp = O.preprocess_f32(f, om)
+            fk2, fi2, fsp2 = O.sort(fk, fi, fsp)
+            assert np.array_equal(fi2, oi2)
+            ref32, _ = O.composite(f, fsp2, front_to_back=False)
+            assert_image_close(img, ref32)
         t = v.last_timings()
         assert t.overflow == 0
     return img
@@ -88,6 +95,11 @@ def test_config3_6m_1080p_all_stages(G, O):
     """BASELINE.json configs[2] at full size: 6M Gaussians at 1920x1080 — every stage still compared
     with the oracle (it finishes in seconds on the host cores)."""
     _full_parity(G, O, 6_000_000, SEED_6M, 1920, 1080)
+
+
+def test_config3_6m_4k_full_size(G, O):
+    """BASELINE.json configs[2], 3840x2160 leg at FULL size: 6M Gaussians, every stage and the image."""
+    _full_parity(G, O, 6_000_000, SEED_6M, 3840, 2160)
 
 
 def test_config3_4k_image(G, O):

@@ -472,3 +472,78 @@ def test_selection_query_rect_and_brush(O):
     f = O.make_frame(view, proj, W, H, query=O.query_pod(2, 0, (20, 20), (44, 36)), highlight=(1, 0, 1, 0.5))
     idx, _, spl = O.preprocess(f, O.ModelRef(0, 0, packed, 25))
     assert np.array_equal(spl["flags"].astype(bool), sel[idx])
+
+
+# ---------------------------------------------------------------------------------------------- cross-checks
+def test_fp32_splat_path_agrees_with_the_f16_record_path(O):
+    """The oracle's own fp32 splats (orc_preprocess_f32: nothing rounded to the product's 32-byte record) against
+    its f16-record path on BASELINE config 1: same visible set / order, images within 1/255 — i.e. the record's
+    f16 colour and opacity cost at most one 8-bit step."""
+    n, W, H = 100_000, 1280, 720
+    packed = O.pack(2, 1, O.gaussian_from_ply(O.synth_scene(0xB2000001, n)))
+    view, proj = O.orbit_camera(width=W, height=H)
+    f = O.make_frame(view, proj, W, H)
+    m = O.ModelRef(2, 1, packed, n)
+    i1, k1, s1 = O.preprocess(f, m)
+    i2, k2, s2 = O.preprocess_f32(f, m)
+    assert np.array_equal(i1, i2) and np.array_equal(k1, k2)
+    for a, b in (("mx", "mx"), ("my", "my"), ("ca", "ca"), ("cb", "cb"), ("cc", "cc")):
+        assert np.array_equal(s1[a], s2[b])
+    assert np.array_equal(s1["radius"].astype(np.float32), s2["radius"])
+    assert np.max(np.abs(s1["r_h"].astype(np.float32) - s2["r"])) <= 2.0 ** -11
+    k1s, i1s, s1s = O.sort(k1, i1, s1)
+    k2s, i2s, s2s = O.sort(k2, i2, s2)
+    assert np.array_equal(i1s, i2s)
+    a, _ = O.composite(f, s1s)
+    b, _ = O.composite(f, s2s)
+    assert np.abs(a.astype(np.int32) - b.astype(np.int32)).max() <= 1
+    img, v, _ = O.render_frame(f, [m], fp32=True)
+    assert v == len(i2) and np.array_equal(img, b)
+
+
+def test_numpy_float64_restatement_agrees_on_config1(O):
+    """SURVEY.md §7 step 2's "slower NumPy cross-check": tests/numpy_ref.py restates §8(c) in float64 NumPy without
+    looking at the C code.  On BASELINE config 1 (100k @ 1280x720): the visible set is identical; the oracle's f32
+    depths are the float64 depths to within a few f32 ulps and its sorted order is a sort of the float64 depths up
+    to that rounding; blended in that order, the float64 image is within 1/255 of the oracle's."""
+    import numpy_ref as NR
+    n, W, H = 100_000, 1280, 720
+    packed = O.pack(2, 1, O.gaussian_from_ply(O.synth_scene(0xB2000001, n)))
+    view, proj = O.orbit_camera(width=W, height=H)
+    f = O.make_frame(view, proj, W, H)
+    m = O.ModelRef(2, 1, packed, n)
+    oi, ok, osp = O.preprocess_f32(f, m)
+    ok2, oi2, osp2 = O.sort(ok, oi, osp)
+    ref, ref_f, _ = O.composite(f, osp2, want_float=True)
+    idx, z, order, img = NR.render(packed, n, view, proj, W, H, near_to_far=oi2)
+    assert np.array_equal(idx, oi)                                         # visible set (and compaction order)
+    ulp = float(np.spacing(np.float32(0.9)))
+    assert np.abs(ok.view(np.float32).astype(np.float64) - z).max() <= 8 * ulp      # depth keys
+    zs = z[np.searchsorted(idx, oi2)]
+    assert np.maximum(0.0, zs[:-1] - zs[1:]).max() <= 8 * ulp              # the oracle's order sorts the f64 depths
+    own = NR.render(packed, n, view, proj, W, H)[2]
+    assert np.mean(own == oi2) > 0.8                                       # (free-running f64 order: near-ties swap)
+    q = np.floor(np.clip(img, 0.0, 1.0) * 255.0 + 0.5).astype(np.int32)
+    assert np.abs(q - ref.astype(np.int32)).max() <= 1
+    assert np.abs(img - ref_f).max() <= 1.5 / 255.0   # (1/255 + an alpha-cut flip between f32 and f64)
+
+
+def test_numpy_float64_restatement_with_model_transform(O):
+    """Same cross-check under a TRS model transform (BASELINE config 4's second transform) on a 20k scene."""
+    import numpy_ref as NR
+    n, W, H = 20_000, 640, 360
+    packed = O.pack(2, 1, O.gaussian_from_ply(O.synth_scene(0xB2000042, n)))
+    view, proj = O.orbit_camera(width=W, height=H)
+    f = O.make_frame(view, proj, W, H, gaussian_size=1.3, sh_deg=2)
+    quat = O.quat_from_euler_zyx_deg((10.0, 0.0, 45.0))
+    m = O.ModelRef(2, 1, packed, n, pos=(0.3, -0.2, 0.1), quat=quat, scale=(1.2, 0.8, 1.0))
+    oi, ok, osp = O.preprocess_f32(f, m)
+    ok2, oi2, osp2 = O.sort(ok, oi, osp)
+    ref, ref_f, _ = O.composite(f, osp2, want_float=True)
+    idx, z, order, img = NR.render(packed, n, view, proj, W, H, sh_deg=2, size=1.3, model_pos=(0.3, -0.2, 0.1),
+                                   model_quat=quat, model_scale=(1.2, 0.8, 1.0), near_to_far=oi2)
+    assert np.array_equal(idx, oi)
+    # (a fragment sitting exactly on the alpha >= 1/255 cut can flip in or out between f32 and f64: one cut step)
+    assert np.abs(img - ref_f).max() <= 1.5 / 255.0
+    q = np.floor(np.clip(img, 0.0, 1.0) * 255.0 + 0.5).astype(np.int32)
+    assert np.abs(q - ref.astype(np.int32)).max() <= 1

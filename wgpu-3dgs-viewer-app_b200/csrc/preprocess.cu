@@ -567,7 +567,8 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
                 // the top digit is usually the same for the whole warp: one vote and one atomic instead of a match
                 const int first = __ffs((int)ballot) - 1;
                 const uint32_t d2 = key >> 22;
-                const bool uniform = __all_sync(0xffffffffu, !vis || d2 == __shfl_sync(0xffffffffu, d2, first));
+                const uint32_t d2_first = __shfl_sync(0xffffffffu, d2, first);   // (every lane takes part: not inside the ||)
+                const bool uniform = __all_sync(0xffffffffu, !vis || d2 == d2_first);
                 if (uniform) {
                     if (lane == first) atomicAdd(&s_hist[2048 + (d2 >> 1)], (uint32_t)__popc(ballot) << (16u * (d2 & 1u)));
                 } else if (vis) {

@@ -191,7 +191,8 @@ k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, uint32
     }
     uint64_t* lb = lookback + own;
 
-    // first ticket
+    // every CTA of the cluster is running (its shared memory may be written from now on); then the first ticket
+    cl_sync();
     if (rank == 0 && tid == 0) {
         const uint32_t t = atomicAdd(ticket, 1u);
 #pragma unroll
