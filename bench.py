@@ -105,23 +105,20 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------ reference arm
 def run_reference(a, rank):
     """The reference's CPU implementation of the path is not buildable here (no rustc/cargo, crate
-    source absent): this arm times the CPU restatement (oracle/), all host threads, one frame of the
-    same workload per step."""
+    source absent; tools/plan_a_probe.py records the probe): this arm times the CPU restatement (oracle/) on
+    EVERY host core, one frame of the same workload per step.  It never imports the product package."""
     if rank != 0:
         return
     from oracle import oracle as O
-    import b200gs as G          # host-side scene generator only (no GPU use in this arm)
-    ply = G.synth_scene(SEED, a.gaussians)
-    packed = G.pack_gaussians(G.SH_NORM8, G.COV3D_HALF, G.gaussian_from_ply(ply))
-    del ply
-    cams = G.view_batch()
+    cores = O.set_num_threads(os.cpu_count())   # torch.distributed.run exports OMP_NUM_THREADS=1: override it
+    packed = O.pack(2, 1, O.gaussian_from_ply(O.synth_scene(SEED, a.gaussians)))
+    cams = O.view_batch(a.width, a.height)
     model = O.ModelRef(2, 1, packed, a.gaussians)
-    asp = np.float32(a.width) / np.float32(a.height)
 
     def frame(i):
-        c = cams[i % len(cams)]
-        f = O.make_frame(c.view(), c.projection(asp), a.width, a.height)
-        return O.render_frame(f, [model], front_to_back=False)
+        view, proj = cams[i % len(cams)]
+        f = O.make_frame(view, proj, a.width, a.height)
+        return O.render_frame(f, [model], front_to_back=False, fp32=True)
 
     for i in range(a.warmup):
         frame(i)
@@ -137,12 +134,27 @@ def run_reference(a, rank):
         "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "frames_per_step": 1},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
-                         "sample": "1 frame (1 view of the batch) per step; CPU restatement of the reference path, "
-                                   "back-to-front blending; stage seconds/frame pre=%.3f sort=%.3f composite=%.3f"
-                                   % tuple(stages / a.steps)},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "1 frame (1 view of the batch) per step; CPU restatement of the reference path in fp32, "
+                                   "back-to-front blending, OpenMP on %d threads; stage seconds/frame pre=%.3f sort=%.3f "
+                                   "composite=%.3f" % ((cores,) + tuple(stages / a.steps)),
+                         "plan_a_probe": plan_a_probe()},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def plan_a_probe():
+    """can the reference's own wgpu pipeline run on this box? (tools/plan_a_probe.py)"""
+    try:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("plan_a_probe", os.path.join(ROOT, "tools", "plan_a_probe.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        r = mod.probe()
+        return {k: r[k] for k in ("runnable", "which_cargo", "which_rustc", "cargo_registry", "crate_source_found", "vulkan_icd",
+                                  "software_adapter_libs", "crates_io_reachable", "nproc", "hostname_kind")}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
 
 
 # ------------------------------------------------------------------------------ our arm
@@ -367,15 +379,16 @@ def run_ours(a, rank, world, local_rank):
 
 
 def cpu_baseline(a, packed, block):
-    """The CPU restatement (oracle/) timed beside the GPU number: 2 frames after 1 warm-up."""
+    """The CPU restatement (oracle/) timed beside the GPU number: 2 frames after 1 warm-up, every host core."""
     from oracle import oracle as O
+    cores = O.set_num_threads(os.cpu_count())
     model = O.ModelRef(2, 1, packed, a.gaussians)
     asp = np.float32(a.width) / np.float32(a.height)
 
     def frame(i):
         c = block[i % len(block)]
         f = O.make_frame(c.view(), c.projection(asp), a.width, a.height)
-        return O.render_frame(f, [model], front_to_back=False)
+        return O.render_frame(f, [model], front_to_back=False, fp32=True)
 
     frame(0)
     t0 = time.perf_counter()
@@ -383,9 +396,10 @@ def cpu_baseline(a, packed, block):
     for i in range(n):
         frame(1 + i)
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "%d frames (views 1..%d of rank 0's block) of the same workload after 1 warm-up frame; CPU "
-                      "restatement of the reference path, OpenMP over all host threads" % (n, n)}
+                      "restatement of the reference path in fp32, OpenMP on %d threads" % (n, n, cores),
+            "plan_a_probe": plan_a_probe()}
 
 
 def main():

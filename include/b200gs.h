@@ -328,6 +328,16 @@ B200GS_API int b200gs_ply_read(b200gs_ply_reader* r, b200gs_ply_gaussian* out, u
 B200GS_API int b200gs_ply_close(b200gs_ply_reader* r);
 /* Gaussians::write_ply  src/app.rs:910-914 (binary little endian) */
 B200GS_API int b200gs_ply_write(const char* path, const b200gs_ply_gaussian* verts, uint64_t count);
+/* Export with edits and mask: Gaussians::write_ply(writer, setting.edit.then_some(&edits), setting.mask.then_some(mask))
+ * src/app.rs:904-914, 935-943 (pods / mask words as downloaded at app.rs:789, 806; either may be NULL = None).
+ * A Gaussian whose mask bit is clear, or whose pod is ENABLED|HIDDEN, is not written; an ENABLED pod is applied to the
+ * Gaussian's base colour and opacity (colour -> contrast -> exposure -> gamma -> alpha, as the preprocess kernel
+ * shows it) and re-quantised to u8 before Gaussian -> PlyGaussianPod; SH bands 1..3 are written unchanged.
+ * b200gs_apply_edits_for_export is the in-memory half (out holds up to `count` Gaussians). */
+B200GS_API int b200gs_ply_write_edited(const char* path, const b200gs_gaussian* gaussians, uint64_t count,
+                                       const b200gs_edit_pod* edits_or_null, const uint32_t* mask_words_or_null);
+B200GS_API int b200gs_apply_edits_for_export(const b200gs_gaussian* in, uint64_t count, const b200gs_edit_pod* edits_or_null,
+                                             const uint32_t* mask_words_or_null, b200gs_gaussian* out, uint64_t* n_out);
 /* camera helpers: glam look_at_rh / perspective_rh as the app uses them  src/app.rs:1236-1244 */
 B200GS_API void b200gs_look_at_rh(const float eye[3], const float target[3], const float up[3], float out[16]);
 B200GS_API void b200gs_perspective_rh(float vfov, float aspect, float z_near, float z_far, float out[16]);

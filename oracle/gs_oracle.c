@@ -967,6 +967,40 @@ uint64_t orc_render_frame_f32(const orc_frame* f, const orc_model* far_to_near, 
     return render_frame_any(f, far_to_near, n_models, front_to_back, 1, rgba8, stage_seconds);
 }
 
+/* ------------------------------------------------------------ export (N4)
+ * Gaussians::write_ply(writer, Option<&edits>, Option<mask>) as called at src/app.rs:904-914, 935-943: masked-out
+ * and hidden Gaussians are dropped, an enabled edit pod is baked into the base colour / opacity (u8), then the
+ * inverse of Gaussian::from(PlyGaussianPod).  [RECALLED: the crate's own treatment is not readable here.] */
+uint64_t orc_export_edited(const b200gs_gaussian* in, uint64_t count, const b200gs_edit_pod* edits, const uint32_t* mask,
+                           b200gs_ply_gaussian* out) {
+    uint64_t k = 0;
+    for (uint64_t i = 0; i < count; i++) {
+        if (mask && !((mask[i >> 5] >> (i & 31)) & 1u)) continue;
+        b200gs_gaussian g = in[i];
+        if (edits) {
+            const b200gs_edit_pod* e = &edits[i];
+            if ((e->flag & B200GS_EDIT_ENABLED) && (e->flag & B200GS_EDIT_HIDDEN)) continue;
+            float rgb[3] = {(float)g.color[0] / 255.0f, (float)g.color[1] / 255.0f, (float)g.color[2] / 255.0f};
+            float op = (float)g.color[3] / 255.0f;
+            orc_apply_edit(e, rgb, &op);
+            for (int c = 0; c < 3; c++) g.color[c] = unorm8(rgb[c]);
+            g.color[3] = unorm8(op);
+        }
+        b200gs_ply_gaussian* p = &out[k++];
+        memcpy(p->pos, g.pos, 12);
+        p->normal[0] = p->normal[1] = p->normal[2] = 0.0f;
+        for (int c = 0; c < 3; c++) p->f_dc[c] = ((float)g.color[c] / 255.0f - 0.5f) / ORC_SH_C0;
+        for (int kk = 0; kk < 15; kk++)
+            for (int c = 0; c < 3; c++) p->f_rest[c * 15 + kk] = g.sh[3 * kk + c];
+        float o = (float)g.color[3] / 255.0f;
+        o = o < 1e-6f ? 1e-6f : (o > 1.0f - 1e-6f ? 1.0f - 1e-6f : o);
+        p->opacity = logf(o / (1.0f - o));
+        for (int a = 0; a < 3; a++) p->scale[a] = logf(g.scale[a]);
+        p->rot[0] = g.rot[3]; p->rot[1] = g.rot[0]; p->rot[2] = g.rot[1]; p->rot[3] = g.rot[2];
+    }
+    return k;
+}
+
 /* ------------------------------------------------------------ mask eval (N2)
  * Replaces mask_evaluator.evaluate (src/tab/scene.rs:2124-2131, 2201-2209) with the op tree
  * of src/app.rs:1816-1837 flattened to postfix.  A Gaussian is tested by its WORLD position

@@ -108,6 +108,9 @@ void orc_eval_mask(const orc_model* m, const b200gs_mask_op* postfix, uint32_t n
 /* N2: selection query (rect / brush, Set/Add/Remove) of f->query applied to m->selection -> words_out */
 void orc_query_selection(const orc_frame* f, const orc_model* m, uint32_t* words_out);
 void orc_apply_edit(const b200gs_edit_pod* e, float rgb[3], float* opacity);
+/* N4: export with edits + mask (either may be NULL); returns the number of vertices written to out (<= count) */
+uint64_t orc_export_edited(const b200gs_gaussian* in, uint64_t count, const b200gs_edit_pod* edits, const uint32_t* mask,
+                           b200gs_ply_gaussian* out);
 int orc_num_threads(void);
 void orc_set_num_threads(int n);
 

@@ -81,6 +81,7 @@ def lib():
         L.orc_render_frame.restype = C.c_uint64
         L.orc_render_frame_f32.restype = C.c_uint64
         L.orc_num_threads.restype = C.c_int
+        L.orc_export_edited.restype = C.c_uint64
         _lib = L
     return _lib
 
@@ -286,6 +287,16 @@ def apply_edit(edit, rgb, opacity):
     return np.array(list(c), np.float32), float(o.value)
 
 
+def export_edited(gaussians, edits=None, mask=None):
+    """PLY vertices of the model as exported with edits and mask (orc_export_edited)."""
+    g = np.ascontiguousarray(gaussians, dtype=GAUSSIAN)
+    e = None if edits is None else np.ascontiguousarray(edits, dtype=EDIT)
+    m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint32)
+    out = np.zeros(len(g), dtype=PLY)
+    k = int(lib().orc_export_edited(_p(g), C.c_uint64(len(g)), _p(e), _p(m), _p(out)))
+    return out[:k].copy()
+
+
 def num_threads():
     return int(lib().orc_num_threads())
 
@@ -304,3 +315,15 @@ def orbit_camera(radius=4.5, elev_deg=20.0, azim_deg=35.0, width=1920, height=10
     view = look_at_rh(eye)
     proj = perspective_rh(np.float32(np.deg2rad(vfov_deg)), np.float32(width) / np.float32(height), z_near, z_far)
     return view, proj
+
+
+def view_batch(width, height, n_az=32, n_el=8, radii=(3.0, 4.5, 6.0, 8.0), el_range=(-10.0, 60.0)):
+    """(view, proj) of the 1024-view batch of SURVEY.md §8d in its fixed order (radius fastest, then elevation, then
+    azimuth) — the oracle's own copy, so that the reference arm of bench.py never imports the product."""
+    out = []
+    for a in range(n_az):
+        for e in range(n_el):
+            el = el_range[0] + (el_range[1] - el_range[0]) * e / max(n_el - 1, 1)
+            for r in radii:
+                out.append(orbit_camera(r, el, 360.0 * a / n_az, width, height))
+    return out

@@ -284,6 +284,19 @@ def write_ply(path, verts):
     _ck(lib().b200gs_ply_write(path.encode(), _p(verts), C.c_uint64(len(verts))))
 
 
+def write_ply_edited(path, gaussians, edits=None, mask=None):
+    """Gaussians::write_ply(writer, Some(&edits), Some(mask)) (reference src/app.rs:904-914): masked-out and hidden
+    Gaussians are dropped, enabled edit pods are baked into colour / opacity."""
+    g = np.ascontiguousarray(gaussians, dtype=GAUSSIAN)
+    e = None if edits is None else np.ascontiguousarray(edits, dtype=EDIT)
+    m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint32)
+    if e is not None and len(e) != len(g):
+        raise ValueError("one edit pod per Gaussian")
+    if m is not None and len(m) != (len(g) + 31) // 32:
+        raise ValueError("mask must hold ceil(N/32) words")
+    _ck(lib().b200gs_ply_write_edited(path.encode(), _p(g), C.c_uint64(len(g)), _p(e), _p(m)))
+
+
 def hit_pos_by_closest(hits, view, proj, size, px, py):
     """gs::query::hit_pos_by_closest (reference src/tab/scene.rs:668-672)."""
     hits = np.ascontiguousarray(hits, dtype=HIT)

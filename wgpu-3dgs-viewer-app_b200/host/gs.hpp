@@ -143,10 +143,13 @@ struct Gaussians {
         check(b200gs_gaussian_from_ply(p, n, out.data()));
         return out;
     }
-    void write_ply(const std::string& path) const {
-        std::vector<PlyGaussianPod> v(gaussians.size());
-        check(b200gs_gaussian_to_ply(gaussians.data(), gaussians.size(), v.data()));
-        check(b200gs_ply_write(path.c_str(), v.data(), v.size()));
+    // Gaussians::write_ply(writer, Option<&[GaussianEditPod]>, Option<mask words>) (src/app.rs:904-914): nullptr = None
+    void write_ply(const std::string& path, const std::vector<b200gs_edit_pod>* edits = nullptr,
+                   const std::vector<uint32_t>* mask = nullptr) const {
+        if (edits && edits->size() != gaussians.size()) throw Error(B200GS_ERR_INVALID, "write_ply: one edit pod per Gaussian");
+        if (mask && mask->size() != (gaussians.size() + 31) / 32) throw Error(B200GS_ERR_INVALID, "write_ply: mask must hold ceil(N/32) words");
+        check(b200gs_ply_write_edited(path.c_str(), gaussians.data(), gaussians.size(), edits ? edits->data() : nullptr,
+                                      mask ? mask->data() : nullptr));
     }
 };
 

@@ -595,6 +595,89 @@ extern "C" int b200gs_ply_close(b200gs_ply_reader* r) {
     return B200GS_OK;
 }
 
+// GaussianEditPod applied to a displayed colour and opacity: colour (HSV shift/scale or override) -> contrast ->
+// exposure -> gamma -> alpha, the same order as the preprocess kernel (csrc/preprocess.cu apply_edit).
+static inline float clamp01f(float x) { return x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x); }
+static void edit_colour(const b200gs_edit_pod& e, float rgb[3], float& op) {
+    if (!(e.flag & B200GS_EDIT_ENABLED)) return;
+    if (e.flag & B200GS_EDIT_OVERRIDE_COLOR) {
+        rgb[0] = e.color[0]; rgb[1] = e.color[1]; rgb[2] = e.color[2];
+    } else {
+        const float mx = fmaxf(rgb[0], fmaxf(rgb[1], rgb[2])), mn = fminf(rgb[0], fminf(rgb[1], rgb[2]));
+        const float d = mx - mn;
+        float h = 0.0f;
+        if (d > 0.0f) {
+            if (mx == rgb[0]) h = (rgb[1] - rgb[2]) / d;
+            else if (mx == rgb[1]) h = 2.0f + (rgb[2] - rgb[0]) / d;
+            else h = 4.0f + (rgb[0] - rgb[1]) / d;
+            h = h / 6.0f;
+            if (h < 0.0f) h = h + 1.0f;
+        }
+        float s = mx > 0.0f ? d / mx : 0.0f, v = mx;
+        h = h + e.color[0];
+        h = h - floorf(h);
+        s = clamp01f(s * e.color[1]);
+        v = v * e.color[2];
+        const float h6 = h * 6.0f, i = floorf(h6), f = h6 - i;
+        int k = ((int)i) % 6;
+        if (k < 0) k += 6;
+        const float p = v * (1.0f - s), q = v * (1.0f - s * f), t = v * (1.0f - s * (1.0f - f));
+        switch (k) {
+            case 0: rgb[0] = v; rgb[1] = t; rgb[2] = p; break;
+            case 1: rgb[0] = q; rgb[1] = v; rgb[2] = p; break;
+            case 2: rgb[0] = p; rgb[1] = v; rgb[2] = t; break;
+            case 3: rgb[0] = p; rgb[1] = q; rgb[2] = v; break;
+            case 4: rgb[0] = t; rgb[1] = p; rgb[2] = v; break;
+            default: rgb[0] = v; rgb[1] = p; rgb[2] = q; break;
+        }
+    }
+    const float ex = exp2f(e.exposure);
+    for (int c = 0; c < 3; c++) {
+        float v = (rgb[c] - 0.5f) * (1.0f + e.contrast) + 0.5f;
+        v = v * ex;
+        rgb[c] = powf(fmaxf(v, 0.0f), e.gamma);
+    }
+    op = clamp01f(op * e.alpha);
+}
+
+// Export of an edited, masked model: Gaussians::write_ply(writer, Option<&[GaussianEditPod]>, Option<mask words>)
+// as the app calls it (src/app.rs:904-914, 935-943; pods and mask words downloaded at app.rs:789, 806).
+extern "C" int b200gs_apply_edits_for_export(const b200gs_gaussian* in, uint64_t count, const b200gs_edit_pod* edits,
+                                             const uint32_t* mask_words, b200gs_gaussian* out, uint64_t* n_out) {
+    if ((!in || !out) && count) { gs_set_error("apply_edits_for_export: null argument"); return B200GS_ERR_INVALID; }
+    if (!n_out) { gs_set_error("apply_edits_for_export: null n_out"); return B200GS_ERR_INVALID; }
+    uint64_t k = 0;
+    for (uint64_t i = 0; i < count; i++) {
+        if (mask_words && !((mask_words[i >> 5] >> (i & 31)) & 1u)) continue;        // masked out: not exported
+        b200gs_gaussian g = in[i];
+        if (edits) {
+            const b200gs_edit_pod& e = edits[i];
+            if ((e.flag & B200GS_EDIT_ENABLED) && (e.flag & B200GS_EDIT_HIDDEN)) continue;   // hidden: not exported
+            float rgb[3] = {(float)g.color[0] / 255.0f, (float)g.color[1] / 255.0f, (float)g.color[2] / 255.0f};
+            float op = (float)g.color[3] / 255.0f;
+            edit_colour(e, rgb, op);
+            for (int c = 0; c < 3; c++) g.color[c] = to_unorm8(rgb[c]);
+            g.color[3] = to_unorm8(op);
+        }
+        out[k++] = g;
+    }
+    *n_out = k;
+    return B200GS_OK;
+}
+
+extern "C" int b200gs_ply_write_edited(const char* path, const b200gs_gaussian* gaussians, uint64_t count,
+                                       const b200gs_edit_pod* edits_or_null, const uint32_t* mask_words_or_null) {
+    if (!path || (!gaussians && count)) { gs_set_error("ply_write_edited: null argument"); return B200GS_ERR_INVALID; }
+    std::vector<b200gs_gaussian> kept(count ? count : 1);
+    uint64_t n = 0;
+    int rc = b200gs_apply_edits_for_export(gaussians, count, edits_or_null, mask_words_or_null, kept.data(), &n);
+    if (rc != B200GS_OK) return rc;
+    std::vector<b200gs_ply_gaussian> verts(n ? n : 1);
+    rc = b200gs_gaussian_to_ply(kept.data(), n, verts.data());
+    if (rc != B200GS_OK) return rc;
+    return b200gs_ply_write(path, verts.data(), n);
+}
+
 extern "C" int b200gs_ply_write(const char* path, const b200gs_ply_gaussian* verts, uint64_t count) {
     if (!path || (!verts && count)) { gs_set_error("ply_write: null argument"); return B200GS_ERR_INVALID; }
     FILE* fp = fopen(path, "wb");
