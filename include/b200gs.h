@@ -42,7 +42,8 @@ enum {
     B200GS_ERR_OOM = 3,      /* device or host allocation failed                */
     B200GS_ERR_IO = 4,       /* PLY / file error (gs::Error::Io, scene.rs:234)  */
     B200GS_ERR_FORMAT = 5,   /* malformed PLY                                    */
-    B200GS_ERR_OVERFLOW = 6  /* tile-entry capacity exceeded in the last frame   */
+    B200GS_ERR_OVERFLOW = 6  /* tile-entry capacity exceeded in the last frame: returned by b200gs_sync,
+                              * b200gs_render_frame_host and _host_end AFTER the (truncated) image was delivered */
 };
 
 /* ------------------------------------------------ record layouts (gs::GaussianPod)
@@ -99,7 +100,11 @@ typedef struct b200gs_edit_pod {
 } b200gs_edit_pod;
 
 /* gs::Query*Pod (scene.rs:1622, 1633; QueryToolset rect/brush scene.rs:1260-1263). */
-typedef enum { B200GS_QUERY_NONE = 0, B200GS_QUERY_HIT = 1, B200GS_QUERY_RECT = 2, B200GS_QUERY_BRUSH = 3 } b200gs_query_kind;
+typedef enum {
+    B200GS_QUERY_NONE = 0, B200GS_QUERY_HIT = 1,
+    B200GS_QUERY_RECT = 2, B200GS_QUERY_BRUSH = 3, /* immediate mode: the shape itself is tested (set_use_texture(false)) */
+    B200GS_QUERY_TEXTURE = 4                       /* non-immediate: the viewer's query texture is sampled (scene.rs:767-791) */
+} b200gs_query_kind;
 typedef enum { B200GS_SELECT_SET = 0, B200GS_SELECT_ADD = 1, B200GS_SELECT_REMOVE = 2 } b200gs_selection_op;
 typedef struct b200gs_query_pod {
     uint32_t kind;   /* b200gs_query_kind */
@@ -192,6 +197,17 @@ B200GS_API int b200gs_set_selection_edit(b200gs_viewer* v, const b200gs_edit_pod
 B200GS_API int b200gs_set_selection_highlight(b200gs_viewer* v, const float rgba[4]);
 /* viewer.update_query(queue, pod)  scene.rs:785 */
 B200GS_API int b200gs_set_query(b200gs_viewer* v, const b200gs_query_pod* pod);
+/* The query texture of gs::QueryToolset in non-immediate mode (query_toolset.set_use_texture(!immediate) +
+ * query_toolset.render(queue, encoder, &viewer.world_buffers.query_texture)  scene.rs:767-791; sized by
+ * update_query_texture_size  scene.rs:740): one u8 per viewport pixel, non-zero = painted.  _paint rasterises one
+ * rect / brush-segment stroke (a B200GS_QUERY_RECT / _BRUSH pod) into it, _clear empties it (toolset.start), _upload
+ * replaces it with host texels (width x height must equal the viewport), _download reads it back.  A preprocess
+ * with query kind B200GS_QUERY_TEXTURE selects (op Set / Add / Remove) the visible Gaussians whose projected centre
+ * falls on a painted texel.  Resizing the viewer clears the texture. */
+B200GS_API int b200gs_query_texture_clear(b200gs_viewer* v);
+B200GS_API int b200gs_query_texture_paint(b200gs_viewer* v, const b200gs_query_pod* stroke);
+B200GS_API int b200gs_query_texture_upload(b200gs_viewer* v, const uint8_t* texels, uint32_t width, uint32_t height);
+B200GS_API int b200gs_query_texture_download(b200gs_viewer* v, uint8_t* texels, size_t cap);
 /* headless clear colour (premultiplied RGBA in 0..1); default transparent black */
 B200GS_API int b200gs_set_background(b200gs_viewer* v, const float rgba[4]);
 /* depth slabs: the frame is binned + composited in n+1 slabs of depth ranks split at these
@@ -219,13 +235,20 @@ B200GS_API int b200gs_host_free(void* p);
  * MultiModelViewerGaussianBuffers::new_empty(device,count) + BindGroups::new +
  * viewer.models.insert(key, ..) + MaskOpTree::Reset  scene.rs:2111-2139 */
 B200GS_API int b200gs_model_create(b200gs_viewer* v, const char* key, uint64_t capacity, b200gs_model** out);
+/* a model of `v` over the packed records already resident in `source` (a model of ANOTHER viewer on the same device
+ * with the same layout): the reference's buffers are ref-counted clones (scene.rs:641, 648); nothing is copied,
+ * the records live until the last model using them is destroyed.  Mask / selection / edits stay per model. */
+B200GS_API int b200gs_model_create_shared(b200gs_viewer* v, const char* key, b200gs_model* source, b200gs_model** out);
 /* viewer.remove_model(key)  scene.rs:2176 */
 B200GS_API int b200gs_model_destroy(b200gs_viewer* v, b200gs_model* m);
 B200GS_API b200gs_model* b200gs_model_find(b200gs_viewer* v, const char* key);
 /* gaussians_buffer.len()  scene.rs:608, 862, 1832 */
 B200GS_API uint64_t b200gs_model_len(const b200gs_model* m);
 /* gaussians_buffer.update_range(queue, start, &[Gaussian])  scene.rs:2076-2084 — unpacked
- * Gaussians are packed on the host into the viewer's layout, then copied H2D */
+ * Gaussians are packed on the host into the viewer's layout, then copied H2D.  Like queue.write_buffer, every upload
+ * below ENQUEUES and returns: the host buffer is borrowed for the call only (it is packed / copied into the viewer's
+ * pinned staging ring before the call returns), nothing is allocated per call and the stream is not synchronised,
+ * so the app can call this every frame while a model loads (scene.rs:341-380). */
 B200GS_API int b200gs_model_update_range(b200gs_model* m, uint64_t start, const b200gs_gaussian* gaussians,
                                          uint64_t count);
 /* same, records already packed (host pointer) */

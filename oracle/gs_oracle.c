@@ -417,7 +417,7 @@ static void sh_basis(float x, float y, float z, uint32_t deg, float b[15]) {
 /* Selection query in immediate mode (gs::QueryToolset rect / brush, src/tab/scene.rs:758-791,
  * 1224-1263; ops src/app.rs:1453): splat centre in viewport pixels (top-left origin) inside the
  * rectangle, or within `radius` of the brush segment. */
-static int query_hit(const b200gs_query_pod* q, float sx, float sy) {
+static int query_shape_hit(const b200gs_query_pod* q, float sx, float sy) {
     if (q->kind == B200GS_QUERY_RECT) return sx >= q->p0[0] && sx <= q->p1[0] && sy >= q->p0[1] && sy <= q->p1[1];
     float vx = q->p1[0] - q->p0[0], vy = q->p1[1] - q->p0[1];
     float wx = sx - q->p0[0], wy = sy - q->p0[1];
@@ -426,6 +426,26 @@ static int query_hit(const b200gs_query_pod* q, float sx, float sy) {
     t = fminf(1.0f, fmaxf(0.0f, t));
     float dx = wx - t * vx, dy = wy - t * vy;
     return dx * dx + dy * dy <= q->radius * q->radius;
+}
+
+/* non-immediate mode (set_use_texture(true), scene.rs:767-791): the texel under the splat centre */
+static int query_hit(const orc_frame* f, float sx, float sy) {
+    if (f->query.kind == B200GS_QUERY_TEXTURE) {
+        float fx = floorf(sx), fy = floorf(sy);
+        if (!f->query_tex || !(fx >= 0.0f && fy >= 0.0f && fx < (float)f->query_tex_w && fy < (float)f->query_tex_h)) return 0;
+        return f->query_tex[(size_t)(uint32_t)fy * f->query_tex_w + (uint32_t)fx] != 0;
+    }
+    return query_shape_hit(&f->query, sx, sy);
+}
+void orc_query_texture_paint(uint8_t* tex, uint32_t w, uint32_t h, const b200gs_query_pod* stroke) {
+    for (uint32_t y = 0; y < h; y++)
+        for (uint32_t x = 0; x < w; x++)
+            if (query_shape_hit(stroke, (float)x + 0.5f, (float)y + 0.5f)) tex[(size_t)y * w + x] = 255;
+}
+void orc_postprocess(uint64_t n, const uint32_t* selection, b200gs_edit_pod* edits, const b200gs_edit_pod* selection_edit) {
+    if (!(selection_edit->flag & B200GS_EDIT_ENABLED)) return;
+    for (uint64_t i = 0; i < n; i++)
+        if ((selection[i >> 5] >> (i & 31)) & 1u) edits[i] = *selection_edit;
 }
 
 /* one Gaussian; returns 1 if visible */
@@ -459,7 +479,7 @@ static int pre_one(const orc_frame* f, const orc_model* m, const pre_ctx* c, uin
     /* selection query: the new selection state is what this frame shows */
     if (f->query.kind >= B200GS_QUERY_RECT) {
         float sx = ((nx + 1.0f) * c->W - 1.0f) * 0.5f + 0.5f, sy = ((1.0f - ny) * c->H - 1.0f) * 0.5f + 0.5f;
-        int hit = query_hit(&f->query, sx, sy);
+        int hit = query_hit(f, sx, sy);
         if (f->query.op == B200GS_SELECT_SET) selected = hit;
         else if (f->query.op == B200GS_SELECT_ADD) selected = selected | hit;
         else selected = selected & !hit;

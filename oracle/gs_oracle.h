@@ -46,7 +46,9 @@ typedef struct orc_frame {
     b200gs_edit_pod selection_edit;
     float highlight[4];
     float background[4];
-    b200gs_query_pod query; /* selection query tested during preprocess (rect / brush) */
+    b200gs_query_pod query; /* selection query tested during preprocess (rect / brush / texture) */
+    const uint8_t* query_tex; /* kind TEXTURE: u8 per pixel, row-major, query_tex_w x query_tex_h (may be NULL) */
+    uint32_t query_tex_w, query_tex_h;
 } orc_frame;
 
 typedef struct orc_model {
@@ -107,6 +109,10 @@ void orc_eval_mask(const orc_model* m, const b200gs_mask_op* postfix, uint32_t n
                    uint32_t n_shapes, uint32_t* words);
 /* N2: selection query (rect / brush, Set/Add/Remove) of f->query applied to m->selection -> words_out */
 void orc_query_selection(const orc_frame* f, const orc_model* m, uint32_t* words_out);
+/* N2: one rect / brush stroke painted into a query texture (query_toolset.render, scene.rs:787-791) */
+void orc_query_texture_paint(uint8_t* tex, uint32_t w, uint32_t h, const b200gs_query_pod* stroke);
+/* N2: postprocess (scene.rs:604-610): the viewer's selection edit committed into the edit pods of the selected Gaussians */
+void orc_postprocess(uint64_t n, const uint32_t* selection, b200gs_edit_pod* edits, const b200gs_edit_pod* selection_edit);
 void orc_apply_edit(const b200gs_edit_pod* e, float rgb[3], float* opacity);
 /* N4: export with edits + mask (either may be NULL); returns the number of vertices written to out (<= count) */
 uint64_t orc_export_edited(const b200gs_gaussian* in, uint64_t count, const b200gs_edit_pod* edits, const uint32_t* mask,

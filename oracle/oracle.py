@@ -42,7 +42,8 @@ class Frame(C.Structure):
     _fields_ = [("view", C.c_float * 16), ("proj", C.c_float * 16), ("size", C.c_float * 2),
                 ("gaussian_size", C.c_float), ("display_mode", C.c_uint32), ("sh_deg", C.c_uint32),
                 ("no_sh0", C.c_uint32), ("selection_edit", EditPod), ("highlight", C.c_float * 4),
-                ("background", C.c_float * 4), ("query", QueryPod)]
+                ("background", C.c_float * 4), ("query", QueryPod), ("query_tex", C.c_void_p),
+                ("query_tex_w", C.c_uint32), ("query_tex_h", C.c_uint32)]
 
 
 class Model(C.Structure):
@@ -151,7 +152,7 @@ def quat_from_euler_zyx_deg(rot_deg):
 
 
 def make_frame(view, proj, width, height, gaussian_size=1.0, display_mode=0, sh_deg=3, no_sh0=0,
-               selection_edit=None, highlight=(0, 0, 0, 0), background=(0, 0, 0, 0), query=None):
+               selection_edit=None, highlight=(0, 0, 0, 0), background=(0, 0, 0, 0), query=None, query_texture=None):
     f = Frame()
     f.view[:] = [float(x) for x in view]
     f.proj[:] = [float(x) for x in proj]
@@ -163,6 +164,10 @@ def make_frame(view, proj, width, height, gaussian_size=1.0, display_mode=0, sh_
     f.background[:] = [float(x) for x in background]
     if query is not None:
         f.query = query
+    if query_texture is not None:   # (h, w) uint8, non-zero = painted; kept alive on the frame object
+        f._tex = np.ascontiguousarray(query_texture, dtype=np.uint8)
+        f.query_tex = f._tex.ctypes.data
+        f.query_tex_h, f.query_tex_w = f._tex.shape
     return f
 
 
@@ -278,6 +283,21 @@ def query_selection(frame, model):
     words = np.zeros((model.n + 31) // 32, np.uint32)
     lib().orc_query_selection(C.byref(frame), C.byref(model.c), _p(words))
     return words
+
+
+def query_texture_paint(tex, stroke):
+    """Paints one rect / brush stroke (a QueryPod of kind 2 / 3) into the (h, w) uint8 texture, in place."""
+    assert tex.dtype == np.uint8 and tex.flags.c_contiguous
+    lib().orc_query_texture_paint(_p(tex), C.c_uint32(tex.shape[1]), C.c_uint32(tex.shape[0]), C.byref(stroke))
+    return tex
+
+
+def postprocess(selection, edits, selection_edit):
+    """Commits the selection edit into the edit pods of the selected Gaussians (returns a new array)."""
+    e = np.ascontiguousarray(edits, dtype=EDIT).copy()
+    sel = np.ascontiguousarray(selection, dtype=np.uint32)
+    lib().orc_postprocess(C.c_uint64(len(e)), _p(sel), _p(e), C.byref(selection_edit))
+    return e
 
 
 def apply_edit(edit, rgb, opacity):

@@ -397,7 +397,9 @@ def test_huge_splat_and_tile_capacity_overflow(G, O):
         ref, _, _ = O.render_frame(f, [O.ModelRef(3, 0, G.pack_gaussians(3, 0, g), 2)])
         assert_image_close(img, ref)
         v.set_tile_entry_capacity(100)
-        v.render_frame_host([m])
+        with pytest.raises(G.GsError) as err:          # the (truncated) frame is delivered, the status says so
+            v.render_frame_host([m])
+        assert err.value.code == G.ERR_OVERFLOW
         assert v.last_timings().overflow == 1
 
 
@@ -512,6 +514,112 @@ def test_selection_query_rect_brush_matches_oracle(G, O):
         m.upload_selection(old)
         v.render_frame_host([m])
         assert np.array_equal(m.download_selection(), old)          # no query: selection untouched
+
+
+def test_selection_query_texture_mode_and_postprocess(G, O):
+    """Non-immediate selection (query_toolset.set_use_texture(true) + query_toolset.render into the query texture,
+    reference scene.rs:767-791): strokes are painted into the viewer's query texture, a preprocess with query kind
+    TEXTURE selects the Gaussians whose centre falls on a painted texel.  Texture, selection bitset and image match
+    the oracle; then postprocess (scene.rs:596-611) commits the selection edit into the edit pods, again checked
+    against the oracle's twin."""
+    W, H, n = 640, 360, 50_000
+    g = G.gaussian_from_ply(G.synth_scene(0xB2000081, n))
+    packed = G.pack_gaussians(2, 1, g)
+    cam = G.OrbitCamera.orbit()
+    view, proj = cam.view(), cam.projection(np.float32(W) / np.float32(H))
+    old = pack_bits(np.arange(n) % 7 == 0)
+    strokes = [(G.QUERY_BRUSH, (50, 300), (300, 100), 30.0), (G.QUERY_BRUSH, (300, 100), (600, 250), 30.0),
+               (G.QUERY_RECT, (10.5, 10.5), (90.25, 70.0), 0.0)]
+    tex = np.zeros((H, W), np.uint8)
+    for kind, p0, p1, rad in strokes:
+        O.query_texture_paint(tex, O.query_pod(kind, 0, p0, p1, rad))
+    edit = dict(flag=1, color=(0.5, 1.2, 0.9), contrast=0.2, exposure=0.5, gamma=1.2, alpha=0.8)
+    with G.Viewer(W, H) as v:
+        m = v.add_model("m", n)
+        m.upload_packed(0, packed)
+        v.update_camera(cam)
+        v.update_selection_highlight((0.0, 1.0, 1.0, 0.4))
+        v.query_texture_clear()
+        for kind, p0, p1, rad in strokes:
+            v.query_texture_paint(G.query_pod(kind, 0, p0, p1, rad))
+        assert np.array_equal(v.query_texture_download(), tex)                 # painted texture: byte-exact
+        for op in (G.SELECT_SET, G.SELECT_ADD, G.SELECT_REMOVE):
+            m.upload_selection(old)
+            v.update_query(G.query_pod(G.QUERY_TEXTURE, op))
+            f = O.make_frame(view, proj, W, H, highlight=(0.0, 1.0, 1.0, 0.4), query=O.query_pod(4, op), query_texture=tex)
+            om = O.ModelRef(2, 1, packed, n, selection=old)
+            img = v.render_frame_host([m]).copy()
+            want = O.query_selection(f, om)
+            assert np.array_equal(m.download_selection(), want), op
+            assert 0 < bits_set(want, n).sum() < n
+            oi, ok, osp = O.preprocess(f, om)
+            ok, oi, osp = O.sort(ok, oi, osp)
+            assert np.array_equal(m.indices(), oi)
+            assert_image_close(img, O.composite(f, osp)[0])
+        # an uploaded texture behaves like a painted one
+        v.query_texture_upload(tex[::-1].copy())
+        m.upload_selection(old)
+        v.update_query(G.query_pod(G.QUERY_TEXTURE, G.SELECT_SET))
+        v.render_frame_host([m])
+        f = O.make_frame(view, proj, W, H, query=O.query_pod(4, 0), query_texture=tex[::-1].copy())
+        sel = O.query_selection(f, O.ModelRef(2, 1, packed, n, selection=old))
+        assert np.array_equal(m.download_selection(), sel)
+        # postprocess: the selection edit lands in the edit pods of exactly the selected Gaussians
+        v.update_query(G.query_pod(G.QUERY_NONE))
+        v.update_selection_edit(G.EditPod.new(**edit))
+        m.postprocess()
+        want_edits = O.postprocess(sel, m_default_edits(O, n), O.edit_pod(**edit))
+        got_edits = m.download_edits()
+        assert got_edits.tobytes() == want_edits.tobytes()
+        # ... and the committed edits draw the same frame as the live selection edit did
+        f2 = O.make_frame(view, proj, W, H, highlight=(0.0, 1.0, 1.0, 0.4))
+        om2 = O.ModelRef(2, 1, packed, n, selection=sel, edits=want_edits)
+        v.update_selection_edit(G.EditPod.default())
+        img = v.render_frame_host([m]).copy()
+        oi, ok, osp = O.preprocess(f2, om2)
+        ok, oi, osp = O.sort(ok, oi, osp)
+        assert_image_close(img, O.composite(f2, osp)[0])
+        # resizing the viewer clears the texture (update_query_texture_size)
+        v.resize(320, 200)
+        assert v.query_texture_download().sum() == 0
+
+
+def m_default_edits(O, n):
+    e = np.zeros(n, dtype=O.EDIT)
+    e["color"] = (0.0, 1.0, 1.0)
+    e["gamma"] = 1.0
+    e["alpha"] = 1.0
+    return e
+
+
+def test_viewers_share_resident_records(G, O):
+    """b200gs_model_create_shared: a second viewer on the same device renders the records resident in the first
+    (ref-counted, like the reference's cloned buffer handles, scene.rs:641): same bytes out, and the records
+    survive the destruction of the model that uploaded them."""
+    W, H, n = 800, 450, 60_000
+    packed = G.pack_gaussians(2, 1, G.gaussian_from_ply(G.synth_scene(0xB2000082, n)))
+    cam = G.OrbitCamera.orbit(4.0, 25.0, 80.0)
+    v1, v2 = G.Viewer(W, H), G.Viewer(W, H)
+    try:
+        m1 = v1.add_model("scene", n)
+        m1.upload_packed(0, packed)                # returns after enqueue: create_shared orders v2 behind it
+        m2 = v2.add_shared_model("scene", m1)
+        v1.update_camera(cam)
+        v2.update_camera(cam)
+        a = v1.render_frame_host([m1]).copy()
+        b = v2.render_frame_host([m2]).copy()
+        assert np.array_equal(a, b)
+        assert m2.download_packed().tobytes() == packed.tobytes()
+        v1.remove_model("scene")                   # the records stay alive for v2
+        v1.sync()
+        c = v2.render_frame_host([m2]).copy()
+        assert np.array_equal(a, c)
+        with pytest.raises(G.GsError):
+            with G.Viewer(W, H, G.SH_HALF, G.COV3D_HALF) as v3:
+                v3.add_shared_model("scene", m2)   # different layout
+    finally:
+        v1.close()
+        v2.close()
 
 
 def _hits_from_oracle(O, f, idx, keys, spl, px, py):

@@ -57,7 +57,7 @@ class QueryPod(C.Structure):
                 ("radius", C.c_float), ("_pad", C.c_uint32)]
 
 
-QUERY_NONE, QUERY_HIT, QUERY_RECT, QUERY_BRUSH = 0, 1, 2, 3
+QUERY_NONE, QUERY_HIT, QUERY_RECT, QUERY_BRUSH, QUERY_TEXTURE = 0, 1, 2, 3, 4
 SELECT_SET, SELECT_ADD, SELECT_REMOVE = 0, 1, 2
 
 
@@ -76,6 +76,9 @@ class Timings(C.Structure):
                 ("composite_ms", C.c_float), ("total_ms", C.c_float), ("visible", C.c_uint64),
                 ("tile_entries", C.c_uint64), ("evals", C.c_uint64), ("staged_entries", C.c_uint64),
                 ("overflow", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+ERR_INVALID, ERR_CUDA, ERR_OOM, ERR_IO, ERR_FORMAT, ERR_OVERFLOW = 1, 2, 3, 4, 5, 6
 
 
 class GsError(RuntimeError):
@@ -485,6 +488,22 @@ class Viewer:
     def update_query(self, pod):
         _ck(lib().b200gs_set_query(self.h, C.byref(pod)))
 
+    def query_texture_clear(self):
+        _ck(lib().b200gs_query_texture_clear(self.h))
+
+    def query_texture_paint(self, stroke):
+        """One rect / brush stroke (a QueryPod of kind QUERY_RECT / QUERY_BRUSH) painted into the query texture."""
+        _ck(lib().b200gs_query_texture_paint(self.h, C.byref(stroke)))
+
+    def query_texture_upload(self, texels):
+        t = np.ascontiguousarray(texels, dtype=np.uint8)
+        _ck(lib().b200gs_query_texture_upload(self.h, _p(t), C.c_uint32(t.shape[1]), C.c_uint32(t.shape[0])))
+
+    def query_texture_download(self):
+        out = np.zeros((self.height, self.width), np.uint8)
+        _ck(lib().b200gs_query_texture_download(self.h, _p(out), C.c_size_t(out.size)))
+        return out
+
     def set_background(self, rgba):
         _ck(lib().b200gs_set_background(self.h, _p(_f(rgba, 4))))
 
@@ -506,6 +525,15 @@ class Viewer:
 
     def image_device(self):
         return lib().b200gs_image_device(self.h)
+
+    def add_shared_model(self, key, source):
+        """A model over the packed records already resident in `source` (a Model of another viewer on the same
+        device): reference-counted, nothing is copied."""
+        h = C.c_void_p()
+        _ck(lib().b200gs_model_create_shared(self.h, key.encode(), source.h, C.byref(h)))
+        m = Model(self, key, h, source.capacity)
+        self.models[key] = m
+        return m
 
     def add_model(self, key, capacity):
         h = C.c_void_p()

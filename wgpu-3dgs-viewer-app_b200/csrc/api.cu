@@ -5,6 +5,7 @@
 //
 // There is no CPU fallback: every compute entry point needs a CUDA device.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -64,11 +65,20 @@ enum {  // model control block layout
 };
 constexpr uint32_t kMaxModelsPerFrame = 64;
 
+// Packed records of a model: reference counted, so that several viewers on one device can render the same
+// resident copy (the reference's buffers are ref-counted clones, src/tab/scene.rs:641, 648).
+struct GsRecStore {
+    uint8_t* p = nullptr;
+    std::atomic<int> refs{1};
+    int device = 0;
+};
+
 struct b200gs_model {
     b200gs_viewer* v = nullptr;
     std::string key;
     uint64_t cap = 0;
-    uint8_t* recs = nullptr;
+    GsRecStore* store = nullptr;
+    uint8_t* recs = nullptr;   // = store->p
     uint32_t* mask = nullptr;
     uint32_t* selection = nullptr;
     b200gs_edit_pod* edits = nullptr;
@@ -122,8 +132,19 @@ struct b200gs_viewer {
     uint32_t last_slabs = 1;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     b200gs_timings last = {};
-    uint32_t* h_small = nullptr;  // pinned scratch
+    uint32_t* h_small = nullptr;  // pinned scratch (words 0..15: downloads; 32..33: overflow flag of the two host-frame slots)
+    // pinned staging ring of the uploads: a host buffer handed to an upload call is copied (or packed) into a slot
+    // before the call returns, so uploads enqueue and return without synchronising the stream
+    uint8_t* stage_buf[2] = {nullptr, nullptr};
+    cudaEvent_t stage_done[2] = {nullptr, nullptr};
+    bool stage_used[2] = {false, false};
+    uint32_t stage_next = 0;
+    uint8_t* mask_scratch = nullptr;   // device: postfix ops | shapes | shape rotations of the last eval_mask
+    uint8_t* query_tex = nullptr;      // device: selection query texture (u8 per pixel), or null
+    uint32_t query_tex_w = 0, query_tex_h = 0;
 };
+constexpr size_t kStageBytes = 8u << 20;
+constexpr size_t kMaskScratchBytes = 64 * sizeof(b200gs_mask_op) + 64 * sizeof(b200gs_mask_shape) + 64 * 36;
 
 static void identity16(float* m) {
     memset(m, 0, 64);
@@ -165,6 +186,9 @@ static GsFrame make_frame(const b200gs_viewer* v) {
     f.tiles_x = (v->W + GS_TILE - 1) / GS_TILE;
     f.tiles_y = (v->H + GS_TILE - 1) / GS_TILE;
     f.query = v->query;
+    f.query_tex = v->query_tex;
+    f.query_tex_w = v->query_tex_w;
+    f.query_tex_h = v->query_tex_h;
     const float (*P)[4] = f.P;
     f.std_proj = (P[0][1] == 0.0f && P[0][2] == 0.0f && P[0][3] == 0.0f && P[1][0] == 0.0f && P[1][2] == 0.0f &&
                   P[1][3] == 0.0f && P[2][0] == 0.0f && P[2][1] == 0.0f && P[3][0] == 0.0f && P[3][1] == 0.0f &&
@@ -230,8 +254,9 @@ static int ensure_frame_buffers(b200gs_viewer* v) {
     const size_t img = (size_t)v->W * v->H * 4;
     if (v->image_bytes < img) {
         CK(cudaStreamSynchronize(v->stream));
+        CK(cudaStreamSynchronize(v->copy_stream));   // a pending host frame may still be reading the old target
         if (v->image) CK(cudaFree(v->image));
-        TRY(dev_alloc(&v->image, img * 2, true, v->stream));
+        TRY(dev_alloc(&v->image, img * 3, true, v->stream));   // two host-frame slots + the hit query's scratch target
         v->image_bytes = img;
     }
     if (!v->layout_dirty) return B200GS_OK;
@@ -336,7 +361,11 @@ extern "C" int b200gs_viewer_create(int device, uint32_t sh, uint32_t cov3d, uin
 }
 
 static void free_model(b200gs_model* m) {
-    void* ps[] = {m->recs, m->mask, m->selection, m->edits, m->ctrl, m->keys_a, m->vals_a, m->keys_b, m->vals_b, m->idx, m->binword,
+    if (m->store && m->store->refs.fetch_sub(1) == 1) {
+        if (m->store->p) cudaFree(m->store->p);
+        delete m->store;
+    }
+    void* ps[] = {m->mask, m->selection, m->edits, m->ctrl, m->keys_a, m->vals_a, m->keys_b, m->vals_b, m->idx, m->binword,
                   m->lb_pre, m->lb_sort};
     for (void* p : ps)
         if (p) cudaFree(p);
@@ -353,6 +382,12 @@ extern "C" int b200gs_viewer_destroy(b200gs_viewer* v) {
     for (void* p : ps)
         if (p) cudaFree(p);
     if (v->h_small) cudaFreeHost(v->h_small);
+    for (int i = 0; i < 2; i++) {
+        if (v->stage_buf[i]) cudaFreeHost(v->stage_buf[i]);
+        if (v->stage_done[i]) cudaEventDestroy(v->stage_done[i]);
+    }
+    if (v->mask_scratch) cudaFree(v->mask_scratch);
+    if (v->query_tex) cudaFree(v->query_tex);
     for (auto& e : v->ev)
         if (e) cudaEventDestroy(e);
     for (auto& row : v->ev_slab)
@@ -389,7 +424,7 @@ extern "C" int b200gs_set_camera(b200gs_viewer* v, const float view[16], const f
     memcpy(v->view, view, 64);
     memcpy(v->proj, proj, 64);
     if (size) {
-        REQUIRE(size[0] >= 1.0f && size[1] >= 1.0f, "invalid size");
+        REQUIRE(size[0] >= 1.0f && size[1] >= 1.0f && size[0] <= 16384.0f && size[1] <= 16384.0f, "invalid size");
         if (v->W != (uint32_t)size[0] || v->H != (uint32_t)size[1]) invalidate_models(v);
         v->size[0] = size[0]; v->size[1] = size[1];
         v->W = (uint32_t)size[0]; v->H = (uint32_t)size[1];
@@ -418,10 +453,55 @@ extern "C" int b200gs_set_selection_highlight(b200gs_viewer* v, const float rgba
 }
 extern "C" int b200gs_set_query(b200gs_viewer* v, const b200gs_query_pod* pod) {
     REQUIRE(v && pod, "null argument");
-    REQUIRE(pod->kind <= B200GS_QUERY_BRUSH, "query kind out of range");
+    REQUIRE(pod->kind <= B200GS_QUERY_TEXTURE, "query kind out of range");
     v->query = *pod;
     return B200GS_OK;
 }
+static int stage_upload(b200gs_viewer* v, void* dst_dev, const void* src_host, size_t bytes);
+
+// the query texture always matches the viewport (update_query_texture_size, scene.rs:740): (re)allocated cleared
+static int ensure_query_texture(b200gs_viewer* v) {
+    if (v->query_tex && v->query_tex_w == v->W && v->query_tex_h == v->H) return B200GS_OK;
+    TRY(set_device(v));
+    if (v->query_tex) {
+        CK(cudaStreamSynchronize(v->stream));
+        CK(cudaFree(v->query_tex));
+        v->query_tex = nullptr;
+    }
+    TRY(dev_alloc(&v->query_tex, (size_t)v->W * v->H, true, v->stream));
+    v->query_tex_w = v->W;
+    v->query_tex_h = v->H;
+    return B200GS_OK;
+}
+extern "C" int b200gs_query_texture_clear(b200gs_viewer* v) {
+    REQUIRE(v, "null viewer");
+    TRY(ensure_query_texture(v));
+    CK(cudaMemsetAsync(v->query_tex, 0, (size_t)v->W * v->H, v->stream));
+    return B200GS_OK;
+}
+extern "C" int b200gs_query_texture_paint(b200gs_viewer* v, const b200gs_query_pod* stroke) {
+    REQUIRE(v && stroke, "null argument");
+    REQUIRE(stroke->kind == B200GS_QUERY_RECT || stroke->kind == B200GS_QUERY_BRUSH, "a stroke is a rect or a brush segment");
+    TRY(ensure_query_texture(v));
+    CK(gs_launch_paint_query_texture(v->query_tex, v->W, v->H, *stroke, v->stream));
+    v->launches += 1;
+    return B200GS_OK;
+}
+extern "C" int b200gs_query_texture_upload(b200gs_viewer* v, const uint8_t* texels, uint32_t width, uint32_t height) {
+    REQUIRE(v && texels, "null argument");
+    REQUIRE(width == v->W && height == v->H, "the query texture has the size of the viewport");
+    TRY(ensure_query_texture(v));
+    return stage_upload(v, v->query_tex, texels, (size_t)width * height);
+}
+extern "C" int b200gs_query_texture_download(b200gs_viewer* v, uint8_t* texels, size_t cap) {
+    REQUIRE(v && texels, "null argument");
+    REQUIRE(cap >= (size_t)v->W * v->H, "buffer too small");
+    TRY(ensure_query_texture(v));
+    CK(cudaMemcpyAsync(texels, v->query_tex, (size_t)v->W * v->H, cudaMemcpyDeviceToHost, v->stream));
+    CK(cudaStreamSynchronize(v->stream));
+    return B200GS_OK;
+}
+
 extern "C" int b200gs_set_background(b200gs_viewer* v, const float rgba[4]) {
     REQUIRE(v && rgba, "null argument");
     memcpy(v->bg, rgba, 16);
@@ -456,7 +536,12 @@ extern "C" int b200gs_enable_timings(b200gs_viewer* v, int on, int count_evals) 
 extern "C" int b200gs_sync(b200gs_viewer* v) {
     REQUIRE(v, "null viewer");
     TRY(set_device(v));
+    if (v->rendered) CK(cudaMemcpyAsync(v->h_small + 34, v->stats + 3, 4, cudaMemcpyDeviceToHost, v->stream));
     CK(cudaStreamSynchronize(v->stream));
+    if (v->rendered && v->h_small[34]) {
+        gs_set_error("tile-entry capacity exceeded in the last frame (b200gs_set_tile_entry_capacity): the image is truncated");
+        return B200GS_ERR_OVERFLOW;
+    }
     return B200GS_OK;
 }
 extern "C" void* b200gs_stream(b200gs_viewer* v) { return v ? (void*)v->stream : nullptr; }
@@ -474,8 +559,42 @@ extern "C" int b200gs_host_free(void* p) {
     return B200GS_OK;
 }
 
+// ---------------------------------------------------------------------------- upload staging
+// A slot of the pinned ring, free to be written by the host: waits only for the copy that last used THIS slot.
+static int stage_acquire(b200gs_viewer* v, uint8_t** buf, int* slot) {
+    for (int i = 0; i < 2; i++) {
+        if (!v->stage_buf[i]) {
+            CK(cudaMallocHost((void**)&v->stage_buf[i], kStageBytes));
+            CK(cudaEventCreateWithFlags(&v->stage_done[i], cudaEventDisableTiming));
+        }
+    }
+    const int k = (int)(v->stage_next++ & 1u);
+    if (v->stage_used[k]) CK(cudaEventSynchronize(v->stage_done[k]));
+    *buf = v->stage_buf[k];
+    *slot = k;
+    return B200GS_OK;
+}
+static int stage_submit(b200gs_viewer* v, int slot, void* dst_dev, size_t bytes) {
+    CK(cudaMemcpyAsync(dst_dev, v->stage_buf[slot], bytes, cudaMemcpyHostToDevice, v->stream));
+    CK(cudaEventRecord(v->stage_done[slot], v->stream));
+    v->stage_used[slot] = true;
+    return B200GS_OK;
+}
+// host -> device through the ring: the host buffer is only borrowed for the call, the call does not wait for the GPU
+static int stage_upload(b200gs_viewer* v, void* dst_dev, const void* src_host, size_t bytes) {
+    for (size_t o = 0; o < bytes; o += kStageBytes) {
+        const size_t c = std::min(kStageBytes, bytes - o);
+        uint8_t* buf;
+        int slot;
+        TRY(stage_acquire(v, &buf, &slot));
+        memcpy(buf, (const uint8_t*)src_host + o, c);
+        TRY(stage_submit(v, slot, (uint8_t*)dst_dev + o, c));
+    }
+    return B200GS_OK;
+}
+
 // ---------------------------------------------------------------------------- models
-extern "C" int b200gs_model_create(b200gs_viewer* v, const char* key, uint64_t capacity, b200gs_model** out) {
+static int model_create(b200gs_viewer* v, const char* key, uint64_t capacity, GsRecStore* shared, b200gs_model** out) {
     REQUIRE(v && key && out, "null argument");
     *out = nullptr;
     REQUIRE(capacity < 0x3fffff00ull, "capacity too large");
@@ -485,9 +604,17 @@ extern "C" int b200gs_model_create(b200gs_viewer* v, const char* key, uint64_t c
     auto* m = new b200gs_model();
     m->v = v; m->key = key; m->cap = capacity;
     cudaStream_t st = v->stream;
-    // records: padded so that the last chunk's 16-byte-rounded TMA copy stays inside the buffer
-    size_t rec_bytes = (size_t)capacity * v->rb + 64;
-    int rc = dev_alloc(&m->recs, rec_bytes, true, st);
+    int rc = B200GS_OK;
+    if (shared) {
+        shared->refs.fetch_add(1);
+        m->store = shared;
+    } else {
+        m->store = new GsRecStore();
+        m->store->device = v->device;
+        // records: padded so that the last chunk's 16-byte-rounded TMA copy stays inside the buffer
+        rc = dev_alloc(&m->store->p, (size_t)capacity * v->rb + 64, true, st);
+    }
+    m->recs = m->store->p;
     if (rc == B200GS_OK) rc = dev_alloc(&m->ctrl, MC_WORDS, true, st);
     if (rc == B200GS_OK) rc = dev_alloc(&m->keys_a, capacity, false, st);
     if (rc == B200GS_OK) rc = dev_alloc(&m->vals_a, capacity, false, st);
@@ -502,6 +629,27 @@ extern "C" int b200gs_model_create(b200gs_viewer* v, const char* key, uint64_t c
     v->layout_dirty = true;
     *out = m;
     return B200GS_OK;
+}
+
+extern "C" int b200gs_model_create(b200gs_viewer* v, const char* key, uint64_t capacity, b200gs_model** out) {
+    return model_create(v, key, capacity, nullptr, out);
+}
+
+// A model of `v` that renders the packed records ALREADY resident in `source` (a model of another viewer on the same
+// device, same layout): the records are reference counted, nothing is copied.  Mask / selection / edit buffers,
+// transform and all per-frame state stay per model.
+extern "C" int b200gs_model_create_shared(b200gs_viewer* v, const char* key, b200gs_model* source, b200gs_model** out) {
+    REQUIRE(v && source && out, "null argument");
+    REQUIRE(source->v->device == v->device, "shared records must live on the viewer's device");
+    REQUIRE(source->v->rb == v->rb && source->v->sh == v->sh && source->v->cov == v->cov, "viewers use different record layouts");
+    TRY(set_device(v));
+    // uploads already enqueued on the source viewer's stream are ordered before anything this viewer does
+    cudaEvent_t ev;
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(ev, source->v->stream));
+    CK(cudaStreamWaitEvent(v->stream, ev, 0));
+    CK(cudaEventDestroy(ev));
+    return model_create(v, key, source->cap, source->store, out);
 }
 
 extern "C" int b200gs_model_destroy(b200gs_viewer* v, b200gs_model* m) {
@@ -530,9 +678,8 @@ extern "C" int b200gs_model_upload_packed(b200gs_model* m, uint64_t start, const
     REQUIRE(start <= m->cap && count <= m->cap - start, "range exceeds the model's capacity");
     if (count == 0) return B200GS_OK;
     TRY(set_device(m->v));
-    CK(cudaMemcpyAsync(m->recs + start * m->v->rb, packed, count * m->v->rb, cudaMemcpyHostToDevice, m->v->stream));
-    CK(cudaStreamSynchronize(m->v->stream));  // the host buffer is only borrowed for the call
-    return B200GS_OK;
+    // the host buffer is only borrowed for the call: it is copied into the pinned ring, the H2D copies are enqueued
+    return stage_upload(m->v, m->recs + start * m->v->rb, packed, count * m->v->rb);
 }
 
 extern "C" int b200gs_model_upload_packed_device(b200gs_model* m, uint64_t start, const void* packed_dev, uint64_t count) {
@@ -548,34 +695,22 @@ extern "C" int b200gs_model_update_range(b200gs_model* m, uint64_t start, const 
     REQUIRE(m && (gaussians || count == 0), "null argument");
     REQUIRE(start <= m->cap && count <= m->cap - start, "range exceeds the model's capacity");
     if (count == 0) return B200GS_OK;
-    TRY(set_device(m->v));
-    // pack on the host in pinned chunks and stream them up (scene.rs:2069-2085)
-    const uint64_t chunk = 1u << 16;
-    const uint32_t rb = m->v->rb;
-    uint8_t* stage[2] = {nullptr, nullptr};
-    cudaEvent_t done[2] = {nullptr, nullptr};
-    int rc = B200GS_OK;
-    for (int i = 0; i < 2; i++) {
-        if (cudaMallocHost((void**)&stage[i], (size_t)chunk * rb) != cudaSuccess || cudaEventCreate(&done[i]) != cudaSuccess) {
-            gs_set_error("update_range: pinned staging allocation failed");
-            rc = B200GS_ERR_OOM;
-        }
+    b200gs_viewer* v = m->v;
+    TRY(set_device(v));
+    // packed on the host straight into the viewer's pinned ring and streamed up chunk by chunk (scene.rs:2069-2085: the
+    // app calls this every frame while a model loads): packing chunk k+1 overlaps the copy of chunk k, no allocation and
+    // no stream synchronisation per call — the call returns once the last chunk is enqueued
+    const uint32_t rb = v->rb;
+    const uint64_t chunk = kStageBytes / rb;
+    for (uint64_t o = 0; o < count; o += chunk) {
+        const uint64_t c = std::min(chunk, count - o);
+        uint8_t* buf;
+        int slot;
+        TRY(stage_acquire(v, &buf, &slot));
+        TRY(b200gs_pack_gaussians(v->sh, v->cov, gaussians + o, c, buf));
+        TRY(stage_submit(v, slot, m->recs + (start + o) * rb, c * rb));
     }
-    for (uint64_t o = 0, k = 0; rc == B200GS_OK && o < count; o += chunk, k++) {
-        uint64_t c = std::min(chunk, count - o);
-        int b = (int)(k & 1);
-        if (k >= 2) cudaEventSynchronize(done[b]);
-        b200gs_pack_gaussians(m->v->sh, m->v->cov, gaussians + o, c, stage[b]);
-        cudaError_t e = cudaMemcpyAsync(m->recs + (start + o) * rb, stage[b], c * rb, cudaMemcpyHostToDevice, m->v->stream);
-        if (e == cudaSuccess) e = cudaEventRecord(done[b], m->v->stream);
-        if (e != cudaSuccess) { gs_set_error("update_range: %s", cudaGetErrorString(e)); rc = B200GS_ERR_CUDA; }
-    }
-    cudaStreamSynchronize(m->v->stream);
-    for (int i = 0; i < 2; i++) {
-        if (stage[i]) cudaFreeHost(stage[i]);
-        if (done[i]) cudaEventDestroy(done[i]);
-    }
-    return rc;
+    return B200GS_OK;
 }
 
 extern "C" int b200gs_model_set_transform(b200gs_model* m, const float pos[3], const float quat_xyzw[4], const float scale[3]) {
@@ -591,9 +726,7 @@ static int upload_words(b200gs_model* m, uint32_t** dst, const uint32_t* words, 
     REQUIRE(words && nwords == need, "bitset must hold ceil(N/32) words");
     TRY(set_device(m->v));
     if (!*dst) TRY(dev_alloc(dst, need, true, m->v->stream));
-    CK(cudaMemcpyAsync(*dst, words, need * 4, cudaMemcpyHostToDevice, m->v->stream));
-    CK(cudaStreamSynchronize(m->v->stream));
-    return B200GS_OK;
+    return stage_upload(m->v, *dst, words, need * 4);
 }
 extern "C" int b200gs_model_upload_mask(b200gs_model* m, const uint32_t* words, uint64_t nwords) {
     REQUIRE(m, "null model");
@@ -615,8 +748,7 @@ extern "C" int b200gs_model_upload_edits(b200gs_model* m, uint64_t start, const 
     REQUIRE(start <= m->cap && count <= m->cap - start, "range exceeds the model's capacity");
     TRY(set_device(m->v));
     TRY(ensure_edits(m));
-    if (count) CK(cudaMemcpyAsync(m->edits + start, pods, count * sizeof(b200gs_edit_pod), cudaMemcpyHostToDevice, m->v->stream));
-    CK(cudaStreamSynchronize(m->v->stream));
+    if (count) TRY(stage_upload(m->v, m->edits + start, pods, count * sizeof(b200gs_edit_pod)));
     return B200GS_OK;
 }
 
@@ -639,31 +771,34 @@ extern "C" int b200gs_model_eval_mask(b200gs_model* m, const b200gs_mask_op* pos
         REQUIRE(sp <= 60, "op tree too deep");
     }
     REQUIRE(sp == 1, "malformed op tree");
-    TRY(set_device(m->v));
-    cudaStream_t st = m->v->stream;
+    REQUIRE(n_shapes <= 64, "too many mask shapes");
+    b200gs_viewer* v = m->v;
+    TRY(set_device(v));
+    cudaStream_t st = v->stream;
     uint64_t need = (m->cap + 31) / 32;
     if (!m->mask) TRY(dev_alloc(&m->mask, need, true, st));
-    b200gs_mask_op* d_ops = nullptr;
-    b200gs_mask_shape* d_shapes = nullptr;
-    float* d_rot = nullptr;
-    std::vector<float> rot(9 * std::max<uint32_t>(n_shapes, 1));
-    for (uint32_t s = 0; s < n_shapes; s++) {
+    if (!v->mask_scratch) TRY(dev_alloc(&v->mask_scratch, kMaskScratchBytes, false, st));
+    // postfix ops | shapes | 3x3 shape rotations, staged in one pinned block (no allocation, no synchronisation:
+    // the evaluation is enqueued behind the upload on the viewer's stream)
+    uint8_t* buf;
+    int slot;
+    TRY(stage_acquire(v, &buf, &slot));
+    b200gs_mask_op* h_ops = reinterpret_cast<b200gs_mask_op*>(buf);
+    b200gs_mask_shape* h_shapes = reinterpret_cast<b200gs_mask_shape*>(buf + 64 * sizeof(b200gs_mask_op));
+    float* h_rot = reinterpret_cast<float*>(buf + 64 * sizeof(b200gs_mask_op) + 64 * sizeof(b200gs_mask_shape));
+    if (n_ops) memcpy(h_ops, postfix, n_ops * sizeof(b200gs_mask_op));
+    if (n_shapes) memcpy(h_shapes, shapes, n_shapes * sizeof(b200gs_mask_shape));
+    for (uint32_t s2 = 0; s2 < n_shapes; s2++) {
         float R[3][3];
-        quat_to_mat3(shapes[s].quat, R);
-        memcpy(&rot[9 * s], R, 36);
+        quat_to_mat3(shapes[s2].quat, R);
+        memcpy(h_rot + 9 * s2, R, 36);
     }
-    TRY(dev_alloc(&d_ops, n_ops, false, st));
-    TRY(dev_alloc(&d_shapes, n_shapes, false, st));
-    TRY(dev_alloc(&d_rot, 9 * (size_t)n_shapes, false, st));
-    if (n_ops) CK(cudaMemcpyAsync(d_ops, postfix, n_ops * sizeof(b200gs_mask_op), cudaMemcpyHostToDevice, st));
-    if (n_shapes) {
-        CK(cudaMemcpyAsync(d_shapes, shapes, n_shapes * sizeof(b200gs_mask_shape), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(d_rot, rot.data(), 36 * (size_t)n_shapes, cudaMemcpyHostToDevice, st));
-    }
+    TRY(stage_submit(v, slot, v->mask_scratch, kMaskScratchBytes));
+    const b200gs_mask_op* d_ops = reinterpret_cast<const b200gs_mask_op*>(v->mask_scratch);
+    const b200gs_mask_shape* d_shapes = reinterpret_cast<const b200gs_mask_shape*>(v->mask_scratch + 64 * sizeof(b200gs_mask_op));
+    const float* d_rot = reinterpret_cast<const float*>(v->mask_scratch + 64 * sizeof(b200gs_mask_op) + 64 * sizeof(b200gs_mask_shape));
     GsModelXf xf = make_xf(m);
-    CK(gs_launch_eval_mask(m->recs, (uint32_t)m->cap, m->v->rb, xf, d_ops, n_ops, d_shapes, d_rot, m->mask, st));
-    CK(cudaStreamSynchronize(st));
-    cudaFree(d_ops); cudaFree(d_shapes); cudaFree(d_rot);
+    CK(gs_launch_eval_mask(m->recs, (uint32_t)m->cap, v->rb, xf, d_ops, n_ops, d_shapes, d_rot, m->mask, st));
     return B200GS_OK;
 }
 
@@ -683,6 +818,7 @@ extern "C" int b200gs_model_preprocess(b200gs_model* m, int use_unedited) {
     TRY(set_device(v));
     TRY(ensure_frame_buffers(v));
     CK(cudaMemsetAsync(m->ctrl, 0, MC_WORDS * 4, v->stream));
+    if (v->query.kind == B200GS_QUERY_TEXTURE) TRY(ensure_query_texture(v));
     GsFrame f = make_frame(v);
     if (f.query.kind >= B200GS_QUERY_RECT && !m->selection)  // a selection query writes the selection bitset
         TRY(dev_alloc(&m->selection, (m->cap + 31) / 32, true, v->stream));
@@ -811,6 +947,7 @@ extern "C" int b200gs_render(b200gs_viewer* v, b200gs_model* const* far_to_near,
     REQUIRE(v && rgba8_out && (far_to_near || n_models == 0), "null argument");
     REQUIRE(n_models <= kMaxModelsPerFrame, "too many models");
     REQUIRE(pitch >= (size_t)v->W * 4, "pitch too small");
+    REQUIRE(pitch % 4 == 0 && ((uintptr_t)rgba8_out & 3u) == 0, "rgba8_out and pitch must be 4-byte aligned (pixels are stored as u32)");
     for (uint32_t i = 0; i < n_models; i++) {
         REQUIRE(far_to_near[i] && far_to_near[i]->v == v, "model does not belong to this viewer");
         REQUIRE(far_to_near[i]->sorted, "render called before preprocess + sort");
@@ -850,6 +987,8 @@ extern "C" int b200gs_render_frame_host_begin(b200gs_viewer* v, b200gs_model* co
     CK(cudaEventRecord(v->ev_rendered[slot], v->stream));
     CK(cudaStreamWaitEvent(v->copy_stream, v->ev_rendered[slot], 0));
     CK(cudaMemcpyAsync(rgba8_host, dev, img, cudaMemcpyDeviceToHost, v->copy_stream));
+    // the frame's overflow flag travels with the image (checked by _end: no extra synchronisation)
+    CK(cudaMemcpyAsync(v->h_small + 32 + slot, v->stats + 3, 4, cudaMemcpyDeviceToHost, v->copy_stream));
     CK(cudaEventRecord(v->ev_copied[slot], v->copy_stream));
     v->ring_pending++;
     return B200GS_OK;
@@ -859,16 +998,24 @@ extern "C" int b200gs_render_frame_host_end(b200gs_viewer* v) {
     REQUIRE(v, "null viewer");
     REQUIRE(v->ring_pending > 0, "no frame in flight");
     TRY(set_device(v));
-    CK(cudaEventSynchronize(v->ev_copied[v->ring_head & 1u]));
+    const uint32_t slot = v->ring_head & 1u;
+    CK(cudaEventSynchronize(v->ev_copied[slot]));
     v->ring_head++;
     v->ring_pending--;
+    if (v->h_small[32 + slot]) {   // the image was delivered, but entries beyond the capacity were dropped
+        gs_set_error("tile-entry capacity exceeded in this frame (b200gs_set_tile_entry_capacity): the image is truncated");
+        return B200GS_ERR_OVERFLOW;
+    }
     return B200GS_OK;
 }
 
 extern "C" int b200gs_render_frame_host(b200gs_viewer* v, b200gs_model* const* far_to_near, uint32_t n_models,
                                         const float view[16], const float proj[16], void* rgba8_host) {
     REQUIRE(v && rgba8_host, "null argument");
-    while (v->ring_pending) TRY(b200gs_render_frame_host_end(v));
+    while (v->ring_pending) {
+        const int rc = b200gs_render_frame_host_end(v);
+        if (rc != B200GS_OK && rc != B200GS_ERR_OVERFLOW) return rc;
+    }
     TRY(b200gs_render_frame_host_begin(v, far_to_near, n_models, view, proj, rgba8_host));
     return b200gs_render_frame_host_end(v);
 }
@@ -1061,9 +1208,10 @@ extern "C" int b200gs_query_hits(b200gs_viewer* v, b200gs_model* const* far_to_n
     for (uint32_t i = 0; i < n_models; i++) REQUIRE(far_to_near[i] && far_to_near[i]->v == v && far_to_near[i]->sorted, "model not rendered");
     TRY(set_device(v));
     cudaStream_t st = v->stream;
-    // the hit list needs the complete per-tile lists: re-bin the frame as a single slab (event-driven call)
+    // the hit list needs the complete per-tile lists: re-bin the frame as a single slab (event-driven call) into the
+    // query's own scratch target — the two host-frame slots may hold frames that are still being copied out
     TRY(ensure_frame_buffers(v));
-    TRY(render_slabs(v, far_to_near, n_models, v->image + v->image_bytes, (size_t)v->W * 4, std::vector<uint32_t>()));
+    TRY(render_slabs(v, far_to_near, n_models, v->image + 2 * v->image_bytes, (size_t)v->W * 4, std::vector<uint32_t>()));
     const uint32_t c32 = (uint32_t)std::min<uint64_t>(cap, 1u << 20);
     uint2* d_out = nullptr;
     uint32_t* d_cnt = nullptr;

@@ -5,6 +5,7 @@
 //    2201-2209; tree built at src/app.rs:1816-1837.  The tree arrives flattened to postfix.
 //  * postprocess: postprocessor.postprocess(...) — reference src/tab/scene.rs:604-610: commit
 //    the viewer's selection edit into the per-Gaussian edit buffer of the selected Gaussians.
+//  * query texture painting: query_toolset.render(queue, encoder, query_texture) — scene.rs:787-791.
 // Compiled with -fmad=false like preprocess.cu so the point-in-shape tests match the oracle.
 #include "common.cuh"
 
@@ -77,7 +78,21 @@ __global__ void __launch_bounds__(256) k_fill_edits(uint32_t n, b200gs_edit_pod*
     edits[i] = e;
 }
 
+// query_toolset.render(queue, encoder, query_texture) (scene.rs:787-791): one stroke painted into the query texture
+__global__ void __launch_bounds__(256) k_paint_query_texture(uint8_t* tex, uint32_t w, uint32_t h,
+                                                             const __grid_constant__ b200gs_query_pod q) {
+    const uint32_t x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= w || y >= h) return;
+    if (gs_query_shape_hit(q, (float)x + 0.5f, (float)y + 0.5f)) tex[(size_t)y * w + x] = 255;
+}
+
 }  // namespace
+
+cudaError_t gs_launch_paint_query_texture(uint8_t* tex, uint32_t w, uint32_t h, const b200gs_query_pod& stroke, cudaStream_t st) {
+    if (w == 0 || h == 0) return cudaSuccess;
+    k_paint_query_texture<<<dim3((w + 31) / 32, (h + 7) / 8), 256, 0, st>>>(tex, w, h, stroke);
+    return cudaGetLastError();
+}
 
 cudaError_t gs_launch_eval_mask(const uint8_t* recs, uint32_t n, uint32_t record_bytes, const GsModelXf& m,
                                 const b200gs_mask_op* ops_dev, uint32_t n_ops, const b200gs_mask_shape* shapes_dev,

@@ -40,7 +40,9 @@ struct GsFrame {
     float bg[4];
     uint32_t tiles_x, tiles_y;
     uint32_t std_proj;  // 1: only P00,P11,P22,P23,P32 are non-zero (glam perspective_rh): kernels skip the zero terms
-    b200gs_query_pod query;  // selection query tested in the preprocess kernel (rect / brush)
+    b200gs_query_pod query;  // selection query tested in the preprocess kernel (rect / brush / texture)
+    const uint8_t* query_tex;  // query texture (u8 per pixel, query_tex_w x query_tex_h), sampled when query.kind == TEXTURE
+    uint32_t query_tex_w, query_tex_h;
 };
 
 // Per-model uniforms (ModelTransformPod, scene.rs:796-802)
@@ -159,6 +161,7 @@ cudaError_t gs_launch_eval_mask(const uint8_t* recs, uint32_t n, uint32_t record
 cudaError_t gs_launch_postprocess(uint32_t n, const uint32_t* selection, b200gs_edit_pod* edits,
                                   b200gs_edit_pod sel_edit, cudaStream_t st);
 cudaError_t gs_launch_fill_default_edits(uint32_t n, b200gs_edit_pod* edits, cudaStream_t st);
+cudaError_t gs_launch_paint_query_texture(uint8_t* tex, uint32_t w, uint32_t h, const b200gs_query_pod& stroke, cudaStream_t st);
 
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__
@@ -214,8 +217,14 @@ __device__ __forceinline__ uint32_t gs_status_flag(uint64_t v, uint32_t epoch) {
 
 // Decoupled look-back executed by ONE full warp, split in two so that callers can put work
 // between publishing their aggregate and needing the prefix.  All lanes return the same value.
+// Values saturate at 2^30 - 1 instead of carrying into the flag bits: a saturated total is larger than any buffer
+// capacity the host allows (< 2^30), so callers that bound their writes by a capacity flag overflow as usual.
+__device__ __forceinline__ uint32_t gs_sat30(uint32_t a, uint32_t b) {
+    const uint32_t s = a + b;
+    return (s < a || s > GS_LOOKBACK_VALUE_MASK) ? GS_LOOKBACK_VALUE_MASK : s;
+}
 __device__ __forceinline__ void gs_lookback_publish(uint64_t* status, uint32_t epoch, uint32_t tile, uint32_t aggregate) {
-    gs_st_status(&status[tile], epoch, (tile == 0 ? GS_LOOKBACK_FLAG_INCL : GS_LOOKBACK_FLAG_AGG) | aggregate);
+    gs_st_status(&status[tile], epoch, (tile == 0 ? GS_LOOKBACK_FLAG_INCL : GS_LOOKBACK_FLAG_AGG) | gs_sat30(aggregate, 0u));
 }
 __device__ __forceinline__ uint32_t gs_lookback_resolve(uint64_t* status, uint32_t epoch, uint32_t tile,
                                                         uint32_t aggregate, int lane) {
@@ -246,7 +255,7 @@ __device__ __forceinline__ uint32_t gs_lookback_resolve(uint64_t* status, uint32
                 const uint32_t needed = first >= 31u ? 0xffffffffu : ((2u << first) - 1u);
                 if (m_inv & needed) stalled = true;  // a needed predecessor has not published yet: retry from here
                 else {
-                    if ((needed >> lane) & 1u) part += (uint32_t)v[j] & GS_LOOKBACK_VALUE_MASK;
+                    if ((needed >> lane) & 1u) part = gs_sat30(part, (uint32_t)v[j] & GS_LOOKBACK_VALUE_MASK);
                     if (first < 32u) done = true;
                     else p -= 32;
                 }
@@ -256,14 +265,29 @@ __device__ __forceinline__ uint32_t gs_lookback_resolve(uint64_t* status, uint32
     }
     uint32_t excl = part;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) excl += __shfl_xor_sync(0xffffffffu, excl, o);
-    if (lane == 0) gs_st_status(&status[tile], epoch, GS_LOOKBACK_FLAG_INCL | (excl + aggregate));
+    for (int o = 16; o > 0; o >>= 1) excl = gs_sat30(excl, __shfl_xor_sync(0xffffffffu, excl, o));
+    if (lane == 0) gs_st_status(&status[tile], epoch, GS_LOOKBACK_FLAG_INCL | gs_sat30(excl, gs_sat30(aggregate, 0u)));
     return excl;
 }
 __device__ __forceinline__ uint32_t gs_lookback_warp(uint64_t* status, uint32_t epoch, uint32_t tile,
                                                      uint32_t aggregate, int lane) {
     if (lane == 0) gs_lookback_publish(status, epoch, tile, aggregate);
     return gs_lookback_resolve(status, epoch, tile, aggregate, lane);
+}
+
+// ---- selection query shapes ---------------------------------------------------------------
+// gs::QueryToolset rect / brush (reference src/tab/scene.rs:758-791, 1224-1263): is the point (viewport pixels,
+// top-left origin, pixel i covers [i, i+1)) inside the rectangle / within `radius` of the brush segment?
+// EXACT class: single-rounding operations, same sequence as the oracle (callers are compiled with -fmad=false).
+__device__ __forceinline__ bool gs_query_shape_hit(const b200gs_query_pod& q, float sx, float sy) {
+    if (q.kind == B200GS_QUERY_RECT) return sx >= q.p0[0] && sx <= q.p1[0] && sy >= q.p0[1] && sy <= q.p1[1];
+    const float vx = q.p1[0] - q.p0[0], vy = q.p1[1] - q.p0[1];
+    const float wx = sx - q.p0[0], wy = sy - q.p0[1];
+    const float vv = vx * vx + vy * vy;
+    float t = vv > 0.0f ? (wx * vx + wy * vy) / vv : 0.0f;
+    t = fminf(1.0f, fmaxf(0.0f, t));
+    const float dx = wx - t * vx, dy = wy - t * vy;
+    return dx * dx + dy * dy <= q.radius * q.radius;
 }
 
 // ---- footprint threshold ------------------------------------------------------------------

@@ -208,18 +208,15 @@ __device__ __forceinline__ bool project_and_cull(const uint32_t* w, const GsFram
     return nz > 0.0f && nz < 1.0f && fabsf(nx) <= GS_CULL_XY && fabsf(ny) <= GS_CULL_XY;
 }
 
-// Selection query (gs::QueryToolset rect / brush in immediate mode, reference src/tab/scene.rs:758-791,
-// 1224-1263): does the splat centre, in viewport pixels (top-left origin), fall inside the shape?
-// EXACT class: same float operations as the oracle.
-__device__ __forceinline__ bool query_hit(const b200gs_query_pod& q, float sx, float sy) {
-    if (q.kind == B200GS_QUERY_RECT) return sx >= q.p0[0] && sx <= q.p1[0] && sy >= q.p0[1] && sy <= q.p1[1];
-    const float vx = q.p1[0] - q.p0[0], vy = q.p1[1] - q.p0[1];
-    const float wx = sx - q.p0[0], wy = sy - q.p0[1];
-    const float vv = vx * vx + vy * vy;
-    float t = vv > 0.0f ? (wx * vx + wy * vy) / vv : 0.0f;
-    t = fminf(1.0f, fmaxf(0.0f, t));
-    const float dx = wx - t * vx, dy = wy - t * vy;
-    return dx * dx + dy * dy <= q.radius * q.radius;
+// Selection query: the splat centre against the shape itself (immediate mode) or against the viewer's query texture
+// (non-immediate mode, scene.rs:767-791).  EXACT class: same float operations as the oracle.
+__device__ __forceinline__ bool query_hit(const GsFrame& f, float sx, float sy) {
+    if (f.query.kind == B200GS_QUERY_TEXTURE) {
+        const float fx = floorf(sx), fy = floorf(sy);
+        if (!(fx >= 0.0f && fy >= 0.0f && fx < (float)f.query_tex_w && fy < (float)f.query_tex_h)) return false;
+        return f.query_tex[(size_t)(uint32_t)fy * f.query_tex_w + (uint32_t)fx] != 0;
+    }
+    return gs_query_shape_hit(f.query, sx, sy);
 }
 
 // mask / hidden-edit / selection tests that precede the frustum cull (reference preprocess bindings,
@@ -423,7 +420,7 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
             // ---------------- selection query: rewrites this warp's selection word (32 Gaussians) -------
             if (f.query.kind >= B200GS_QUERY_RECT && selection) {
                 const float sx = ((nx + 1.0f) * f.W - 1.0f) * 0.5f + 0.5f, sy = ((1.0f - ny) * f.H - 1.0f) * 0.5f + 0.5f;
-                const bool hit = vis && query_hit(f.query, sx, sy);
+                const bool hit = vis && query_hit(f, sx, sy);
                 const uint32_t hits = __ballot_sync(0xffffffffu, hit);
                 if (i - lane < n) {  // warp-uniform: the word exists
                     uint32_t word = lane == 0 ? selection[i >> 5] : 0u;
