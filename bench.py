@@ -7,11 +7,13 @@
 Workload (BASELINE.json `metric`, configs[2] + configs[4]): the synthetic 6M-Gaussian SH3 scene
 (seed 0xB2000006, Norm8 SH + Half Cov3d, 76 B/record) at 1920x1080, rendered from the 1024-view
 orbit batch of SURVEY.md §8d.  One step = every rank renders `--views` consecutive views of ITS
-contiguous block of the batch (weak scaling: per-GPU work is fixed); the scene is replicated
-(broadcast once with NCCL), no collective runs inside a frame, finished images are gathered to
-rank 0 with NCCL on the side.  Every GPU runs `--viewers` viewer handles (one CUDA stream + one
-scene replica each, default 2) and deals the views of a step round-robin, so independent frames
-overlap on the device.  `value` = frames/s over all ranks with the scene resident in HBM;
+contiguous block of the batch (weak scaling: per-GPU work is fixed; default 64 views per step, so the
+default 20 steps render 1280 frames per GPU); the scene is replicated (broadcast once with NCCL), no
+collective runs inside a frame, finished images are gathered to rank 0 with NCCL on the side and a sample
+of them is verified byte for byte against a local re-render.  Every GPU runs `--viewers` viewer handles
+(one CUDA stream each, default 2, sharing ONE resident copy of the scene) and deals the views of a step
+round-robin, so independent frames overlap on the device.  `strong_scaling` times the whole 1024-view batch
+divided over the ranks.  `value` = frames/s over all ranks with the scene resident in HBM;
 `e2e` = the same through b200gs_render_frame_host_begin/_end (host camera in, RGBA8 image out to
 pinned host memory, D2H inside the timed region).  `--impl reference` times the CPU restatement of the
 reference path (oracle/, all host threads) on a bounded sample of the same workload.
@@ -40,7 +42,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--views", type=int, default=8, help="views rendered per step per GPU")
+    ap.add_argument("--views", type=int, default=64, help="views rendered per step per GPU")
     ap.add_argument("--viewers", type=int, default=2,
                     help="viewer handles (one CUDA stream + one scene replica each) per GPU; the views of a step are "
                          "dealt round-robin, so independent frames overlap on the device")
@@ -48,6 +50,7 @@ def parse():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs stage timings (1M, 6M@4K, config 4)")
     ap.add_argument("--no-gather", action="store_true", help="diagnostic: skip the NCCL image gather")
     return ap.parse_args()
 
@@ -158,15 +161,100 @@ def plan_a_probe():
 
 
 # ------------------------------------------------------------------------------ our arm
+def stage_times(G, v, m, mats, W, H, frames=14):
+    """median per-stage device times (CUDA events on the viewer's stream) of `frames` consecutive views"""
+    v.enable_timings(True, True)
+    rows = []
+    for s in range(frames):
+        view, proj = mats[s % len(mats)]
+        v.update_camera_matrices(view, proj, (W, H))
+        v.render_frame([m])
+        tm = v.last_timings()
+        rows.append((tm.preprocess_ms, tm.sort_ms, tm.bin_ms, tm.composite_ms, tm.total_ms, tm.visible, tm.tile_entries, tm.evals))
+    v.enable_timings(False, False)
+    return np.median(np.array(rows[2:], dtype=np.float64), axis=0)
+
+
+def extra_config_times(G, local_rank):
+    """The other BASELINE.json configs on one stream (CUDA events, median over views of the batch): configs[1]
+    1M @ 1080p, configs[2] second leg 6M @ 3840x2160 (reuses nothing of the timed run), configs[3] three 2M models
+    with per-model transforms, colour edits on a rect-selected half and a composite mask."""
+    out = {}
+    cams = G.view_batch()
+
+    def mats_for(W, H):
+        asp = np.float32(W) / np.float32(H)
+        return [(c.view(), c.projection(asp)) for c in cams[:16]]
+
+    for name, n, seed, W, H in (("1M@1920x1080", 1_000_000, 0xB2000002, 1920, 1080), ("6M@3840x2160", 6_000_000, SEED, 3840, 2160)):
+        packed = G.pack_gaussians(G.SH_NORM8, G.COV3D_HALF, G.gaussian_from_ply(G.synth_scene(seed, n)))
+        with G.Viewer(W, H, G.SH_NORM8, G.COV3D_HALF, device=local_rank) as v:
+            m = v.add_model("scene", n)
+            m.upload_packed(0, packed)
+            pre, srt, bn, comp, tot, vis, ent, ev = stage_times(G, v, m, mats_for(W, H), W, H)
+        out[name] = {"frame_ms": tot, "frames_per_s_one_stream": 1e3 / tot, "preprocess_ms": pre, "sort_ms": srt, "bin_ms": bn,
+                     "composite_ms": comp, "visible": int(vis), "tile_entries": int(ent)}
+        del packed
+    # config 4 (SURVEY.md §8d)
+    W, H, n = 1920, 1080, 2_000_000
+    xf = [((-2, 0, 0), (0, 30, 0), (1, 1, 1)), ((0, 0, 0), (10, 0, 45), (1.2, 0.8, 1)), ((2, 0.5, 0), (0, -60, 0), (0.7, 0.7, 0.7))]
+    with G.Viewer(W, H, G.SH_NORM8, G.COV3D_HALF, device=local_rank) as v:
+        models, centers = [], []
+        for k, seed in enumerate((0xB2000041, 0xB2000042, 0xB2000043)):
+            g = G.gaussian_from_ply(G.synth_scene(seed, n))
+            mm = v.add_model("m%d" % k, n)
+            mm.update_range(0, g)
+            pos, rot, scale = xf[k]
+            mm.set_transform(pos, G.quat_from_euler_zyx_deg(rot), scale)
+            centers.append(g["pos"].mean(axis=0))
+            models.append(mm)
+            del g
+        shapes = np.zeros(3, dtype=G.MASK_SHAPE)
+        shapes["kind"] = (G.MASK_BOX, G.MASK_ELLIPSOID, G.MASK_BOX)
+        shapes["pos"] = ((-0.5, 0, 0), (0.5, 0, 0), (0, 0, 0))
+        shapes["quat"] = (0, 0, 0, 1)
+        shapes["scale"] = ((3, 3, 3), (4, 2, 4), (1, 1, 1))
+        ops = np.array([(G.MASKOP_SHAPE, 0), (G.MASKOP_SHAPE, 1), (G.MASKOP_UNION, 0), (G.MASKOP_SHAPE, 2), (G.MASKOP_DIFFERENCE, 0)],
+                       dtype=G.MASK_OP)
+        models[1].eval_mask(ops, shapes)
+        # edit on a rect-selected half of model 2: select with a query, commit with postprocess
+        v.update_camera(cams[5])
+        v.update_query(G.query_pod(G.QUERY_RECT, G.SELECT_SET, (0, 0), (W / 2, H)))
+        models[2].preprocess()
+        v.update_query(G.query_pod(G.QUERY_NONE))
+        v.update_selection_edit(G.EditPod.new(G.EDIT_ENABLED, (0.5, 1.2, 0.9), 0.2, 0.5, 1.2, 0.8))
+        models[2].postprocess()
+        v.update_selection_edit(G.EditPod.default())
+        rows = []
+        v.enable_timings(True, False)
+        for c in cams[:14]:
+            v.update_camera(c)
+            order = v.order_models(models, np.array(centers, np.float32))
+            v.render_frame([models[i] for i in order])
+            tm = v.last_timings()
+            rows.append((tm.total_ms, tm.bin_ms, tm.composite_ms, tm.visible, tm.tile_entries))
+        r = np.median(np.array(rows[2:], np.float64), axis=0)
+        out["config4 3x2M + transforms + edits + mask @1920x1080"] = {
+            "frame_ms": r[0], "frames_per_s_one_stream": 1e3 / r[0], "bin_ms": r[1], "composite_ms": r[2],
+            "visible": int(r[3]), "tile_entries": int(r[4])}
+    return out
+
+
 def run_ours(a, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     import b200gs as G
 
+    nccl_init_ms = 0.0
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
+        t0 = time.perf_counter()
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        x = torch.zeros(1, device=torch.device("cuda", local_rank))
+        dist.all_reduce(x)                      # communicator set-up happens on the first collective: keep it out of
+        torch.cuda.synchronize()                # the broadcast's time
+        nccl_init_ms = (time.perf_counter() - t0) * 1e3
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     W, H, B, N = a.width, a.height, a.views, a.gaussians
@@ -174,21 +262,22 @@ def run_ours(a, rank, world, local_rank):
 
     # K viewer handles per GPU: frames of a view batch are independent, so they are dealt round-robin to K
     # viewers (one stream each) and the latency-bound kernels of one frame overlap the issue-bound kernels
-    # of another.  Viewer 0 doubles as the single-stream viewer of the per-stage measurements.
+    # of another.  The viewers SHARE one resident copy of the packed scene (b200gs_model_create_shared).
     K = max(1, a.viewers)
     viewers = [G.Viewer(W, H, G.SH_NORM8, G.COV3D_HALF, device=local_rank) for _ in range(K)]
-    models = [vv.add_model("scene", N) for vv in viewers]
+    models = [viewers[0].add_model("scene", N)]
     streams = [torch.cuda.ExternalStream(vv.stream(), device=dev) for vv in viewers]
     v, m, stream = viewers[0], models[0], streams[0]
 
-    # ---- scene: generated on rank 0, broadcast once over NCCL/NVLink, replicated on every GPU
+    # ---- scene: generated on rank 0, broadcast once over NCCL/NVLink, one resident replica per GPU
     t0 = time.perf_counter()
+    packed = None
     if rank == 0:
         ply = G.synth_scene(SEED, N)
         packed = G.pack_gaussians(G.SH_NORM8, G.COV3D_HALF, G.gaussian_from_ply(ply))
         del ply
     scene_build_s = time.perf_counter() - t0
-    bcast_ms = 0.0
+    bcast_ms = upload_ms = 0.0
     if world > 1:
         buf = torch.empty(N * rb, dtype=torch.uint8, device=dev)
         if rank == 0:
@@ -200,15 +289,16 @@ def run_ours(a, rank, world, local_rank):
         e1.record()
         torch.cuda.synchronize()
         bcast_ms = e0.elapsed_time(e1)
-        for vv, mm in zip(viewers, models):
-            mm.upload_packed_device(0, buf.data_ptr(), N)
-            vv.sync()
+        m.upload_packed_device(0, buf.data_ptr(), N)
+        v.sync()
         del buf
     else:
         t1 = time.perf_counter()
-        for mm in models:
-            mm.upload_packed(0, packed)
-        bcast_ms = (time.perf_counter() - t1) * 1e3
+        m.upload_packed(0, packed)              # host -> pinned ring -> HBM
+        v.sync()
+        upload_ms = (time.perf_counter() - t1) * 1e3
+    for vv in viewers[1:]:
+        models.append(vv.add_shared_model("scene", m))
 
     # ---- this rank's contiguous block of the 1024-view batch
     cams = G.view_batch()
@@ -222,15 +312,19 @@ def run_ours(a, rank, world, local_rank):
     gathered = [[torch.empty((B, H, W, 4), dtype=torch.uint8, device=dev) for _ in range(world)] for _ in range(2)] \
         if (world > 1 and rank == 0) else None
     pending = [None, None]
+    rendered = [torch.cuda.Event() for _ in range(K)]
 
     def step(s):
-        """render B views into ring[s % 2]; gather the previous use of that slot must be done"""
+        """render B views of this rank's block into ring[s % 2] (the gather of the slot's previous use is done),
+        then hand the slot to an asynchronous NCCL gather that runs behind the next step's rendering"""
         slot = s % 2
         if pending[slot] is not None:
-            pending[slot].wait()
+            pending[slot].wait()                # (on `stream`: orders later work of viewer 0 behind the gather)
             pending[slot] = None
+            done = torch.cuda.Event()
+            done.record(stream)
             for st in streams[1:]:
-                st.wait_stream(stream)          # the gather that read this slot ran behind viewer 0's stream
+                st.wait_event(done)
         base = ring[slot].data_ptr()
         for j in range(B):
             view, proj = mats[(s * B + j) % len(mats)]
@@ -238,8 +332,9 @@ def run_ours(a, rank, world, local_rank):
             viewers[k].update_camera_matrices(view, proj, (W, H))
             viewers[k].render_frame([models[k]], base + j * img_bytes, W * 4)
         if world > 1 and not a.no_gather:
-            for st in streams[1:]:
-                stream.wait_stream(st)          # every image of the slot is complete before it is gathered
+            for k in range(1, K):               # the slot is complete when every viewer's last frame of it is
+                rendered[k].record(streams[k])
+                stream.wait_event(rendered[k])
             pending[slot] = dist.gather(ring[slot], gathered[slot] if rank == 0 else None, dst=0, async_op=True)
 
     def barrier():
@@ -247,9 +342,18 @@ def run_ours(a, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def drain():
+        for p in pending:
+            if p is not None:
+                p.wait()
+        pending[0] = pending[1] = None
+        for st in streams[1:]:
+            stream.wait_stream(st)
+
     with torch.cuda.stream(stream):
         for s in range(a.warmup):
             step(s)
+        drain()
         barrier()
         sampler = ClockSampler(local_rank) if rank == 0 else None
         if sampler:
@@ -261,12 +365,7 @@ def run_ours(a, rank, world, local_rank):
         e0.record(stream)                       # every stream is idle here (barrier above)
         for s in range(a.warmup, a.warmup + a.steps):
             step(s)
-        for p in pending:
-            if p is not None:
-                p.wait()
-        pending[0] = pending[1] = None
-        for st in streams[1:]:
-            stream.wait_stream(st)              # e1 is behind the last frame of every viewer
+        drain()                                 # e1 is behind the last frame of every viewer and the last gather
         e1.record(stream)
         barrier()
         launches_timed = sum(vv.launch_count() for vv in viewers) - launches_before
@@ -276,8 +375,46 @@ def run_ours(a, rank, world, local_rank):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
+
+        # ---- are the gathered bytes right?  rank 0 re-renders, on its own GPU, a sample of the views every rank sent
+        # in the last step and compares them byte for byte with what arrived (same view -> same bytes on every rank)
+        gather_verified = None
+        if world > 1 and not a.no_gather:
+            ok = True
+            if rank == 0:
+                s_last = a.warmup + a.steps - 1
+                check = torch.empty((H, W, 4), dtype=torch.uint8, device=dev)
+                for r in range(world):
+                    rlo, rhi = G.partition_views(len(cams), world, r)
+                    for j in (0, B // 2, B - 1):
+                        c = cams[rlo + (s_last * B + j) % (rhi - rlo)]
+                        v.update_camera_matrices(c.view(), c.projection(asp), (W, H))
+                        v.render_frame([m], check.data_ptr(), W * 4)
+                        v.sync()
+                        ok = ok and bool(torch.equal(check, gathered[s_last % 2][r][j]))
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.broadcast(flag, 0)
+            gather_verified = bool(flag.item())
     frames = a.steps * B * world
     value = frames / (elapsed_ms * 1e-3)
+
+    # ---- strong scaling beside the weak number: the WHOLE 1024-view batch, each rank its block, images gathered
+    strong = None
+    with torch.cuda.stream(stream):
+        nsteps = (len(block) + B - 1) // B
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for s in range(nsteps):
+            step(s)
+        drain()
+        s1.record(stream)
+        barrier()
+        t = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        strong = {"views": nsteps * B * world, "ms": float(t.item()), "frames_per_s": nsteps * B * world / (float(t.item()) * 1e-3),
+                  "note": "fixed 1024-view batch divided over the ranks (total work fixed), gather included"}
 
     # ---- end to end: host camera in, host image out (pinned), D2H inside the timed region.
     # Two frames in flight (b200gs_render_frame_host_begin/_end): the D2H copy of frame i overlaps the
@@ -298,11 +435,12 @@ def run_ours(a, rank, world, local_rank):
                 viewers[k].render_frame_host_end()
                 inflight[k] -= 1
 
-    e2e_loop(max(3, a.warmup) * 2, 0)
+    e2e_frames = a.steps * B
+    e2e_loop(32, 0)
     barrier()
     launches1 = sum(vv.launch_count() for vv in viewers)
     t0 = time.perf_counter()
-    e2e_loop(a.steps * B, 0)
+    e2e_loop(e2e_frames, 0)
     barrier()
     e2e_s = time.perf_counter() - t0
     launches_e2e = sum(vv.launch_count() for vv in viewers) - launches1
@@ -311,25 +449,16 @@ def run_ours(a, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = frames / float(t.item())
 
-    # ---- per-stage device times (CUDA events on the viewer's stream), separate short loop
-    v.enable_timings(True, True)
-    rows = []
-    for s in range(12):
-        view, proj = mats[s % len(mats)]
-        v.update_camera_matrices(view, proj, (W, H))
-        v.render_frame([m])
-        tm = v.last_timings()
-        rows.append((tm.preprocess_ms, tm.sort_ms, tm.bin_ms, tm.composite_ms, tm.total_ms, tm.visible, tm.tile_entries, tm.evals))
-    v.enable_timings(False, False)
-    rows = np.array(rows[2:], dtype=np.float64)
-    pre_ms, sort_ms, bin_ms, comp_ms, tot_ms, vis, entries, evals = np.median(rows, axis=0)
+    # ---- per-stage device times (CUDA events on the viewer's stream), separate short loop on one stream
+    pre_ms, sort_ms, bin_ms, comp_ms, tot_ms, vis, entries, evals = stage_times(G, v, m, mats, W, H)
 
     if rank == 0:
         peak, peak_src = peaks()
-        # algorithmic bytes: preprocess = N*R + 8*V (key+index) + 32*V (projected splat) + 4*V (bin
-        # word); sort = 68*V (histogram read + 4 x (read 8 + write 8))
-        b_pre_survey = N * rb + 8 * vis
-        b_pre = b_pre_survey + 36 * vis
+        # ALGORITHMIC bytes: preprocess = N*R + 8*V (key + index); sort = 68*V (histogram read + 4 x (read 8 +
+        # write 8)).  The kernel also writes this design's intermediates (32-byte projected splat + 4-byte bin word per
+        # visible Gaussian): reported separately as frac_with_intermediates.
+        b_pre = N * rb + 8 * vis
+        b_pre_all = b_pre + 36 * vis
         b_sort = 68 * vis
         ach_pre = b_pre / (pre_ms * 1e-3) / 1e9
         traffic = None
@@ -344,18 +473,21 @@ def run_ours(a, rank, world, local_rank):
             "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "views_per_step_per_gpu": B, "viewers_per_gpu": K, "gaussians": N,
-                       "record_bytes": rb, "parallelism": "views partitioned over %d GPU(s), scene replicated; "
-                       "images gathered to rank 0 with NCCL off the critical path" % world,
+                       "record_bytes": rb, "scene_replicas_per_gpu": 1,
+                       "parallelism": "views partitioned over %d GPU(s), scene replicated; images gathered to rank 0 with NCCL "
+                                      "off the critical path" % world,
                        "l2": "inputs larger than L2: the %.0f MB packed scene is re-streamed every frame (L2 = 126 MB); "
                              "camera changes every frame" % (N * rb / 1e6)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 136, "d2h_bytes_per_step": B * img_bytes,
                     "call": "b200gs_render_frame_host_begin/_end, %d viewer(s) x 2 frames in flight (camera pod in, RGBA8 "
                             "image out to pinned host memory)" % K, "gpu_launches": int(launches_e2e)},
             "gpu_launches": int(launches_timed),
+            "gather_verified": gather_verified,
+            "strong_scaling": strong,
             "roofline": {"bound": "hbm", "kernel": "k_preprocess", "achieved": ach_pre, "peak": peak, "unit": "GB/s",
                          "frac": ach_pre / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": b_pre,
-                         "frac_survey_formula": (b_pre_survey / (pre_ms * 1e-3) / 1e9) / peak},
+                         "frac_with_intermediates": (b_pre_all / (pre_ms * 1e-3) / 1e9) / peak},
             "stages": {
                 "preprocess_ms": pre_ms, "sort_ms": sort_ms, "bin_ms": bin_ms, "composite_ms": comp_ms, "frame_ms": tot_ms,
                 "frames_per_s_one_stream": 1e3 / tot_ms,   # one viewer, frames back to back on its stream
@@ -364,15 +496,23 @@ def run_ours(a, rank, world, local_rank):
                 "sort_hbm_frac": (b_sort / (sort_ms * 1e-3) / 1e9) / peak,
                 "pre_plus_sort_hbm_frac": ((b_pre + b_sort) / ((pre_ms + sort_ms) * 1e-3) / 1e9) / peak,
                 "composite_gevals_per_s": evals / (comp_ms * 1e-3) / 1e9,
+                "sort_cluster": v.info("sort.cluster"), "sort_resident_clusters": v.info("sort.resident_clusters"),
             },
             "clocks": clocks,
-            "setup": {"scene_build_s": scene_build_s, "scene_upload_or_broadcast_ms": bcast_ms},
+            "setup": {"scene_build_s": scene_build_s, "nccl_init_ms": nccl_init_ms, "scene_broadcast_ms": bcast_ms,
+                      "scene_upload_ms": upload_ms,
+                      "scene_upload_gb_per_s": (N * rb / 1e9) / (upload_ms * 1e-3) if upload_ms else None},
         }
+    for vv in viewers:
+        vv.close()
+    del ring, gathered
+    torch.cuda.empty_cache()
+    if rank == 0:
+        if world == 1 and not a.no_extra:
+            out["extra_configs"] = extra_config_times(G, local_rank)
         if world == 1 and not a.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(a, packed, block)
         print(json.dumps(out))
-    for vv in viewers:
-        vv.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

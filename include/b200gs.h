@@ -178,6 +178,12 @@ B200GS_API int b200gs_device_count(int* out);
 /* bytes of one packed record of the layout; 0 if the layout is invalid */
 B200GS_API uint32_t b200gs_record_bytes(uint32_t sh, uint32_t cov3d);
 
+/* process-wide tuning knobs (set BEFORE viewers are created) and read-only facts for benches / profiles.
+ * knobs: "sort.cluster" = CTAs per thread-block cluster of the radix sort (8 default, 4, 2, 1 = no clusters).
+ * info:  "sort.cluster", "sort.resident_clusters" (after the first sort on the viewer's device), "num_sms". */
+B200GS_API int b200gs_set_tuning(const char* name, int64_t value);
+B200GS_API int b200gs_get_info(b200gs_viewer* v, const char* name, int64_t* out);
+
 /* ------------------------------------------------------------------ viewer
  * gs::MultiModelViewer::<G>::new_with(device, format, depth_stencil, uvec2)  scene.rs:1969-1980 */
 B200GS_API int b200gs_viewer_create(int device, uint32_t sh, uint32_t cov3d, uint32_t width, uint32_t height,

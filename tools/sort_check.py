@@ -4,6 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import b200gs as G
 rng = np.random.default_rng(7)
+if len(sys.argv) > 1:
+    G.set_tuning("sort.cluster", int(sys.argv[1]))
 ok = True
 with G.Viewer(64, 64) as v:
     for n in (1, 33, 4096, 4097, 32768, 32769, 100_000, 1_000_003, 5_900_000):

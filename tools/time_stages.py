@@ -10,6 +10,8 @@ W = int(sys.argv[3]) if len(sys.argv) > 3 else 1920
 H = int(sys.argv[4]) if len(sys.argv) > 4 else 1080
 packed = G.pack_gaussians(G.SH_NORM8, G.COV3D_HALF, G.gaussian_from_ply(G.synth_scene(0xB2000006, N)))
 cams = G.view_batch()
+if os.environ.get("SORT_CLUSTER"):
+    G.set_tuning("sort.cluster", int(os.environ["SORT_CLUSTER"]))
 with G.Viewer(W, H) as v:
     m = v.add_model("scene", N)
     m.upload_packed(0, packed)
@@ -23,5 +25,6 @@ with G.Viewer(W, H) as v:
         t = v.last_timings()
         rows.append((t.preprocess_ms, t.sort_ms, t.bin_ms, t.composite_ms, t.total_ms))
     r = np.median(np.array(rows[4:]), 0)
-    print("slabs=%r" % os.environ.get("SLABS"), "entries", t.tile_entries)
+    print("slabs=%r" % os.environ.get("SLABS"), "entries", t.tile_entries, "sort.cluster", v.info("sort.cluster"),
+          "resident clusters", v.info("sort.resident_clusters"))
     print("median ms: pre %.3f sort %.3f bin %.3f comp %.3f total %.3f" % tuple(r))

@@ -430,6 +430,10 @@ class Model:
         return out
 
 
+def set_tuning(name, value):
+    _ck(lib().b200gs_set_tuning(name.encode(), C.c_int64(int(value))))
+
+
 class Viewer:
     """gs::MultiModelViewer::<G>::new_with(device, format, depth_stencil, size) — scene.rs:1969-1980.
 
@@ -506,6 +510,11 @@ class Viewer:
 
     def set_background(self, rgba):
         _ck(lib().b200gs_set_background(self.h, _p(_f(rgba, 4))))
+
+    def info(self, name):
+        out = C.c_int64(0)
+        _ck(lib().b200gs_get_info(self.h, name.encode(), C.byref(out)))
+        return int(out.value)
 
     def set_depth_slabs(self, fractions):
         fr = np.ascontiguousarray(fractions, dtype=np.float32)

@@ -306,6 +306,23 @@ extern "C" int b200gs_device_count(int* out) {
 
 extern "C" uint32_t b200gs_record_bytes(uint32_t sh, uint32_t cov3d) { return gs_record_bytes(sh, cov3d); }
 
+// process-wide tuning knobs (set before viewers are created) and read-only facts for the bench / profiles
+extern "C" int b200gs_set_tuning(const char* name, int64_t value) {
+    REQUIRE(name, "null name");
+    if (!strcmp(name, "sort.cluster")) {
+        REQUIRE(gs_sort_set_cluster((int)value) == cudaSuccess, "sort.cluster must be 1, 2, 4 or 8");
+        return B200GS_OK;
+    }
+    REQUIRE(false, "unknown tuning knob");
+}
+extern "C" int b200gs_get_info(b200gs_viewer* v, const char* name, int64_t* out) {
+    REQUIRE(name && out, "null argument");
+    if (!strcmp(name, "sort.cluster")) { *out = gs_sort_get_cluster(); return B200GS_OK; }
+    if (!strcmp(name, "sort.resident_clusters")) { REQUIRE(v, "null viewer"); *out = gs_sort_resident_clusters(v->device); return B200GS_OK; }
+    if (!strcmp(name, "num_sms")) { REQUIRE(v, "null viewer"); *out = v->num_sms; return B200GS_OK; }
+    REQUIRE(false, "unknown info name");
+}
+
 // ---------------------------------------------------------------------------- viewer
 extern "C" int b200gs_viewer_create(int device, uint32_t sh, uint32_t cov3d, uint32_t width, uint32_t height,
                                     b200gs_viewer** out) {

@@ -22,6 +22,8 @@
 // Ranking uses no shared-memory atomics: per-warp u16 histograms are updated by one leader lane per digit.
 // Super-tiles are handed out by an atomic ticket (drawn by CTA 0 of the cluster, distributed through DSMEM),
 // so that every predecessor a super-tile waits on is owned by a running cluster.
+#include <atomic>
+#include <initializer_list>
 #include <mutex>
 
 #include "common.cuh"
@@ -32,11 +34,10 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kKpt = 16;                         // keys per thread
 constexpr int kTile = kThreads * kKpt;           // 4096 keys per CTA
-constexpr int kCluster = 8;                      // CTAs per cluster
-constexpr int kSuper = kTile * kCluster;         // 32768 keys per super-tile
+constexpr int kMaxCluster = 8;                   // CTAs per cluster: 8 (default), 4, 2 or 1 (tuning knob, gs_sort_set_cluster)
 constexpr int kBins = GS_SORT_BINS;              // 2048
 constexpr int kWarpSpan = 32 * kKpt;             // 512 consecutive keys per warp
-static_assert(kBins == kCluster * kThreads, "one owned digit per thread");
+static_assert(kBins == kMaxCluster * kThreads, "one owned digit per thread at the largest cluster size");
 
 // ------------------------------------------------------------------ histogram kernel (raw sort API only)
 // hist[pass][digit] += count.  The frame path never runs it: the preprocess kernel and the tile-finish
@@ -125,7 +126,7 @@ __device__ __forceinline__ uint32_t digit_peers(uint32_t key, uint32_t shift) {
     return peers;
 }
 
-template <int BITS>
+template <int BITS, int CL>
 __global__ void __launch_bounds__(kThreads, 3)
 k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, uint32_t* __restrict__ keys_b,
             uint32_t* __restrict__ vals_b, const uint32_t* d_n, uint32_t n_max, const uint32_t* __restrict__ hist_all,
@@ -134,7 +135,9 @@ k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, uint32
     extern __shared__ __align__(16) uint8_t smem_raw[];
     PassSmem& sm = *reinterpret_cast<PassSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t rank = cl_rank();
+    constexpr int kSuper = kTile * CL;        // keys per super-tile (one cluster)
+    constexpr int kOwn = kMaxCluster / CL;    // digits owned per thread: (rank * 256 + tid) * kOwn + j
+    const uint32_t rank = CL > 1 ? cl_rank() : 0u;
     uint32_t n = *d_n;
     if (n > n_max) n = n_max;
     const uint32_t nsuper = (n + kSuper - 1) / kSuper;
@@ -164,9 +167,9 @@ k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, uint32
     uint32_t* __restrict__ vals_out = src_b ? vals_a : vals_b;
     const bool synth_vals = vals_identity && executed_before == 0;  // first executed pass: value = input position
 
-    // global base of the digit this thread owns: exclusive prefix of the pass's histogram
-    const uint32_t own = rank * kThreads + tid;
-    uint32_t gbase;
+    // global bases of the digits this thread owns: exclusive prefix of the pass's histogram
+    const uint32_t own = (rank * kThreads + tid) * kOwn;
+    uint32_t gbase[kOwn];
     {
         const uint4* h4 = reinterpret_cast<const uint4*>(hist_all + pass * kBins) + 2 * tid;
         const uint4 x = h4[0], y = h4[1];
@@ -187,18 +190,22 @@ k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, uint32
 #pragma unroll
         for (int j = 0; j < 8; j++) { sm.exch_k[8 * tid + j] = run; run += c[j]; }
         __syncthreads();
-        gbase = sm.exch_k[own];
+#pragma unroll
+        for (int j = 0; j < kOwn; j++) gbase[j] = sm.exch_k[own + j];
     }
     uint64_t* lb = lookback + own;
 
     // every CTA of the cluster is running (its shared memory may be written from now on); then the first ticket
-    cl_sync();
+    if (CL > 1) cl_sync();
     if (rank == 0 && tid == 0) {
         const uint32_t t = atomicAdd(ticket, 1u);
+        if (CL > 1) {
 #pragma unroll
-        for (int r = 0; r < kCluster; r++) cl_st_u32(cl_map(&sm.tile_id[0], r), t);
+            for (int r = 0; r < CL; r++) cl_st_u32(cl_map(&sm.tile_id[0], r), t);
+        } else sm.tile_id[0] = t;
     }
-    cl_sync();
+    if (CL > 1) cl_sync();
+    else __syncthreads();
 
     for (uint32_t it = 0;; it++) {
         const uint32_t super = sm.tile_id[it & 1u];
@@ -293,52 +300,90 @@ k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, uint32
                 sm.exch_v[pos] = val[k];
             }
         }
-        cl_sync();   // A: every CTA's counts are final, nobody reads whist any more (gpos may be written)
+        // A: every CTA's counts are final, nobody reads whist any more (gpos may be written)
+        if (CL > 1) cl_sync();
+        else __syncthreads();
         // ---- the next super-tile's ticket travels under barrier B
         if (rank == 0 && tid == 0) {
             const uint32_t t = atomicAdd(ticket, 1u);
+            if (CL > 1) {
 #pragma unroll
-            for (int r = 0; r < kCluster; r++) cl_st_u32(cl_map(&sm.tile_id[(it + 1) & 1u], r), t);
+                for (int r = 0; r < CL; r++) cl_st_u32(cl_map(&sm.tile_id[(it + 1) & 1u], r), t);
+            } else sm.tile_id[(it + 1) & 1u] = t;
         }
-        // ---- owner of digit `own`: counts of the 8 CTAs, the super-tile's total, look-back, global bases
+        // ---- owner of digits own .. own+kOwn-1: counts of the CTAs, the super-tile's totals, look-back, global bases
         {
-            uint32_t c[kCluster], total = 0;
+            uint32_t c[CL][kOwn], total[kOwn];
 #pragma unroll
-            for (int r = 0; r < kCluster; r++) { c[r] = cl_ld_u16(cl_map(&sm.cta_count[own], r)); total += c[r]; }
+            for (int j = 0; j < kOwn; j++) total[j] = 0;
+#pragma unroll
+            for (int r = 0; r < CL; r++)
+#pragma unroll
+                for (int j = 0; j < kOwn; j++) {
+                    c[r][j] = CL > 1 ? cl_ld_u16(cl_map(&sm.cta_count[own + j], r)) : (uint32_t)sm.cta_count[own + j];
+                    total[j] += c[r][j];
+                }
             uint64_t* my = lb + (size_t)super * kBins;
-            uint32_t excl = 0;
-            if (super == 0) gs_st_status(my, epoch, GS_LOOKBACK_FLAG_INCL | total);
-            else {
-                gs_st_status(my, epoch, GS_LOOKBACK_FLAG_AGG | total);
-                constexpr int kLb = 4;   // status words per round trip
-                int64_t p = (int64_t)super - 1;
-                bool done = false;
-                while (!done) {
-                    uint64_t v[kLb];
+            uint32_t excl[kOwn];
 #pragma unroll
-                    for (int j = 0; j < kLb; j++)
-                        v[j] = (p - j >= 0) ? gs_ld_status(lb + (size_t)(p - j) * kBins) : (((uint64_t)epoch << 32) | GS_LOOKBACK_FLAG_INCL);
+            for (int j = 0; j < kOwn; j++) excl[j] = 0;
+            if (super == 0) {
+#pragma unroll
+                for (int j = 0; j < kOwn; j++) gs_st_status(my + j, epoch, GS_LOOKBACK_FLAG_INCL | total[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < kOwn; j++) gs_st_status(my + j, epoch, GS_LOOKBACK_FLAG_AGG | total[j]);
+                constexpr int kLb = kOwn == 1 ? 4 : (kOwn == 2 ? 2 : 1);   // predecessors per round trip (8 loads in flight)
+                int64_t p = (int64_t)super - 1;
+                uint32_t pending = (1u << kOwn) - 1u;   // digits whose inclusive prefix has not been met yet
+                while (pending) {
+                    uint64_t v[kLb][kOwn];
+#pragma unroll
+                    for (int q = 0; q < kLb; q++)
+#pragma unroll
+                        for (int j = 0; j < kOwn; j++)
+                            v[q][j] = (p - q >= 0) ? gs_ld_status(lb + (size_t)(p - q) * kBins + j)
+                                                   : (((uint64_t)epoch << 32) | GS_LOOKBACK_FLAG_INCL);
                     int used = 0;
 #pragma unroll
-                    for (int j = 0; j < kLb; j++) {
-                        if (!done && used == j) {
-                            const uint32_t fl = gs_status_flag(v[j], epoch);
-                            if (fl != 0u) {
-                                excl += (uint32_t)v[j] & GS_LOOKBACK_VALUE_MASK;
-                                used = j + 1;
-                                done = fl == 2u;
+                    for (int q = 0; q < kLb; q++) {
+                        if (pending && used == q) {
+                            // a predecessor is consumed once ALL still-pending digits find it published
+                            bool ready = true;
+#pragma unroll
+                            for (int j = 0; j < kOwn; j++)
+                                if (((pending >> j) & 1u) && gs_status_flag(v[q][j], epoch) == 0u) ready = false;
+                            if (ready) {
+#pragma unroll
+                                for (int j = 0; j < kOwn; j++) {
+                                    if ((pending >> j) & 1u) {
+                                        excl[j] += (uint32_t)v[q][j] & GS_LOOKBACK_VALUE_MASK;
+                                        if (gs_status_flag(v[q][j], epoch) == 2u) pending &= ~(1u << j);
+                                    }
+                                }
+                                used = q + 1;
                             }
                         }
                     }
                     p -= used;
                 }
-                gs_st_status(my, epoch, GS_LOOKBACK_FLAG_INCL | (excl + total));
-            }
-            uint32_t g = gbase + excl;
 #pragma unroll
-            for (int r = 0; r < kCluster; r++) { cl_st_u32(cl_map(&sm.gpos[own], r), g); g += c[r]; }
+                for (int j = 0; j < kOwn; j++) gs_st_status(my + j, epoch, GS_LOOKBACK_FLAG_INCL | (excl[j] + total[j]));
+            }
+#pragma unroll
+            for (int j = 0; j < kOwn; j++) {
+                uint32_t g = gbase[j] + excl[j];
+#pragma unroll
+                for (int r = 0; r < CL; r++) {
+                    if (CL > 1) cl_st_u32(cl_map(&sm.gpos[own + j], r), g);
+                    else sm.gpos[own + j] = g;
+                    g += c[r][j];
+                }
+            }
         }
-        cl_sync();   // B: gpos of every digit has arrived from its owner
+        // B: gpos of every digit has arrived from its owner
+        if (CL > 1) cl_sync();
+        else __syncthreads();
         // ---- write out: consecutive positions of one digit are consecutive addresses
 #pragma unroll
         for (int k = 0; k < kKpt; k++) {
@@ -355,34 +400,87 @@ k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, uint32
     }
 }
 
-struct DevInfo { int clusters = 0; };   // co-resident clusters of the pass kernel
+// co-resident clusters of the pass kernel, per device and per cluster size (index log2(CL))
+struct DevInfo { int clusters[4] = {0, 0, 0, 0}; };
 std::mutex g_mu;
 DevInfo g_dev[64];
+std::atomic<int> g_cluster{kMaxCluster};
 
-template <int BITS>
-cudaError_t setup_kernel(int* clusters) {
-    auto kern = k_sort_pass<BITS>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
-    if (e != cudaSuccess) return e;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(kCluster, 1, 1);
-    cfg.blockDim = dim3(kThreads, 1, 1);
-    cfg.dynamicSmemBytes = sizeof(PassSmem);
-    cudaLaunchAttribute at[1];
+using PassKernel = void (*)(uint32_t*, uint32_t*, uint32_t*, uint32_t*, const uint32_t*, uint32_t, const uint32_t*, uint32_t, uint32_t,
+                            uint64_t*, uint32_t, uint32_t*, uint32_t*, uint32_t);
+
+template <int CL>
+PassKernel pick_kernel(uint32_t bits) {
+    if (bits <= 2) return k_sort_pass<2, CL>;
+    if (bits <= 5) return k_sort_pass<5, CL>;
+    if (bits <= 8) return k_sort_pass<8, CL>;
+    if (bits <= 10) return k_sort_pass<10, CL>;
+    return k_sort_pass<11, CL>;
+}
+PassKernel pick_kernel(int cl, uint32_t bits) {
+    return cl == 8 ? pick_kernel<8>(bits) : cl == 4 ? pick_kernel<4>(bits) : cl == 2 ? pick_kernel<2>(bits) : pick_kernel<1>(bits);
+}
+
+void fill_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at, int cl, uint32_t clusters, cudaStream_t st) {
+    *cfg = cudaLaunchConfig_t{};
+    cfg->gridDim = dim3(clusters * cl, 1, 1);
+    cfg->blockDim = dim3(kThreads, 1, 1);
+    cfg->dynamicSmemBytes = sizeof(PassSmem);
+    cfg->stream = st;
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = kCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    int nc = 0;
-    e = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
-    if (e != cudaSuccess) return e;
-    if (*clusters == 0 || nc < *clusters) *clusters = nc < 1 ? 1 : nc;
+    at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg->attrs = at;
+    cfg->numAttrs = cl > 1 ? 1 : 0;
+}
+
+cudaError_t setup_device(int cl, int* clusters) {
+    int nc_min = 0;
+    for (uint32_t bits : {2u, 5u, 8u, 10u, 11u}) {
+        PassKernel kern = pick_kernel(cl, bits);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
+        if (e != cudaSuccess) return e;
+        int nc = 0;
+        if (cl > 1) {
+            cudaLaunchConfig_t cfg;
+            cudaLaunchAttribute at[1];
+            fill_config(&cfg, at, cl, 1, nullptr);
+            e = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
+            if (e != cudaSuccess) return e;
+        } else {
+            int bps = 0, sms = 0, dev = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kThreads, sizeof(PassSmem));
+            if (e == cudaSuccess) e = cudaGetDevice(&dev);
+            if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (e != cudaSuccess) return e;
+            nc = bps * sms;
+        }
+        if (nc < 1) nc = 1;
+        if (nc_min == 0 || nc < nc_min) nc_min = nc;
+    }
+    *clusters = nc_min;
     return cudaSuccess;
 }
 
+int cluster_index(int cl) { return cl == 8 ? 3 : cl == 4 ? 2 : cl == 2 ? 1 : 0; }
+
 }  // namespace
 
+// tuning knob: CTAs per cluster (8, 4, 2 or 1 = no clusters).  Process-wide; set it before viewers are created
+// (look-back buffers are sized from it).
+cudaError_t gs_sort_set_cluster(int cl) {
+    if (cl != 1 && cl != 2 && cl != 4 && cl != 8) return cudaErrorInvalidValue;
+    g_cluster.store(cl);
+    return cudaSuccess;
+}
+int gs_sort_get_cluster() { return g_cluster.load(); }
+int gs_sort_resident_clusters(int device) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    return (device >= 0 && device < 64) ? g_dev[device].clusters[cluster_index(g_cluster.load())] : 0;
+}
+
 size_t gs_sort_lookback_words(uint32_t n_max, uint32_t key_bits) {
-    size_t supers = ((size_t)n_max + kSuper - 1) / kSuper;
+    const size_t super = (size_t)kTile * g_cluster.load();
+    size_t supers = ((size_t)n_max + super - 1) / super;
     if (supers < 1) supers = 1;
     return supers * kBins * gs_sort_passes(key_bits);
 }
@@ -391,7 +489,9 @@ cudaError_t gs_launch_sort(const GsSortArgs& a, int num_sms, cudaStream_t st) {
     (void)num_sms;
     if (a.key_bits < 1 || a.key_bits > 32 || !a.result_in_b) return cudaErrorInvalidValue;
     const uint32_t passes = gs_sort_passes(a.key_bits);
-    size_t supers = ((size_t)a.n_max + kSuper - 1) / kSuper;
+    const int cl = g_cluster.load();
+    const size_t super = (size_t)kTile * cl;
+    size_t supers = ((size_t)a.n_max + super - 1) / super;
     if (supers < 1) supers = 1;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -400,17 +500,12 @@ cudaError_t gs_launch_sort(const GsSortArgs& a, int num_sms, cudaStream_t st) {
     int clusters;
     {
         std::lock_guard<std::mutex> lock(g_mu);
-        if (g_dev[dev].clusters == 0) {
-            int nc = 0;
-            e = setup_kernel<11>(&nc);
-            if (e == cudaSuccess) e = setup_kernel<10>(&nc);
-            if (e == cudaSuccess) e = setup_kernel<8>(&nc);
-            if (e == cudaSuccess) e = setup_kernel<5>(&nc);
-            if (e == cudaSuccess) e = setup_kernel<2>(&nc);
-            if (e != cudaSuccess) return e;
-            g_dev[dev].clusters = nc;
+        int& c = g_dev[dev].clusters[cluster_index(cl)];
+        if (c == 0) {
+            e = setup_device(cl, &c);
+            if (e != cudaSuccess) { c = 0; return e; }
         }
-        clusters = g_dev[dev].clusters;
+        clusters = c;
     }
     if (!a.hist_prefilled) {
         uint32_t grid = 296;
@@ -426,22 +521,10 @@ cudaError_t gs_launch_sort(const GsSortArgs& a, int num_sms, cudaStream_t st) {
         // key and set only in the 0xffffffff padding, so real digits are unchanged and padding still sorts last
         const uint32_t shift = GS_SORT_DIGIT_BITS * p;
         const uint32_t bits = a.key_bits - shift < GS_SORT_DIGIT_BITS ? a.key_bits - shift : GS_SORT_DIGIT_BITS;
-        void (*kern)(uint32_t*, uint32_t*, uint32_t*, uint32_t*, const uint32_t*, uint32_t, const uint32_t*, uint32_t, uint32_t,
-                     uint64_t*, uint32_t, uint32_t*, uint32_t*, uint32_t) = nullptr;
-        if (bits <= 2) kern = k_sort_pass<2>;
-        else if (bits <= 5) kern = k_sort_pass<5>;
-        else if (bits <= 8) kern = k_sort_pass<8>;
-        else if (bits <= 10) kern = k_sort_pass<10>;
-        else kern = k_sort_pass<11>;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid_clusters * kCluster, 1, 1);
-        cfg.blockDim = dim3(kThreads, 1, 1);
-        cfg.dynamicSmemBytes = sizeof(PassSmem);
-        cfg.stream = st;
+        PassKernel kern = pick_kernel(cl, bits);
+        cudaLaunchConfig_t cfg;
         cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = kCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
+        fill_config(&cfg, at, cl, grid_clusters, st);
         e = cudaLaunchKernelEx(&cfg, kern, a.keys_a, a.vals_a, a.keys_b, a.vals_b, a.d_n, a.n_max, (const uint32_t*)a.hist, p, a.key_bits,
                                a.lookback + (size_t)p * supers * kBins, a.epoch, a.tickets + p, a.result_in_b,
                                a.vals_identity ? 1u : 0u);
