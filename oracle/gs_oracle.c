@@ -4,8 +4,9 @@
  *
  * Build: gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC gs_oracle.c -o _build/libgs_oracle.so -lm
  * Every float expression below is meant to be evaluated exactly as written, one rounding
- * per operation, left to right.  Do not "simplify" the arithmetic: the CUDA kernels are
- * compared bit-for-bit against it for culling, depth keys and pixel bounds.
+ * per operation, left to right, and fused multiply-adds ONLY where fmaf() is spelled out (libm's
+ * fmaf is correctly rounded with or without hardware FMA).  Do not "simplify" the arithmetic: the
+ * CUDA kernels are compared bit-for-bit against it for culling, depth keys and pixel bounds.
  */
 #include "gs_oracle.h"
 
@@ -463,12 +464,14 @@ static int pre_one(const orc_frame* f, const orc_model* m, const pre_ctx* c, uin
     uint8_t col[4];
     decode_record(m, (const uint8_t*)m->packed + (size_t)i * rb, p, col, sh, cv);
 
-    /* world = q*(s⊙p)+t  (src/app.rs:1044-1046) */
+    /* world = q*(s⊙p)+t  (src/app.rs:1044-1046).  Dot products are written as explicit fused chains (fmaf): the
+     * CUDA kernel issues the same chain as FFMA, and a fused multiply-add is what a GPU shader compiler emits for
+     * `a*b + c` in the reference's WGSL as well. */
     float ps[3] = {c->s[0] * p[0], c->s[1] * p[1], c->s[2] * p[2]};
     float pw[3], pv[3], pc[4];
-    for (int r = 0; r < 3; r++) pw[r] = c->R[r][0] * ps[0] + c->R[r][1] * ps[1] + c->R[r][2] * ps[2] + c->t[r];
-    for (int r = 0; r < 3; r++) pv[r] = c->V[r][0] * pw[0] + c->V[r][1] * pw[1] + c->V[r][2] * pw[2] + c->V[r][3];
-    for (int r = 0; r < 4; r++) pc[r] = c->P[r][0] * pv[0] + c->P[r][1] * pv[1] + c->P[r][2] * pv[2] + c->P[r][3];
+    for (int r = 0; r < 3; r++) pw[r] = fmaf(c->R[r][0], ps[0], fmaf(c->R[r][1], ps[1], fmaf(c->R[r][2], ps[2], c->t[r])));
+    for (int r = 0; r < 3; r++) pv[r] = fmaf(c->V[r][0], pw[0], fmaf(c->V[r][1], pw[1], fmaf(c->V[r][2], pw[2], c->V[r][3])));
+    for (int r = 0; r < 4; r++) pc[r] = fmaf(c->P[r][0], pv[0], fmaf(c->P[r][1], pv[1], fmaf(c->P[r][2], pv[2], c->P[r][3])));
     if (!(pc[3] > 0.0f)) return 0;
     float iw = 1.0f / pc[3]; /* one IEEE reciprocal, then multiplies */
     float nx = pc[0] * iw, ny = pc[1] * iw, nz = pc[2] * iw;
@@ -478,7 +481,7 @@ static int pre_one(const orc_frame* f, const orc_model* m, const pre_ctx* c, uin
     memcpy(key, &nz, 4);
     /* selection query: the new selection state is what this frame shows */
     if (f->query.kind >= B200GS_QUERY_RECT) {
-        float sx = ((nx + 1.0f) * c->W - 1.0f) * 0.5f + 0.5f, sy = ((1.0f - ny) * c->H - 1.0f) * 0.5f + 0.5f;
+        float sx = fmaf(nx + 1.0f, c->W, -1.0f) * 0.5f + 0.5f, sy = fmaf(1.0f - ny, c->H, -1.0f) * 0.5f + 0.5f;
         int hit = query_hit(f, sx, sy);
         if (f->query.op == B200GS_SELECT_SET) selected = hit;
         else if (f->query.op == B200GS_SELECT_ADD) selected = selected | hit;
@@ -490,10 +493,10 @@ static int pre_one(const orc_frame* f, const orc_model* m, const pre_ctx* c, uin
     float S[3][3] = {{cv[0], cv[1], cv[2]}, {cv[1], cv[3], cv[4]}, {cv[2], cv[4], cv[5]}};
     float B[3][3], Sw[3][3];
     for (int r = 0; r < 3; r++)
-        for (int k = 0; k < 3; k++) B[r][k] = c->M[r][0] * S[0][k] + c->M[r][1] * S[1][k] + c->M[r][2] * S[2][k];
+        for (int k = 0; k < 3; k++) B[r][k] = fmaf(c->M[r][0], S[0][k], fmaf(c->M[r][1], S[1][k], c->M[r][2] * S[2][k]));
     for (int r = 0; r < 3; r++)
         for (int k = 0; k < 3; k++)
-            Sw[r][k] = (B[r][0] * c->M[k][0] + B[r][1] * c->M[k][1] + B[r][2] * c->M[k][2]) * c->sz2;
+            Sw[r][k] = fmaf(B[r][0], c->M[k][0], fmaf(B[r][1], c->M[k][1], B[r][2] * c->M[k][2])) * c->sz2;
     /* make it exactly symmetric the same way the kernel does: use the upper triangle */
     Sw[1][0] = Sw[0][1]; Sw[2][0] = Sw[0][2]; Sw[2][1] = Sw[1][2];
 
@@ -509,26 +512,26 @@ static int pre_one(const orc_frame* f, const orc_model* m, const pre_ctx* c, uin
     float J11 = -(c->fy * itz), J12 = -((c->fy * yc) * itz2);
     float T0[3], T1[3];
     for (int k = 0; k < 3; k++) {
-        T0[k] = J00 * c->V[0][k] + J02 * c->V[2][k];
-        T1[k] = J11 * c->V[1][k] + J12 * c->V[2][k];
+        T0[k] = fmaf(J00, c->V[0][k], J02 * c->V[2][k]);
+        T1[k] = fmaf(J11, c->V[1][k], J12 * c->V[2][k]);
     }
     float U0[3], U1[3];
     for (int k = 0; k < 3; k++) {
-        U0[k] = T0[0] * Sw[0][k] + T0[1] * Sw[1][k] + T0[2] * Sw[2][k];
-        U1[k] = T1[0] * Sw[0][k] + T1[1] * Sw[1][k] + T1[2] * Sw[2][k];
+        U0[k] = fmaf(T0[0], Sw[0][k], fmaf(T0[1], Sw[1][k], T0[2] * Sw[2][k]));
+        U1[k] = fmaf(T1[0], Sw[0][k], fmaf(T1[1], Sw[1][k], T1[2] * Sw[2][k]));
     }
-    float a = U0[0] * T0[0] + U0[1] * T0[1] + U0[2] * T0[2];
-    float b = U0[0] * T1[0] + U0[1] * T1[1] + U0[2] * T1[2];
-    float d = U1[0] * T1[0] + U1[1] * T1[1] + U1[2] * T1[2];
+    float a = fmaf(U0[0], T0[0], fmaf(U0[1], T0[1], U0[2] * T0[2]));
+    float b = fmaf(U0[0], T1[0], fmaf(U0[1], T1[1], U0[2] * T1[2]));
+    float d = fmaf(U1[0], T1[0], fmaf(U1[1], T1[1], U1[2] * T1[2]));
     a = a + ORC_LOWPASS;
     d = d + ORC_LOWPASS;
-    float det = a * d - b * b;
+    float det = fmaf(a, d, -(b * b));
     float ca = 0.0f, cb = 0.0f, cc = 0.0f, radf = 0.0f;
     if (det > 0.0f) {
         float di = 1.0f / det;
         ca = d * di; cb = -b * di; cc = a * di;
         float mid = 0.5f * (a + d);
-        float disc = mid * mid - det;
+        float disc = fmaf(mid, mid, -det);
         if (disc < ORC_MIN_DISC) disc = ORC_MIN_DISC;
         float lam = mid + sqrtf(disc);
         radf = ceilf(ORC_EXTENT_SIGMA * sqrtf(lam));
@@ -562,8 +565,8 @@ static int pre_one(const orc_frame* f, const orc_model* m, const pre_ctx* c, uin
     }
     for (int ch = 0; ch < 3; ch++) rgb[ch] = clamp01(rgb[ch]);
 
-    out->mx = ((nx + 1.0f) * c->W - 1.0f) * 0.5f;
-    out->my = ((1.0f - ny) * c->H - 1.0f) * 0.5f;
+    out->mx = fmaf(nx + 1.0f, c->W, -1.0f) * 0.5f;
+    out->my = fmaf(1.0f - ny, c->H, -1.0f) * 0.5f;
     out->radius = radf;
     out->opacity = op;
     out->r = rgb[0]; out->g = rgb[1]; out->b = rgb[2];

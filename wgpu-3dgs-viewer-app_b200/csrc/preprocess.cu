@@ -19,8 +19,9 @@
 //
 // THIS FILE IS COMPILED WITH -fmad=false: in the EXACT class (position chain, cull, depth key,
 // pixel centre, covariance -> conic/extent) every float operation rounds separately, in source
-// order, so that those results are bit-identical to the CPU oracle's (built with
-// -ffp-contract=off).  Do not re-associate that arithmetic.  The TOLERANCE class (SH colour,
+// order, and multiply-adds are fused ONLY where __fmaf_rn is spelled out — the oracle (built with
+// -ffp-contract=off) spells fmaf() in the same places — so that those results are bit-identical
+// to the CPU oracle's.  Do not re-associate that arithmetic.  The TOLERANCE class (SH colour,
 // edits) uses explicit __fmaf_rn / rsqrtf and is compared within the RGBA tolerance.
 #include <mutex>
 
@@ -179,28 +180,29 @@ __device__ __forceinline__ void sh_colour(const uint32_t* shw, float dx, float d
 }
 
 // EXACT class: model/view/projection chain, frustum cull.  Returns visibility; pw/pv/ndc out.
+template <bool FAST>
 __device__ __forceinline__ bool project_and_cull(const uint32_t* w, const GsFrame& f, const GsModelXf& m, float pw[3],
                                                  float pv[3], float& nx, float& ny, float& nz) {
     const float p0 = __uint_as_float(w[0]), p1 = __uint_as_float(w[1]), p2 = __uint_as_float(w[2]);
-    if (m.identity) {  // bit-identical to the general form when R = I, s = 1, t = 0
+    if (FAST || m.identity) {  // bit-identical to the general form when R = I, s = 1, t = 0
         pw[0] = p0; pw[1] = p1; pw[2] = p2;
     } else {
         // world = q*(s⊙p)+t  (src/app.rs:1044-1046)
         const float ps0 = m.s[0] * p0, ps1 = m.s[1] * p1, ps2 = m.s[2] * p2;
 #pragma unroll
-        for (int r = 0; r < 3; r++) pw[r] = m.R[r][0] * ps0 + m.R[r][1] * ps1 + m.R[r][2] * ps2 + m.t[r];
+        for (int r = 0; r < 3; r++) pw[r] = __fmaf_rn(m.R[r][0], ps0, __fmaf_rn(m.R[r][1], ps1, __fmaf_rn(m.R[r][2], ps2, m.t[r])));
     }
 #pragma unroll
-    for (int r = 0; r < 3; r++) pv[r] = f.V[r][0] * pw[0] + f.V[r][1] * pw[1] + f.V[r][2] * pw[2] + f.V[r][3];
+    for (int r = 0; r < 3; r++) pv[r] = __fmaf_rn(f.V[r][0], pw[0], __fmaf_rn(f.V[r][1], pw[1], __fmaf_rn(f.V[r][2], pw[2], f.V[r][3])));
     float pc[4];
-    if (f.std_proj) {  // zero terms of glam's perspective_rh skipped: same bits
+    if (FAST || f.std_proj) {  // zero terms of glam's perspective_rh skipped: fma(0, x, y) = y, so the bits are the same
         pc[0] = f.P[0][0] * pv[0];
         pc[1] = f.P[1][1] * pv[1];
-        pc[2] = f.P[2][2] * pv[2] + f.P[2][3];
+        pc[2] = __fmaf_rn(f.P[2][2], pv[2], f.P[2][3]);
         pc[3] = f.P[3][2] * pv[2];
     } else {
 #pragma unroll
-        for (int r = 0; r < 4; r++) pc[r] = f.P[r][0] * pv[0] + f.P[r][1] * pv[1] + f.P[r][2] * pv[2] + f.P[r][3];
+        for (int r = 0; r < 4; r++) pc[r] = __fmaf_rn(f.P[r][0], pv[0], __fmaf_rn(f.P[r][1], pv[1], __fmaf_rn(f.P[r][2], pv[2], f.P[r][3])));
     }
     if (!(pc[3] > 0.0f)) return false;
     const float iw = 1.0f / pc[3];
@@ -242,7 +244,10 @@ __device__ __forceinline__ bool pre_tests(uint32_t i, uint32_t n, const uint32_t
     return vis;
 }
 
-template <int SH, int COV>
+// FAST: the launcher found the common frame — identity model transform, glam perspective projection, no mask /
+// selection / edit buffers, no selection query, Splat display, SH degree 3 with SH0 — and picks the instantiation in
+// which those uniform branches (and the loads of their operands) are compiled out.  Same arithmetic, same bits.
+template <int SH, int COV, bool FAST>
 __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restrict__ recs, uint32_t n,
                                                          const uint32_t* __restrict__ mask, uint32_t* selection,
                                                          const b200gs_edit_pod* __restrict__ edits,
@@ -262,8 +267,8 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
     uint32_t* s_chunk = reinterpret_cast<uint32_t*>(bars + NSTAGE);  // NSTAGE
     uint32_t* s_wcount_all = s_chunk + NSTAGE + 1;                   // 4 x 8 warp counts (by sequence number & 3)
-    uint32_t* s_base_all = s_wcount_all + 32;                        // 4
-    uint32_t* s_hist = s_base_all + 4;                               // kHistWords (only if sort_hist): u16 counters, two per word
+    uint32_t* s_base_all = s_wcount_all + 32;                        // 4 x 8 output bases of the warps (by sequence number & 3)
+    uint32_t* s_hist = s_base_all + 32;                              // kHistWords (only if sort_hist): u16 counters, two per word
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t nchunks = (n + kChunk - 1) / kChunk;
@@ -301,22 +306,29 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
         // ------------------------------------------------------------ control warp
         // publish(j+1) happens one iteration BEFORE resolve(j+1): by the time a chunk's prefix is
         // resolved, its predecessors (drawn at the same moment by other CTAs) have long published.
-        auto publish = [&](uint32_t j, uint32_t c) -> uint32_t {
+        // (woff: this lane's warp's offset inside the chunk, lanes 0..7 — the exclusive scan of the 8 warp counts)
+        auto publish = [&](uint32_t j, uint32_t c, uint32_t& woff) -> uint32_t {
             bar_sync(kBarCounts + (int)(j & 3u));  // counts of chunk j are in smem
-            uint32_t total = lane < 8 ? s_wcount_all[(j & 3u) * 8 + lane] : 0u;
+            const uint32_t cnt = lane < 8 ? s_wcount_all[(j & 3u) * 8 + lane] : 0u;
+            uint32_t incl = cnt;
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-            total = __shfl_sync(0xffffffffu, total, 0);
+            for (int o = 1; o < 8; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            woff = incl - cnt;
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 7);
             if (lane == 0) gs_lookback_publish(lookback, epoch, c, total);
             return total;
         };
         uint32_t drawn = NSTAGE;   // chunks drawn by this CTA so far (see kMaxChunksPerCta)
         uint32_t c = s_chunk[0];
-        uint32_t total = c < nchunks ? publish(0, c) : 0u;
+        uint32_t woff = 0, woff_next = 0;
+        uint32_t total = c < nchunks ? publish(0, c, woff) : 0u;
         for (uint32_t j = 0; c < nchunks; j++) {
             // the compute warps count chunk j+1 at the start of their iteration j
             const uint32_t c_next = s_chunk[(j + 1) % NSTAGE];
-            const uint32_t total_next = c_next < nchunks ? publish(j + 1, c_next) : 0u;
+            const uint32_t total_next = c_next < nchunks ? publish(j + 1, c_next, woff_next) : 0u;
             if (j > 0) {
                 // chunk j-1's stage was read for the last time in its heavy phase: refill it
                 bar_sync(kBarFree + (int)((j - 1) & 3u));
@@ -329,13 +341,12 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
                 __syncwarp();
             }
             const uint32_t excl = gs_lookback_resolve(lookback, epoch, c, total, lane);
-            if (lane == 0) {
-                s_base_all[j & 3u] = excl;
-                if (c == nchunks - 1) ctrl[GS_CTRL_VISIBLE] = excl + total;
-            }
+            if (lane < 8) s_base_all[(j & 3u) * 8 + lane] = excl + woff;   // output base of every warp of the chunk
+            if (lane == 0 && c == nchunks - 1) ctrl[GS_CTRL_VISIBLE] = excl + total;
             bar_arrive(kBarBase + (int)(j & 3u));
             c = c_next;
             total = total_next;
+            woff = woff_next;
         }
     } else {
         // ------------------------------------------------------------ compute warps
@@ -353,10 +364,10 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
             const uint32_t* w = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)stage * STAGE_BYTES) + tid * RW;
             bool selected;
             b200gs_edit_pod ed;
-            r.vis = pre_tests(i, n, mask, selection, edits, f, selected, ed);
+            r.vis = FAST ? i < n : pre_tests(i, n, mask, selection, edits, f, selected, ed);
             if (r.vis) {
                 float pw[3];
-                r.vis = project_and_cull(w, f, m, pw, r.pv, r.nx, r.ny, r.nz);
+                r.vis = project_and_cull<FAST>(w, f, m, pw, r.pv, r.nx, r.ny, r.nz);
             }
             r.ballot = __ballot_sync(0xffffffffu, r.vis);
             if (lane == 0) s_wcount_all[(j & 3u) * 8 + warp] = __popc(r.ballot);
@@ -374,9 +385,7 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
             if (!pend.valid) return;   // (CTA-uniform)
             bar_sync(kBarBase + (int)(pend.seq & 3u));
             if (pend.vis) {
-                uint32_t off = s_base_all[pend.seq & 3u];
-                for (int k = 0; k < warp; k++) off += s_wcount_all[(pend.seq & 3u) * 8 + k];
-                off += __popc(pend.ballot & ((1u << lane) - 1u));
+                const uint32_t off = s_base_all[(pend.seq & 3u) * 8 + warp] + __popc(pend.ballot & ((1u << lane) - 1u));
                 keys[off] = pend.key;
                 idx[off] = pend.index;
                 uint4* sp = reinterpret_cast<uint4*>(splats + off);
@@ -405,21 +414,22 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
             bool selected = false;
             b200gs_edit_pod ed;
             ed.flag = 0;
-            if (mask || selection || edits) (void)pre_tests(i, n, mask, selection, edits, f, selected, ed);
+            if (!FAST && (mask || selection || edits)) (void)pre_tests(i, n, mask, selection, edits, f, selected, ed);
             float pw[3];
             {
                 const float p0 = __uint_as_float(w[0]), p1 = __uint_as_float(w[1]), p2 = __uint_as_float(w[2]);
-                if (m.identity) { pw[0] = p0; pw[1] = p1; pw[2] = p2; }
+                if (FAST || m.identity) { pw[0] = p0; pw[1] = p1; pw[2] = p2; }
                 else {
                     const float ps0 = m.s[0] * p0, ps1 = m.s[1] * p1, ps2 = m.s[2] * p2;
 #pragma unroll
-                    for (int r = 0; r < 3; r++) pw[r] = m.R[r][0] * ps0 + m.R[r][1] * ps1 + m.R[r][2] * ps2 + m.t[r];
+                    for (int r = 0; r < 3; r++)
+                        pw[r] = __fmaf_rn(m.R[r][0], ps0, __fmaf_rn(m.R[r][1], ps1, __fmaf_rn(m.R[r][2], ps2, m.t[r])));
                 }
             }
 
             // ---------------- selection query: rewrites this warp's selection word (32 Gaussians) -------
-            if (f.query.kind >= B200GS_QUERY_RECT && selection) {
-                const float sx = ((nx + 1.0f) * f.W - 1.0f) * 0.5f + 0.5f, sy = ((1.0f - ny) * f.H - 1.0f) * 0.5f + 0.5f;
+            if (!FAST && f.query.kind >= B200GS_QUERY_RECT && selection) {
+                const float sx = __fmaf_rn(nx + 1.0f, f.W, -1.0f) * 0.5f + 0.5f, sy = __fmaf_rn(1.0f - ny, f.H, -1.0f) * 0.5f + 0.5f;
                 const bool hit = vis && query_hit(f, sx, sy);
                 const uint32_t hits = __ballot_sync(0xffffffffu, hit);
                 if (i - lane < n) {  // warp-uniform: the word exists
@@ -450,7 +460,7 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
                 }
                 // Σ' = (R_m S_m) Σ (R_m S_m)^T · size²  (upper triangle; exact class)
                 float Sw[3][3];
-                if (m.identity) {
+                if (FAST || m.identity) {
                     Sw[0][0] = cv[0] * f.sz2; Sw[0][1] = cv[1] * f.sz2; Sw[0][2] = cv[2] * f.sz2;
                     Sw[1][1] = cv[3] * f.sz2; Sw[1][2] = cv[4] * f.sz2; Sw[2][2] = cv[5] * f.sz2;
                 } else {
@@ -459,12 +469,12 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
 #pragma unroll
                     for (int r = 0; r < 3; r++)
 #pragma unroll
-                        for (int k = 0; k < 3; k++) B[r][k] = m.M[r][0] * S[0][k] + m.M[r][1] * S[1][k] + m.M[r][2] * S[2][k];
+                        for (int k = 0; k < 3; k++) B[r][k] = __fmaf_rn(m.M[r][0], S[0][k], __fmaf_rn(m.M[r][1], S[1][k], m.M[r][2] * S[2][k]));
 #pragma unroll
                     for (int r = 0; r < 3; r++)
 #pragma unroll
                         for (int k = r; k < 3; k++)
-                            Sw[r][k] = (B[r][0] * m.M[k][0] + B[r][1] * m.M[k][1] + B[r][2] * m.M[k][2]) * f.sz2;
+                            Sw[r][k] = __fmaf_rn(B[r][0], m.M[k][0], __fmaf_rn(B[r][1], m.M[k][1], B[r][2] * m.M[k][2])) * f.sz2;
                 }
                 Sw[1][0] = Sw[0][1]; Sw[2][0] = Sw[0][2]; Sw[2][1] = Sw[1][2];
 
@@ -481,31 +491,31 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
                 float T0[3], T1[3], U0[3], U1[3];
 #pragma unroll
                 for (int k = 0; k < 3; k++) {
-                    T0[k] = J00 * f.V[0][k] + J02 * f.V[2][k];
-                    T1[k] = J11 * f.V[1][k] + J12 * f.V[2][k];
+                    T0[k] = __fmaf_rn(J00, f.V[0][k], J02 * f.V[2][k]);
+                    T1[k] = __fmaf_rn(J11, f.V[1][k], J12 * f.V[2][k]);
                 }
 #pragma unroll
                 for (int k = 0; k < 3; k++) {
-                    U0[k] = T0[0] * Sw[0][k] + T0[1] * Sw[1][k] + T0[2] * Sw[2][k];
-                    U1[k] = T1[0] * Sw[0][k] + T1[1] * Sw[1][k] + T1[2] * Sw[2][k];
+                    U0[k] = __fmaf_rn(T0[0], Sw[0][k], __fmaf_rn(T0[1], Sw[1][k], T0[2] * Sw[2][k]));
+                    U1[k] = __fmaf_rn(T1[0], Sw[0][k], __fmaf_rn(T1[1], Sw[1][k], T1[2] * Sw[2][k]));
                 }
-                float a = U0[0] * T0[0] + U0[1] * T0[1] + U0[2] * T0[2];
-                const float b = U0[0] * T1[0] + U0[1] * T1[1] + U0[2] * T1[2];
-                float d = U1[0] * T1[0] + U1[1] * T1[1] + U1[2] * T1[2];
+                float a = __fmaf_rn(U0[0], T0[0], __fmaf_rn(U0[1], T0[1], U0[2] * T0[2]));
+                const float b = __fmaf_rn(U0[0], T1[0], __fmaf_rn(U0[1], T1[1], U0[2] * T1[2]));
+                float d = __fmaf_rn(U1[0], T1[0], __fmaf_rn(U1[1], T1[1], U1[2] * T1[2]));
                 a = a + GS_LOWPASS;
                 d = d + GS_LOWPASS;
-                const float det = a * d - b * b;
+                const float det = __fmaf_rn(a, d, -(b * b));
                 float ca = 0.0f, cb = 0.0f, cc = 0.0f, radf = 0.0f;
                 if (det > 0.0f) {
                     const float di = 1.0f / det;
                     ca = d * di; cb = -b * di; cc = a * di;
                     const float mid = 0.5f * (a + d);
-                    float disc = mid * mid - det;
+                    float disc = __fmaf_rn(mid, mid, -det);
                     if (disc < GS_MIN_DISC) disc = GS_MIN_DISC;
                     const float lam = mid + sqrtf(disc);
                     radf = ceilf(GS_EXTENT_SIGMA * sqrtf(lam));
                 }
-                if (f.display_mode == B200GS_DISPLAY_POINT) {
+                if (!FAST && f.display_mode == B200GS_DISPLAY_POINT) {
                     ca = GS_FLAT_D2 / (GS_POINT_RADIUS * GS_POINT_RADIUS); cb = 0.0f; cc = ca;
                     radf = ceilf(GS_POINT_RADIUS);
                 }
@@ -519,8 +529,9 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
                 const uint32_t colw = w[3];
                 float rgb[3];
 #pragma unroll
-                for (int ch = 0; ch < 3; ch++) rgb[ch] = f.no_sh0 ? 0.0f : byte_to_float(colw, ch) * (1.0f / 255.0f);
-                if (SH != 3) {  // the degree is uniform per frame: one fully unrolled variant per degree
+                for (int ch = 0; ch < 3; ch++) rgb[ch] = (!FAST && f.no_sh0) ? 0.0f : byte_to_float(colw, ch) * (1.0f / 255.0f);
+                if (SH != 3 && FAST) sh_colour<SH, 3>(shw, dx, dy, dz, rgb);
+                else if (SH != 3) {  // the degree is uniform per frame: one fully unrolled variant per degree
                     switch (f.sh_deg) {
                         case 1: sh_colour<SH, 1>(shw, dx, dy, dz, rgb); break;
                         case 2: sh_colour<SH, 2>(shw, dx, dy, dz, rgb); break;
@@ -531,8 +542,8 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
 #pragma unroll
                 for (int ch = 0; ch < 3; ch++) rgb[ch] = clamp01(rgb[ch]);
                 float op = (float)(colw >> 24) * (1.0f / 255.0f);
-                if (edits) apply_edit(ed, rgb, op);
-                if (selected) {
+                if (!FAST && edits) apply_edit(ed, rgb, op);
+                if (!FAST && selected) {
                     apply_edit(f.sel_edit, rgb, op);
                     const float ha = f.hl[3];
 #pragma unroll
@@ -541,8 +552,8 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
 #pragma unroll
                 for (int ch = 0; ch < 3; ch++) rgb[ch] = clamp01(rgb[ch]);
 
-                const float mx = ((nx + 1.0f) * f.W - 1.0f) * 0.5f;
-                const float my = ((1.0f - ny) * f.H - 1.0f) * 0.5f;
+                const float mx = __fmaf_rn(nx + 1.0f, f.W, -1.0f) * 0.5f;
+                const float my = __fmaf_rn(1.0f - ny, f.H, -1.0f) * 0.5f;
                 q0.x = __float_as_uint(mx);
                 q0.y = __float_as_uint(my);
                 q0.z = (uint32_t)radf | ((uint32_t)__half_as_ushort(__float2half_rn(op)) << 16);
@@ -554,7 +565,7 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
                 q1.w = (uint32_t)__half_as_ushort(__float2half_rn(rgb[2])) | ((selected ? 1u : 0u) << 16);
                 // bin word (from the STORED record, exactly as the binning kernel decodes big splats): the tile
                 // tests of the common small splats are done here, where the splat is in registers
-                bw = gs_make_bin_word(q0, q1, f.W, f.H, f.display_mode != B200GS_DISPLAY_SPLAT, f.tiles_x);
+                bw = gs_make_bin_word(q0, q1, f.W, f.H, !FAST && f.display_mode != B200GS_DISPLAY_SPLAT, f.tiles_x);
             }
             bar_arrive(kBarFree + (int)(it & 3u));  // every read of this stage's shared memory is done
 
@@ -598,16 +609,16 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
     if (n == 0 && blockIdx.x == 0 && tid == 0) ctrl[GS_CTRL_VISIBLE] = 0;
 }
 
-struct DevInfo { int blocks_per_sm[8] = {0, 0, 0, 0, 0, 0, 0, 0}; };   // per layout
+struct DevInfo { int blocks_per_sm[16] = {0}; };   // per layout x {general, FAST}
 std::mutex g_mu;
 DevInfo g_dev[64];   // attributes and occupancy are per device: a process may hold viewers on several GPUs
 
-template <int SH, int COV>
+template <int SH, int COV, bool FAST>
 cudaError_t launch_t(const GsPreprocessArgs& a, const GsFrame& f, const GsModelXf& m, int num_sms, cudaStream_t st) {
     constexpr int RB = 16 + ShBytes<SH>::v + CovBytes<COV>::v;
     constexpr int NSTAGE = 3;
-    constexpr size_t smem = (size_t)NSTAGE * kChunk * RB + NSTAGE * 8 + (NSTAGE + 1) * 4 + 32 * 4 + 4 * 4 + kHistWords * 4 + 16;
-    auto kern = k_preprocess<SH, COV>;
+    constexpr size_t smem = (size_t)NSTAGE * kChunk * RB + NSTAGE * 8 + (NSTAGE + 1) * 4 + 32 * 4 + 32 * 4 + kHistWords * 4 + 16;
+    auto kern = k_preprocess<SH, COV, FAST>;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -615,7 +626,7 @@ cudaError_t launch_t(const GsPreprocessArgs& a, const GsFrame& f, const GsModelX
     int blocks_per_sm;
     {
         std::lock_guard<std::mutex> lock(g_mu);
-        int& b = g_dev[dev].blocks_per_sm[SH * 2 + COV];
+        int& b = g_dev[dev].blocks_per_sm[(SH * 2 + COV) * 2 + (FAST ? 1 : 0)];
         if (b == 0) {
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
@@ -642,15 +653,20 @@ cudaError_t launch_t(const GsPreprocessArgs& a, const GsFrame& f, const GsModelX
 
 cudaError_t gs_launch_preprocess(const GsPreprocessArgs& a, const GsFrame& f, const GsModelXf& m, int num_sms,
                                  cudaStream_t st) {
+    const bool fast = m.identity && f.std_proj && !a.mask && !a.selection && !a.edits && f.query.kind < B200GS_QUERY_RECT &&
+                      f.display_mode == B200GS_DISPLAY_SPLAT && f.sh_deg == 3 && !f.no_sh0;
+#define GS_PRE_CASE(k, SH, COV) \
+    case k: return fast ? launch_t<SH, COV, true>(a, f, m, num_sms, st) : launch_t<SH, COV, false>(a, f, m, num_sms, st)
     switch (a.sh * 2 + a.cov) {
-        case 0: return launch_t<0, 0>(a, f, m, num_sms, st);
-        case 1: return launch_t<0, 1>(a, f, m, num_sms, st);
-        case 2: return launch_t<1, 0>(a, f, m, num_sms, st);
-        case 3: return launch_t<1, 1>(a, f, m, num_sms, st);
-        case 4: return launch_t<2, 0>(a, f, m, num_sms, st);
-        case 5: return launch_t<2, 1>(a, f, m, num_sms, st);
-        case 6: return launch_t<3, 0>(a, f, m, num_sms, st);
-        case 7: return launch_t<3, 1>(a, f, m, num_sms, st);
+        GS_PRE_CASE(0, 0, 0);
+        GS_PRE_CASE(1, 0, 1);
+        GS_PRE_CASE(2, 1, 0);
+        GS_PRE_CASE(3, 1, 1);
+        GS_PRE_CASE(4, 2, 0);
+        GS_PRE_CASE(5, 2, 1);
+        GS_PRE_CASE(6, 3, 0);
+        GS_PRE_CASE(7, 3, 1);
     }
+#undef GS_PRE_CASE
     return cudaErrorInvalidValue;
 }
