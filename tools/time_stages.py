@@ -10,6 +10,8 @@ W = int(sys.argv[3]) if len(sys.argv) > 3 else 1920
 H = int(sys.argv[4]) if len(sys.argv) > 4 else 1080
 packed = G.pack_gaussians(G.SH_NORM8, G.COV3D_HALF, G.gaussian_from_ply(G.synth_scene(0xB2000006, N)))
 cams = G.view_batch()
+if os.environ.get("SORT_CLAIM"):
+    G.set_tuning("sort.claim", int(os.environ["SORT_CLAIM"]))
 if os.environ.get("SORT_CLUSTER"):
     G.set_tuning("sort.cluster", int(os.environ["SORT_CLUSTER"]))
 with G.Viewer(W, H) as v:

@@ -313,11 +313,13 @@ extern "C" int b200gs_set_tuning(const char* name, int64_t value) {
         REQUIRE(gs_sort_set_cluster((int)value) == cudaSuccess, "sort.cluster must be 1, 2, 4 or 8");
         return B200GS_OK;
     }
+    if (!strcmp(name, "sort.claim")) { gs_sort_set_claim((int)value); return B200GS_OK; }
     REQUIRE(false, "unknown tuning knob");
 }
 extern "C" int b200gs_get_info(b200gs_viewer* v, const char* name, int64_t* out) {
     REQUIRE(name && out, "null argument");
     if (!strcmp(name, "sort.cluster")) { *out = gs_sort_get_cluster(); return B200GS_OK; }
+    if (!strcmp(name, "sort.claim")) { *out = gs_sort_get_claim(); return B200GS_OK; }
     if (!strcmp(name, "sort.resident_clusters")) { REQUIRE(v, "null viewer"); *out = gs_sort_resident_clusters(v->device); return B200GS_OK; }
     if (!strcmp(name, "num_sms")) { REQUIRE(v, "null viewer"); *out = v->num_sms; return B200GS_OK; }
     REQUIRE(false, "unknown info name");

@@ -75,30 +75,39 @@ __device__ __forceinline__ uint32_t cl_map(const void* p, uint32_t rank) {  // m
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(gs_smem_u32(p)), "r"(rank));
     return r;
 }
-__device__ __forceinline__ uint32_t cl_ld_u16(uint32_t addr) {
-    uint16_t v;
-    asm volatile("ld.shared::cluster.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
-    return v;
-}
 __device__ __forceinline__ void cl_st_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+// Full cluster barrier with release / acquire semantics.  ptxas implements the cluster-scope release as MEMBAR.ALL.GPU
+// (+ CCTL.IVALL on the acquire side), far too heavy for a per-tile handshake: it is used ONCE, at kernel start.
 __device__ __forceinline__ void cl_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Asynchronous DSMEM store that signals the destination CTA's mbarrier with the bytes it delivered (SASS: STAS): data
+// and completion travel together, so the receiver needs no fence — it waits on its own mbarrier.
+__device__ __forceinline__ void cl_st_async_u32(uint32_t addr, uint32_t v, uint32_t mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr), "r"(v), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void cl_st_async_v4(uint32_t addr, uint4 v, uint32_t mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w), "r"(mbar)
+                 : "memory");
 }
 
 // ---------------------------------------------------------------------- digit pass
 struct __align__(16) PassSmem {
     union {
         uint16_t whist[kWarps][kBins];   // per-warp digit counts -> exclusive offsets of the warp inside the CTA's digit run
-        uint32_t gpos[kBins];            // (after the scatter) global index of this CTA's first key of each digit, written by the digit's owner
+        uint32_t gpos[kBins];            // (after the scatter) global index of this CTA's first key of each digit, sent by the digit's owner
     };
     uint32_t exch_k[kTile];              // keys / values of the CTA in digit order
     uint32_t exch_v[kTile];
-    uint16_t cta_count[kBins];           // this CTA's count per digit (read by the owner CTA through DSMEM)
+    uint16_t rcnt[kBins];                // owner side: [r][x] = count in CTA r of my x-th owned digit, pushed by CTA r
     uint16_t tile_start[kBins];          // first position of each digit inside the sorted tile
     uint32_t scan_tmp[kWarps];
-    uint32_t tile_id[2];                 // super-tile of this / the next iteration (written by CTA 0 of the cluster)
+    uint32_t tile_id[2];                 // super-tile of this / the next iteration (sent by CTA 0 of the cluster)
+    uint64_t bar_cnt;                    // mbarrier: one phase per tile, completes when all CTAs' counts of my digits are here
+    uint64_t bar_gpos;                   // mbarrier: one phase per tile, completes when gpos[] (and the next ticket) are here
 };
 
 // peers of this lane = lanes of the warp whose digit equals mine.  One ballot per digit bit (4 instructions:
@@ -126,7 +135,10 @@ __device__ __forceinline__ uint32_t digit_peers(uint32_t key, uint32_t shift) {
     return peers;
 }
 
-template <int BITS, int CL>
+// CLAIM: wide digits are spread — most rows of 32 keys hold 32 DIFFERENT digits — so a row first tries the cheap
+// test: every lane stores its lane id into a per-warp claim table at its digit and reads it back; if every lane reads
+// its own id the row is collision-free, each lane is the only peer of its digit, and the eleven ballots are skipped.
+template <int BITS, int CL, bool CLAIM>
 __global__ void __launch_bounds__(kThreads, 3)
 k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, uint32_t* __restrict__ keys_b,
             uint32_t* __restrict__ vals_b, const uint32_t* d_n, uint32_t n_max, const uint32_t* __restrict__ hist_all,
@@ -195,8 +207,22 @@ k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, uint32
     }
     uint64_t* lb = lookback + own;
 
-    // every CTA of the cluster is running (its shared memory may be written from now on); then the first ticket
-    if (CL > 1) cl_sync();
+    // Cluster protocol (CL > 1).  Per tile, every CTA pushes its digit counts to the digits' owners and every owner
+    // pushes the global bases back, both with st.async + complete_tx on the receiver's mbarrier: no cluster barrier
+    // and no fence inside the loop.  Each mbarrier runs one phase per tile (one arrival: thread 0's expect_tx, armed a
+    // whole tile ahead; the transaction bytes do the rest).
+    constexpr uint32_t kCntBytes = kBins * 2;          // counts of my owned digits from all CTAs
+    constexpr uint32_t kGposBytes = kBins * 4 + 4;     // gpos[] + the next ticket
+    if (CL > 1) {
+        if (tid == 0) {
+            gs_mbar_init(&sm.bar_cnt, 1);
+            gs_mbar_init(&sm.bar_gpos, 1);
+            gs_fence_mbar_init();
+            gs_mbar_expect_tx(&sm.bar_cnt, kCntBytes);
+            gs_mbar_expect_tx(&sm.bar_gpos, kGposBytes);
+        }
+        cl_sync();   // every CTA of the cluster is running, its barriers are armed: its shared memory may be written
+    }
     if (rank == 0 && tid == 0) {
         const uint32_t t = atomicAdd(ticket, 1u);
         if (CL > 1) {
@@ -233,17 +259,30 @@ k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, uint32
         // ---- rank inside the warp: position among the warp's earlier keys of the same digit
         uint32_t rk[kKpt / 2];   // two u16 ranks per register
         uint16_t* wh = sm.whist[warp];
+        uint8_t* claim = reinterpret_cast<uint8_t*>(sm.exch_k) + warp * kBins;   // (the exchange buffer is idle while ranking)
         const uint32_t lane_lt = (1u << lane) - 1u;
 #pragma unroll
         for (int k = 0; k < kKpt; k++) {
             const uint32_t d = (key[k] >> shift) & dmask;
-            const uint32_t peers = digit_peers<BITS>(key[k], shift);
-            const uint32_t before = wh[d];                    // every peer reads the same counter ...
-            const uint32_t mine = __popc(peers & lane_lt);
+            bool alone = false;
+            if (CLAIM) {
+                claim[d] = (uint8_t)lane;
+                __syncwarp();
+                alone = !__any_sync(0xffffffffu, claim[d] != (uint8_t)lane);
+            }
+            uint32_t r;
+            if (alone) {            // (warp-uniform) 32 different digits: every lane advances its own counter
+                r = wh[d];
+                wh[d] = (uint16_t)(r + 1u);
+            } else {
+                const uint32_t peers = digit_peers<BITS>(key[k], shift);
+                const uint32_t before = wh[d];                    // every peer reads the same counter ...
+                const uint32_t mine = __popc(peers & lane_lt);
+                __syncwarp();
+                if (mine == 0) wh[d] = (uint16_t)(before + __popc(peers));   // ... and the first peer advances it
+                r = before + mine;
+            }
             __syncwarp();
-            if (mine == 0) wh[d] = (uint16_t)(before + __popc(peers));   // ... and the first peer advances it
-            __syncwarp();
-            const uint32_t r = before + mine;
             if (k & 1) rk[k >> 1] |= r << 16;
             else rk[k >> 1] = r;
         }
@@ -251,6 +290,7 @@ k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, uint32
         // ---- per digit: exclusive scan over the warps (thread t owns digits 8t .. 8t+7 = one 16-byte word per warp
         // row; two u16 counters per u32 add, no carry: a CTA holds 4096 keys), the CTA's count, and the exclusive
         // scan of the counts over all digits -> start of each digit's run in the sorted tile
+        uint4 cnt8;   // this CTA's counts of digits 8 tid .. 8 tid + 7 (u16 x 8)
         {
             uint4 run = make_uint4(0, 0, 0, 0);
 #pragma unroll
@@ -260,7 +300,7 @@ k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, uint32
                 *p = run;
                 run.x += v.x; run.y += v.y; run.z += v.z; run.w += v.w;
             }
-            reinterpret_cast<uint4*>(sm.cta_count)[tid] = run;
+            cnt8 = run;
             const uint32_t c[8] = {run.x & 0xffffu, run.x >> 16, run.y & 0xffffu, run.y >> 16,
                                    run.z & 0xffffu, run.z >> 16, run.w & 0xffffu, run.w >> 16};
             uint32_t sum = 0;
@@ -300,15 +340,26 @@ k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, uint32
                 sm.exch_v[pos] = val[k];
             }
         }
-        // A: every CTA's counts are final, nobody reads whist any more (gpos may be written)
-        if (CL > 1) cl_sync();
-        else __syncthreads();
-        // ---- the next super-tile's ticket travels under barrier B
+        // ---- counts of digits 8 tid .. 8 tid + 7 go to their owner: one 16-byte asynchronous DSMEM store, issued AFTER
+        // the CTA's barrier — every thread of the CTA is done reading whist and writing the exchange buffer.  An owner
+        // sends global bases only once the counts of every CTA have arrived, so gpos[] (which aliases whist) is never
+        // written under a reader.
+        constexpr uint32_t kOwnedPerCta = kBins / CL;
+        const uint32_t cnt_owner = (8u * tid) / kOwnedPerCta, cnt_x = 8u * tid - cnt_owner * kOwnedPerCta;
+        if (CL == 1) *reinterpret_cast<uint4*>(&sm.rcnt[cnt_x]) = cnt8;
+        __syncthreads();
+        if (CL > 1) cl_st_async_v4(cl_map(&sm.rcnt[rank * kOwnedPerCta + cnt_x], cnt_owner), cnt8, cl_map(&sm.bar_cnt, cnt_owner));
+        const uint32_t parity = it & 1u;
+        if (CL > 1) {
+            gs_mbar_wait(&sm.bar_cnt, parity);
+            if (tid == 0) gs_mbar_expect_tx(&sm.bar_cnt, kCntBytes);   // next tile's phase
+        }
+        // ---- the next super-tile's ticket travels with the global bases
         if (rank == 0 && tid == 0) {
             const uint32_t t = atomicAdd(ticket, 1u);
             if (CL > 1) {
 #pragma unroll
-                for (int r = 0; r < CL; r++) cl_st_u32(cl_map(&sm.tile_id[(it + 1) & 1u], r), t);
+                for (int r = 0; r < CL; r++) cl_st_async_u32(cl_map(&sm.tile_id[(it + 1) & 1u], r), t, cl_map(&sm.bar_gpos, r));
             } else sm.tile_id[(it + 1) & 1u] = t;
         }
         // ---- owner of digits own .. own+kOwn-1: counts of the CTAs, the super-tile's totals, look-back, global bases
@@ -320,7 +371,7 @@ k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, uint32
             for (int r = 0; r < CL; r++)
 #pragma unroll
                 for (int j = 0; j < kOwn; j++) {
-                    c[r][j] = CL > 1 ? cl_ld_u16(cl_map(&sm.cta_count[own + j], r)) : (uint32_t)sm.cta_count[own + j];
+                    c[r][j] = sm.rcnt[r * kOwnedPerCta + tid * kOwn + j];
                     total[j] += c[r][j];
                 }
             uint64_t* my = lb + (size_t)super * kBins;
@@ -375,15 +426,17 @@ k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, uint32
                 uint32_t g = gbase[j] + excl[j];
 #pragma unroll
                 for (int r = 0; r < CL; r++) {
-                    if (CL > 1) cl_st_u32(cl_map(&sm.gpos[own + j], r), g);
+                    if (CL > 1) cl_st_async_u32(cl_map(&sm.gpos[own + j], r), g, cl_map(&sm.bar_gpos, r));
                     else sm.gpos[own + j] = g;
                     g += c[r][j];
                 }
             }
         }
-        // B: gpos of every digit has arrived from its owner
-        if (CL > 1) cl_sync();
-        else __syncthreads();
+        // ---- gpos of every digit (and the next ticket) has arrived from the owners
+        if (CL > 1) {
+            gs_mbar_wait(&sm.bar_gpos, parity);
+            if (tid == 0) gs_mbar_expect_tx(&sm.bar_gpos, kGposBytes);   // next tile's phase
+        } else __syncthreads();
         // ---- write out: consecutive positions of one digit are consecutive addresses
 #pragma unroll
         for (int k = 0; k < kKpt; k++) {
@@ -405,20 +458,22 @@ struct DevInfo { int clusters[4] = {0, 0, 0, 0}; };
 std::mutex g_mu;
 DevInfo g_dev[64];
 std::atomic<int> g_cluster{kMaxCluster};
+std::atomic<int> g_claim{1};
 
 using PassKernel = void (*)(uint32_t*, uint32_t*, uint32_t*, uint32_t*, const uint32_t*, uint32_t, const uint32_t*, uint32_t, uint32_t,
                             uint64_t*, uint32_t, uint32_t*, uint32_t*, uint32_t);
 
 template <int CL>
-PassKernel pick_kernel(uint32_t bits) {
-    if (bits <= 2) return k_sort_pass<2, CL>;
-    if (bits <= 5) return k_sort_pass<5, CL>;
-    if (bits <= 8) return k_sort_pass<8, CL>;
-    if (bits <= 10) return k_sort_pass<10, CL>;
-    return k_sort_pass<11, CL>;
+PassKernel pick_kernel(uint32_t bits, bool claim) {
+    if (bits <= 2) return k_sort_pass<2, CL, false>;
+    if (bits <= 5) return k_sort_pass<5, CL, false>;
+    if (bits <= 8) return k_sort_pass<8, CL, false>;
+    if (bits <= 10) return claim ? k_sort_pass<10, CL, true> : k_sort_pass<10, CL, false>;
+    return claim ? k_sort_pass<11, CL, true> : k_sort_pass<11, CL, false>;
 }
-PassKernel pick_kernel(int cl, uint32_t bits) {
-    return cl == 8 ? pick_kernel<8>(bits) : cl == 4 ? pick_kernel<4>(bits) : cl == 2 ? pick_kernel<2>(bits) : pick_kernel<1>(bits);
+PassKernel pick_kernel(int cl, uint32_t bits, bool claim) {
+    return cl == 8 ? pick_kernel<8>(bits, claim) : cl == 4 ? pick_kernel<4>(bits, claim)
+         : cl == 2 ? pick_kernel<2>(bits, claim) : pick_kernel<1>(bits, claim);
 }
 
 void fill_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at, int cl, uint32_t clusters, cudaStream_t st) {
@@ -435,8 +490,8 @@ void fill_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at, int cl, uint3
 
 cudaError_t setup_device(int cl, int* clusters) {
     int nc_min = 0;
-    for (uint32_t bits : {2u, 5u, 8u, 10u, 11u}) {
-        PassKernel kern = pick_kernel(cl, bits);
+    for (uint32_t variant : {2u, 5u, 8u, 10u, 11u, 110u, 111u}) {   // (1xx: the claim instantiations)
+        PassKernel kern = pick_kernel(cl, variant % 100u, variant >= 100u);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
         if (e != cudaSuccess) return e;
         int nc = 0;
@@ -473,6 +528,9 @@ cudaError_t gs_sort_set_cluster(int cl) {
     return cudaSuccess;
 }
 int gs_sort_get_cluster() { return g_cluster.load(); }
+// tuning knob: try the collision-free fast path per row of wide (10/11-bit) digits before the ballots (default on)
+void gs_sort_set_claim(int on) { g_claim.store(on ? 1 : 0); }
+int gs_sort_get_claim() { return g_claim.load(); }
 int gs_sort_resident_clusters(int device) {
     std::lock_guard<std::mutex> lock(g_mu);
     return (device >= 0 && device < 64) ? g_dev[device].clusters[cluster_index(g_cluster.load())] : 0;
@@ -521,7 +579,7 @@ cudaError_t gs_launch_sort(const GsSortArgs& a, int num_sms, cudaStream_t st) {
         // key and set only in the 0xffffffff padding, so real digits are unchanged and padding still sorts last
         const uint32_t shift = GS_SORT_DIGIT_BITS * p;
         const uint32_t bits = a.key_bits - shift < GS_SORT_DIGIT_BITS ? a.key_bits - shift : GS_SORT_DIGIT_BITS;
-        PassKernel kern = pick_kernel(cl, bits);
+        PassKernel kern = pick_kernel(cl, bits, g_claim.load() != 0);
         cudaLaunchConfig_t cfg;
         cudaLaunchAttribute at[1];
         fill_config(&cfg, at, cl, grid_clusters, st);
