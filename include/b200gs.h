@@ -180,7 +180,7 @@ B200GS_API uint32_t b200gs_record_bytes(uint32_t sh, uint32_t cov3d);
 
 /* process-wide tuning knobs (set BEFORE viewers are created) and read-only facts for benches / profiles.
  * knobs: "sort.cluster" = CTAs per thread-block cluster of the radix sort (8 default, 4, 2, 1 = no clusters);
- *        "sort.claim" = 1 (default) / 0: collision-free fast path of the ranking for 10/11-bit digits.
+ *        "sort.claim" = 0 (default) / 1: collision-free fast path of the ranking for 10/11-bit digits.
  * info:  "sort.cluster", "sort.resident_clusters" (after the first sort on the viewer's device), "num_sms". */
 B200GS_API int b200gs_set_tuning(const char* name, int64_t value);
 B200GS_API int b200gs_get_info(b200gs_viewer* v, const char* name, int64_t* out);

@@ -103,7 +103,7 @@ size_t gs_sort_lookback_words(uint32_t n_max, uint32_t key_bits);
 cudaError_t gs_launch_sort(const GsSortArgs& a, int num_sms, cudaStream_t st);
 cudaError_t gs_sort_set_cluster(int ctas_per_cluster);   // tuning knob: 8 (default), 4, 2, 1
 int gs_sort_get_cluster();
-void gs_sort_set_claim(int on);                          // tuning knob: collision-free fast path of the ranking (default on)
+void gs_sort_set_claim(int on);                          // tuning knob: collision-free fast path of the ranking (default off)
 int gs_sort_get_claim();
 int gs_sort_resident_clusters(int device);               // co-resident clusters of the pass kernel (0 until the first sort)
 

@@ -110,28 +110,18 @@ struct __align__(16) PassSmem {
     uint64_t bar_gpos;                   // mbarrier: one phase per tile, completes when gpos[] (and the next ticket) are here
 };
 
-// peers of this lane = lanes of the warp whose digit equals mine.  One ballot per digit bit (4 instructions:
-// bit test -> predicate, vote, flip by my own bit, and); MATCH.ANY costs ADU cycles per DISTINCT value and 11-bit
-// digits are spread (measured in round 1: a MATCH.ANY pass over spread digits was ADU-bound).
+// peers of this lane = lanes of the warp whose digit equals mine.  One ballot per digit bit; MATCH.ANY costs ADU cycles
+// per DISTINCT value and 11-bit digits are spread (measured in round 1: a MATCH.ANY pass over spread digits was
+// ADU-bound).  The ballots of a row are independent of each other: they are issued back to back and only then
+// combined (a serial vote -> xor -> and chain per bit left the warp waiting on the vote latency eleven times per row).
 template <int BITS>
 __device__ __forceinline__ uint32_t digit_peers(uint32_t key, uint32_t shift) {
+    uint32_t bal[BITS];
+#pragma unroll
+    for (int b = 0; b < BITS; b++) bal[b] = __ballot_sync(0xffffffffu, (key >> (shift + b)) & 1u);
     uint32_t peers = 0xffffffffu;
 #pragma unroll
-    for (int b = 0; b < BITS; b++) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            ".reg .b32 t, bal, sx;\n"
-            "and.b32 t, %1, %2;\n"
-            "setp.ne.u32 p, t, 0;\n"
-            "vote.sync.ballot.b32 bal, p, 0xffffffff;\n"
-            "selp.b32 sx, 0, -1, p;\n"
-            "xor.b32 bal, bal, sx;\n"
-            "and.b32 %0, %0, bal;\n"
-            "}\n"
-            : "+r"(peers)
-            : "r"(key), "r"(1u << (shift + b)));
-    }
+    for (int b = 0; b < BITS; b++) peers &= ((key >> (shift + b)) & 1u) ? bal[b] : ~bal[b];
     return peers;
 }
 
@@ -257,32 +247,40 @@ k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, uint32
         }
         __syncthreads();
         // ---- rank inside the warp: position among the warp's earlier keys of the same digit
+        // Two phases, so that the votes of all 16 rows can overlap (they touch no memory and do not depend on each
+        // other), and only the short counter update runs as a dependent chain through shared memory:
+        //   1. peer masks of every row;
+        //   2. row by row: every peer reads the warp's counter of its digit, the first peer advances it.
         uint32_t rk[kKpt / 2];   // two u16 ranks per register
         uint16_t* wh = sm.whist[warp];
-        uint8_t* claim = reinterpret_cast<uint8_t*>(sm.exch_k) + warp * kBins;   // (the exchange buffer is idle while ranking)
         const uint32_t lane_lt = (1u << lane) - 1u;
+        uint32_t peers[kKpt];
+        if (CLAIM) {
+            // rows whose 32 digits are all different (the common case for spread digits) skip the votes: every lane
+            // stores its lane id into a per-warp claim table at its digit and reads it back
+            uint8_t* claim = reinterpret_cast<uint8_t*>(sm.exch_k) + warp * kBins;   // (the exchange buffer is idle while ranking)
+#pragma unroll
+            for (int k = 0; k < kKpt; k++) {
+                const uint32_t d = (key[k] >> shift) & dmask;
+                claim[d] = (uint8_t)lane;
+                __syncwarp();
+                const bool alone = !__any_sync(0xffffffffu, claim[d] != (uint8_t)lane);
+                __syncwarp();
+                peers[k] = alone ? (1u << lane) : digit_peers<BITS>(key[k], shift);   // (warp-uniform branch)
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kKpt; k++) peers[k] = digit_peers<BITS>(key[k], shift);
+        }
 #pragma unroll
         for (int k = 0; k < kKpt; k++) {
             const uint32_t d = (key[k] >> shift) & dmask;
-            bool alone = false;
-            if (CLAIM) {
-                claim[d] = (uint8_t)lane;
-                __syncwarp();
-                alone = !__any_sync(0xffffffffu, claim[d] != (uint8_t)lane);
-            }
-            uint32_t r;
-            if (alone) {            // (warp-uniform) 32 different digits: every lane advances its own counter
-                r = wh[d];
-                wh[d] = (uint16_t)(r + 1u);
-            } else {
-                const uint32_t peers = digit_peers<BITS>(key[k], shift);
-                const uint32_t before = wh[d];                    // every peer reads the same counter ...
-                const uint32_t mine = __popc(peers & lane_lt);
-                __syncwarp();
-                if (mine == 0) wh[d] = (uint16_t)(before + __popc(peers));   // ... and the first peer advances it
-                r = before + mine;
-            }
+            const uint32_t before = wh[d];                    // every peer reads the same counter ...
+            const uint32_t mine = __popc(peers[k] & lane_lt);
             __syncwarp();
+            if (mine == 0) wh[d] = (uint16_t)(before + __popc(peers[k]));   // ... and the first peer advances it
+            __syncwarp();
+            const uint32_t r = before + mine;
             if (k & 1) rk[k >> 1] |= r << 16;
             else rk[k >> 1] = r;
         }
@@ -384,39 +382,67 @@ k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a, uint32
             } else {
 #pragma unroll
                 for (int j = 0; j < kOwn; j++) gs_st_status(my + j, epoch, GS_LOOKBACK_FLAG_AGG | total[j]);
-                constexpr int kLb = kOwn == 1 ? 4 : (kOwn == 2 ? 2 : 1);   // predecessors per round trip (8 loads in flight)
-                int64_t p = (int64_t)super - 1;
-                uint32_t pending = (1u << kOwn) - 1u;   // digits whose inclusive prefix has not been met yet
-                while (pending) {
-                    uint64_t v[kLb][kOwn];
+                if (kOwn == 1) {
+                    // one digit per thread (cluster of 8): kLb predecessors per round trip, consumed in order up to the
+                    // first one that carries an inclusive prefix
+                    constexpr int kLb = 8;
+                    int64_t p = (int64_t)super - 1;
+                    bool done = false;
+                    while (!done) {
+                        uint64_t v[kLb];
 #pragma unroll
-                    for (int q = 0; q < kLb; q++)
+                        for (int q = 0; q < kLb; q++)
+                            v[q] = (p - q >= 0) ? gs_ld_status(lb + (size_t)(p - q) * kBins) : (((uint64_t)epoch << 32) | GS_LOOKBACK_FLAG_INCL);
+                        int used = 0;
 #pragma unroll
-                        for (int j = 0; j < kOwn; j++)
-                            v[q][j] = (p - q >= 0) ? gs_ld_status(lb + (size_t)(p - q) * kBins + j)
-                                                   : (((uint64_t)epoch << 32) | GS_LOOKBACK_FLAG_INCL);
-                    int used = 0;
-#pragma unroll
-                    for (int q = 0; q < kLb; q++) {
-                        if (pending && used == q) {
-                            // a predecessor is consumed once ALL still-pending digits find it published
-                            bool ready = true;
-#pragma unroll
-                            for (int j = 0; j < kOwn; j++)
-                                if (((pending >> j) & 1u) && gs_status_flag(v[q][j], epoch) == 0u) ready = false;
-                            if (ready) {
-#pragma unroll
-                                for (int j = 0; j < kOwn; j++) {
-                                    if ((pending >> j) & 1u) {
-                                        excl[j] += (uint32_t)v[q][j] & GS_LOOKBACK_VALUE_MASK;
-                                        if (gs_status_flag(v[q][j], epoch) == 2u) pending &= ~(1u << j);
-                                    }
+                        for (int q = 0; q < kLb; q++) {
+                            if (!done && used == q) {
+                                const uint32_t fl = gs_status_flag(v[q], epoch);
+                                if (fl != 0u) {
+                                    excl[0] += (uint32_t)v[q] & GS_LOOKBACK_VALUE_MASK;
+                                    used = q + 1;
+                                    done = fl == 2u;
                                 }
-                                used = q + 1;
                             }
                         }
+                        p -= used;
                     }
-                    p -= used;
+                } else {
+                    // several digits per thread (smaller clusters): a predecessor is consumed once ALL still-pending
+                    // digits find it published
+                    constexpr int kLb = kOwn == 2 ? 2 : 1;   // predecessors per round trip
+                    int64_t p = (int64_t)super - 1;
+                    uint32_t pending = (1u << kOwn) - 1u;   // digits whose inclusive prefix has not been met yet
+                    while (pending) {
+                        uint64_t v[kLb][kOwn];
+#pragma unroll
+                        for (int q = 0; q < kLb; q++)
+#pragma unroll
+                            for (int j = 0; j < kOwn; j++)
+                                v[q][j] = (p - q >= 0) ? gs_ld_status(lb + (size_t)(p - q) * kBins + j)
+                                                       : (((uint64_t)epoch << 32) | GS_LOOKBACK_FLAG_INCL);
+                        int used = 0;
+#pragma unroll
+                        for (int q = 0; q < kLb; q++) {
+                            if (pending && used == q) {
+                                bool ready = true;
+#pragma unroll
+                                for (int j = 0; j < kOwn; j++)
+                                    if (((pending >> j) & 1u) && gs_status_flag(v[q][j], epoch) == 0u) ready = false;
+                                if (ready) {
+#pragma unroll
+                                    for (int j = 0; j < kOwn; j++) {
+                                        if ((pending >> j) & 1u) {
+                                            excl[j] += (uint32_t)v[q][j] & GS_LOOKBACK_VALUE_MASK;
+                                            if (gs_status_flag(v[q][j], epoch) == 2u) pending &= ~(1u << j);
+                                        }
+                                    }
+                                    used = q + 1;
+                                }
+                            }
+                        }
+                        p -= used;
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < kOwn; j++) gs_st_status(my + j, epoch, GS_LOOKBACK_FLAG_INCL | (excl[j] + total[j]));
@@ -458,7 +484,7 @@ struct DevInfo { int clusters[4] = {0, 0, 0, 0}; };
 std::mutex g_mu;
 DevInfo g_dev[64];
 std::atomic<int> g_cluster{kMaxCluster};
-std::atomic<int> g_claim{1};
+std::atomic<int> g_claim{0};
 
 using PassKernel = void (*)(uint32_t*, uint32_t*, uint32_t*, uint32_t*, const uint32_t*, uint32_t, const uint32_t*, uint32_t, uint32_t,
                             uint64_t*, uint32_t, uint32_t*, uint32_t*, uint32_t);
@@ -528,7 +554,7 @@ cudaError_t gs_sort_set_cluster(int cl) {
     return cudaSuccess;
 }
 int gs_sort_get_cluster() { return g_cluster.load(); }
-// tuning knob: try the collision-free fast path per row of wide (10/11-bit) digits before the ballots (default on)
+// tuning knob: try the collision-free fast path per row of wide (10/11-bit) digits before the ballots (default off)
 void gs_sort_set_claim(int on) { g_claim.store(on ? 1 : 0); }
 int gs_sort_get_claim() { return g_claim.load(); }
 int gs_sort_resident_clusters(int device) {
