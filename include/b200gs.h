@@ -341,6 +341,10 @@ B200GS_API int b200gs_hit_pos_by_alpha_range(const b200gs_hit* hits, uint64_t n,
 B200GS_API int b200gs_sort_pairs_device(b200gs_viewer* v, uint32_t* keys_dev, uint32_t* values_dev, uint64_t n,
                                         uint32_t bits);
 B200GS_API int b200gs_sort_pairs_host(b200gs_viewer* v, uint32_t* keys, uint32_t* values, uint64_t n, uint32_t bits);
+/* the same through the 11-bit-digit cluster sort that orders the bin ids of the binning stage (bits = 1..32) */
+B200GS_API int b200gs_sort_pairs_wide_device(b200gs_viewer* v, uint32_t* keys_dev, uint32_t* values_dev, uint64_t n,
+                                             uint32_t bits);
+B200GS_API int b200gs_sort_pairs_wide_host(b200gs_viewer* v, uint32_t* keys, uint32_t* values, uint64_t n, uint32_t bits);
 
 /* -------------------------------------------- host side (no GPU required)
  * Packing: GaussiansBuffer::update_range's host half (scene.rs:2069-2085). */

@@ -4,6 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import b200gs as G
 rng = np.random.default_rng(7)
+WIDE = os.environ.get("WIDE", "1") == "1"
 if len(sys.argv) > 1:
     G.set_tuning("sort.cluster", int(sys.argv[1]))
 ok = True
@@ -15,7 +16,7 @@ with G.Viewer(64, 64) as v:
                 keys = rng.uniform(0.8, 0.99, n).astype(np.float32).view(np.uint32)
             vals = np.arange(n, dtype=np.uint32)
             t0 = time.time()
-            k2, v2 = v.sort_pairs(keys, vals, bits)
+            k2, v2 = v.sort_pairs(keys, vals, bits, wide=WIDE)
             order = np.argsort(keys, kind="stable")
             good = np.array_equal(k2, keys[order]) and np.array_equal(v2, vals[order])
             ok &= good

@@ -627,10 +627,12 @@ class Viewer:
         _ck(lib().b200gs_last_timings(self.h, C.byref(t)))
         return t
 
-    def sort_pairs(self, keys, values, bits=32):
+    def sort_pairs(self, keys, values, bits=32, wide=False):
+        """Raw sort: the 8-bit-digit depth sort (bits 16 / 32), or with wide=True the 11-bit cluster sort (bits 1..32)."""
         keys = np.ascontiguousarray(keys, dtype=np.uint32).copy()
         values = np.ascontiguousarray(values, dtype=np.uint32).copy()
-        _ck(lib().b200gs_sort_pairs_host(self.h, _p(keys), _p(values), C.c_uint64(len(keys)), C.c_uint32(bits)))
+        fn = lib().b200gs_sort_pairs_wide_host if wide else lib().b200gs_sort_pairs_host
+        _ck(fn(self.h, _p(keys), _p(values), C.c_uint64(len(keys)), C.c_uint32(bits)))
         return keys, values
 
     def sort_pairs_device(self, keys_ptr, values_ptr, n, bits=32):

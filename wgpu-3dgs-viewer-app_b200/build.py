@@ -23,6 +23,7 @@ CU = {
     "preprocess.cu": ["-fmad=false"],
     "aux.cu": ["-fmad=false"],
     "sort.cu": [],
+    "sort_wide.cu": [],
     "bin.cu": [],
     "composite.cu": [],
     "api.cu": [],

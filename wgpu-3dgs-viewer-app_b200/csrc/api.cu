@@ -54,14 +54,14 @@ enum {  // viewer control block (u32 words), zeroed at the start of every render
     VC_TILE_TICKET = 201,  // tile-finish kernel: chunk ticket, finished-CTA counter
     VC_TILE_DONE = 202,
     VC_TILE_BUCKETS = 256, // 256: tiles per list-length bucket (launch order)
-    VC_TSORT_HIST = 512,   // 2 x 2048: 11-bit digit histograms of the tile ids (accumulated by the tile-finish kernel)
+    VC_TSORT_HIST = 512,   // 2 x 2048: digit histograms of the tile-sort keys (accumulated by the tile-finish kernel)
     VC_WORDS = 512 + 2 * 2048
 };
 enum {  // model control block layout
     MC_CTRL = 0,               // GS_CTRL_WORDS
     MC_SORT_TICKET = 16,       // 4
-    MC_SORT_HIST = 32,         // 3 x 2048: 11-bit digit histograms of the depth keys (accumulated by the preprocess kernel)
-    MC_WORDS = 32 + 3 * 2048
+    MC_SORT_HIST = 32,         // 4 x 256: digit histograms of the depth keys (accumulated by the preprocess kernel)
+    MC_WORDS = 32 + 1024
 };
 constexpr uint32_t kMaxModelsPerFrame = 64;
 
@@ -88,7 +88,6 @@ struct b200gs_model {
     uint64_t *lb_pre = nullptr, *lb_sort = nullptr;
     uint64_t arena_offset = 0;
     bool preprocessed = false, sorted = false;
-    bool hist_filled = false;   // the last preprocess accumulated the depth-key histograms
 };
 
 struct b200gs_viewer {
@@ -281,7 +280,7 @@ static int ensure_frame_buffers(b200gs_viewer* v) {
             TRY(dev_alloc(p, want, false, v->stream));
         }
         if (v->lb_tsort) CK(cudaFree(v->lb_tsort));
-        TRY(dev_alloc(&v->lb_tsort, gs_sort_lookback_words((uint32_t)want, 22), true, v->stream));
+        TRY(dev_alloc(&v->lb_tsort, gs_sort_lookback_words((uint32_t)want, 3), true, v->stream));
         v->entry_cap = want;
     }
     uint64_t lbw = (maxcap + 1023) / 1024 + 1;
@@ -642,7 +641,7 @@ static int model_create(b200gs_viewer* v, const char* key, uint64_t capacity, Gs
     if (rc == B200GS_OK) rc = dev_alloc(&m->idx, capacity, false, st);
     if (rc == B200GS_OK) rc = dev_alloc(&m->binword, capacity, false, st);
     if (rc == B200GS_OK) rc = dev_alloc(&m->lb_pre, (capacity + 255) / 256 + 1, true, st);
-    if (rc == B200GS_OK) rc = dev_alloc(&m->lb_sort, gs_sort_lookback_words((uint32_t)capacity, 32), true, st);
+    if (rc == B200GS_OK) rc = dev_alloc(&m->lb_sort, gs_sort_lookback_words((uint32_t)capacity, 4), true, st);
     if (rc != B200GS_OK) { free_model(m); return rc; }
     v->models.push_back(m);
     v->layout_dirty = true;
@@ -849,7 +848,6 @@ extern "C" int b200gs_model_preprocess(b200gs_model* m, int use_unedited) {
     a.ctrl = m->ctrl + MC_CTRL; a.lookback = m->lb_pre; a.epoch = ++v->epoch;
     a.keys = m->keys_a; a.idx = m->idx; a.splats = v->arena + m->arena_offset;
     a.sort_hist = m->ctrl + MC_SORT_HIST;
-    a.hist_filled = &m->hist_filled;
     a.binword = m->binword;
     if (v->timing) CK(cudaEventRecord(v->ev[0], v->stream));
     CK(gs_launch_preprocess(a, f, xf, v->num_sms, v->stream));
@@ -870,10 +868,11 @@ extern "C" int b200gs_model_sort(b200gs_model* m) {
     a.keys_a = m->keys_a; a.vals_a = m->vals_a; a.keys_b = m->keys_b; a.vals_b = m->vals_b;
     a.d_n = m->ctrl + MC_CTRL + GS_CTRL_VISIBLE; a.n_max = (uint32_t)m->cap;
     a.hist = m->ctrl + MC_SORT_HIST; a.lookback = m->lb_sort; a.epoch = ++v->epoch;
-    a.tickets = m->ctrl + MC_SORT_TICKET; a.key_bits = 32; a.hist_prefilled = m->hist_filled; a.vals_identity = true;
+    a.tickets = m->ctrl + MC_SORT_TICKET; a.passes = 4; a.hist_prefilled = true; a.vals_identity = true;
+    a.vote_mask = 0x3;  // depth keys: the two low bytes are spread, the two high bytes concentrated
     a.result_in_b = m->ctrl + MC_CTRL + GS_CTRL_SORT_IN_B;
     CK(gs_launch_sort(a, v->num_sms, v->stream));
-    v->launches += gs_sort_passes(a.key_bits) + (a.hist_prefilled ? 0 : 1);
+    v->launches += a.passes;
     if (v->timing) CK(cudaEventRecord(v->ev[2], v->stream));
     m->sorted = true;
     return B200GS_OK;
@@ -931,12 +930,11 @@ static int render_slabs(b200gs_viewer* v, b200gs_model* const* far_to_near, uint
             CK(gs_launch_bin(b, f, v->num_sms, st));
             v->launches += 1;
         }
-        // tile ids are sorted on as many bits as they have, 11 per onesweep pass (<= 2048 tiles: one pass)
-        uint32_t tbits = 1;
-        while ((1u << tbits) < n_tiles) tbits++;
+        // tile ids are sorted on 16 bits (2 onesweep passes); viewports with more than 65536 tiles take a third
+        const uint32_t tpasses = n_tiles > 65536u ? 3u : 2u;
         GsTileRangesArgs tr;
         tr.tile_count = v->tile_count; tr.ranges = v->ranges; tr.n_tiles = n_tiles;
-        tr.hist = v->vctrl + VC_TSORT_HIST; tr.key_bits = tbits; tr.entry_stat = v->stats + 2;
+        tr.hist = v->vctrl + VC_TSORT_HIST; tr.passes = tpasses; tr.entry_stat = v->stats + 2;
         tr.lookback = v->lb_tiles; tr.epoch = ++v->epoch;
         tr.ticket = v->vctrl + VC_TILE_TICKET; tr.done_ctr = v->vctrl + VC_TILE_DONE; tr.buckets = v->vctrl + VC_TILE_BUCKETS;
         CK(gs_launch_tile_ranges(tr, st));
@@ -944,7 +942,8 @@ static int render_slabs(b200gs_viewer* v, b200gs_model* const* far_to_near, uint
         s.keys_a = v->tk_a; s.vals_a = v->tv_a; s.keys_b = v->tk_b; s.vals_b = v->tv_b;
         s.d_n = v->vctrl + VC_ENTRY_TOTAL + n_seg; s.n_max = (uint32_t)v->entry_cap;
         s.hist = v->vctrl + VC_TSORT_HIST; s.lookback = v->lb_tsort; s.epoch = ++v->epoch;
-        s.tickets = v->vctrl + VC_TSORT_TICKET; s.key_bits = tbits; s.hist_prefilled = true; s.vals_identity = false;
+        s.tickets = v->vctrl + VC_TSORT_TICKET; s.passes = tpasses; s.hist_prefilled = true; s.vals_identity = false;
+        s.vote_mask = 0x1;  // tile ids: the low byte is spread, the row-band bytes concentrated
         s.result_in_b = v->vctrl + VC_TSORT_IN_B;
         CK(gs_launch_sort(s, v->num_sms, st));
         if (v->timing) CK(cudaEventRecord(v->ev_slab[sl][1], st));
@@ -955,7 +954,7 @@ static int render_slabs(b200gs_viewer* v, b200gs_model* const* far_to_near, uint
         c.state = v->pix_state; c.tile_done = v->tile_done; c.resume = sl > 0; c.last = last;
         CK(gs_launch_composite(c, f, st));
         if (v->timing) CK(cudaEventRecord(v->ev_slab[sl][2], st));
-        v->launches += gs_sort_passes(tbits) + 2;  // tile sort passes, tile finish, compositor
+        v->launches += tpasses + 2;  // tile sort passes, tile finish, compositor
     }
     if (v->timing) CK(cudaEventRecord(v->ev[4], st));
     v->rendered = true;
@@ -1288,9 +1287,10 @@ extern "C" int b200gs_query_hits(b200gs_viewer* v, b200gs_model* const* far_to_n
 }
 
 // ---------------------------------------------------------------------------- raw sort
-extern "C" int b200gs_sort_pairs_device(b200gs_viewer* v, uint32_t* keys_dev, uint32_t* values_dev, uint64_t n, uint32_t bits) {
+// raw sort entry points: bits = 16 / 32 run the 8-bit-digit sort (K2), `wide` != 0 the 11-bit cluster sort (K2w, any bits)
+static int sort_pairs_device(b200gs_viewer* v, uint32_t* keys_dev, uint32_t* values_dev, uint64_t n, uint32_t bits, bool wide) {
     REQUIRE(v && (keys_dev || n == 0) && (values_dev || n == 0), "null argument");
-    REQUIRE(bits == 16 || bits == 32, "bits must be 16 or 32");
+    REQUIRE(wide ? (bits >= 1 && bits <= 32) : (bits == 16 || bits == 32), "bits must be 16 or 32 (1..32 for the wide sort)");
     REQUIRE(n < 0x3fffff00ull, "too many elements");
     if (n == 0) return B200GS_OK;
     TRY(set_device(v));
@@ -1300,15 +1300,25 @@ extern "C" int b200gs_sort_pairs_device(b200gs_viewer* v, uint32_t* keys_dev, ui
     TRY(dev_alloc(&kb, n, false, st));
     TRY(dev_alloc(&vb, n, false, st));
     TRY(dev_alloc(&ctl, 1024 + 3 * 2048, true, st));
-    TRY(dev_alloc(&lb, gs_sort_lookback_words((uint32_t)n, bits), true, st));
+    TRY(dev_alloc(&lb, wide ? gs_sort_wide_lookback_words((uint32_t)n, bits) : gs_sort_lookback_words((uint32_t)n, bits / 8), true, st));
     uint32_t nn = (uint32_t)n;
     CK(cudaMemcpyAsync(ctl, &nn, 4, cudaMemcpyHostToDevice, st));
-    GsSortArgs a;
-    a.keys_a = keys_dev; a.vals_a = values_dev; a.keys_b = kb; a.vals_b = vb;
-    a.d_n = ctl; a.n_max = nn; a.hist = ctl + 1024; a.lookback = lb; a.epoch = ++v->epoch;
-    a.tickets = ctl + 8; a.key_bits = bits; a.hist_prefilled = false; a.vals_identity = false;
-    a.result_in_b = ctl + 16;
-    CK(gs_launch_sort(a, v->num_sms, st));
+    if (wide) {
+        GsSortWideArgs a;
+        a.keys_a = keys_dev; a.vals_a = values_dev; a.keys_b = kb; a.vals_b = vb;
+        a.d_n = ctl; a.n_max = nn; a.hist = ctl + 1024; a.lookback = lb; a.epoch = ++v->epoch;
+        a.tickets = ctl + 8; a.key_bits = bits; a.hist_prefilled = false; a.vals_identity = false;
+        a.result_in_b = ctl + 16;
+        CK(gs_launch_sort_wide(a, v->num_sms, st));
+    } else {
+        GsSortArgs a;
+        a.keys_a = keys_dev; a.vals_a = values_dev; a.keys_b = kb; a.vals_b = vb;
+        a.d_n = ctl; a.n_max = nn; a.hist = ctl + 1024; a.lookback = lb; a.epoch = ++v->epoch;
+        a.tickets = ctl + 8; a.passes = bits / 8; a.hist_prefilled = false; a.vals_identity = false;
+        a.vote_mask = 0xf;  // arbitrary keys: assume spread digits
+        a.result_in_b = ctl + 16;
+        CK(gs_launch_sort(a, v->num_sms, st));
+    }
     CK(cudaMemcpyAsync(v->h_small, ctl + 16, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (v->h_small[0]) {  // an odd number of passes ran: the result is in the scratch buffers
@@ -1319,8 +1329,14 @@ extern "C" int b200gs_sort_pairs_device(b200gs_viewer* v, uint32_t* keys_dev, ui
     cudaFree(kb); cudaFree(vb); cudaFree(ctl); cudaFree(lb);
     return B200GS_OK;
 }
+extern "C" int b200gs_sort_pairs_device(b200gs_viewer* v, uint32_t* keys_dev, uint32_t* values_dev, uint64_t n, uint32_t bits) {
+    return sort_pairs_device(v, keys_dev, values_dev, n, bits, false);
+}
+extern "C" int b200gs_sort_pairs_wide_device(b200gs_viewer* v, uint32_t* keys_dev, uint32_t* values_dev, uint64_t n, uint32_t bits) {
+    return sort_pairs_device(v, keys_dev, values_dev, n, bits, true);
+}
 
-extern "C" int b200gs_sort_pairs_host(b200gs_viewer* v, uint32_t* keys, uint32_t* values, uint64_t n, uint32_t bits) {
+static int sort_pairs_host(b200gs_viewer* v, uint32_t* keys, uint32_t* values, uint64_t n, uint32_t bits, bool wide) {
     REQUIRE(v && (keys || n == 0) && (values || n == 0), "null argument");
     if (n == 0) return B200GS_OK;
     TRY(set_device(v));
@@ -1329,7 +1345,7 @@ extern "C" int b200gs_sort_pairs_host(b200gs_viewer* v, uint32_t* keys, uint32_t
     TRY(dev_alloc(&dv, n, false, v->stream));
     CK(cudaMemcpyAsync(dk, keys, n * 4, cudaMemcpyHostToDevice, v->stream));
     CK(cudaMemcpyAsync(dv, values, n * 4, cudaMemcpyHostToDevice, v->stream));
-    int rc = b200gs_sort_pairs_device(v, dk, dv, n, bits);
+    int rc = sort_pairs_device(v, dk, dv, n, bits, wide);
     if (rc == B200GS_OK) {
         CK(cudaMemcpyAsync(keys, dk, n * 4, cudaMemcpyDeviceToHost, v->stream));
         CK(cudaMemcpyAsync(values, dv, n * 4, cudaMemcpyDeviceToHost, v->stream));
@@ -1337,4 +1353,10 @@ extern "C" int b200gs_sort_pairs_host(b200gs_viewer* v, uint32_t* keys, uint32_t
     }
     cudaFree(dk); cudaFree(dv);
     return rc;
+}
+extern "C" int b200gs_sort_pairs_host(b200gs_viewer* v, uint32_t* keys, uint32_t* values, uint64_t n, uint32_t bits) {
+    return sort_pairs_host(v, keys, values, n, bits, false);
+}
+extern "C" int b200gs_sort_pairs_wide_host(b200gs_viewer* v, uint32_t* keys, uint32_t* values, uint64_t n, uint32_t bits) {
+    return sort_pairs_host(v, keys, values, n, bits, true);
 }

@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(kThreads) k_bin(const uint32_t* __restrict__ s
 constexpr int kTfTiles = 64;
 __global__ void __launch_bounds__(256) k_tile_finish(uint32_t* __restrict__ replicas, uint32_t copies, uint32_t stride,
                                                      uint32_t n_tiles, uint32_t n_chunks, uint32_t* __restrict__ ranges,
-                                                     uint32_t* __restrict__ hist, uint32_t key_bits,
+                                                     uint32_t* __restrict__ hist, uint32_t passes,
                                                      unsigned long long* entry_stat, uint64_t* lookback, uint32_t epoch,
                                                      uint32_t* ticket, uint32_t* done_ctr, uint32_t* buckets) {
     __shared__ uint32_t s_part[4][kTfTiles];
@@ -368,8 +368,7 @@ __global__ void __launch_bounds__(256) k_tile_finish(uint32_t* __restrict__ repl
                 ranges[t] = run;
                 ranges[n_tiles + t] = run + cnt;
                 if (cnt)
-                    for (uint32_t p = 0; p * GS_SORT_DIGIT_BITS < key_bits; p++)
-                        atomicAdd(&hist[p * GS_SORT_BINS + ((t >> (GS_SORT_DIGIT_BITS * p)) & (GS_SORT_BINS - 1u))], cnt);
+                    for (uint32_t p = 0; p < passes; p++) atomicAdd(&hist[p * 256 + ((t >> (8 * p)) & 0xffu)], cnt);
                 const uint32_t bk = 255u - min(255u, (cnt + 255u) >> 8);   // bucket 0 = longest
                 tmp[t] = (bk << 24) | atomicAdd(&buckets[bk], 1u);
             }
@@ -457,7 +456,7 @@ size_t gs_tile_lookback_words(uint32_t n_tiles) { return (size_t)(n_tiles + kTfT
 cudaError_t gs_launch_tile_ranges(const GsTileRangesArgs& a, cudaStream_t st) {
     const uint32_t n_chunks = (a.n_tiles + kTfTiles - 1) / kTfTiles;
     k_tile_finish<<<n_chunks, 256, 0, st>>>(a.tile_count, gs_tile_count_copies(a.n_tiles), a.n_tiles, a.n_tiles, n_chunks,
-                                            a.ranges, a.hist, a.key_bits, a.entry_stat, a.lookback, a.epoch, a.ticket,
+                                            a.ranges, a.hist, a.passes, a.entry_stat, a.lookback, a.epoch, a.ticket,
                                             a.done_ctr, a.buckets);
     return cudaGetLastError();
 }

@@ -75,23 +75,41 @@ struct GsPreprocessArgs {
     uint32_t epoch;
     uint32_t* keys; uint32_t* idx; b200gs_splat* splats;
     uint32_t* binword;    // per compaction slot: bin word of the splat (gs_make_bin_word; consumed by k_bin)
-    uint32_t* sort_hist;  // 3 x 2048 digit histogram of the emitted keys, 11-bit digits (zeroed before launch), or null
-    bool* hist_filled;    // out (host): the kernel accumulates sort_hist (false: model too large for the per-CTA counters)
+    uint32_t* sort_hist;  // 4 x 256 digit histogram of the emitted keys (zeroed before launch), or null
 };
 cudaError_t gs_launch_preprocess(const GsPreprocessArgs& a, const GsFrame& f, const GsModelXf& m, int num_sms,
                                  cudaStream_t st);
 
-// Onesweep LSD radix sort of (key,value) u32 pairs on the low `key_bits` bits, 11 bits per pass (sort.cu);
-// n is read from the device (*d_n).
-#define GS_SORT_DIGIT_BITS 11u
-#define GS_SORT_BINS 2048u
-__host__ __device__ inline uint32_t gs_sort_passes(uint32_t key_bits) { return (key_bits + GS_SORT_DIGIT_BITS - 1u) / GS_SORT_DIGIT_BITS; }
+// K2 (sort.cu): onesweep LSD radix sort of (key,value) u32 pairs, 8-bit digits, CTA-local tiles; n is read from the
+// device (*d_n).  Sorts the depth keys.
 struct GsSortArgs {
     uint32_t* keys_a; uint32_t* vals_a;   // input, and final output
     uint32_t* keys_b; uint32_t* vals_b;   // scratch (ping-pong)
     const uint32_t* d_n; uint32_t n_max;  // element count on device, and its upper bound
+    uint32_t* hist;      // 4 x 256 global digit histogram (zeroed before launch unless prefilled)
+    uint64_t* lookback;  // passes x tiles x 256 status words (epoch-tagged, never cleared)
+    uint32_t epoch;
+    uint32_t* tickets;   // passes words, zeroed before launch
+    uint32_t passes;     // 1..4 (bits = 8*passes, starting at bit 0)
+    uint32_t* result_in_b; // device flag written by the last pass: 1 = the sorted data is in keys_b/vals_b
+    bool hist_prefilled; // histogram already accumulated by the producer
+    bool vals_identity;  // the first executed pass synthesises value = input position instead of reading vals_a
+    uint32_t vote_mask;  // bit p: pass p finds same-digit peers with ballots (spread digits) instead of MATCH.ANY (concentrated)
+};
+size_t gs_sort_lookback_words(uint32_t n_max, uint32_t passes);
+cudaError_t gs_launch_sort(const GsSortArgs& a, int num_sms, cudaStream_t st);
+
+// K2w (sort_wide.cu): the same sort with 11-bit digits and one thread-block cluster per 32768-key super-tile; sorts
+// the bin ids of the binning stage in ONE pass (<= 2048 bins).
+#define GS_SORT_DIGIT_BITS 11u
+#define GS_SORT_BINS 2048u
+__host__ __device__ inline uint32_t gs_sort_passes(uint32_t key_bits) { return (key_bits + GS_SORT_DIGIT_BITS - 1u) / GS_SORT_DIGIT_BITS; }
+struct GsSortWideArgs {
+    uint32_t* keys_a; uint32_t* vals_a;   // input, and final output
+    uint32_t* keys_b; uint32_t* vals_b;   // scratch (ping-pong)
+    const uint32_t* d_n; uint32_t n_max;  // element count on device, and its upper bound
     uint32_t* hist;      // passes x 2048 global digit histogram: digit p = (key >> 11 p) & 2047 (zeroed before launch unless prefilled)
-    uint64_t* lookback;  // gs_sort_lookback_words(n_max, key_bits) status words (epoch-tagged, never cleared)
+    uint64_t* lookback;  // gs_sort_wide_lookback_words(n_max, key_bits) status words (epoch-tagged, never cleared)
     uint32_t epoch;
     uint32_t* tickets;   // passes words, zeroed before launch
     uint32_t key_bits;   // 1..32: keys are < 2^key_bits; passes = ceil(key_bits / 11)
@@ -99,14 +117,13 @@ struct GsSortArgs {
     bool hist_prefilled; // histogram already accumulated by the producer
     bool vals_identity;  // the first executed pass synthesises value = input position instead of reading vals_a
 };
-size_t gs_sort_lookback_words(uint32_t n_max, uint32_t key_bits);
-cudaError_t gs_launch_sort(const GsSortArgs& a, int num_sms, cudaStream_t st);
+size_t gs_sort_wide_lookback_words(uint32_t n_max, uint32_t key_bits);
+cudaError_t gs_launch_sort_wide(const GsSortWideArgs& a, int num_sms, cudaStream_t st);
 cudaError_t gs_sort_set_cluster(int ctas_per_cluster);   // tuning knob: 8 (default), 4, 2, 1
 int gs_sort_get_cluster();
 void gs_sort_set_claim(int on);                          // tuning knob: collision-free fast path of the ranking (default off)
 int gs_sort_get_claim();
 int gs_sort_resident_clusters(int device);               // co-resident clusters of the pass kernel (0 until the first sort)
-
 // Binning: expand depth-sorted splats into (tile, splat) entries in depth order.
 struct GsBinArgs {
     const uint32_t* sorted_slot;   // per depth rank: slot of the splat in `splats` (compaction order)
@@ -135,7 +152,7 @@ struct GsTileRangesArgs {
     uint32_t* tile_count;          // replicated per-tile counters (cleared on the way)
     uint32_t* ranges;              // 4 x n_tiles: start, end, launch order, scratch
     uint32_t n_tiles;
-    uint32_t* hist; uint32_t key_bits; // passes x 2048 digit histogram of the tile ids, 11-bit digits (zeroed before launch)
+    uint32_t* hist; uint32_t passes;   // passes x 256 digit histogram of the tile ids (zeroed before launch)
     unsigned long long* entry_stat;    // += total entries (may be null)
     uint64_t* lookback; uint32_t epoch;   // gs_tile_lookback_words(n_tiles) status words (epoch-tagged, never cleared)
     uint32_t* ticket; uint32_t* done_ctr; uint32_t* buckets;   // 1 + 1 + 256 words, zeroed before launch

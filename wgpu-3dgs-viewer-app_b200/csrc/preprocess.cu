@@ -30,14 +30,6 @@
 namespace {
 
 constexpr int kChunk = 256;
-// Digit histograms of the emitted depth keys for the sort (11-bit digits: bits 0..10, 11..21, 22..31 -> 2048 + 2048 +
-// 1024 counters), kept per CTA as u16 counters packed two per shared-memory word (one 32-bit atomic adds 1 or 1 << 16).
-// A CTA therefore stops drawing chunks after kMaxChunksPerCta (65280 Gaussians: no counter can wrap); the launcher
-// falls back to the sort's own histogram kernel when the grid could not cover the model under that cap.
-constexpr int kHistCounters = 2048 + 2048 + 1024;
-constexpr int kHistWords = kHistCounters / 2;
-constexpr uint32_t kMaxChunksPerCta = 255;
-
 template <int SH> struct ShBytes { static constexpr int v = SH == 0 ? 180 : SH == 1 ? 92 : SH == 2 ? 48 : 0; };
 template <int COV> struct CovBytes { static constexpr int v = COV == 0 ? 24 : 12; };
 
@@ -248,7 +240,7 @@ __device__ __forceinline__ bool pre_tests(uint32_t i, uint32_t n, const uint32_t
 // selection / edit buffers, no selection query, Splat display, SH degree 3 with SH0 — and picks the instantiation in
 // which those uniform branches (and the loads of their operands) are compiled out.  Same arithmetic, same bits.
 template <int SH, int COV, bool FAST>
-__global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restrict__ recs, uint32_t n,
+__global__ void __launch_bounds__(kThreads, 3) k_preprocess(const uint8_t* __restrict__ recs, uint32_t n,
                                                          const uint32_t* __restrict__ mask, uint32_t* selection,
                                                          const b200gs_edit_pod* __restrict__ edits,
                                                          const __grid_constant__ GsFrame f,
@@ -268,7 +260,7 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
     uint32_t* s_chunk = reinterpret_cast<uint32_t*>(bars + NSTAGE);  // NSTAGE
     uint32_t* s_wcount_all = s_chunk + NSTAGE + 1;                   // 4 x 8 warp counts (by sequence number & 3)
     uint32_t* s_base_all = s_wcount_all + 32;                        // 4 x 8 output bases of the warps (by sequence number & 3)
-    uint32_t* s_hist = s_base_all + 32;                              // kHistWords (only if sort_hist): u16 counters, two per word
+    uint32_t* s_hist = s_base_all + 32;                              // 4 x 256 (only if sort_hist)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t nchunks = (n + kChunk - 1) / kChunk;
@@ -283,6 +275,14 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
         uint32_t bytes = (cnt * RB + 15u) & ~15u;  // buffer is padded, see api.cu
         gs_mbar_expect_tx(&bars[stage], bytes);
         gs_tma_load_1d(stage_mem + (size_t)stage * STAGE_BYTES, recs + (size_t)c * STAGE_BYTES, bytes, &bars[stage]);
+        // Chunks are handed out in order, so chunk c + 2 * gridDim.x is what SOME CTA will draw two rounds from now: pull
+        // it into L2 today, and that CTA's bulk copy then completes in an L2 round trip instead of a DRAM one (the
+        // stage refill is issued only one heavy phase before the data is needed; 14 % of warp time used to wait on it).
+        const uint32_t cp = c + 2u * gridDim.x;
+        if (cp < nchunks) {
+            const uint32_t pb = (min((uint32_t)kChunk, n - cp * kChunk) * RB) & ~15u;
+            if (pb) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(recs + (size_t)cp * STAGE_BYTES), "r"(pb) : "memory");
+        }
     };
 
     if (tid == kChunk) {
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
         }
     }
     if (sort_hist)
-        for (int i = tid; i < kHistWords; i += kThreads) s_hist[i] = 0;
+        for (int i = tid; i < 1024; i += kThreads) s_hist[i] = 0;
     __syncthreads();
 
     // The CTA works through the chunks it drew, j = 0, 1, 2, ... (stage j % 3).  The cull/count of
@@ -321,7 +321,6 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
             if (lane == 0) gs_lookback_publish(lookback, epoch, c, total);
             return total;
         };
-        uint32_t drawn = NSTAGE;   // chunks drawn by this CTA so far (see kMaxChunksPerCta)
         uint32_t c = s_chunk[0];
         uint32_t woff = 0, woff_next = 0;
         uint32_t total = c < nchunks ? publish(0, c, woff) : 0u;
@@ -333,8 +332,7 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
                 // chunk j-1's stage was read for the last time in its heavy phase: refill it
                 bar_sync(kBarFree + (int)((j - 1) & 3u));
                 if (lane == 0) {
-                    const uint32_t c2 = (!sort_hist || drawn < kMaxChunksPerCta) ? atomicAdd(&ctrl[GS_CTRL_TICKET], 1u) : 0xffffffffu;
-                    drawn++;
+                    const uint32_t c2 = atomicAdd(&ctrl[GS_CTRL_TICKET], 1u);
                     s_chunk[(j - 1) % NSTAGE] = c2;
                     issue((int)((j - 1) % NSTAGE), c2);
                 }
@@ -374,26 +372,27 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
             bar_arrive(kBarCounts + (int)(j & 3u));
             return r;
         };
-        // The outputs of chunk it are written one phase 1 LATER (after phase 1 of chunk it+2, at the start of
-        // iteration it+1): the chunk's output base needs the counts of all 8 warps and the control warp's
-        // look-back, and a warp that runs ahead of its CTA would otherwise sit at the base barrier.
+        // The outputs of chunk it are written TWO iterations later (after phase 1 of chunk it+3, at the start of
+        // iteration it+2): the chunk's output base needs the counts of all 8 warps and the control warp's
+        // look-back; written one iteration later, 11 % of warp time still sat at the base barrier.
         struct Pending { bool valid, vis; uint32_t seq, ballot, key, index, bw; uint4 q0, q1; };
-        Pending pend;
+        Pending pend, pend2;   // pend: chunk it-1, pend2: chunk it-2 (the one written in iteration it)
         pend.valid = false; pend.vis = false; pend.seq = pend.ballot = pend.key = pend.index = pend.bw = 0;
         pend.q0 = pend.q1 = make_uint4(0, 0, 0, 0);
-        auto flush = [&]() {
-            if (!pend.valid) return;   // (CTA-uniform)
-            bar_sync(kBarBase + (int)(pend.seq & 3u));
-            if (pend.vis) {
-                const uint32_t off = s_base_all[(pend.seq & 3u) * 8 + warp] + __popc(pend.ballot & ((1u << lane) - 1u));
-                keys[off] = pend.key;
-                idx[off] = pend.index;
+        pend2 = pend;
+        auto flush = [&](Pending& pd) {
+            if (!pd.valid) return;   // (CTA-uniform)
+            bar_sync(kBarBase + (int)(pd.seq & 3u));
+            if (pd.vis) {
+                const uint32_t off = s_base_all[(pd.seq & 3u) * 8 + warp] + __popc(pd.ballot & ((1u << lane) - 1u));
+                keys[off] = pd.key;
+                idx[off] = pd.index;
                 uint4* sp = reinterpret_cast<uint4*>(splats + off);
-                sp[0] = pend.q0;
-                sp[1] = pend.q1;
-                binword[off] = pend.bw;
+                sp[0] = pd.q0;
+                sp[1] = pd.q1;
+                binword[off] = pd.bw;
             }
-            pend.valid = false;
+            pd.valid = false;
         };
         Phase1 cur = phase1(0);
         for (uint32_t it = 0;; it++) {
@@ -402,7 +401,8 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
             if (c >= nchunks) break;
             // chunk it+1 is culled and counted BEFORE the heavy phase of chunk it (see above)
             const Phase1 nxt = phase1(it + 1);
-            flush();   // chunk it-1
+            flush(pend2);   // chunk it-2: its base has had two heavy phases to resolve
+            pend2 = pend;
 
             const uint32_t i = c * kChunk + tid;
             const uint32_t* w = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)stage * STAGE_BYTES) + tid * RW;
@@ -569,26 +569,29 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
             }
             bar_arrive(kBarFree + (int)(it & 3u));  // every read of this stage's shared memory is done
 
-            // digit histograms of the emitted keys for the depth sort (saves its histogram kernel)
+            // digit histograms of the emitted keys for the depth sort (saves its histogram kernel);
+            // warp-aggregated: depth keys share their top bytes
             if (sort_hist && ballot) {
                 const uint32_t key = __float_as_uint(nz);
-                // the top digit is usually the same for the whole warp: one vote and one atomic instead of a match
                 const int first = __ffs((int)ballot) - 1;
-                const uint32_t d2 = key >> 22;
-                const uint32_t d2_first = __shfl_sync(0xffffffffu, d2, first);   // (every lane takes part: not inside the ||)
-                const bool uniform = __all_sync(0xffffffffu, !vis || d2 == d2_first);
-                if (uniform) {
-                    if (lane == first) atomicAdd(&s_hist[2048 + (d2 >> 1)], (uint32_t)__popc(ballot) << (16u * (d2 & 1u)));
-                } else if (vis) {
-                    const uint32_t peers = __match_any_sync(ballot, d2);
-                    if (lane == __ffs((int)peers) - 1) atomicAdd(&s_hist[2048 + (d2 >> 1)], (uint32_t)__popc(peers) << (16u * (d2 & 1u)));
+                const uint32_t key0 = __shfl_sync(0xffffffffu, key, first);
+#pragma unroll
+                for (int p = 3; p >= 2; p--) {
+                    const uint32_t dgt = (key >> (8 * p)) & 0xffu;
+                    // the top bytes are usually the same for the whole warp: one vote instead of a match
+                    const bool uniform = __all_sync(0xffffffffu, !vis || dgt == ((key0 >> (8 * p)) & 0xffu));
+                    if (uniform) {
+                        if (lane == first) atomicAdd(&s_hist[p * 256 + dgt], (uint32_t)__popc(ballot));
+                    } else if (vis) {
+                        const uint32_t peers = __match_any_sync(ballot, dgt);
+                        if (lane == __ffs((int)peers) - 1) atomicAdd(&s_hist[p * 256 + dgt], (uint32_t)__popc(peers));
+                    }
                 }
-                // the two low digits are spread: ~32 distinct values among 32 lanes, where MATCH.ANY costs more ADU
-                // cycles than 32 fire-and-forget shared-memory atomics cost the LSU
+                // the low bytes are spread: ~30 distinct values among 32 lanes, where MATCH.ANY costs more ADU
+                // cycles than 32 fire-and-forget shared-memory atomics cost the (idle) LSU
                 if (vis) {
-                    const uint32_t d1 = (key >> 11) & 2047u, d0 = key & 2047u;
-                    atomicAdd(&s_hist[1024 + (d1 >> 1)], 1u << (16u * (d1 & 1u)));
-                    atomicAdd(&s_hist[d0 >> 1], 1u << (16u * (d0 & 1u)));
+                    atomicAdd(&s_hist[256 + ((key >> 8) & 0xffu)], 1u);
+                    atomicAdd(&s_hist[key & 0xffu], 1u);
                 }
             }
 
@@ -596,14 +599,14 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(const uint8_t* __restri
             pend.key = __float_as_uint(nz); pend.index = i; pend.bw = bw; pend.q0 = q0; pend.q1 = q1;
             cur = nxt;
         }
-        flush();
+        flush(pend2);
+        flush(pend);
     }
     if (sort_hist) {
         __syncthreads();
-        for (int i = tid; i < kHistWords; i += kThreads) {
-            const uint32_t w = s_hist[i];
-            if (w & 0xffffu) atomicAdd(&sort_hist[2 * i], w & 0xffffu);
-            if (w >> 16) atomicAdd(&sort_hist[2 * i + 1], w >> 16);
+        for (int i = tid; i < 1024; i += kThreads) {
+            const uint32_t cnt = s_hist[i];
+            if (cnt) atomicAdd(&sort_hist[i], cnt);
         }
     }
     if (n == 0 && blockIdx.x == 0 && tid == 0) ctrl[GS_CTRL_VISIBLE] = 0;
@@ -617,7 +620,7 @@ template <int SH, int COV, bool FAST>
 cudaError_t launch_t(const GsPreprocessArgs& a, const GsFrame& f, const GsModelXf& m, int num_sms, cudaStream_t st) {
     constexpr int RB = 16 + ShBytes<SH>::v + CovBytes<COV>::v;
     constexpr int NSTAGE = 3;
-    constexpr size_t smem = (size_t)NSTAGE * kChunk * RB + NSTAGE * 8 + (NSTAGE + 1) * 4 + 32 * 4 + 32 * 4 + kHistWords * 4 + 16;
+    constexpr size_t smem = (size_t)NSTAGE * kChunk * RB + NSTAGE * 8 + (NSTAGE + 1) * 4 + 32 * 4 + 32 * 4 + 1024 * 4 + 16;
     auto kern = k_preprocess<SH, COV, FAST>;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -640,12 +643,8 @@ cudaError_t launch_t(const GsPreprocessArgs& a, const GsFrame& f, const GsModelX
     uint32_t grid = (uint32_t)(blocks_per_sm * num_sms);
     if (grid > nchunks) grid = nchunks;
     if (grid < 1) grid = 1;
-    // the per-CTA u16 histogram counters cap a CTA at kMaxChunksPerCta chunks: a model the grid cannot cover under
-    // that cap is preprocessed without histograms (the sort then runs its own histogram kernel)
-    const bool fill_hist = a.sort_hist != nullptr && (uint64_t)nchunks <= (uint64_t)grid * kMaxChunksPerCta;
-    if (a.hist_filled) *a.hist_filled = fill_hist;
     kern<<<grid, kThreads, smem, st>>>(a.recs, a.n, a.mask, a.selection, a.edits, f, m, a.ctrl, a.lookback, a.epoch,
-                                       a.keys, a.idx, a.splats, a.binword, fill_hist ? a.sort_hist : nullptr);
+                                       a.keys, a.idx, a.splats, a.binword, a.sort_hist);
     return cudaGetLastError();
 }
 
