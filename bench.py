@@ -229,8 +229,7 @@ def extra_config_times(G, local_rank):
         v.enable_timings(True, False)
         for c in cams[:14]:
             v.update_camera(c)
-            order = v.order_models(models, np.array(centers, np.float32))
-            v.render_frame([models[i] for i in order])
+            v.render_frame(v.order_models(models, np.array(centers, np.float32)))   # (returns the models, farthest first)
             tm = v.last_timings()
             rows.append((tm.total_ms, tm.bin_ms, tm.composite_ms, tm.visible, tm.tile_entries))
         r = np.median(np.array(rows[2:], np.float64), axis=0)
@@ -509,7 +508,10 @@ def run_ours(a, rank, world, local_rank):
     torch.cuda.empty_cache()
     if rank == 0:
         if world == 1 and not a.no_extra:
-            out["extra_configs"] = extra_config_times(G, local_rank)
+            try:
+                out["extra_configs"] = extra_config_times(G, local_rank)
+            except Exception as e:  # noqa: BLE001  (a side table must never cost the headline line)
+                out["extra_configs"] = {"error": repr(e)}
         if world == 1 and not a.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(a, packed, block)
         print(json.dumps(out))
