@@ -217,12 +217,8 @@ B200GS_API int b200gs_query_texture_upload(b200gs_viewer* v, const uint8_t* texe
 B200GS_API int b200gs_query_texture_download(b200gs_viewer* v, uint8_t* texels, size_t cap);
 /* headless clear colour (premultiplied RGBA in 0..1); default transparent black */
 B200GS_API int b200gs_set_background(b200gs_viewer* v, const float rgba[4]);
-/* depth slabs: the frame is binned + composited in n+1 slabs of depth ranks split at these
- * increasing fractions of the nearest model's visible count; tiles finished by a nearer slab take no
- * entries from farther ones.  Default n = 0 (single slab: on the benchmark scene too few tiles finish
- * early for the extra passes to pay off).  The image does not depend on the setting. */
-B200GS_API int b200gs_set_depth_slabs(b200gs_viewer* v, const float* fractions, uint32_t n);
-/* capacity of the (tile, splat) entry list per frame; default 8 x total Gaussian capacity */
+/* capacity of the (bin, splat) entry list per frame (one entry per 32x32-pixel bin a splat touches); default 8 x total
+ * Gaussian capacity */
 B200GS_API int b200gs_set_tile_entry_capacity(b200gs_viewer* v, uint64_t entries);
 /* record per-stage CUDA-event times (and optionally count splat evaluations) for
  * b200gs_last_timings; off by default */

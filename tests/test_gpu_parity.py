@@ -392,7 +392,7 @@ def test_huge_splat_and_tile_capacity_overflow(G, O):
         v.update_camera(cam)
         img = v.render_frame_host([m]).copy()
         t = v.last_timings()
-        assert t.tile_entries == 2 * ((W + 15) // 16) * ((H + 15) // 16) and t.overflow == 0
+        assert t.tile_entries == 2 * ((W + 31) // 32) * ((H + 31) // 32) and t.overflow == 0   # one entry per 32-pixel bin
         f = O.make_frame(cam.view(), cam.projection(np.float32(W) / np.float32(H)), W, H)
         ref, _, _ = O.render_frame(f, [O.ModelRef(3, 0, G.pack_gaussians(3, 0, g), 2)])
         assert_image_close(img, ref)
@@ -403,11 +403,11 @@ def test_huge_splat_and_tile_capacity_overflow(G, O):
         assert v.last_timings().overflow == 1
 
 
-def test_viewport_with_more_than_65536_tiles(G, O):
-    """4112 x 4112 pixels = 257 x 257 = 66049 tiles: tile ids need 17 bits, so the tile sort takes a third
-    onesweep pass and bin words carry 20-bit tile ids; a screen-filling splat exercises the huge class (rows
-    of more than 32 tiles), the scene the small / medium classes."""
-    W = H = 4112
+def test_viewport_with_more_than_65536_bins(G, O):
+    """8208 x 8208 pixels = 257 x 257 = 66049 bins of 32 pixels: bin ids need 17 bits, so the bin sort takes a third
+    onesweep pass; a screen-filling splat exercises the huge class (a side of more than 32 tiles), the scene the
+    regular one."""
+    W = H = 8208
     n = 20_000
     g = G.gaussian_from_ply(G.synth_scene(SEED_100K, n))
     big = make_gaussians(G.GAUSSIAN, [[0, 0, 0.2]], scale=2.0, color=(40, 160, 220, 90))
@@ -695,28 +695,26 @@ def test_hit_query_list_and_positions(G, O):
                     assert abs(h["alpha"] - d[int(h["index"])][1]) < 2e-3 and h["depth"] == np.float32(d[int(h["index"])][2])
 
 
-def test_depth_slabs_do_not_change_the_image(G, O):
-    """b200gs_set_depth_slabs: binning + compositing in depth slabs with finished-tile skipping is an
-    execution strategy only — same bytes as the single-slab frame, for one and for several models."""
-    W, H, n = 640, 360, 120_000
+def test_partial_bins_and_quadrants_at_odd_viewports(G, O):
+    """Binning is per 32x32-pixel bin, compositing per 16x16 tile (a quadrant of its bin, fed through the quadrant mask of
+    every entry): viewports whose last bin column / row is partial — down to a single pixel, with whole quadrants
+    outside — must match the oracle like any other, for one and for two layered models."""
+    n = 60_000
     cam = G.OrbitCamera.orbit(3.0, 10.0, 40.0)
-    with G.Viewer(W, H) as v:
-        ms = []
-        for k, seed in enumerate((0xB2000082, 0xB2000083)):
-            m = v.add_model("m%d" % k, n)
-            m.upload_packed(0, G.pack_gaussians(2, 1, G.gaussian_from_ply(G.synth_scene(seed, n))))
-            m.set_transform((0.5 * k, 0, 0), G.quat_from_euler_zyx_deg([0, 20 * k, 0]), (1, 1, 1))
-            ms.append(m)
-        v.update_camera(cam)
-        v.enable_timings(True, True)
-        for models in ([ms[0]], ms):
-            v.set_depth_slabs([])
-            ref = v.render_frame_host(models).copy()
-            e0 = v.last_timings().tile_entries
-            for fr in ([0.125], [0.05, 0.3], [0.02, 0.1, 0.5]):
-                v.set_depth_slabs(fr)
-                img = v.render_frame_host(models).copy()
-                assert np.array_equal(img, ref), fr
-                assert v.last_timings().tile_entries <= e0
-        with pytest.raises(G.GsError):
-            v.set_depth_slabs([0.5, 0.25])
+    packs = [G.pack_gaussians(2, 1, G.gaussian_from_ply(G.synth_scene(seed, n))) for seed in (0xB2000082, 0xB2000083)]
+    for W, H in ((333, 217), (353, 97), (64, 33), (17, 48)):
+        with G.Viewer(W, H) as v:
+            ms = []
+            for k in range(2):
+                m = v.add_model("m%d" % k, n)
+                m.upload_packed(0, packs[k])
+                m.set_transform((0.5 * k, 0, 0), G.quat_from_euler_zyx_deg([0, 20 * k, 0]), (1, 1, 1))
+                ms.append(m)
+            v.update_camera(cam)
+            f = O.make_frame(cam.view(), cam.projection(np.float32(W) / np.float32(H)), W, H)
+            oms = [O.ModelRef(2, 1, packs[k], n, pos=(0.5 * k, 0, 0), quat=G.quat_from_euler_zyx_deg([0, 20 * k, 0])) for k in range(2)]
+            for sel in ([0], [0, 1]):
+                img = v.render_frame_host([ms[i] for i in sel]).copy()
+                assert v.last_timings().overflow == 0
+                ref, _, _ = O.render_frame(f, [oms[i] for i in sel])
+                assert_image_close(img, ref)

@@ -18,7 +18,6 @@ with G.Viewer(W, H) as v:
     v.update_query(G.query_pod(G.QUERY_RECT, G.SELECT_ADD, (50, 40), (200, 150)))
     for i, cam in enumerate(G.view_batch()[:3]):
         v.update_camera(cam)
-        v.set_depth_slabs([0.1] if i == 1 else [])
         img = v.render_frame_host(ms)
     hits = v.query_hits(ms, 160, 90)
     k, val = v.sort_pairs(np.arange(10000, dtype=np.uint32)[::-1].copy(), np.arange(10000, dtype=np.uint32))

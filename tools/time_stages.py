@@ -18,8 +18,6 @@ with G.Viewer(W, H) as v:
     m = v.add_model("scene", N)
     m.upload_packed(0, packed)
     v.enable_timings(True, False)
-    if os.environ.get("SLABS") is not None:
-        v.set_depth_slabs([float(x) for x in os.environ["SLABS"].split(",") if x])
     rows = []
     for i in range(frames):
         v.update_camera(cams[i % 8])
@@ -27,6 +25,6 @@ with G.Viewer(W, H) as v:
         t = v.last_timings()
         rows.append((t.preprocess_ms, t.sort_ms, t.bin_ms, t.composite_ms, t.total_ms))
     r = np.median(np.array(rows[4:]), 0)
-    print("slabs=%r" % os.environ.get("SLABS"), "entries", t.tile_entries, "sort.cluster", v.info("sort.cluster"),
+    print("entries", t.tile_entries, "sort.cluster", v.info("sort.cluster"),
           "resident clusters", v.info("sort.resident_clusters"))
     print("median ms: pre %.3f sort %.3f bin %.3f comp %.3f total %.3f" % tuple(r))

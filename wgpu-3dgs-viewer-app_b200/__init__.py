@@ -516,10 +516,6 @@ class Viewer:
         _ck(lib().b200gs_get_info(self.h, name.encode(), C.byref(out)))
         return int(out.value)
 
-    def set_depth_slabs(self, fractions):
-        fr = np.ascontiguousarray(fractions, dtype=np.float32)
-        _ck(lib().b200gs_set_depth_slabs(self.h, _p(fr) if len(fr) else None, C.c_uint32(len(fr))))
-
     def set_tile_entry_capacity(self, entries):
         _ck(lib().b200gs_set_tile_entry_capacity(self.h, C.c_uint64(entries)))
 

@@ -113,12 +113,8 @@ struct b200gs_viewer {
     uint32_t* ranges = nullptr;
     uint32_t* tile_count = nullptr;        // per tile: entries written by the binning kernel (cleared by the tile scan)
     uint32_t ranges_tiles = 0;
-    uint8_t* tile_done = nullptr;          // per tile: finished by a nearer depth slab
-    float4* pix_state = nullptr;           // per pixel (Cr, Cg, Cb, T) between depth slabs
-    size_t pix_state_px = 0;
     unsigned long long* stats = nullptr;   // [0] evals, [1] staged entries, [2] tile entries (per frame)
-    std::vector<uint32_t> slab_q;          // depth-slab boundaries as 16.16 fractions of V (default: none = one slab)
-    cudaEvent_t ev_slab[4][3] = {};        // per slab: start, after binning, after compositing
+    cudaEvent_t ev_bin[3] = {};            // render: start, after binning + bin sort, after compositing
     uint32_t* vctrl = nullptr;
     uint8_t* image = nullptr;  // internal RGBA8 targets for render_frame_host (2 slots, image + image_bytes)
     size_t image_bytes = 0;
@@ -128,7 +124,6 @@ struct b200gs_viewer {
     uint64_t launches = 0;     // kernels launched by this viewer (b200gs_launch_count)
     uint32_t epoch = 0;
     bool timing = false, count_evals = false, rendered = false;
-    uint32_t last_slabs = 1;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     b200gs_timings last = {};
     uint32_t* h_small = nullptr;  // pinned scratch (words 0..15: downloads; 32..33: overflow flag of the two host-frame slots)
@@ -184,6 +179,8 @@ static GsFrame make_frame(const b200gs_viewer* v) {
     memcpy(f.bg, v->bg, 16);
     f.tiles_x = (v->W + GS_TILE - 1) / GS_TILE;
     f.tiles_y = (v->H + GS_TILE - 1) / GS_TILE;
+    f.bins_x = (v->W + GS_BIN - 1) / GS_BIN;
+    f.bins_y = (v->H + GS_BIN - 1) / GS_BIN;
     f.query = v->query;
     f.query_tex = v->query_tex;
     f.query_tex_w = v->query_tex_w;
@@ -231,24 +228,16 @@ static int dev_alloc(T** p, size_t count, bool zero, cudaStream_t st) {
 
 // (re)build the viewer-level buffers whose size depends on the set of models / the viewport
 static int ensure_frame_buffers(b200gs_viewer* v) {
-    const uint32_t n_tiles = ((v->W + GS_TILE - 1) / GS_TILE) * ((v->H + GS_TILE - 1) / GS_TILE);
+    const uint32_t n_tiles = ((v->W + GS_BIN - 1) / GS_BIN) * ((v->H + GS_BIN - 1) / GS_BIN);   // 32-pixel bins
     if (v->ranges_tiles < n_tiles) {
         CK(cudaStreamSynchronize(v->stream));
         if (v->ranges) CK(cudaFree(v->ranges));
         TRY(dev_alloc(&v->ranges, (size_t)n_tiles * 4, true, v->stream));
         if (v->lb_tiles) CK(cudaFree(v->lb_tiles));
         TRY(dev_alloc(&v->lb_tiles, gs_tile_lookback_words(n_tiles), true, v->stream));
-        if (v->tile_done) CK(cudaFree(v->tile_done));
-        TRY(dev_alloc(&v->tile_done, (size_t)n_tiles, true, v->stream));
         if (v->tile_count) CK(cudaFree(v->tile_count));
         TRY(dev_alloc(&v->tile_count, gs_tile_count_words(n_tiles), true, v->stream));
         v->ranges_tiles = n_tiles;
-    }
-    if (v->pix_state_px < (size_t)v->W * v->H) {
-        CK(cudaStreamSynchronize(v->stream));
-        if (v->pix_state) CK(cudaFree(v->pix_state));
-        TRY(dev_alloc(&v->pix_state, (size_t)v->W * v->H, false, v->stream));
-        v->pix_state_px = (size_t)v->W * v->H;
     }
     const size_t img = (size_t)v->W * v->H * 4;
     if (v->image_bytes < img) {
@@ -361,8 +350,7 @@ extern "C" int b200gs_viewer_create(int device, uint32_t sh, uint32_t cov3d, uin
     if (e == cudaSuccess) e = cudaMallocHost((void**)&v->h_small, 4096);
     if (e == cudaSuccess) e = cudaMalloc((void**)&v->stats, 64);
     if (e == cudaSuccess) e = cudaMemsetAsync(v->stats, 0, 64, v->stream);
-    for (int k = 0; k < 4 && e == cudaSuccess; k++)
-        for (int j = 0; j < 3 && e == cudaSuccess; j++) e = cudaEventCreate(&v->ev_slab[k][j]);
+    for (int j = 0; j < 3 && e == cudaSuccess; j++) e = cudaEventCreate(&v->ev_bin[j]);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) {
         e = cudaEventCreateWithFlags(&v->ev_rendered[i], cudaEventDisableTiming);
@@ -396,7 +384,7 @@ extern "C" int b200gs_viewer_destroy(b200gs_viewer* v) {
     if (v->stream) cudaStreamSynchronize(v->stream);
     for (auto* m : v->models) free_model(m);
     void* ps[] = {v->arena, v->tk_a, v->tv_a, v->tk_b, v->tv_b, v->lb_bin, v->lb_tsort, v->lb_tiles, v->tile_count,
-                  v->ranges, v->vctrl, v->image, v->tile_done, v->pix_state, v->stats};
+                  v->ranges, v->vctrl, v->image, v->stats};
     for (void* p : ps)
         if (p) cudaFree(p);
     if (v->h_small) cudaFreeHost(v->h_small);
@@ -408,9 +396,8 @@ extern "C" int b200gs_viewer_destroy(b200gs_viewer* v) {
     if (v->query_tex) cudaFree(v->query_tex);
     for (auto& e : v->ev)
         if (e) cudaEventDestroy(e);
-    for (auto& row : v->ev_slab)
-        for (auto& e : row)
-            if (e) cudaEventDestroy(e);
+    for (auto& e : v->ev_bin)
+        if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) {
         if (v->ev_rendered[i]) cudaEventDestroy(v->ev_rendered[i]);
         if (v->ev_copied[i]) cudaEventDestroy(v->ev_copied[i]);
@@ -523,19 +510,6 @@ extern "C" int b200gs_query_texture_download(b200gs_viewer* v, uint8_t* texels, 
 extern "C" int b200gs_set_background(b200gs_viewer* v, const float rgba[4]) {
     REQUIRE(v && rgba, "null argument");
     memcpy(v->bg, rgba, 16);
-    return B200GS_OK;
-}
-extern "C" int b200gs_set_depth_slabs(b200gs_viewer* v, const float* fractions, uint32_t n) {
-    REQUIRE(v && (fractions || n == 0), "null argument");
-    REQUIRE(n <= 3, "at most 3 slab boundaries (4 slabs)");
-    std::vector<uint32_t> q;
-    for (uint32_t i = 0; i < n; i++) {
-        REQUIRE(fractions[i] > 0.0f && fractions[i] < 1.0f, "fractions must lie in (0, 1)");
-        const uint32_t x = (uint32_t)(fractions[i] * 65536.0f);
-        REQUIRE(x > (q.empty() ? 0u : q.back()), "fractions must increase");
-        q.push_back(x);
-    }
-    v->slab_q = q;
     return B200GS_OK;
 }
 extern "C" int b200gs_set_tile_entry_capacity(b200gs_viewer* v, uint64_t entries) {
@@ -878,84 +852,65 @@ extern "C" int b200gs_model_sort(b200gs_model* m) {
     return B200GS_OK;
 }
 
-// One frame = one or more DEPTH SLABS.  Slab 0 holds the nearest ranks of the nearest model; each
-// slab is binned, tile-sorted and composited on its own, and tiles whose pixels all reached
-// T < eps are marked done so that later (farther) slabs emit no entries for them — most of a tile
-// list is occluded, so most of the binning work disappears.  Pixel state is carried between slabs,
-// the arithmetic per pixel is unchanged (same splats, same order): the image is bit-identical to
-// the single-slab one.
-static int render_slabs(b200gs_viewer* v, b200gs_model* const* far_to_near, uint32_t n_models, void* rgba8_out,
-                        size_t pitch, const std::vector<uint32_t>& slab_q) {
+// Binning (nearest model first: its splats come first in every bin's front-to-back list), per-bin ranges + launch order,
+// the bin sort, and the compositor.  (An earlier revision could split the frame into depth slabs with finished-tile
+// skipping; on the benchmark scene the extra launches cost more than the skipped entries saved, and it was removed when
+// binning moved to 32-pixel bins.)
+static int render_binned(b200gs_viewer* v, b200gs_model* const* far_to_near, uint32_t n_models, void* rgba8_out, size_t pitch) {
     cudaStream_t st = v->stream;
     GsFrame f = make_frame(v);
-    const uint32_t n_tiles = f.tiles_x * f.tiles_y;
-    std::vector<uint32_t> bounds = {0};
-    if (n_models > 0)
-        for (uint32_t q : slab_q)
-            if (q > bounds.back() && q < 65536 && bounds.size() < 4) bounds.push_back(q);
-    bounds.push_back(65536);
-    const uint32_t n_slabs = (uint32_t)bounds.size() - 1;
+    const uint32_t n_bins = f.bins_x * f.bins_y;
     CK(cudaMemsetAsync(v->stats, 0, 64, st));
-    if (n_slabs > 1) CK(cudaMemsetAsync(v->tile_done, 0, n_tiles, st));
-    v->last_slabs = n_slabs;
-    for (uint32_t sl = 0; sl < n_slabs; sl++) {
-        const bool last = sl + 1 == n_slabs;
-        if (v->timing) CK(cudaEventRecord(v->ev_slab[sl][0], st));
-        CK(cudaMemsetAsync(v->vctrl, 0, VC_WORDS * 4, st));
-        // nearest model first: its splats come first in every tile's front-to-back list; the
-        // models behind it are expanded whole in the last slab
-        const uint32_t n_seg = last ? n_models : std::min<uint32_t>(n_models, 1);
-        for (uint32_t k = 0; k < n_seg; k++) {
-            b200gs_model* m = far_to_near[n_models - 1 - k];
-            GsBinArgs b;
-            b.sorted_slot = m->vals_a;
-            b.sorted_slot_b = m->vals_b;
-            b.sorted_in_b = m->ctrl + MC_CTRL + GS_CTRL_SORT_IN_B;
-            b.splats = v->arena + m->arena_offset;
-            b.binword = m->binword;
-            b.d_v = m->ctrl + MC_CTRL + GS_CTRL_VISIBLE;
-            b.v_max = (uint32_t)m->cap;
-            b.splat_base = (uint32_t)m->arena_offset;
-            b.lookback = v->lb_bin + (size_t)k * v->lb_bin_words;
-            b.epoch = ++v->epoch;
-            b.ticket = v->vctrl + VC_BIN_TICKET + k;
-            b.entry_base_in = v->vctrl + VC_ENTRY_TOTAL + k;
-            b.entry_total_out = v->vctrl + VC_ENTRY_TOTAL + k + 1;
-            b.overflow = (uint32_t*)(v->stats + 3);
-            b.tile_keys = v->tk_a; b.tile_vals = v->tv_a; b.capacity = (uint32_t)v->entry_cap;
-            b.tile_count = v->tile_count;
-            b.q_lo = k == 0 ? bounds[sl] : 0;
-            b.q_hi = k == 0 ? bounds[sl + 1] : 65536;
-            b.tile_done = sl > 0 ? v->tile_done : nullptr;
-            CK(gs_launch_bin(b, f, v->num_sms, st));
-            v->launches += 1;
-        }
-        // tile ids are sorted on 16 bits (2 onesweep passes); viewports with more than 65536 tiles take a third
-        const uint32_t tpasses = n_tiles > 65536u ? 3u : 2u;
-        GsTileRangesArgs tr;
-        tr.tile_count = v->tile_count; tr.ranges = v->ranges; tr.n_tiles = n_tiles;
-        tr.hist = v->vctrl + VC_TSORT_HIST; tr.passes = tpasses; tr.entry_stat = v->stats + 2;
-        tr.lookback = v->lb_tiles; tr.epoch = ++v->epoch;
-        tr.ticket = v->vctrl + VC_TILE_TICKET; tr.done_ctr = v->vctrl + VC_TILE_DONE; tr.buckets = v->vctrl + VC_TILE_BUCKETS;
-        CK(gs_launch_tile_ranges(tr, st));
-        GsSortArgs s;
-        s.keys_a = v->tk_a; s.vals_a = v->tv_a; s.keys_b = v->tk_b; s.vals_b = v->tv_b;
-        s.d_n = v->vctrl + VC_ENTRY_TOTAL + n_seg; s.n_max = (uint32_t)v->entry_cap;
-        s.hist = v->vctrl + VC_TSORT_HIST; s.lookback = v->lb_tsort; s.epoch = ++v->epoch;
-        s.tickets = v->vctrl + VC_TSORT_TICKET; s.passes = tpasses; s.hist_prefilled = true; s.vals_identity = false;
-        s.vote_mask = 0x1;  // tile ids: the low byte is spread, the row-band bytes concentrated
-        s.result_in_b = v->vctrl + VC_TSORT_IN_B;
-        CK(gs_launch_sort(s, v->num_sms, st));
-        if (v->timing) CK(cudaEventRecord(v->ev_slab[sl][1], st));
-        GsCompositeArgs c;
-        c.tile_vals = v->tv_a; c.tile_vals_b = v->tv_b; c.tile_in_b = s.result_in_b; c.ranges = v->ranges; c.splats = v->arena;
-        c.out = (uint8_t*)rgba8_out; c.pitch = pitch;
-        c.evals = v->count_evals ? v->stats : nullptr;
-        c.state = v->pix_state; c.tile_done = v->tile_done; c.resume = sl > 0; c.last = last;
-        CK(gs_launch_composite(c, f, st));
-        if (v->timing) CK(cudaEventRecord(v->ev_slab[sl][2], st));
-        v->launches += tpasses + 2;  // tile sort passes, tile finish, compositor
+    if (v->timing) CK(cudaEventRecord(v->ev_bin[0], st));
+    CK(cudaMemsetAsync(v->vctrl, 0, VC_WORDS * 4, st));
+    for (uint32_t k = 0; k < n_models; k++) {
+        b200gs_model* m = far_to_near[n_models - 1 - k];
+        GsBinArgs b;
+        b.sorted_slot = m->vals_a;
+        b.sorted_slot_b = m->vals_b;
+        b.sorted_in_b = m->ctrl + MC_CTRL + GS_CTRL_SORT_IN_B;
+        b.splats = v->arena + m->arena_offset;
+        b.binword = m->binword;
+        b.d_v = m->ctrl + MC_CTRL + GS_CTRL_VISIBLE;
+        b.v_max = (uint32_t)m->cap;
+        b.splat_base = (uint32_t)m->arena_offset;
+        b.lookback = v->lb_bin + (size_t)k * v->lb_bin_words;
+        b.epoch = ++v->epoch;
+        b.ticket = v->vctrl + VC_BIN_TICKET + k;
+        b.entry_base_in = v->vctrl + VC_ENTRY_TOTAL + k;
+        b.entry_total_out = v->vctrl + VC_ENTRY_TOTAL + k + 1;
+        b.overflow = (uint32_t*)(v->stats + 3);
+        b.tile_keys = v->tk_a; b.tile_vals = v->tv_a; b.capacity = (uint32_t)v->entry_cap;
+        b.tile_count = v->tile_count;
+        CK(gs_launch_bin(b, f, v->num_sms, st));
+        v->launches += 1;
     }
+    // bin ids are sorted on 16 bits (2 onesweep passes); viewports with more than 65536 bins take a third.  The
+    // quadrant masks in the top key bits ride along untouched.
+    const uint32_t tpasses = n_bins > 65536u ? 3u : 2u;
+    GsTileRangesArgs tr;
+    tr.tile_count = v->tile_count; tr.ranges = v->ranges; tr.n_tiles = n_bins;
+    tr.hist = v->vctrl + VC_TSORT_HIST; tr.passes = tpasses; tr.entry_stat = v->stats + 2;
+    tr.lookback = v->lb_tiles; tr.epoch = ++v->epoch;
+    tr.ticket = v->vctrl + VC_TILE_TICKET; tr.done_ctr = v->vctrl + VC_TILE_DONE; tr.buckets = v->vctrl + VC_TILE_BUCKETS;
+    CK(gs_launch_tile_ranges(tr, st));
+    GsSortArgs s;
+    s.keys_a = v->tk_a; s.vals_a = v->tv_a; s.keys_b = v->tk_b; s.vals_b = v->tv_b;
+    s.d_n = v->vctrl + VC_ENTRY_TOTAL + n_models; s.n_max = (uint32_t)v->entry_cap;
+    s.hist = v->vctrl + VC_TSORT_HIST; s.lookback = v->lb_tsort; s.epoch = ++v->epoch;
+    s.tickets = v->vctrl + VC_TSORT_TICKET; s.passes = tpasses; s.hist_prefilled = true; s.vals_identity = false;
+    s.vote_mask = 0x1;  // bin ids: the low byte is spread, the row-band bytes concentrated
+    s.result_in_b = v->vctrl + VC_TSORT_IN_B;
+    CK(gs_launch_sort(s, v->num_sms, st));
+    if (v->timing) CK(cudaEventRecord(v->ev_bin[1], st));
+    GsCompositeArgs c;
+    c.tile_keys = v->tk_a; c.tile_vals = v->tv_a; c.tile_keys_b = v->tk_b; c.tile_vals_b = v->tv_b;
+    c.tile_in_b = s.result_in_b; c.ranges = v->ranges; c.splats = v->arena;
+    c.out = (uint8_t*)rgba8_out; c.pitch = pitch;
+    c.evals = v->count_evals ? v->stats : nullptr;
+    CK(gs_launch_composite(c, f, st));
+    if (v->timing) CK(cudaEventRecord(v->ev_bin[2], st));
+    v->launches += tpasses + 2;  // bin sort passes, tile finish, compositor
     if (v->timing) CK(cudaEventRecord(v->ev[4], st));
     v->rendered = true;
     return B200GS_OK;
@@ -973,7 +928,7 @@ extern "C" int b200gs_render(b200gs_viewer* v, b200gs_model* const* far_to_near,
     TRY(set_device(v));
     TRY(ensure_frame_buffers(v));
     for (uint32_t i = 0; i < n_models; i++) REQUIRE(far_to_near[i]->sorted, "model layout changed; preprocess + sort again");
-    return render_slabs(v, far_to_near, n_models, rgba8_out, pitch, v->slab_q);
+    return render_binned(v, far_to_near, n_models, rgba8_out, pitch);
 }
 
 extern "C" int b200gs_render_frame(b200gs_viewer* v, b200gs_model* const* far_to_near, uint32_t n_models, void* rgba8_out, size_t pitch) {
@@ -1192,10 +1147,8 @@ extern "C" int b200gs_last_timings(b200gs_viewer* v, b200gs_timings* out) {
         float t;
         if (cudaEventElapsedTime(&t, v->ev[0], v->ev[1]) == cudaSuccess) out->preprocess_ms = t;
         if (cudaEventElapsedTime(&t, v->ev[1], v->ev[2]) == cudaSuccess) out->sort_ms = t;
-        for (uint32_t sl = 0; sl < v->last_slabs && sl < 4; sl++) {
-            if (cudaEventElapsedTime(&t, v->ev_slab[sl][0], v->ev_slab[sl][1]) == cudaSuccess) out->bin_ms += t;
-            if (cudaEventElapsedTime(&t, v->ev_slab[sl][1], v->ev_slab[sl][2]) == cudaSuccess) out->composite_ms += t;
-        }
+        if (cudaEventElapsedTime(&t, v->ev_bin[0], v->ev_bin[1]) == cudaSuccess) out->bin_ms = t;
+        if (cudaEventElapsedTime(&t, v->ev_bin[1], v->ev_bin[2]) == cudaSuccess) out->composite_ms = t;
         if (cudaEventElapsedTime(&t, v->ev[0], v->ev[4]) == cudaSuccess) out->total_ms = t;
         (void)cudaGetLastError();
     }
@@ -1226,10 +1179,10 @@ extern "C" int b200gs_query_hits(b200gs_viewer* v, b200gs_model* const* far_to_n
     for (uint32_t i = 0; i < n_models; i++) REQUIRE(far_to_near[i] && far_to_near[i]->v == v && far_to_near[i]->sorted, "model not rendered");
     TRY(set_device(v));
     cudaStream_t st = v->stream;
-    // the hit list needs the complete per-tile lists: re-bin the frame as a single slab (event-driven call) into the
+    // the hit list needs the per-bin lists of THIS frame: re-bin it (event-driven call) into the
     // query's own scratch target — the two host-frame slots may hold frames that are still being copied out
     TRY(ensure_frame_buffers(v));
-    TRY(render_slabs(v, far_to_near, n_models, v->image + 2 * v->image_bytes, (size_t)v->W * 4, std::vector<uint32_t>()));
+    TRY(render_binned(v, far_to_near, n_models, v->image + 2 * v->image_bytes, (size_t)v->W * 4));
     const uint32_t c32 = (uint32_t)std::min<uint64_t>(cap, 1u << 20);
     uint2* d_out = nullptr;
     uint32_t* d_cnt = nullptr;
@@ -1237,7 +1190,8 @@ extern "C" int b200gs_query_hits(b200gs_viewer* v, b200gs_model* const* far_to_n
     TRY(dev_alloc(&d_cnt, 1, true, st));
     GsFrame f = make_frame(v);
     GsCompositeArgs c;
-    c.tile_vals = v->tv_a; c.tile_vals_b = v->tv_b; c.tile_in_b = v->vctrl + VC_TSORT_IN_B; c.ranges = v->ranges;
+    c.tile_keys = v->tk_a; c.tile_vals = v->tv_a; c.tile_keys_b = v->tk_b; c.tile_vals_b = v->tv_b;
+    c.tile_in_b = v->vctrl + VC_TSORT_IN_B; c.ranges = v->ranges;
     c.splats = v->arena; c.out = nullptr; c.pitch = 0; c.evals = nullptr;
     CK(gs_launch_query_hits(c, f, px, py, d_out, c32, d_cnt, st));
     std::vector<uint2> raw(c32);

@@ -1,29 +1,33 @@
-// bin.cu — K3a: tile binning for the compositor.
+// bin.cu — K3a: binning for the compositor.
 //
 // Part of the replacement of renderer.render_with_pass (reference src/tab/scene.rs:2302-2314):
 // the reference draws one instanced quad per visible Gaussian in sorted order and lets the
 // rasteriser find the covered pixels; here every depth-sorted splat is expanded into one
-// (tile id, splat id) entry per 16x16 tile it can actually touch.  Entries are produced IN
-// DEPTH ORDER, so a STABLE sort by tile id alone (onesweep passes over the tile id bits, sort.cu)
-// yields per-tile lists that are still front-to-back.  Models are expanded nearest first, each
+// (bin id, splat id) entry per 32x32-pixel BIN its candidate rectangle touches.  A bin is 2 x 2 compositor
+// tiles (16x16 pixels, one CTA each); every entry's key also carries, above the bin id, the mask of the
+// bin's quadrants the rectangle reaches, and the compositor CTA of a quadrant stages only the entries with
+// its bit.  Binning at 32 pixels emits ~40 % fewer entries than binning at 16 (a garden-scale splat is
+// 5-15 pixels across), which is what the bin sort and this kernel are paid per.  Entries are produced IN
+// DEPTH ORDER, so a STABLE sort by bin id alone (onesweep passes over the bin id bits, sort.cu)
+// yields per-bin lists that are still front-to-back.  Models are expanded nearest first, each
 // appended after the previous one, which reproduces the reference's per-model layering
 // (scene.rs:533-558).
 //
 // One kernel, k_bin, persistent CTAs over chunks of 1024 depth ranks:
-//   * the preprocess kernel left a 4-byte BIN WORD per compaction slot (candidate tile rectangle of the
-//     splat: first tile, row length, count; common.cuh).  A thread reads sorted slot -> bin word (an
-//     L2-resident 4-byte gather) and knows its entry count without touching the 32-byte splat;
-//   * the common small splat (<= 4 candidate tiles: ~95 % of a garden-scale frame) is expanded by its
-//     thread; a bigger one by its whole warp, 32 candidate tiles per round; only the rare huge splat
-//     (a side of more than 32 tiles) has its rectangle rebuilt from the stored record;
+//   * the preprocess kernel left a 4-byte BIN WORD per compaction slot (candidate rectangle of the splat in
+//     16-pixel tiles; common.cuh).  A thread reads sorted slot -> bin word (an L2-resident 4-byte gather) and
+//     knows its entry count without touching the 32-byte splat;
+//   * the common small splat (<= 4 bins) is expanded by its thread; a bigger one by its whole warp, 32 bins
+//     per round; only the rare huge splat (a side of more than 32 tiles) has its rectangle rebuilt from the
+//     stored record;
 //   * order-preserving compaction: per-rank counts -> block scan -> decoupled look-back over the chunks
 //     (pipelined by one chunk: chunk c+1 is counted and published before chunk c is resolved and
 //     written), entries written at their final depth-ordered position;
-//   * every written entry bumps its tile's counter (RED), from which k_tile_finish derives the per-tile
-//     list boundaries, the digit histograms of the tile sort and the compositor's launch order — no pass
+//   * every written entry bumps its bin's counter (RED), from which k_tile_finish derives the per-bin
+//     list boundaries, the digit histograms of the bin sort and the compositor's launch order — no pass
 //     over the entries is needed for any of them.
 // The candidate rectangle is kept whole (see common.cuh): the compositor culls every staged splat against
-// its sub-tiles exactly, so a kept tile the splat cannot reach costs one staged record, not pixels.
+// its sub-tiles exactly, so a kept quadrant the splat cannot reach costs one staged record, not pixels.
 #include <mutex>
 
 #include "common.cuh"
@@ -36,67 +40,50 @@ constexpr int kIpt = 4;                      // depth ranks per thread
 constexpr int kChunk = kThreads * kIpt;      // 1024 ranks per chunk; rank = chunk base + k * 256 + tid
 constexpr uint32_t kStage = 4096;            // entries of one chunk staged in shared memory for a coalesced write-out
 
-using Cand = GsCand;
-
-// tile id of candidate e (< 4) of a small splat's bin word
-__device__ __forceinline__ uint32_t small_key(uint32_t w, uint32_t e, uint32_t tiles_x) {
-    const uint32_t nx = ((w >> 20) & 3u) + 1u;
-    const uint32_t y = (e >= nx ? 1u : 0u) + (e >= 2u * nx ? 1u : 0u) + (e >= 3u * nx ? 1u : 0u);
-    return (w & 0xfffffu) + y * tiles_x + (e - y * nx);
+// candidate rectangle of a splat in 16-pixel tiles: from the bin word, or rebuilt from the stored record for a huge
+// one (every lane for its own splat, so the loads of a warp's huge splats are in flight together)
+struct Rect { uint32_t tx0, ty0, tx1, ty1; };
+__device__ __forceinline__ Rect word_rect(uint32_t w) {
+    Rect r;
+    r.tx0 = w & 1023u; r.ty0 = (w >> 10) & 1023u;
+    r.tx1 = r.tx0 + ((w >> 20) & 31u); r.ty1 = r.ty0 + ((w >> 25) & 31u);
+    return r;
 }
-// candidate rectangle of a big splat as (first tile id, row length, candidates): from the bin word for a
-// medium splat, rebuilt from the stored record for a huge one (every lane for its own splat, so the loads
-// of a warp's huge splats are in flight together)
-__device__ __forceinline__ void big_rect(uint32_t w, const b200gs_splat* __restrict__ splats, uint32_t slot, float W,
-                                         float H, bool flat, uint32_t tiles_x, uint32_t& origin, uint32_t& nx,
-                                         uint32_t& total) {
-    origin = nx = total = 0;
-    if (!(w & GS_BIN_BIG)) return;
-    if (w & GS_BIN_HUGE) {
-        const uint4* sp = reinterpret_cast<const uint4*>(splats + slot);
-        const uint4 q0 = __ldg(sp), q1 = __ldg(sp + 1);
-        GsCand cd;
-        if (gs_make_rect(q0, q1, W, H, flat, cd)) {
-            origin = cd.ty0 * tiles_x + cd.tx0;
-            nx = cd.nx;
-            total = cd.nx * cd.ny;
-        }
-    } else {
-        origin = w & 0xfffffu;
-        nx = ((w >> 20) & 31u) + 1u;
-        total = nx * (((w >> 25) & 31u) + 1u);
-    }
+__device__ __forceinline__ uint32_t rect_bins(const Rect& r) { return ((r.tx1 >> 1) - (r.tx0 >> 1) + 1u) * ((r.ty1 >> 1) - (r.ty0 >> 1) + 1u); }
+__device__ __forceinline__ uint32_t word_count(uint32_t w) {
+    if (w & GS_BIN_HUGE) return w & 0x3fffffffu;
+    return w ? rect_bins(word_rect(w)) : 0u;
 }
-// the whole warp walks the candidates of ONE big splat, 32 per round; returns the number kept
-template <bool WRITE>
-__device__ __forceinline__ uint32_t big_rounds(uint32_t origin, uint32_t nx, uint32_t total, uint32_t tiles_x,
-                                               const uint8_t* __restrict__ tile_done, int lane, uint32_t o, uint32_t val,
-                                               uint32_t capacity, uint32_t* tile_keys, uint32_t* tile_vals,
-                                               uint32_t* __restrict__ tile_count) {
-    const uint32_t lane_lt = (1u << lane) - 1u;
-    const float inv_nx = __frcp_rn((float)nx);
-    uint32_t kept = 0;
+__device__ __forceinline__ Rect huge_rect(const b200gs_splat* __restrict__ splats, uint32_t slot, float W, float H, bool flat) {
+    const uint4* sp = reinterpret_cast<const uint4*>(splats + slot);
+    const uint4 q0 = __ldg(sp), q1 = __ldg(sp + 1);
+    GsCand cd;
+    Rect r = {1u, 1u, 0u, 0u};
+    if (gs_make_rect(q0, q1, W, H, flat, cd)) { r.tx0 = cd.tx0; r.ty0 = cd.ty0; r.tx1 = cd.tx0 + cd.nx - 1u; r.ty1 = cd.ty0 + cd.ny - 1u; }
+    return r;
+}
+// the whole warp walks the bins of ONE big splat, 32 per round
+__device__ __forceinline__ void big_rounds(const Rect r, uint32_t bins_x, int lane, uint32_t o, uint32_t val,
+                                           uint32_t capacity, uint32_t* tile_keys, uint32_t* tile_vals,
+                                           uint32_t* __restrict__ tile_count) {
+    const uint32_t bx0 = r.tx0 >> 1, by0 = r.ty0 >> 1, nbx = (r.tx1 >> 1) - bx0 + 1u;
+    const uint32_t total = nbx * ((r.ty1 >> 1) - by0 + 1u);
+    const float inv_nx = __frcp_rn((float)nbx);
     for (uint32_t e0 = 0; e0 < total; e0 += 32) {
         const uint32_t e = e0 + lane;
-        // e / nx without the integer-division sequence (e < 2^24, nx <= 1024: exact after one fix-up)
+        // e / nbx without the integer-division sequence (e < 2^24, nbx <= 512: exact after one fix-up)
         uint32_t y = (uint32_t)(((float)e + 0.5f) * inv_nx);
-        if (y * nx > e) y--;
-        else if ((y + 1) * nx <= e) y++;
-        const uint32_t key = origin + y * tiles_x + (e - y * nx);
-        // tiles already finished by a nearer depth slab take no more entries
-        const bool keep = e < total && !(tile_done && tile_done[key]);
-        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-        if (WRITE) {
-            const uint32_t g = o + kept + __popc(bal & lane_lt);
-            if (keep && g < capacity) {
-                tile_keys[g] = key;
-                tile_vals[g] = val;
-                atomicAdd(&tile_count[key], 1u);
-            }
+        if (y * nbx > e) y--;
+        else if ((y + 1) * nbx <= e) y++;
+        const uint32_t bx = bx0 + (e - y * nbx), by = by0 + y;
+        const uint32_t g = o + e;
+        if (e < total && g < capacity) {
+            const uint32_t bin = by * bins_x + bx;
+            tile_keys[g] = bin | (gs_quadrant_mask(bx, by, r.tx0, r.tx1, r.ty0, r.ty1) << GS_QMASK_SHIFT);
+            tile_vals[g] = val;
+            atomicAdd(&tile_count[bin], 1u);
         }
-        kept += __popc(bal);
     }
-    return kept;
 }
 
 __global__ void __launch_bounds__(kThreads) k_bin(const uint32_t* __restrict__ sorted_a, const uint32_t* __restrict__ sorted_b,
@@ -108,28 +95,25 @@ __global__ void __launch_bounds__(kThreads) k_bin(const uint32_t* __restrict__ s
                                                   uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ tile_vals,
                                                   uint32_t capacity, uint32_t* __restrict__ tile_count,
                                                   uint32_t count_copies, uint32_t count_stride, float W, float H,
-                                                  uint32_t tiles_x, uint32_t flat, uint32_t q_lo, uint32_t q_hi,
-                                                  const uint8_t* __restrict__ tile_done) {
+                                                  uint32_t bins_x, uint32_t flat) {
     __shared__ uint32_t s_cnt[kIpt][kWarps];   // per (k, warp) kept counts -> exclusive offsets
     __shared__ uint32_t s_keys[kStage], s_vals[kStage];   // the chunk's entries, in order, before the write-out
     __shared__ uint32_t s_total;
     __shared__ uint32_t s_chunk, s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t* __restrict__ sorted_slot = (sorted_in_b && *sorted_in_b) ? sorted_b : sorted_a;
-    // per-tile entry counters are replicated (copy = SM id mod copies): same-address atomics from many SMs
-    // serialise in L2 and the centre tiles of a frame are hot
+    // per-bin entry counters are replicated (copy = SM id mod copies): same-address atomics from many SMs
+    // serialise in L2 and the centre bins of a frame are hot
     {
         uint32_t smid;
         asm("mov.u32 %0, %%smid;" : "=r"(smid));
         tile_count += (size_t)(smid & (count_copies - 1u)) * count_stride;
     }
-    uint32_t vis = *d_v;
-    if (vis > v_max) vis = v_max;
-    // depth slab: ranks [lo, v) of this model, as 16.16 fractions of the visible count
-    const uint32_t lo = (uint32_t)(((uint64_t)vis * q_lo) >> 16), v = (uint32_t)(((uint64_t)vis * q_hi) >> 16);
-    const uint32_t nchunks = (v - lo + kChunk - 1) / kChunk;
+    uint32_t v = *d_v;
+    if (v > v_max) v = v_max;
+    const uint32_t nchunks = (v + kChunk - 1) / kChunk;
     const uint32_t ebase = *entry_base_in;
-    if (v == lo) {
+    if (v == 0) {
         if (blockIdx.x == 0 && tid == 0) *entry_total_out = ebase;
         return;
     }
@@ -152,7 +136,7 @@ __global__ void __launch_bounds__(kThreads) k_bin(const uint32_t* __restrict__ s
         for (int k = 0; k < kIpt; k++) w[k] = slot[k] = loc[k] = 0;
         if (valid) {
             // ---------------- phase A: entry count of every rank of the chunk (no splat is touched)
-            const uint32_t r0 = lo + c * kChunk + tid;
+            const uint32_t r0 = c * kChunk + tid;
 #pragma unroll
             for (int k = 0; k < kIpt; k++) {
                 const uint32_t r = r0 + k * kThreads;
@@ -165,35 +149,7 @@ __global__ void __launch_bounds__(kThreads) k_bin(const uint32_t* __restrict__ s
             }
 #pragma unroll
             for (int k = 0; k < kIpt; k++) {
-                uint32_t n;
-                if (!tile_done) {
-                    if (!(w[k] & GS_BIN_BIG)) n = __popc((w[k] >> 22) & 15u);
-                    else if (w[k] & GS_BIN_HUGE) n = w[k] & 0x3fffffffu;
-                    else n = (((w[k] >> 20) & 31u) + 1u) * (((w[k] >> 25) & 31u) + 1u);
-                } else {
-                    // depth slabs: tiles finished by a nearer slab take no more entries
-                    n = 0;
-                    if (!(w[k] & GS_BIN_BIG) && w[k]) {
-                        uint32_t m = (w[k] >> 22) & 15u;
-#pragma unroll
-                        for (uint32_t e = 0; e < GS_BIN_INLINE; e++)
-                            if (((m >> e) & 1u) && tile_done[small_key(w[k], e, tiles_x)]) m &= ~(1u << e);
-                        w[k] = m ? ((w[k] & 0x3fffffu) | (m << 22)) : 0u;
-                        n = __popc(m);
-                    }
-                    uint32_t b_origin, b_nx, b_total;
-                    big_rect(w[k], splats, slot[k], W, H, is_flat, tiles_x, b_origin, b_nx, b_total);
-                    uint32_t big = __ballot_sync(0xffffffffu, (w[k] & GS_BIN_BIG) != 0u);
-                    while (big) {
-                        const int src = __ffs((int)big) - 1;
-                        big &= big - 1;
-                        const uint32_t kept = big_rounds<false>(__shfl_sync(0xffffffffu, b_origin, src),
-                                                                __shfl_sync(0xffffffffu, b_nx, src),
-                                                                __shfl_sync(0xffffffffu, b_total, src), tiles_x, tile_done,
-                                                                lane, 0, 0, 0, nullptr, nullptr, nullptr);
-                        if (lane == src) n = kept;
-                    }
-                }
+                const uint32_t n = word_count(w[k]);
                 // warp-inclusive scan of the counts of slot k
                 uint32_t incl = n;
 #pragma unroll
@@ -240,7 +196,7 @@ __global__ void __launch_bounds__(kThreads) k_bin(const uint32_t* __restrict__ s
             }
             __syncthreads();
             const uint32_t gbase = ebase + s_base;
-            // Entries go through shared memory (the usual chunk holds ~2 K of them) so that the global writes
+            // Entries go through shared memory (the usual chunk holds ~1.2 K of them) so that the global writes
             // are whole lines; a chunk that does not fit (the nearest, hugest splats) writes directly.  Either
             // way an entry past the capacity is dropped together with its count.
             const bool staged = p_total <= kStage;
@@ -252,38 +208,40 @@ __global__ void __launch_bounds__(kThreads) k_bin(const uint32_t* __restrict__ s
 #pragma unroll
             for (int k = 0; k < kIpt; k++) {
                 const uint32_t wk = p_w[k];
-                uint32_t o = obase + p_loc[k];
+                const uint32_t o = obase + p_loc[k];
                 const uint32_t val = splat_base + p_slot[k];
-                if (!(wk & GS_BIN_BIG)) {
-                    // the <= 4 candidate tiles of a small splat form a 1xN / Nx1 run or a 2x2 block: their
-                    // ids follow from two strides
-                    const uint32_t m = (wk >> 22) & 15u, nx = ((wk >> 20) & 3u) + 1u, k0 = wk & 0xfffffu;
-                    const uint32_t d1 = nx > 1u ? 1u : tiles_x;
-                    const uint32_t k2 = nx == 2u ? k0 + tiles_x : k0 + 2u * d1;
-                    const uint32_t keys[4] = {k0, k0 + d1, k2, k2 + d1};
+                Rect r = word_rect(wk);
+                const bool huge = (wk & GS_BIN_HUGE) != 0u;
+                uint32_t n = 0;
+                if (wk && !huge) {
+                    const uint32_t bx0 = r.tx0 >> 1, by0 = r.ty0 >> 1, nbx = (r.tx1 >> 1) - bx0 + 1u;
+                    n = nbx * ((r.ty1 >> 1) - by0 + 1u);
+                    if (n <= GS_BIN_INLINE) {
+                        // the <= 4 bins of a small splat: a 1xN / Nx1 run or a 2x2 block
 #pragma unroll
-                    for (uint32_t e = 0; e < GS_BIN_INLINE; e++) {
-                        if ((m >> e) & 1u) {
-                            if (o < cap) {
-                                dst_k[o] = keys[e];
-                                dst_v[o] = val;
-                                atomicAdd(&tile_count[keys[e]], 1u);
+                        for (uint32_t e = 0; e < GS_BIN_INLINE; e++) {
+                            if (e < n && o + e < cap) {
+                                const uint32_t y = (e >= nbx ? 1u : 0u) + (e >= 2u * nbx ? 1u : 0u) + (e >= 3u * nbx ? 1u : 0u);
+                                const uint32_t bx = bx0 + (e - y * nbx), by = by0 + y, bin = by * bins_x + bx;
+                                dst_k[o + e] = bin | (gs_quadrant_mask(bx, by, r.tx0, r.tx1, r.ty0, r.ty1) << GS_QMASK_SHIFT);
+                                dst_v[o + e] = val;
+                                atomicAdd(&tile_count[bin], 1u);
                             }
-                            o++;
                         }
                     }
                 }
-                uint32_t big = __ballot_sync(0xffffffffu, (wk & GS_BIN_BIG) != 0u);
+                uint32_t big = __ballot_sync(0xffffffffu, huge || n > GS_BIN_INLINE);
                 if (big) {
-                    uint32_t b_origin, b_nx, b_total;
-                    big_rect(wk, splats, p_slot[k], W, H, is_flat, tiles_x, b_origin, b_nx, b_total);
+                    if (huge) r = huge_rect(splats, p_slot[k], W, H, is_flat);
                     while (big) {
                         const int src = __ffs((int)big) - 1;
                         big &= big - 1;
-                        big_rounds<true>(__shfl_sync(0xffffffffu, b_origin, src), __shfl_sync(0xffffffffu, b_nx, src),
-                                         __shfl_sync(0xffffffffu, b_total, src), tiles_x, tile_done, lane,
-                                         __shfl_sync(0xffffffffu, o, src), __shfl_sync(0xffffffffu, val, src), cap,
-                                         dst_k, dst_v, tile_count);
+                        Rect rr;
+                        rr.tx0 = __shfl_sync(0xffffffffu, r.tx0, src); rr.ty0 = __shfl_sync(0xffffffffu, r.ty0, src);
+                        rr.tx1 = __shfl_sync(0xffffffffu, r.tx1, src); rr.ty1 = __shfl_sync(0xffffffffu, r.ty1, src);
+                        if (rr.tx0 <= rr.tx1)
+                            big_rounds(rr, bins_x, lane, __shfl_sync(0xffffffffu, o, src), __shfl_sync(0xffffffffu, val, src), cap,
+                                       dst_k, dst_v, tile_count);
                     }
                 }
             }
@@ -305,8 +263,8 @@ __global__ void __launch_bounds__(kThreads) k_bin(const uint32_t* __restrict__ s
     }
 }
 
-// Everything the tile sort and the compositor need from the replicated per-tile counters, in one kernel:
-// per-tile sums (counters cleared on the way for the next frame), exclusive scan -> per-tile list
+// Everything the bin sort and the compositor need from the replicated per-bin counters, in one kernel
+// ("tile" in the names below is a 32-pixel bin): per-bin sums (counters cleared on the way for the next frame), exclusive scan -> per-tile list
 // boundaries (ranges[tile] = first entry, ranges[n_tiles + tile] = one past the last), the digit
 // histograms of the tile sort, the total, and the compositor's launch order: longest list first (LPT), so
 // that the few very long tiles of a frame start at once instead of wherever their index falls — a counting
@@ -438,7 +396,7 @@ cudaError_t gs_launch_bin(const GsBinArgs& a, const GsFrame& f, int num_sms, cud
         bps = bps_dev[dev];
     }
     const uint32_t flat = f.display_mode != B200GS_DISPLAY_SPLAT ? 1u : 0u;
-    const uint32_t n_tiles = f.tiles_x * f.tiles_y;
+    const uint32_t n_bins = f.bins_x * f.bins_y;
     uint32_t nchunks = (a.v_max + kChunk - 1) / kChunk;
     uint32_t grid = (uint32_t)(bps * num_sms);
     if (grid > nchunks) grid = nchunks;
@@ -446,8 +404,7 @@ cudaError_t gs_launch_bin(const GsBinArgs& a, const GsFrame& f, int num_sms, cud
     k_bin<<<grid, kThreads, 0, st>>>(a.sorted_slot, a.sorted_slot_b, a.sorted_in_b, a.binword, a.splats, a.d_v, a.v_max,
                                      a.splat_base, a.lookback, a.epoch, a.ticket, a.entry_base_in, a.entry_total_out,
                                      a.overflow, a.tile_keys, a.tile_vals, a.capacity, a.tile_count,
-                                     gs_tile_count_copies(n_tiles), n_tiles, f.W, f.H, f.tiles_x, flat, a.q_lo, a.q_hi,
-                                     a.tile_done);
+                                     gs_tile_count_copies(n_bins), n_bins, f.W, f.H, f.bins_x, flat);
     return cudaGetLastError();
 }
 

@@ -21,7 +21,9 @@
 #define GS_FLAT_D2 4.0f                 // Ellipse / Point display modes
 #define GS_POINT_RADIUS 1.5f
 
-#define GS_TILE 16                      // compositor tile edge in pixels
+#define GS_TILE 16                      // compositor tile edge in pixels (one CTA)
+#define GS_BIN 32                       // binning tile edge in pixels: a bin is 2 x 2 compositor tiles (its quadrants)
+#define GS_QMASK_SHIFT 28               // an entry's sort key is bin id | quadrant mask << 28 (bit q = ty&1 * 2 + tx&1)
 #define GS_NUM_SMS_FALLBACK 148
 
 // Per-frame uniforms (CameraPod + GaussianTransformPod + selection pods of the reference,
@@ -38,7 +40,8 @@ struct GsFrame {
     b200gs_edit_pod sel_edit;
     float hl[4];
     float bg[4];
-    uint32_t tiles_x, tiles_y;
+    uint32_t tiles_x, tiles_y;   // 16-pixel compositor tiles
+    uint32_t bins_x, bins_y;     // 32-pixel binning tiles
     uint32_t std_proj;  // 1: only P00,P11,P22,P23,P32 are non-zero (glam perspective_rh): kernels skip the zero terms
     b200gs_query_pod query;  // selection query tested in the preprocess kernel (rect / brush / texture)
     const uint8_t* query_tex;  // query texture (u8 per pixel, query_tex_w x query_tex_h), sampled when query.kind == TEXTURE
@@ -141,9 +144,7 @@ struct GsBinArgs {
     uint32_t* entry_total_out;     // entry_base_in + this model's entries (a different word)
     uint32_t* overflow;            // set to 1 when the capacity is exceeded
     uint32_t* tile_keys; uint32_t* tile_vals; uint32_t capacity;
-    uint32_t* tile_count;          // gs_tile_count_words(n_tiles) words: replicated per-tile entry counters (all zero between frames)
-    uint32_t q_lo, q_hi;           // depth slab: ranks [V*q_lo >> 16, V*q_hi >> 16) of this model
-    const uint8_t* tile_done;      // tiles finished by nearer slabs (null in the first slab)
+    uint32_t* tile_count;          // gs_tile_count_words(n_bins) words: replicated per-bin entry counters (all zero between frames)
 };
 cudaError_t gs_launch_bin(const GsBinArgs& a, const GsFrame& f, int num_sms, cudaStream_t st);
 size_t gs_tile_count_words(uint32_t n_tiles);
@@ -161,16 +162,15 @@ size_t gs_tile_lookback_words(uint32_t n_tiles);
 cudaError_t gs_launch_tile_ranges(const GsTileRangesArgs& a, cudaStream_t st);
 
 struct GsCompositeArgs {
-    const uint32_t* tile_vals;      // entries sorted by tile, depth order inside a tile
-    const uint32_t* tile_vals_b;    // the tile sort's other buffer, selected when *tile_in_b != 0
+    const uint32_t* tile_keys;      // entries sorted by bin, depth order inside a bin: key = bin | quadrant mask << 28 ...
+    const uint32_t* tile_vals;      // ... value = splat id in the frame arena
+    const uint32_t* tile_keys_b;    // the bin sort's other buffers, selected when *tile_in_b != 0
+    const uint32_t* tile_vals_b;
     const uint32_t* tile_in_b;
-    const uint32_t* ranges;         // [tile] = start, [n_tiles + tile] = end, [2 n_tiles + i] = i-th tile to launch
+    const uint32_t* ranges;         // [bin] = start, [n_bins + bin] = end, [2 n_bins + i] = i-th bin to launch
     const b200gs_splat* splats;     // frame arena
     uint8_t* out; size_t pitch;     // RGBA8
     unsigned long long* evals;      // optional work counters: [0] evaluations, [1] entries staged (may be null)
-    float4* state;                  // per-pixel (Cr, Cg, Cb, T) carried between depth slabs
-    uint8_t* tile_done;             // per-tile: every pixel reached T < eps in an earlier slab
-    bool resume, last;              // not the first slab / the last slab of the frame
 };
 cudaError_t gs_launch_composite(const GsCompositeArgs& a, const GsFrame& f, cudaStream_t st);
 cudaError_t gs_launch_query_hits(const GsCompositeArgs& a, const GsFrame& f, uint32_t px, uint32_t py, uint2* out,
@@ -316,11 +316,23 @@ __device__ __forceinline__ bool gs_query_shape_hit(const b200gs_query_pod& q, fl
 // A splat contributes to a pixel only if alpha = o*exp(-q/2) >= 1/255, i.e. q <= tau with
 // q = a dx^2 + 2 b dx dy + c dy^2 and tau = 2 ln(255 o) (flat display modes: tau = GS_FLAT_D2).
 // footprint threshold (with slack so that rounding can never cull a contributing pixel)
+// single-instruction MUFU forms (flush-to-zero, no denormal fix-up code around them): both are deterministic, so the
+// translation units that rebuild a rectangle (preprocess: bin word, binning: enumeration of a huge splat) agree
+__device__ __forceinline__ float gs_rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float gs_lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float gs_footprint_tau(float opacity, bool flat) {
     if (!(opacity * 255.0f >= 1.0f)) return -1.0f;  // alpha < 1/255 everywhere
     // explicit single-rounding ops: this value feeds the candidate tile rectangle, which must come out
-    // identical in translation units compiled with and without -fmad
-    const float t = flat ? GS_FLAT_D2 : __fmul_rn(2.0f, __logf(__fmul_rn(opacity, 255.0f)));
+    // identical in translation units compiled with and without -fmad.  2 ln x = (2 ln 2) lg2 x
+    const float t = flat ? GS_FLAT_D2 : __fmul_rn(1.3862943611198906f, gs_lg2_approx(__fmul_rn(opacity, 255.0f)));
     return __fadd_rn(__fmul_rn(t, 1.001f), 0.01f);
 }
 // ---- candidate tile rectangle of a projected splat (shared by preprocess and binning) --------
@@ -336,29 +348,8 @@ struct GsCand {
 // sqrt(tau * cov_xx), sqrt(tau * cov_yy), inflated): tiles outside it cannot be touched.
 // Deterministic function of the STORED record, so the preprocess kernel (bin word: candidate count of a
 // huge splat) and the binning kernel (its enumeration) agree exactly.
-__device__ __forceinline__ bool gs_make_rect(const uint4& q0, const uint4& q1, float W, float H, bool flat, GsCand& c) {
-    const uint32_t radius = q0.z & 0xffffu;
-    if (radius == 0) return false;
-    c.mx = __uint_as_float(q0.x);
-    c.my = __uint_as_float(q0.y);
-    const float op = __half2float(__ushort_as_half((unsigned short)(q0.z >> 16)));
-    c.tau = gs_footprint_tau(op, flat);
-    if (c.tau < 0.0f) return false;
-    c.a = __uint_as_float(q1.x);
-    c.b = __uint_as_float(q1.y);
-    c.c = __uint_as_float(q1.z);
-    const float r = (float)radius;
-    float rx = r, ry = r;
-    // (explicit single-rounding ops, see gs_footprint_tau)
-    const float det = __fsub_rn(__fmul_rn(c.a, c.c), __fmul_rn(c.b, c.b));
-    if (det > 0.0f) {
-        const float k = __fdividef(c.tau, det);
-        // sqrt(x) as x * rsqrt(x) (MUFU.RSQ: ~1 ulp, covered by the inflation; a NaN from x = 0 or inf
-        // leaves the extent radius in place)
-        const float vx = __fmul_rn(k, c.c), vy = __fmul_rn(k, c.a);
-        rx = fminf(r, __fadd_rn(__fmul_rn(__fmul_rn(vx, rsqrtf(vx)), 1.002f), 0.02f));
-        ry = fminf(r, __fadd_rn(__fmul_rn(__fmul_rn(vy, rsqrtf(vy)), 1.002f), 0.02f));
-    }
+// pixel bounds + tile rectangle from the centre and the half-widths of the candidate box
+__device__ __forceinline__ bool gs_rect_from_box(float rx, float ry, float W, float H, GsCand& c) {
     // (rx, ry <= r and rounding is monotonic, so this box never reaches beyond the extent square itself)
     c.fx0 = ceilf(__fsub_rn(c.mx, rx)); c.fx1 = floorf(__fadd_rn(c.mx, rx));
     c.fy0 = ceilf(__fsub_rn(c.my, ry)); c.fy1 = floorf(__fadd_rn(c.my, ry));
@@ -373,30 +364,85 @@ __device__ __forceinline__ bool gs_make_rect(const uint4& q0, const uint4& q1, f
     c.ny = (uint32_t)c.fy1 / GS_TILE - c.ty0 + 1;
     return true;
 }
+// half-width of the footprint box along one axis: min(r, sqrt(v) inflated), v = tau * covariance of that axis.
+// sqrt(x) as x * rsqrt(x) (MUFU.RSQ: ~1 ulp, covered by the inflation; a NaN from x = 0 or inf leaves the extent
+// radius in place).  Explicit single-rounding ops, see gs_footprint_tau.
+__device__ __forceinline__ float gs_box_halfwidth(float r, float v) {
+    return fminf(r, __fadd_rn(__fmul_rn(__fmul_rn(v, gs_rsqrt_approx(v)), 1.002f), 0.02f));
+}
+__device__ __forceinline__ bool gs_make_rect(const uint4& q0, const uint4& q1, float W, float H, bool flat, GsCand& c) {
+    const uint32_t radius = q0.z & 0xffffu;
+    if (radius == 0) return false;
+    c.mx = __uint_as_float(q0.x);
+    c.my = __uint_as_float(q0.y);
+    const float op = __half2float(__ushort_as_half((unsigned short)(q0.z >> 16)));
+    c.tau = gs_footprint_tau(op, flat);
+    if (c.tau < 0.0f) return false;
+    c.a = __uint_as_float(q1.x);
+    c.b = __uint_as_float(q1.y);
+    c.c = __uint_as_float(q1.z);
+    const float r = (float)radius;
+    float rx = r, ry = r;
+    const float det = __fsub_rn(__fmul_rn(c.a, c.c), __fmul_rn(c.b, c.b));
+    if (det > 0.0f) {
+        const float k = __fdividef(c.tau, det);
+        rx = gs_box_halfwidth(r, __fmul_rn(k, c.c));
+        ry = gs_box_halfwidth(r, __fmul_rn(k, c.a));
+    }
+    return gs_rect_from_box(rx, ry, W, H, c);
+}
 
 // ---- bin word: what the binning kernel needs to know about a splat, one u32 per compaction slot ----
 // Written by the preprocess kernel (which has the projected splat in registers), so that the binning
-// kernel expands splats from a 4-byte L2-resident gather instead of a 32-byte one.  The candidate tile
-// rectangle (gs_make_rect: extent square ∩ bounding box of the alpha >= 1/255 footprint) is kept whole:
-// measured on the garden-scale scenes an exact per-tile footprint test would drop only 4-9 % of the
-// entries, less than it costs, and the compositor culls every staged splat exactly anyway.
-//   0                         : touches no tile
-//   bit 31 clear (small)      : bits 0..19 first tile id (ty0 * tiles_x + tx0), bits 20..21 nx - 1,
-//                               bits 22..25 kept mask over the nx * ny <= 4 candidates (row-major)
-//   bits 31..30 = 10 (medium) : bits 0..19 first tile id, bits 20..24 nx - 1, bits 25..29 ny - 1 (nx, ny <= 32)
-//   bits 31..30 = 11 (huge)   : bits 0..29 number of candidate tiles; the binning kernel rebuilds the
-//                               rectangle from the stored splat
+// kernel expands splats from a 4-byte L2-resident gather instead of a 32-byte one.  The candidate rectangle
+// (gs_make_rect: extent square ∩ bounding box of the alpha >= 1/255 footprint) is kept whole and is spelled in
+// 16-pixel COMPOSITOR tiles; the binning kernel derives from it the 32-pixel bins the splat falls in (one entry
+// each) and, per entry, which of the bin's four quadrants (compositor tiles) the rectangle reaches — the
+// compositor CTA of a quadrant stages only the entries that carry its bit.
+//   0                  : touches nothing
+//   bit 31 clear       : bit 30 set; bits 0..9 tx0, 10..19 ty0 (first tile column / row), bits 20..24 nx - 1,
+//                        bits 25..29 ny - 1 (nx, ny <= 32 tiles)
+//   bit 31 set (huge)  : bits 0..29 number of BINS of the rectangle; the binning kernel rebuilds the rectangle from the
+//                        stored splat
 #define GS_BIN_INLINE 4u
-#define GS_BIN_BIG 0x80000000u
-#define GS_BIN_HUGE 0x40000000u
-__device__ __forceinline__ uint32_t gs_make_bin_word(const uint4& q0, const uint4& q1, float W, float H, bool flat,
-                                                     uint32_t tiles_x) {
+#define GS_BIN_VALID 0x40000000u
+#define GS_BIN_HUGE 0x80000000u
+// bins covered by the tile range [t0, t0 + n - 1] along one axis
+__device__ __forceinline__ uint32_t gs_bins_of_tiles(uint32_t t0, uint32_t n) { return ((t0 + n - 1u) >> 1) - (t0 >> 1) + 1u; }
+// quadrant mask of bin (bx, by) for the tile rectangle [tx0, tx1] x [ty0, ty1] (the bin is known to intersect it)
+__device__ __forceinline__ uint32_t gs_quadrant_mask(uint32_t bx, uint32_t by, uint32_t tx0, uint32_t tx1, uint32_t ty0, uint32_t ty1) {
+    const uint32_t col = (2u * bx >= tx0 ? 1u : 0u) | (2u * bx + 1u <= tx1 ? 2u : 0u);
+    const uint32_t row = (2u * by >= ty0 ? 1u : 0u) | (2u * by + 1u <= ty1 ? 2u : 0u);
+    return ((row & 1u) ? col : 0u) | ((row & 2u) ? col << 2 : 0u);
+}
+__device__ __forceinline__ uint32_t gs_encode_bin_word(const GsCand& cd) {
+    if (cd.nx <= 32u && cd.ny <= 32u && cd.tx0 < 1024u && cd.ty0 < 1024u)
+        return GS_BIN_VALID | cd.tx0 | (cd.ty0 << 10) | ((cd.nx - 1u) << 20) | ((cd.ny - 1u) << 25);
+    return GS_BIN_HUGE | (gs_bins_of_tiles(cd.tx0, cd.nx) * gs_bins_of_tiles(cd.ty0, cd.ny));
+}
+__device__ __forceinline__ uint32_t gs_make_bin_word(const uint4& q0, const uint4& q1, float W, float H, bool flat) {
     GsCand cd;
     if (!gs_make_rect(q0, q1, W, H, flat, cd)) return 0u;
-    const uint32_t cand = cd.nx * cd.ny, origin = cd.ty0 * tiles_x + cd.tx0;
-    if (cand <= GS_BIN_INLINE) return origin | ((cd.nx - 1u) << 20) | (((1u << cand) - 1u) << 22);
-    if (cd.nx <= 32u && cd.ny <= 32u) return GS_BIN_BIG | origin | ((cd.nx - 1u) << 20) | ((cd.ny - 1u) << 25);
-    return GS_BIN_BIG | GS_BIN_HUGE | cand;
+    return gs_encode_bin_word(cd);
+}
+// The same word for the Splat display mode from what the preprocess kernel holds in registers: the footprint box
+// half-widths are sqrt(tau * cov_xx), sqrt(tau * cov_yy) with the 2-D covariance itself (the stored conic is its
+// inverse: tau * conic_c / det(conic) is the same number up to rounding, far inside the box's 0.2 % + 0.02 px
+// inflation).  A regular word spells its rectangle out, so it need not be reproducible from the record; a HUGE one
+// is a count the binning kernel re-derives from the stored record, so that case defers to gs_make_bin_word.
+__device__ __forceinline__ uint32_t gs_make_bin_word_cov(const uint4& q0, const uint4& q1, float radf, float cov_xx, float cov_yy,
+                                                         float W, float H) {
+    if (!(radf > 0.0f)) return 0u;
+    GsCand cd;
+    cd.mx = __uint_as_float(q0.x);
+    cd.my = __uint_as_float(q0.y);
+    const float op = __half2float(__ushort_as_half((unsigned short)(q0.z >> 16)));   // the stored (f16) opacity
+    const float tau = gs_footprint_tau(op, false);
+    if (tau < 0.0f) return 0u;
+    if (!gs_rect_from_box(gs_box_halfwidth(radf, __fmul_rn(tau, cov_xx)), gs_box_halfwidth(radf, __fmul_rn(tau, cov_yy)), W, H, cd))
+        return 0u;
+    if (cd.nx > 32u || cd.ny > 32u) return gs_make_bin_word(q0, q1, W, H, false);
+    return gs_encode_bin_word(cd);
 }
 
 #endif

@@ -10,11 +10,21 @@
 // culls the staged splats against it 32 at a time with a ballot (exact ellipse-vs-rectangle
 // footprint test, one splat per lane), so only splats that can reach alpha >= 1/255 inside the
 // sub-tile are evaluated.  FP32-pipe + MUFU bound, not HBM bound.
+//
+// Lists are per 32x32-pixel BIN (bin.cu): the four tiles of a bin (its quadrants) are four CTAs that walk the same
+// list, and every entry's key says which quadrants its splat can reach.  A ninth PRODUCER warp per CTA streams the
+// bin's (key, splat id) entries, keeps the ids that carry this quadrant's bit and feeds them, in order, through a
+// shared-memory ring to the eight compositing warps — which therefore gather, convert and cull exactly the splats a
+// 16-pixel binning would have given them, while the binning stage and the bin sort handle ~40 % fewer entries.
 #include "common.cuh"
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kConsumers = 256;              // 8 compositing warps: one 8x4 sub-tile each
+constexpr int kThreads = kConsumers + 32;    // + the producer warp
+constexpr uint32_t kRing = 2048;             // ring of filtered splat ids (8 rounds)
+constexpr uint32_t kPrologue = 2048;         // entries filtered cooperatively by the compositing warps at CTA start
+constexpr uint32_t kBatch = 256;             // entries examined per producer step (8 per lane)
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -24,28 +34,124 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 template <bool FLAT, bool COUNT>
-__global__ void __launch_bounds__(kThreads) k_composite(float4* __restrict__ state, uint8_t* tile_done, uint32_t resume,
-                                                        uint32_t last,
-                                                        const uint32_t* __restrict__ tile_vals_a,
-                                                        const uint32_t* __restrict__ tile_vals_b,
-                                                        const uint32_t* tile_in_b,
-                                                        const uint32_t* __restrict__ ranges,
-                                                        const b200gs_splat* __restrict__ splats, uint8_t* out,
-                                                        size_t pitch, uint32_t W, uint32_t H, uint32_t tiles_x,
-                                                        uint32_t n_tiles, float bg0, float bg1, float bg2, float bg3,
-                                                        unsigned long long* evals) {
+__global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __restrict__ tile_keys_a,
+                                                           const uint32_t* __restrict__ tile_vals_a,
+                                                           const uint32_t* __restrict__ tile_keys_b,
+                                                           const uint32_t* __restrict__ tile_vals_b,
+                                                           const uint32_t* tile_in_b,
+                                                           const uint32_t* __restrict__ ranges,
+                                                           const b200gs_splat* __restrict__ splats, uint8_t* out,
+                                                           size_t pitch, uint32_t W, uint32_t H, uint32_t bins_x,
+                                                           uint32_t n_bins, float bg0, float bg1, float bg2, float bg3,
+                                                           unsigned long long* evals) {
     // 64 bytes per staged splat as four float4 planes [j][splat] (a lane reading its own splat in the cull
     // loop touches consecutive 16-byte words: no bank conflicts): {mx, my, a', b'} {c', opacity, red, green}
     // {cx, hx, cy, hy} {blue, tau', -, -}; conic pre-scaled so that power is in log2 units, extent
     // square clipped to the viewport stored as centre / half-size (exact: half-integers).
     // Double-buffered: the next round's splats are in flight while this round is blended.
-    __shared__ float4 sS[2][4 * kThreads];
+    __shared__ float4 sS[2][4 * kConsumers];
+    __shared__ uint32_t s_ring[kRing];   // splat ids of this quadrant, in list order; position p lives in slot p % kRing
+    __shared__ uint32_t s_wcnt[8];       // prologue: ids kept by each compositing warp
+    __shared__ uint32_t s_prod;          // ids produced so far; bit 31: the list is exhausted (the count is final)
+    constexpr uint32_t kDone = 0x80000000u;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t* __restrict__ tile_vals = *tile_in_b ? tile_vals_b : tile_vals_a;
-    const uint32_t tile = ranges[2 * n_tiles + blockIdx.x];  // longest lists first
-    const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
-    const uint32_t start = ranges[tile], end = ranges[n_tiles + tile];
+    const bool in_b = *tile_in_b != 0;
+    const uint32_t* __restrict__ tile_keys = in_b ? tile_keys_b : tile_keys_a;
+    const uint32_t* __restrict__ tile_vals = in_b ? tile_vals_b : tile_vals_a;
+    const uint32_t bin = ranges[2 * n_bins + (blockIdx.x >> 2)];  // longest lists first; the 4 quadrants of a bin are neighbours
+    const uint32_t quad = blockIdx.x & 3u;
+    const uint32_t tx = 2u * (bin % bins_x) + (quad & 1u), ty = 2u * (bin / bins_x) + (quad >> 1);
+    if (tx * GS_TILE >= W || ty * GS_TILE >= H) return;   // quadrant outside the viewport (CTA-uniform)
+    const uint32_t start = ranges[bin], end = ranges[n_bins + bin];
+    const uint32_t qbit = 1u << (GS_QMASK_SHIFT + quad);
+    const uint32_t lane_lt = (1u << lane) - 1u;
+
+    // Every barrier of this kernel is CTA-wide and executed by all nine warps in the same order (A, B, C, then one per
+    // round), so shared memory needs no flags, fences or polling: what a warp wrote before a barrier is there after it.
+    if (warp == kConsumers / 32) {
+        // ------------------------------------------------------------ producer warp
+        // Streams the bin's entries beyond the prologue kBatch at a time (8 independent coalesced loads of key and id
+        // per lane), keeps the ids whose key carries this quadrant's bit and appends them to the ring in list (= depth)
+        // order, a few rounds ahead of the compositing warps.
+        uint32_t next = min(end, start + kPrologue);   // next entry to examine
+        uint32_t k[8], v[8];
+        auto load_batch = [&]() {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t e = next + 32u * j + lane;
+                const bool ok = e < end;
+                k[j] = ok ? __ldg(tile_keys + e) : 0u;
+                v[j] = ok ? __ldg(tile_vals + e) : 0u;
+            }
+        };
+        bool loaded = next < end;
+        if (loaded) load_batch();          // in flight across barrier A
+        __syncthreads();                   // A: the prologue counts are in s_wcnt
+        uint32_t w = 0;                    // ids in the ring so far
+#pragma unroll
+        for (int i = 0; i < 8; i++) w += s_wcnt[i];
+        // append batches while ids are wanted (w < want) and the ring has room (w + kBatch <= cap)
+        auto produce = [&](uint32_t want, uint32_t cap) {
+            while (next < end && w < want && w + kBatch <= cap) {
+                if (!loaded) load_batch();
+                loaded = false;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const bool keep = (k[j] & qbit) != 0u;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+                    if (keep) s_ring[(w + __popc(bal & lane_lt)) & (kRing - 1u)] = v[j];
+                    w += __popc(bal);
+                }
+                next += kBatch;
+            }
+            if (lane == 0) s_prod = next < end ? w : (w | kDone);
+        };
+        produce(2u * kConsumers, kRing);   // rounds 0 and 1 are fetched right after B (nothing has been read yet)
+        __syncthreads();                   // B
+        produce(4u * kConsumers, kRing);   // (the compositing warps are reading positions < 512: none may be overwritten yet)
+        __syncthreads();                   // C
+        for (uint32_t round = 0;; round++) {
+            if (next >= end && w <= round * kConsumers) break;   // the compositing warps leave at the top of this round
+            // the barrier that ends round r is followed by the fetch of round r + 2; everything the compositing warps
+            // read before the PREVIOUS barrier (ids of rounds <= r) may be overwritten
+            produce((round + 5u) * kConsumers, (round + 1u) * kConsumers + kRing);
+            if (__syncthreads_and(1)) break;   // every pixel of the tile has stopped
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------- compositing warps
+    // prologue: the first kPrologue entries of the list are filtered by these eight warps together (one memory round
+    // trip for all of them, warp w takes entries [256 w, 256 w + 256)), which for most tiles is everything they will
+    // ever consume; the producer warp continues from there
+    {
+        uint32_t k[8], v[8], bal[8], cnt = 0;
+        const uint32_t e0 = start + 256u * warp + lane;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t e = e0 + 32u * j;
+            const bool ok = e < end;
+            k[j] = ok ? __ldg(tile_keys + e) : 0u;
+            v[j] = ok ? __ldg(tile_vals + e) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            bal[j] = __ballot_sync(0xffffffffu, (k[j] & qbit) != 0u);
+            cnt += __popc(bal[j]);
+        }
+        if (lane == 0) s_wcnt[warp] = cnt;
+        __syncthreads();                   // A
+        uint32_t pos = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) pos += i < warp ? s_wcnt[i] : 0u;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (k[j] & qbit) s_ring[pos + __popc(bal[j] & lane_lt)] = v[j];   // (< kPrologue <= kRing: no wrap)
+            pos += __popc(bal[j]);
+        }
+        __syncthreads();                   // B: ids of rounds 0 and 1 are in the ring (or the list is exhausted)
+    }
 
     // warp -> 8x4 sub-tile, lane -> pixel
     const int wx0 = (int)(tx * GS_TILE) + (warp & 1) * 8, wy0 = (int)(ty * GS_TILE) + (warp >> 1) * 4;
@@ -58,22 +164,11 @@ __global__ void __launch_bounds__(kThreads) k_composite(float4* __restrict__ sta
     bool done = !inside;
     unsigned long long my_evals = 0;
     const float Wf = (float)W, Hf = (float)H;
-    // depth slabs: a tile finished by a nearer slab has its final pixels already; otherwise pick up
-    // the accumulated colour / transmittance where the previous slab left them
-    if (resume) {
-        if (tile_done[tile]) return;
-        if (inside) {
-            const float4 st = state[(size_t)py * W + px];
-            Cr = st.x; Cg = st.y; Cb = st.z; T = st.w;
-            done = T < GS_T_EPS;
-        }
-    }
 
-    // software pipeline of the staging: entry ids two rounds ahead, splat records one round ahead in
-    // registers, converted into the other shared-memory buffer at the end of the current round, so a
+    // software pipeline of the staging: the splat records of the next round are in registers (fetched one round
+    // ahead through the ring), converted into the other shared-memory buffer at the end of the current round, so a
     // round costs ONE barrier (which also carries the early-exit vote)
     uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
-    uint32_t id_next = 0;
     auto stage = [&](float4* dst) {
         const float mx = __uint_as_float(q0.x), my = __uint_as_float(q0.y);
         const float r = (float)(q0.z & 0xffffu);
@@ -89,22 +184,28 @@ __global__ void __launch_bounds__(kThreads) k_composite(float4* __restrict__ sta
         if (fx1 > Wf - 1.0f) fx1 = Wf - 1.0f;
         if (fy1 > Hf - 1.0f) fy1 = Hf - 1.0f;
         dst[tid] = make_float4(mx, my, -0.5f * kLog2e * ca, -kLog2e * cbq);
-        dst[kThreads + tid] = make_float4(-0.5f * kLog2e * cc, op, cr, cg);
-        dst[2 * kThreads + tid] = make_float4(0.5f * (fx0 + fx1), 0.5f * (fx1 - fx0), 0.5f * (fy0 + fy1), 0.5f * (fy1 - fy0));
-        dst[3 * kThreads + tid] = make_float4(cb, 0.5f * kLog2e * gs_footprint_tau(op, FLAT), r, 0.0f);
+        dst[kConsumers + tid] = make_float4(-0.5f * kLog2e * cc, op, cr, cg);
+        dst[2 * kConsumers + tid] = make_float4(0.5f * (fx0 + fx1), 0.5f * (fx1 - fx0), 0.5f * (fy0 + fy1), 0.5f * (fy1 - fy0));
+        dst[3 * kConsumers + tid] = make_float4(cb, 0.5f * kLog2e * gs_footprint_tau(op, FLAT), r, 0.0f);
     };
-    auto load_splat = [&](uint32_t id) {
-        const uint4* sp = reinterpret_cast<const uint4*>(splats + id);
+    // splat record of filtered position `pos` into the registers; false if the list ended before it.  (Called right
+    // after a barrier before which the producer made sure the position exists unless the list is exhausted.)
+    auto fetch = [&](uint32_t pos) -> bool {
+        if (pos >= (*(volatile uint32_t*)&s_prod & ~kDone)) return false;
+        const uint4* sp = reinterpret_cast<const uint4*>(splats + s_ring[pos & (kRing - 1u)]);
         q0 = __ldg(sp); q1 = __ldg(sp + 1);
+        return true;
     };
-    if (start + tid < end) { load_splat(tile_vals[start + tid]); stage(sS[0]); }              // round 0 -> buffer 0
-    if (start + kThreads + tid < end) load_splat(tile_vals[start + kThreads + tid]);            // round 1 -> registers
-    if (start + 2 * kThreads + tid < end) id_next = tile_vals[start + 2 * kThreads + tid];      // round 2 ids
-    __syncthreads();
+    if (fetch((uint32_t)tid)) stage(sS[0]);                          // round 0 -> buffer 0
+    bool have_next = fetch((uint32_t)(kConsumers + tid));            // round 1 -> registers
+    __syncthreads();                                                 // C
 
     uint32_t buf = 0;
-    for (uint32_t base = start; base < end; base += kThreads, buf ^= 1u) {
-        const uint32_t cnt = min((uint32_t)kThreads, end - base);
+    for (uint32_t round = 0;; round++, buf ^= 1u) {
+        // (before the barrier just passed the producer had delivered this whole round and the next, or the whole list)
+        const uint32_t produced = *(volatile uint32_t*)&s_prod & ~kDone, first = round * kConsumers;
+        if (produced <= first) break;
+        const uint32_t cnt = min((uint32_t)kConsumers, produced - first);
         if (COUNT && tid == 0) atomicAdd(evals + 1, (unsigned long long)cnt);  // entries staged before the tile finished
         const float4* sSb = sS[buf];
 
@@ -115,13 +216,13 @@ __global__ void __launch_bounds__(kThreads) k_composite(float4* __restrict__ sta
                 if (s < cnt) {
                     // splat s against this warp's 8x4 sub-tile: extent-square overlap first, then the exact
                     // footprint test (can any pixel of the overlap reach alpha >= 1/255?)
-                    const float4 C = sSb[2 * kThreads + s];
+                    const float4 C = sSb[2 * kConsumers + s];
                     const float x0 = fmaxf(C.x - C.y, fwx0), x1 = fminf(C.x + C.y, fwx1);
                     const float y0 = fmaxf(C.z - C.w, fwy0), y1 = fminf(C.z + C.w, fwy1);
                     if (x0 <= x1 && y0 <= y1) {
                         const float4 A = sSb[s];
-                        const float4 D = sSb[3 * kThreads + s];
-                        const float pa = -A.z, pb = -0.5f * A.w, pc = -sSb[kThreads + s].x;  // 0.5*log2e * (a, b, c)
+                        const float4 D = sSb[3 * kConsumers + s];
+                        const float pa = -A.z, pb = -0.5f * A.w, pc = -sSb[kConsumers + s].x;  // 0.5*log2e * (a, b, c)
                         const float dx0 = x0 - A.x, dx1 = x1 - A.x, dy0 = y0 - A.y, dy1 = y1 - A.y;
                         const bool inx = dx0 <= 0.0f && dx1 >= 0.0f, iny = dy0 <= 0.0f && dy1 >= 0.0f;
                         float best = (inx && iny) ? 0.0f : 3.0e38f;
@@ -147,8 +248,8 @@ __global__ void __launch_bounds__(kThreads) k_composite(float4* __restrict__ sta
                     const bool has_b = m != 0;
                     const int sb = has_b ? (int)g + __ffs((int)m) - 1 : sa;
                     m &= m - 1;  // no-op when m == 0
-                    const float4 Aa = sSb[sa], Ba = sSb[kThreads + sa], Ca = sSb[2 * kThreads + sa];
-                    const float4 Ab = sSb[sb], Bb = sSb[kThreads + sb], Cbb = sSb[2 * kThreads + sb];
+                    const float4 Aa = sSb[sa], Ba = sSb[kConsumers + sa], Ca = sSb[2 * kConsumers + sa];
+                    const float4 Ab = sSb[sb], Bb = sSb[kConsumers + sb], Cbb = sSb[2 * kConsumers + sb];
                     const float dxa = fpx - Aa.x, dya = fpy - Aa.y, dxb = fpx - Ab.x, dyb = fpy - Ab.y;
                     const bool ina = fabsf(fpx - Ca.x) <= Ca.y && fabsf(fpy - Ca.z) <= Ca.w;
                     const bool inb = has_b && fabsf(fpx - Cbb.x) <= Cbb.y && fabsf(fpy - Cbb.z) <= Cbb.w;
@@ -167,7 +268,7 @@ __global__ void __launch_bounds__(kThreads) k_composite(float4* __restrict__ sta
                         const float w = ala * T;
                         Cr = __fmaf_rn(Ba.z, w, Cr);
                         Cg = __fmaf_rn(Ba.w, w, Cg);
-                        Cb = __fmaf_rn(sSb[3 * kThreads + sa].x, w, Cb);
+                        Cb = __fmaf_rn(sSb[3 * kConsumers + sa].x, w, Cb);
                         T -= w;
                         done = T < GS_T_EPS;
                     }
@@ -176,7 +277,7 @@ __global__ void __launch_bounds__(kThreads) k_composite(float4* __restrict__ sta
                         const float w = alb * T;
                         Cr = __fmaf_rn(Bb.z, w, Cr);
                         Cg = __fmaf_rn(Bb.w, w, Cg);
-                        Cb = __fmaf_rn(sSb[3 * kThreads + sb].x, w, Cb);
+                        Cb = __fmaf_rn(sSb[3 * kConsumers + sb].x, w, Cb);
                         T -= w;
                         done = T < GS_T_EPS;
                     }
@@ -184,24 +285,13 @@ __global__ void __launch_bounds__(kThreads) k_composite(float4* __restrict__ sta
                 if (__all_sync(0xffffffffu, done)) break;
             }
         }
-        // next round: registers -> the other buffer, then fetch the round after it
-        if (base + kThreads + tid < end) stage(sS[buf ^ 1u]);
-        if (base + 2 * kThreads + tid < end) load_splat(id_next);
-        if (base + 3 * kThreads + tid < end) id_next = tile_vals[base + 3 * kThreads + tid];
+        // next round: registers -> the other buffer, then (behind the barrier) fetch the round after it
+        if (have_next) stage(sS[buf ^ 1u]);
         if (__syncthreads_and(done)) break;
+        have_next = fetch((round + 2u) * kConsumers + tid);
     }
 
-    bool final_write = true;
-    if (!last) {
-        // not the last slab: only finished tiles write pixels now, the others park their state
-        const bool all_done = __syncthreads_and(done) != 0;
-        if (all_done) { if (tid == 0) tile_done[tile] = 1; }
-        else {
-            final_write = false;
-            if (inside) state[(size_t)py * W + px] = make_float4(Cr, Cg, Cb, T);
-        }
-    }
-    if (inside && final_write) {
+    if (inside) {
         const float r = Cr + bg0 * T, g = Cg + bg1 * T, b = Cb + bg2 * T, a = (1.0f - T) + bg3 * T;
         auto q = [](float v) -> uint32_t {
             v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
@@ -220,15 +310,19 @@ __global__ void __launch_bounds__(kThreads) k_composite(float4* __restrict__ sta
 // Hit query (row N3): the ordered list of splats contributing to ONE pixel — a single-warp walk of
 // the pixel's tile list with the compositor's own alpha rule.  Replaces the query_results buffer
 // the reference renderer appends to (src/tab/scene.rs:635-657).
-__global__ void __launch_bounds__(32) k_query_hits(const uint32_t* __restrict__ tile_vals_a,
-                                                   const uint32_t* __restrict__ tile_vals_b, const uint32_t* tile_in_b,
+__global__ void __launch_bounds__(32) k_query_hits(const uint32_t* __restrict__ tile_keys_a, const uint32_t* __restrict__ tile_vals_a,
+                                                   const uint32_t* __restrict__ tile_keys_b, const uint32_t* __restrict__ tile_vals_b,
+                                                   const uint32_t* tile_in_b,
                                                    const uint32_t* __restrict__ ranges,
                                                    const b200gs_splat* __restrict__ splats, uint32_t W, uint32_t H,
-                                                   uint32_t tiles_x, uint32_t n_tiles, uint32_t px, uint32_t py,
+                                                   uint32_t bins_x, uint32_t n_bins, uint32_t px, uint32_t py,
                                                    uint32_t flat, uint2* out, uint32_t cap, uint32_t* count) {
-    const uint32_t* __restrict__ tile_vals = *tile_in_b ? tile_vals_b : tile_vals_a;
-    const uint32_t tile = (py / GS_TILE) * tiles_x + px / GS_TILE;
-    const uint32_t start = ranges[tile], end = ranges[n_tiles + tile];
+    const bool in_b = *tile_in_b != 0;
+    const uint32_t* __restrict__ tile_keys = in_b ? tile_keys_b : tile_keys_a;
+    const uint32_t* __restrict__ tile_vals = in_b ? tile_vals_b : tile_vals_a;
+    const uint32_t bin = (py / GS_BIN) * bins_x + px / GS_BIN;
+    const uint32_t qbit = 1u << (GS_QMASK_SHIFT + (((py / GS_TILE) & 1u) * 2u + ((px / GS_TILE) & 1u)));   // the pixel's quadrant of the bin
+    const uint32_t start = ranges[bin], end = ranges[n_bins + bin];
     const int lane = threadIdx.x;
     const float fpx = (float)px, fpy = (float)py, Wf = (float)W, Hf = (float)H;
     uint32_t n_out = 0;
@@ -237,7 +331,7 @@ __global__ void __launch_bounds__(32) k_query_hits(const uint32_t* __restrict__ 
         bool ok = false;
         uint32_t id = 0;
         float al = 0.0f;
-        if (e < end) {
+        if (e < end && (tile_keys[e] & qbit)) {
             id = tile_vals[e];
             const uint4* sp = reinterpret_cast<const uint4*>(splats + id);
             const uint4 q0 = __ldg(sp), q1 = __ldg(sp + 1);
@@ -264,20 +358,21 @@ __global__ void __launch_bounds__(32) k_query_hits(const uint32_t* __restrict__ 
 
 cudaError_t gs_launch_query_hits(const GsCompositeArgs& a, const GsFrame& f, uint32_t px, uint32_t py, uint2* out,
                                  uint32_t cap, uint32_t* count, cudaStream_t st) {
-    k_query_hits<<<1, 32, 0, st>>>(a.tile_vals, a.tile_vals_b, a.tile_in_b, a.ranges, a.splats, (uint32_t)f.W, (uint32_t)f.H,
-                                   f.tiles_x, f.tiles_x * f.tiles_y, px, py, f.display_mode != B200GS_DISPLAY_SPLAT ? 1u : 0u,
-                                   out, cap, count);
+    k_query_hits<<<1, 32, 0, st>>>(a.tile_keys, a.tile_vals, a.tile_keys_b, a.tile_vals_b, a.tile_in_b, a.ranges, a.splats,
+                                   (uint32_t)f.W, (uint32_t)f.H, f.bins_x, f.bins_x * f.bins_y, px, py,
+                                   f.display_mode != B200GS_DISPLAY_SPLAT ? 1u : 0u, out, cap, count);
     return cudaGetLastError();
 }
 
 cudaError_t gs_launch_composite(const GsCompositeArgs& a, const GsFrame& f, cudaStream_t st) {
-    const uint32_t n_tiles = f.tiles_x * f.tiles_y;
+    const uint32_t n_bins = f.bins_x * f.bins_y;
     const bool flat = f.display_mode != B200GS_DISPLAY_SPLAT;
     const uint32_t W = (uint32_t)f.W, H = (uint32_t)f.H;
+    // one CTA per compositor tile: 4 per bin (quadrants outside the viewport exit at once)
 #define GS_LAUNCH_COMPOSITE(FLAT, COUNT)                                                                              \
-    k_composite<FLAT, COUNT><<<n_tiles, kThreads, 0, st>>>(a.state, a.tile_done, a.resume ? 1u : 0u, a.last ? 1u : 0u, a.tile_vals, a.tile_vals_b, a.tile_in_b, a.ranges, a.splats, a.out, a.pitch, W, H,      \
-                                                           f.tiles_x, n_tiles, f.bg[0], f.bg[1], f.bg[2], f.bg[3],     \
-                                                           a.evals)
+    k_composite<FLAT, COUNT><<<4u * n_bins, kThreads, 0, st>>>(a.tile_keys, a.tile_vals, a.tile_keys_b, a.tile_vals_b, a.tile_in_b,  \
+                                                               a.ranges, a.splats, a.out, a.pitch, W, H, f.bins_x, n_bins,  \
+                                                               f.bg[0], f.bg[1], f.bg[2], f.bg[3], a.evals)
     if (flat) {
         if (a.evals) GS_LAUNCH_COMPOSITE(true, true);
         else GS_LAUNCH_COMPOSITE(true, false);

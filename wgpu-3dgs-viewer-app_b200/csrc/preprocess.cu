@@ -395,6 +395,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_preprocess(const uint8_t* __res
             pd.valid = false;
         };
         Phase1 cur = phase1(0);
+#pragma unroll 2
         for (uint32_t it = 0;; it++) {
             const int stage = it % NSTAGE;
             const uint32_t c = s_chunk[stage];
@@ -539,8 +540,10 @@ __global__ void __launch_bounds__(kThreads, 3) k_preprocess(const uint8_t* __res
                         default: break;
                     }
                 }
+                if (!FAST) {   // (FAST has no edits: the clamp after them is the only one needed)
 #pragma unroll
-                for (int ch = 0; ch < 3; ch++) rgb[ch] = clamp01(rgb[ch]);
+                    for (int ch = 0; ch < 3; ch++) rgb[ch] = clamp01(rgb[ch]);
+                }
                 float op = (float)(colw >> 24) * (1.0f / 255.0f);
                 if (!FAST && edits) apply_edit(ed, rgb, op);
                 if (!FAST && selected) {
@@ -565,7 +568,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_preprocess(const uint8_t* __res
                 q1.w = (uint32_t)__half_as_ushort(__float2half_rn(rgb[2])) | ((selected ? 1u : 0u) << 16);
                 // bin word (from the STORED record, exactly as the binning kernel decodes big splats): the tile
                 // tests of the common small splats are done here, where the splat is in registers
-                bw = gs_make_bin_word(q0, q1, f.W, f.H, !FAST && f.display_mode != B200GS_DISPLAY_SPLAT, f.tiles_x);
+                if (FAST || f.display_mode == B200GS_DISPLAY_SPLAT) bw = gs_make_bin_word_cov(q0, q1, radf, a, d, f.W, f.H);
+                else bw = gs_make_bin_word(q0, q1, f.W, f.H, true);
             }
             bar_arrive(kBarFree + (int)(it & 3u));  // every read of this stage's shared memory is done
 
