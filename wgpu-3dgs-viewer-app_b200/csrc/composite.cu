@@ -23,8 +23,8 @@ namespace {
 constexpr int kConsumers = 256;              // 8 compositing warps: one 8x4 sub-tile each
 constexpr int kThreads = kConsumers + 32;    // + the producer warp
 constexpr uint32_t kRing = 2048;             // ring of filtered splat ids (8 rounds)
-constexpr uint32_t kPrologue = 2048;         // entries filtered cooperatively by the compositing warps at CTA start
-constexpr uint32_t kBatch = 256;             // entries examined per producer step (8 per lane)
+constexpr uint32_t kPrologue = 1024;         // entries filtered cooperatively by the compositing warps at CTA start
+constexpr uint32_t kBatch = 512;             // entries examined per producer step (16 per lane)
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -59,7 +59,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
     const bool in_b = *tile_in_b != 0;
     const uint32_t* __restrict__ tile_keys = in_b ? tile_keys_b : tile_keys_a;
     const uint32_t* __restrict__ tile_vals = in_b ? tile_vals_b : tile_vals_a;
-    const uint32_t bin = ranges[2 * n_bins + (blockIdx.x >> 2)];  // longest lists first; the 4 quadrants of a bin are neighbours
+    // longest lists first; the 4 quadrants of a bin are neighbours in the launch order, so that they run at the same time and
+    // share the bin's entries and the splats that straddle quadrants in L2 (measured: quadrant-major order 384 us vs 334 us)
+    const uint32_t bin = ranges[2 * n_bins + (blockIdx.x >> 2)];
     const uint32_t quad = blockIdx.x & 3u;
     const uint32_t tx = 2u * (bin % bins_x) + (quad & 1u), ty = 2u * (bin / bins_x) + (quad >> 1);
     if (tx * GS_TILE >= W || ty * GS_TILE >= H) return;   // quadrant outside the viewport (CTA-uniform)
@@ -75,47 +77,56 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
         // per lane), keeps the ids whose key carries this quadrant's bit and appends them to the ring in list (= depth)
         // order, a few rounds ahead of the compositing warps.
         uint32_t next = min(end, start + kPrologue);   // next entry to examine
-        uint32_t k[8], v[8];
-        auto load_batch = [&]() {
+        constexpr int kPer = kBatch / 32;
+        uint32_t k[kPer], v[kPer];
+        bool loaded = false;                           // k / v hold the batch at `next` (its loads may still be in flight)
+        auto prefetch = [&]() {
+            if (loaded || next >= end) return;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
+            for (int j = 0; j < kPer; j++) {
                 const uint32_t e = next + 32u * j + lane;
                 const bool ok = e < end;
                 k[j] = ok ? __ldg(tile_keys + e) : 0u;
                 v[j] = ok ? __ldg(tile_vals + e) : 0u;
             }
+            loaded = true;
         };
-        bool loaded = next < end;
-        if (loaded) load_batch();          // in flight across barrier A
-        __syncthreads();                   // A: the prologue counts are in s_wcnt
         uint32_t w = 0;                    // ids in the ring so far
+        auto append = [&]() {              // filter the loaded batch into the ring
 #pragma unroll
-        for (int i = 0; i < 8; i++) w += s_wcnt[i];
-        // append batches while ids are wanted (w < want) and the ring has room (w + kBatch <= cap)
-        auto produce = [&](uint32_t want, uint32_t cap) {
-            while (next < end && w < want && w + kBatch <= cap) {
-                if (!loaded) load_batch();
-                loaded = false;
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const bool keep = (k[j] & qbit) != 0u;
-                    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-                    if (keep) s_ring[(w + __popc(bal & lane_lt)) & (kRing - 1u)] = v[j];
-                    w += __popc(bal);
-                }
-                next += kBatch;
+            for (int j = 0; j < kPer; j++) {
+                const bool keep = (k[j] & qbit) != 0u;
+                const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+                if (keep) s_ring[(w + __popc(bal & lane_lt)) & (kRing - 1u)] = v[j];
+                w += __popc(bal);
             }
+            next += kBatch;
+            loaded = false;
+        };
+        // One phase = the time between two barriers.  A batch whose loads were issued in the previous phase is filtered for
+        // free (if the ring has room and the compositing warps are less than `ahead` ids ahead served); only when the ids
+        // the NEXT fetch needs are still missing does the warp wait on memory inside a phase; then it issues the loads of
+        // the following batch and goes to the barrier, so that it is never what the other eight warps wait for.
+        auto phase = [&](uint32_t need, uint32_t ahead, uint32_t cap) {
+            if (loaded && w < ahead && w + kBatch <= cap) append();
+            while (next < end && w < need) { prefetch(); append(); }   // (need <= cap - kBatch by construction)
+            if (w < ahead || ahead == 0u) prefetch();
             if (lane == 0) s_prod = next < end ? w : (w | kDone);
         };
-        produce(2u * kConsumers, kRing);   // rounds 0 and 1 are fetched right after B (nothing has been read yet)
-        __syncthreads();                   // B
-        produce(4u * kConsumers, kRing);   // (the compositing warps are reading positions < 512: none may be overwritten yet)
-        __syncthreads();                   // C
+        prefetch();                        // in flight across barrier A
+        __syncthreads();                   // A: the prologue counts are in s_wcnt
+#pragma unroll
+        for (int i = 0; i < 8; i++) w += s_wcnt[i];
+        // (before B and C only what the next fetch needs: the compositing warps are waiting to start)
+        phase(1u * kConsumers, 0u, kRing);   // round 0 is fetched right after B
+        __syncthreads();                     // B
+        phase(2u * kConsumers, 0u, kRing);   // round 1 is fetched right after C
+        __syncthreads();                     // C
         for (uint32_t round = 0;; round++) {
             if (next >= end && w <= round * kConsumers) break;   // the compositing warps leave at the top of this round
             // the barrier that ends round r is followed by the fetch of round r + 2; everything the compositing warps
             // read before the PREVIOUS barrier (ids of rounds <= r) may be overwritten
-            produce((round + 5u) * kConsumers, (round + 1u) * kConsumers + kRing);
+            phase((round + 3u) * kConsumers, (round + 5u) * kConsumers, (round + 1u) * kConsumers + kRing);
             if (__syncthreads_and(1)) break;   // every pixel of the tile has stopped
         }
         return;
@@ -123,20 +134,21 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
 
     // ---------------------------------------------------------------- compositing warps
     // prologue: the first kPrologue entries of the list are filtered by these eight warps together (one memory round
-    // trip for all of them, warp w takes entries [256 w, 256 w + 256)), which for most tiles is everything they will
+    // trip for all of them, warp w takes entries [128 w, 128 w + 128)), which for most tiles is most of what they will
     // ever consume; the producer warp continues from there
     {
-        uint32_t k[8], v[8], bal[8], cnt = 0;
-        const uint32_t e0 = start + 256u * warp + lane;
+        constexpr int kPer = kPrologue / kConsumers;
+        uint32_t k[kPer], v[kPer], bal[kPer], cnt = 0;
+        const uint32_t e0 = start + 32u * kPer * warp + lane;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
+        for (int j = 0; j < kPer; j++) {
             const uint32_t e = e0 + 32u * j;
             const bool ok = e < end;
             k[j] = ok ? __ldg(tile_keys + e) : 0u;
             v[j] = ok ? __ldg(tile_vals + e) : 0u;
         }
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
+        for (int j = 0; j < kPer; j++) {
             bal[j] = __ballot_sync(0xffffffffu, (k[j] & qbit) != 0u);
             cnt += __popc(bal[j]);
         }
@@ -146,11 +158,11 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
 #pragma unroll
         for (int i = 0; i < 8; i++) pos += i < warp ? s_wcnt[i] : 0u;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
+        for (int j = 0; j < kPer; j++) {
             if (k[j] & qbit) s_ring[pos + __popc(bal[j] & lane_lt)] = v[j];   // (< kPrologue <= kRing: no wrap)
             pos += __popc(bal[j]);
         }
-        __syncthreads();                   // B: ids of rounds 0 and 1 are in the ring (or the list is exhausted)
+        __syncthreads();                   // B: the ids of round 0 are in the ring (or the list is exhausted)
     }
 
     // warp -> 8x4 sub-tile, lane -> pixel
@@ -197,8 +209,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
         return true;
     };
     if (fetch((uint32_t)tid)) stage(sS[0]);                          // round 0 -> buffer 0
+    __syncthreads();                                                 // C: the ids of round 1 are in the ring, too
     bool have_next = fetch((uint32_t)(kConsumers + tid));            // round 1 -> registers
-    __syncthreads();                                                 // C
 
     uint32_t buf = 0;
     for (uint32_t round = 0;; round++, buf ^= 1u) {
