@@ -162,15 +162,21 @@ def plan_a_probe():
 
 # ------------------------------------------------------------------------------ our arm
 def stage_times(G, v, m, mats, W, H, frames=14):
-    """median per-stage device times (CUDA events on the viewer's stream) of `frames` consecutive views"""
-    v.enable_timings(True, True)
+    """median per-stage device times (CUDA events on the viewer's stream) of `frames` consecutive views, timed with the
+    production kernels; the work counters (evaluations) come from a second pass over the same views with the counting
+    instantiation of the compositor, whose atomics would otherwise sit inside the timed numbers"""
     rows = []
-    for s in range(frames):
-        view, proj = mats[s % len(mats)]
-        v.update_camera_matrices(view, proj, (W, H))
-        v.render_frame([m])
-        tm = v.last_timings()
-        rows.append((tm.preprocess_ms, tm.sort_ms, tm.bin_ms, tm.composite_ms, tm.total_ms, tm.visible, tm.tile_entries, tm.evals))
+    for counting in (False, True):
+        v.enable_timings(True, counting)
+        for s in range(frames):
+            view, proj = mats[s % len(mats)]
+            v.update_camera_matrices(view, proj, (W, H))
+            v.render_frame([m])
+            tm = v.last_timings()
+            if not counting:
+                rows.append([tm.preprocess_ms, tm.sort_ms, tm.bin_ms, tm.composite_ms, tm.total_ms, tm.visible, tm.tile_entries, 0])
+            else:
+                rows[s][7] = tm.evals
     v.enable_timings(False, False)
     return np.median(np.array(rows[2:], dtype=np.float64), axis=0)
 
