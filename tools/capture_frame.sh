@@ -11,5 +11,5 @@ ncu --set full --clock-control none --import-source on -k regex:k_ -s $((2*L)) -
     python tools/profile_frame.py 6000000 3 > /dev/null 2>&1
 ncu -i /tmp/${TAG}_frame_full.ncu-rep --page raw --csv > gpurun_out/${TAG}_frame_full_raw.csv 2>/dev/null
 ncu -i /tmp/${TAG}_frame_full.ncu-rep --page source --csv --launch-skip 0 --launch-count 1 > gpurun_out/${TAG}_src_k_preprocess.csv 2>/dev/null
-python tools/ncu_summary.py gpurun_out/${TAG}_frame_full_raw.csv gpurun_out/${TAG}_frame_full_summary.json > gpurun_out/${TAG}_frame_full_summary.md
+python tools/ncu_summary.py gpurun_out/${TAG}_frame_full_raw.csv gpurun_out/${TAG}_frame_full_summary.json gpurun_out/${TAG}_traffic.json > gpurun_out/${TAG}_frame_full_summary.md
 cat gpurun_out/${TAG}_launches_table.txt gpurun_out/${TAG}_frame_full_summary.md

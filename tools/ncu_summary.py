@@ -44,3 +44,12 @@ print("\nTotal: %.1f µs" % tot)
 if len(sys.argv) > 2:
     import json
     json.dump({"kernels": out, "total_us": tot}, open(sys.argv[2], "w"), indent=1)
+if len(sys.argv) > 3:
+    # traffic of the roofline kernel (bench.py reads it): DRAM bytes of ONE k_preprocess launch of this capture
+    import json
+    pre = next((o for o in out if o["kernel"].startswith("k_preprocess")), None)
+    if pre:
+        json.dump({"source": "%s (ncu --set full, one launch of %s, written by tools/ncu_summary.py)" % (sys.argv[1], pre["kernel"]),
+                   "preprocess_dram_bytes_per_launch": (pre["dram_rd"] + pre["dram_wr"]) * 1e6,
+                   "preprocess_dram_read_MB": pre["dram_rd"], "preprocess_dram_write_MB": pre["dram_wr"]},
+                  open(sys.argv[3], "w"), indent=1)

@@ -8,7 +8,7 @@ import collections, glob, os, re, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, sys.argv[1] if len(sys.argv) > 1 else "profiles")
 KEY = re.compile(r"\b(UBLKCP|SYNCS|UCGABAR|MAPA|MATCH|VOTE|MUFU|REDG|RED|ATOMS|ATOMG|ELECT|FFMA2|LDGSTS|UTMA\w*|BAR|CCTL|ERRBAR|MEMBAR|FENCE|ACQBULK|ST\.E\.\w*\.?CLUSTER|LD\.E)\b")
-WANT = {"k_preprocess": "ILi2ELi1ELb1", "k_sort_pass": "ILi11ELi8ELb1", "k_bin": "", "k_tile_finish": "", "k_composite": "ILb0ELb0",
+WANT = {"k_preprocess": "ILi2ELi1ELb1", "k_sort_pass": "k_sort_passILi5EE", "k_sort_pass_wide": "ILi11ELi8ELb1", "k_bin": "", "k_tile_finish": "", "k_composite": "ILb0ELb0",
         "k_eval_mask": "", "k_postprocess": "", "k_paint_query_texture": "", "k_query_hits": "", "k_sort_hist": ""}
 
 
@@ -22,7 +22,7 @@ def main():
                 parts = re.split(r"\n\s*\.section\s+\.text\.", txt)
                 for part in parts[1:]:
                     name = part.split(",", 1)[0]
-                    short = next((k for k in WANT if k in name and WANT[k] in name), None)
+                    short = next((k for k in WANT if k.replace("_wide", "") in name and WANT[k] in name), None)
                     if not short:
                         continue
                     cur, ops, keys, n = "?", collections.Counter(), [], 0
