@@ -1,6 +1,9 @@
 """Builds libb200gs.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
 
-    python wgpu-3dgs-viewer-app_b200/build.py [--force] [--verbose]
+    python wgpu-3dgs-viewer-app_b200/build.py [--force] [--verbose] [--synccheck]
+
+--synccheck builds the variant compute-sanitizer's synccheck can follow (the compositor's two barrier helpers kept out
+of line, csrc/composite.cu); it forces a rebuild of composite.cu — run plain `build.py --force` afterwards to go back.
 
 Cross-compiles without a GPU.  preprocess.cu and aux.cu are built with -fmad=false (one
 rounding per float operation: bit parity with the CPU oracle); host code with
@@ -46,7 +49,7 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, synccheck=False):
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.join(HERE, h) for h in HEADERS] + [os.path.abspath(__file__)]
     jobs, objs = [], []
@@ -54,8 +57,10 @@ def build(force=False, verbose=False):
         s = os.path.join(HERE, "csrc", src)
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(o)
-        if force or _stale(o, [s] + hdrs):
-            jobs.append([_nvcc()] + ARCH + NVCC_COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+        sc = synccheck and src == "composite.cu"
+        if force or sc or _stale(o, [s] + hdrs):
+            jobs.append([_nvcc()] + ARCH + NVCC_COMMON + extra + (["-DB200GS_SYNCCHECK_BUILD"] if sc else []) +
+                        (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
     for src in CPP:
         s = os.path.join(HERE, src)
         o = os.path.join(OBJ, os.path.basename(src).replace(".cpp", ".o"))
@@ -79,4 +84,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, synccheck="--synccheck" in sys.argv))

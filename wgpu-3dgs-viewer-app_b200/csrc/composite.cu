@@ -33,6 +33,35 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+// The producer warp and the compositing warps run different code between barriers, so the barriers are spelled as PTX named
+// barriers with an explicit thread count (what warp-specialised kernels use) rather than as __syncthreads(), whose C++
+// contract wants one call site for the whole CTA.  Every warp executes the same sequence of them.
+// compute-sanitizer's synccheck reports "divergent thread(s) in block" whenever a block-wide rendezvous is reached from two
+// code addresses, correct or not (tools/scratch/bar_pattern.cu is the minimal reproducer: right answer, flagged; the same
+// program with the barrier in a non-inlined function: clean).  Building with -DB200GS_SYNCCHECK_BUILD (build.py
+// --synccheck, used by tools/sanitize.sh) keeps the two helpers out of line — one barrier instruction at one address for
+// both roles — which synccheck accepts; the production build inlines them (the call costs 16 us per frame: 334 -> 350).
+#ifdef B200GS_SYNCCHECK_BUILD
+#define GS_BAR_FN __noinline__
+#else
+#define GS_BAR_FN __forceinline__
+#endif
+__device__ GS_BAR_FN void cta_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
+__device__ GS_BAR_FN bool cta_bar_and(bool pred) {
+    uint32_t r;
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.ne.u32 p, %1, 0;\n"
+        "bar.red.and.pred q, 1, %2, p;\n"
+        "selp.u32 %0, 1, 0, q;\n"
+        "}\n"
+        : "=r"(r)
+        : "r"((uint32_t)pred), "n"(kThreads)
+        : "memory");
+    return r != 0;
+}
+
 template <bool FLAT, bool COUNT>
 __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __restrict__ tile_keys_a,
                                                            const uint32_t* __restrict__ tile_vals_a,
@@ -52,7 +81,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
     __shared__ float4 sS[2][4 * kConsumers];
     __shared__ uint32_t s_ring[kRing];   // splat ids of this quadrant, in list order; position p lives in slot p % kRing
     __shared__ uint32_t s_wcnt[8];       // prologue: ids kept by each compositing warp
-    __shared__ uint32_t s_prod;          // ids produced so far; bit 31: the list is exhausted (the count is final)
+    __shared__ uint32_t s_prod[2];       // ids produced so far; bit 31: the list is exhausted (the count is final).  Written before
+                                         // barrier number i into word i & 1 and read after it, so no word is ever written while read
     constexpr uint32_t kDone = 0x80000000u;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -107,27 +137,29 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
         // free (if the ring has room and the compositing warps are less than `ahead` ids ahead served); only when the ids
         // the NEXT fetch needs are still missing does the warp wait on memory inside a phase; then it issues the loads of
         // the following batch and goes to the barrier, so that it is never what the other eight warps wait for.
+        uint32_t barrier_no = 0;           // barriers passed since A: B is number 0, C number 1, the one ending round r number r + 2
         auto phase = [&](uint32_t need, uint32_t ahead, uint32_t cap) {
             if (loaded && w < ahead && w + kBatch <= cap) append();
             while (next < end && w < need) { prefetch(); append(); }   // (need <= cap - kBatch by construction)
             if (w < ahead || ahead == 0u) prefetch();
-            if (lane == 0) s_prod = next < end ? w : (w | kDone);
+            if (lane == 0) s_prod[barrier_no & 1u] = next < end ? w : (w | kDone);
+            barrier_no++;
         };
         prefetch();                        // in flight across barrier A
-        __syncthreads();                   // A: the prologue counts are in s_wcnt
+        cta_bar();                         // A: the prologue counts are in s_wcnt
 #pragma unroll
         for (int i = 0; i < 8; i++) w += s_wcnt[i];
         // (before B and C only what the next fetch needs: the compositing warps are waiting to start)
         phase(1u * kConsumers, 0u, kRing);   // round 0 is fetched right after B
-        __syncthreads();                     // B
+        cta_bar();                           // B
         phase(2u * kConsumers, 0u, kRing);   // round 1 is fetched right after C
-        __syncthreads();                     // C
+        cta_bar();                           // C
         for (uint32_t round = 0;; round++) {
             if (next >= end && w <= round * kConsumers) break;   // the compositing warps leave at the top of this round
             // the barrier that ends round r is followed by the fetch of round r + 2; everything the compositing warps
             // read before the PREVIOUS barrier (ids of rounds <= r) may be overwritten
             phase((round + 3u) * kConsumers, (round + 5u) * kConsumers, (round + 1u) * kConsumers + kRing);
-            if (__syncthreads_and(1)) break;   // every pixel of the tile has stopped
+            if (cta_bar_and(true)) break;   // every pixel of the tile has stopped
         }
         return;
     }
@@ -153,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
             cnt += __popc(bal[j]);
         }
         if (lane == 0) s_wcnt[warp] = cnt;
-        __syncthreads();                   // A
+        cta_bar();                         // A
         uint32_t pos = 0;
 #pragma unroll
         for (int i = 0; i < 8; i++) pos += i < warp ? s_wcnt[i] : 0u;
@@ -162,7 +194,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
             if (k[j] & qbit) s_ring[pos + __popc(bal[j] & lane_lt)] = v[j];   // (< kPrologue <= kRing: no wrap)
             pos += __popc(bal[j]);
         }
-        __syncthreads();                   // B: the ids of round 0 are in the ring (or the list is exhausted)
+        cta_bar();                         // B: the ids of round 0 are in the ring (or the list is exhausted)
     }
 
     // warp -> 8x4 sub-tile, lane -> pixel
@@ -202,20 +234,20 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
     };
     // splat record of filtered position `pos` into the registers; false if the list ended before it.  (Called right
     // after a barrier before which the producer made sure the position exists unless the list is exhausted.)
-    auto fetch = [&](uint32_t pos) -> bool {
-        if (pos >= (*(volatile uint32_t*)&s_prod & ~kDone)) return false;
+    auto fetch = [&](uint32_t pos, uint32_t barrier_no) -> bool {
+        if (pos >= (s_prod[barrier_no & 1u] & ~kDone)) return false;
         const uint4* sp = reinterpret_cast<const uint4*>(splats + s_ring[pos & (kRing - 1u)]);
         q0 = __ldg(sp); q1 = __ldg(sp + 1);
         return true;
     };
-    if (fetch((uint32_t)tid)) stage(sS[0]);                          // round 0 -> buffer 0
-    __syncthreads();                                                 // C: the ids of round 1 are in the ring, too
-    bool have_next = fetch((uint32_t)(kConsumers + tid));            // round 1 -> registers
+    if (fetch((uint32_t)tid, 0u)) stage(sS[0]);                      // round 0 -> buffer 0
+    cta_bar();                                                       // C: the ids of round 1 are in the ring, too
+    bool have_next = fetch((uint32_t)(kConsumers + tid), 1u);        // round 1 -> registers
 
     uint32_t buf = 0;
     for (uint32_t round = 0;; round++, buf ^= 1u) {
         // (before the barrier just passed the producer had delivered this whole round and the next, or the whole list)
-        const uint32_t produced = *(volatile uint32_t*)&s_prod & ~kDone, first = round * kConsumers;
+        const uint32_t produced = s_prod[(round + 1u) & 1u] & ~kDone, first = round * kConsumers;   // (barrier number round + 1 was the last)
         if (produced <= first) break;
         const uint32_t cnt = min((uint32_t)kConsumers, produced - first);
         if (COUNT && tid == 0) atomicAdd(evals + 1, (unsigned long long)cnt);  // entries staged before the tile finished
@@ -299,8 +331,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
         }
         // next round: registers -> the other buffer, then (behind the barrier) fetch the round after it
         if (have_next) stage(sS[buf ^ 1u]);
-        if (__syncthreads_and(done)) break;
-        have_next = fetch((round + 2u) * kConsumers + tid);
+        if (cta_bar_and(done)) break;
+        have_next = fetch((round + 2u) * kConsumers + tid, round + 2u);
     }
 
     if (inside) {
