@@ -222,3 +222,18 @@ def test_cpp_gs_mirror_host_side(G, tmp_path):
     r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "host-only ok" in r.stdout
+
+
+def test_rust_sys_binding_is_current_and_complete(G):
+    """integration/rust/b200gs-sys/src/lib.rs is generated from include/b200gs.h (tools/gen_rust_sys.py): it must be up to
+    date and declare every function the header declares (there is no Rust toolchain here to compile it)."""
+    import importlib.util, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_rust_sys", os.path.join(root, "tools", "gen_rust_sys.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    text, names = mod.generate()
+    assert open(mod.OUT).read() == text, "stale binding: run python tools/gen_rust_sys.py"
+    declared = set(re.findall(r"B200GS_API[^;(]*?\b(b200gs_\w+)\s*\(", open(mod.HDR).read()))
+    assert declared and declared == set(names)
+    assert len(re.findall(r"pub fn b200gs_", text)) == len(declared)
