@@ -75,9 +75,12 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
                                                            unsigned long long* evals) {
     // 64 bytes per staged splat as four float4 planes [j][splat] (a lane reading its own splat in the cull
     // loop touches consecutive 16-byte words: no bank conflicts): {mx, my, a', b'} {c', opacity, red, green}
-    // {cx, hx, cy, hy} {blue, tau', -, -}; conic pre-scaled so that power is in log2 units, extent
-    // square clipped to the viewport stored as centre / half-size (exact: half-integers).
-    // Double-buffered: the next round's splats are in flight while this round is blended.
+    // {blue, extent masks, tau', -} {cx, hx, cy, hy}; conic pre-scaled so that power is in log2 units.  The extent
+    // square clipped to the viewport is stored twice: as centre / half-size (exact: half-integers) for the cull, and,
+    // clipped to this tile, as two 16-bit masks (columns x0..x1 | rows y0..y1 << 16) for the blend loop, where "is my
+    // pixel inside the square" is then ONE logic instruction against a per-lane constant instead of two subtractions and
+    // two compares on a fourth 16-byte load.  Double-buffered: the next round's splats are in flight while this round is
+    // blended.
     __shared__ float4 sS[2][4 * kConsumers];
     __shared__ uint32_t s_ring[kRing];   // splat ids of this quadrant, in list order; position p lives in slot p % kRing
     __shared__ uint32_t s_wcnt[8];       // prologue: ids kept by each compositing warp
@@ -203,9 +206,12 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
     const int px = wx0 + (lane & 7), py = wy0 + (lane >> 3);
     const float fpx = (float)px, fpy = (float)py;
     const bool inside = px < (int)W && py < (int)H;
+    const int tpx0 = (int)(tx * GS_TILE), tpy0 = (int)(ty * GS_TILE);
+    const uint32_t sel = (1u << (px - tpx0)) | (0x10000u << (py - tpy0));   // this pixel's column bit | row bit << 16
 
-    float T = 1.0f, Cr = 0.0f, Cg = 0.0f, Cb = 0.0f;
-    bool done = !inside;
+    // A pixel has stopped when T < 1/1024; pixels outside the viewport start stopped (T = 0).  "Stopped" is always read off
+    // T itself: no separate flag to carry through the blend loop.
+    float T = inside ? 1.0f : 0.0f, Cr = 0.0f, Cg = 0.0f, Cb = 0.0f;
     unsigned long long my_evals = 0;
     const float Wf = (float)W, Hf = (float)H;
 
@@ -227,10 +233,14 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
         if (fy0 < 0.0f) fy0 = 0.0f;
         if (fx1 > Wf - 1.0f) fx1 = Wf - 1.0f;
         if (fy1 > Hf - 1.0f) fy1 = Hf - 1.0f;
+        // the square clipped to this tile, as column / row bit masks (empty masks if it misses the tile)
+        const int x0 = max((int)fx0 - tpx0, 0), x1 = min((int)fx1 - tpx0, GS_TILE - 1);
+        const int y0 = max((int)fy0 - tpy0, 0), y1 = min((int)fy1 - tpy0, GS_TILE - 1);
+        const uint32_t xm = x0 <= x1 ? (2u << x1) - (1u << x0) : 0u, ym = y0 <= y1 ? (2u << y1) - (1u << y0) : 0u;
         dst[tid] = make_float4(mx, my, -0.5f * kLog2e * ca, -kLog2e * cbq);
         dst[kConsumers + tid] = make_float4(-0.5f * kLog2e * cc, op, cr, cg);
-        dst[2 * kConsumers + tid] = make_float4(0.5f * (fx0 + fx1), 0.5f * (fx1 - fx0), 0.5f * (fy0 + fy1), 0.5f * (fy1 - fy0));
-        dst[3 * kConsumers + tid] = make_float4(cb, 0.5f * kLog2e * gs_footprint_tau(op, FLAT), r, 0.0f);
+        dst[2 * kConsumers + tid] = make_float4(cb, __uint_as_float(xm | (ym << 16)), 0.5f * kLog2e * gs_footprint_tau(op, FLAT), 0.0f);
+        dst[3 * kConsumers + tid] = make_float4(0.5f * (fx0 + fx1), 0.5f * (fx1 - fx0), 0.5f * (fy0 + fy1), 0.5f * (fy1 - fy0));
     };
     // splat record of filtered position `pos` into the registers; false if the list ended before it.  (Called right
     // after a barrier before which the producer made sure the position exists unless the list is exhausted.)
@@ -253,19 +263,19 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
         if (COUNT && tid == 0) atomicAdd(evals + 1, (unsigned long long)cnt);  // entries staged before the tile finished
         const float4* sSb = sS[buf];
 
-        if (!__all_sync(0xffffffffu, done)) {
+        if (!__all_sync(0xffffffffu, T < GS_T_EPS)) {
             for (uint32_t g = 0; g < cnt; g += 32) {
                 const uint32_t s = g + lane;
                 bool ov = false;
                 if (s < cnt) {
                     // splat s against this warp's 8x4 sub-tile: extent-square overlap first, then the exact
                     // footprint test (can any pixel of the overlap reach alpha >= 1/255?)
-                    const float4 C = sSb[2 * kConsumers + s];
+                    const float4 C = sSb[3 * kConsumers + s];
                     const float x0 = fmaxf(C.x - C.y, fwx0), x1 = fminf(C.x + C.y, fwx1);
                     const float y0 = fmaxf(C.z - C.w, fwy0), y1 = fminf(C.z + C.w, fwy1);
                     if (x0 <= x1 && y0 <= y1) {
                         const float4 A = sSb[s];
-                        const float4 D = sSb[3 * kConsumers + s];
+                        const float tau = sSb[2 * kConsumers + s].z;
                         const float pa = -A.z, pb = -0.5f * A.w, pc = -sSb[kConsumers + s].x;  // 0.5*log2e * (a, b, c)
                         const float dx0 = x0 - A.x, dx1 = x1 - A.x, dy0 = y0 - A.y, dy1 = y1 - A.y;
                         const bool inx = dx0 <= 0.0f && dx1 >= 0.0f, iny = dy0 <= 0.0f && dy1 >= 0.0f;
@@ -280,7 +290,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
                             const float dx = fminf(dx1, fmaxf(dx0, __fdividef(-pb * dy, pa)));
                             best = fminf(best, pa * dx * dx + 2.0f * pb * dx * dy + pc * dy * dy);
                         }
-                        ov = best <= D.y;
+                        ov = best <= tau;
                     }
                 }
                 uint32_t m = __ballot_sync(0xffffffffu, ov);
@@ -292,11 +302,13 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
                     const bool has_b = m != 0;
                     const int sb = has_b ? (int)g + __ffs((int)m) - 1 : sa;
                     m &= m - 1;  // no-op when m == 0
-                    const float4 Aa = sSb[sa], Ba = sSb[kConsumers + sa], Ca = sSb[2 * kConsumers + sa];
-                    const float4 Ab = sSb[sb], Bb = sSb[kConsumers + sb], Cbb = sSb[2 * kConsumers + sb];
+                    const float4 Aa = sSb[sa], Ba = sSb[kConsumers + sa];
+                    const float4 Ab = sSb[sb], Bb = sSb[kConsumers + sb];
+                    const float2 Ca = *reinterpret_cast<const float2*>(&sSb[2 * kConsumers + sa]);   // {blue, extent masks}
+                    const float2 Cbb = *reinterpret_cast<const float2*>(&sSb[2 * kConsumers + sb]);
                     const float dxa = fpx - Aa.x, dya = fpy - Aa.y, dxb = fpx - Ab.x, dyb = fpy - Ab.y;
-                    const bool ina = fabsf(fpx - Ca.x) <= Ca.y && fabsf(fpy - Ca.z) <= Ca.w;
-                    const bool inb = has_b && fabsf(fpx - Cbb.x) <= Cbb.y && fabsf(fpy - Cbb.z) <= Cbb.w;
+                    const bool ina = (__float_as_uint(Ca.y) & sel) == sel;
+                    const bool inb = has_b && (__float_as_uint(Cbb.y) & sel) == sel;
                     const float pa2 = __fmaf_rn(__fmaf_rn(Aa.w, dya, Aa.z * dxa), dxa, (Ba.x * dya) * dya);
                     const float pb2 = __fmaf_rn(__fmaf_rn(Ab.w, dyb, Ab.z * dxb), dxb, (Bb.x * dyb) * dyb);
                     float ala, alb;
@@ -307,31 +319,29 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
                         ala = fminf(GS_ALPHA_MAX, Ba.y * ex2_approx(pa2));
                         alb = fminf(GS_ALPHA_MAX, Bb.y * ex2_approx(pb2));
                     }
-                    if (COUNT) my_evals += (ina && !done) ? 1ull : 0ull;
-                    if (ina && !done && pa2 <= 0.0f && ala >= GS_ALPHA_MIN) {
+                    if (COUNT) my_evals += (ina && T >= GS_T_EPS) ? 1ull : 0ull;
+                    if (ina && T >= GS_T_EPS && pa2 <= 0.0f && ala >= GS_ALPHA_MIN) {
                         const float w = ala * T;
                         Cr = __fmaf_rn(Ba.z, w, Cr);
                         Cg = __fmaf_rn(Ba.w, w, Cg);
-                        Cb = __fmaf_rn(sSb[3 * kConsumers + sa].x, w, Cb);
+                        Cb = __fmaf_rn(Ca.x, w, Cb);
                         T -= w;
-                        done = T < GS_T_EPS;
                     }
-                    if (COUNT) my_evals += (inb && !done) ? 1ull : 0ull;
-                    if (inb && !done && pb2 <= 0.0f && alb >= GS_ALPHA_MIN) {
+                    if (COUNT) my_evals += (inb && T >= GS_T_EPS) ? 1ull : 0ull;
+                    if (inb && T >= GS_T_EPS && pb2 <= 0.0f && alb >= GS_ALPHA_MIN) {
                         const float w = alb * T;
                         Cr = __fmaf_rn(Bb.z, w, Cr);
                         Cg = __fmaf_rn(Bb.w, w, Cg);
-                        Cb = __fmaf_rn(sSb[3 * kConsumers + sb].x, w, Cb);
+                        Cb = __fmaf_rn(Cbb.x, w, Cb);
                         T -= w;
-                        done = T < GS_T_EPS;
                     }
                 }
-                if (__all_sync(0xffffffffu, done)) break;
+                if (__all_sync(0xffffffffu, T < GS_T_EPS)) break;
             }
         }
         // next round: registers -> the other buffer, then (behind the barrier) fetch the round after it
         if (have_next) stage(sS[buf ^ 1u]);
-        if (cta_bar_and(done)) break;
+        if (cta_bar_and(T < GS_T_EPS)) break;
         have_next = fetch((round + 2u) * kConsumers + tid, round + 2u);
     }
 
