@@ -25,6 +25,7 @@ constexpr int kThreads = kConsumers + 32;    // + the producer warp
 constexpr uint32_t kRing = 2048;             // ring of filtered splat ids (8 rounds)
 constexpr uint32_t kPrologue = 1024;         // entries filtered cooperatively by the compositing warps at CTA start
 constexpr uint32_t kBatch = 512;             // entries examined per producer step (16 per lane)
+constexpr int kPlane = kConsumers + 1;        // entries per staged plane: 256 splats + one NULL splat (empty extent masks)
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -81,7 +82,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
     // pixel inside the square" is then ONE logic instruction against a per-lane constant instead of two subtractions and
     // two compares on a fourth 16-byte load.  Double-buffered: the next round's splats are in flight while this round is
     // blended.
-    __shared__ float4 sS[2][4 * kConsumers];
+    __shared__ float4 sS[2][4 * kPlane];
+    __shared__ __align__(8) uint32_t s_hit[kConsumers / 32][34];   // per warp: shared-memory byte offsets of the splats that hit its sub-tile
     __shared__ uint32_t s_ring[kRing];   // splat ids of this quadrant, in list order; position p lives in slot p % kRing
     __shared__ uint32_t s_wcnt[8];       // prologue: ids kept by each compositing warp
     __shared__ uint32_t s_prod[2];       // ids produced so far; bit 31: the list is exhausted (the count is final).  Written before
@@ -188,6 +190,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
             cnt += __popc(bal[j]);
         }
         if (lane == 0) s_wcnt[warp] = cnt;
+        if (tid < 2) sS[tid][2 * kPlane + kConsumers] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // the NULL splat: empty extent masks
         cta_bar();                         // A
         uint32_t pos = 0;
 #pragma unroll
@@ -238,9 +241,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
         const int y0 = max((int)fy0 - tpy0, 0), y1 = min((int)fy1 - tpy0, GS_TILE - 1);
         const uint32_t xm = x0 <= x1 ? (2u << x1) - (1u << x0) : 0u, ym = y0 <= y1 ? (2u << y1) - (1u << y0) : 0u;
         dst[tid] = make_float4(mx, my, -0.5f * kLog2e * ca, -kLog2e * cbq);
-        dst[kConsumers + tid] = make_float4(-0.5f * kLog2e * cc, op, cr, cg);
-        dst[2 * kConsumers + tid] = make_float4(cb, __uint_as_float(xm | (ym << 16)), 0.5f * kLog2e * gs_footprint_tau(op, FLAT), 0.0f);
-        dst[3 * kConsumers + tid] = make_float4(0.5f * (fx0 + fx1), 0.5f * (fx1 - fx0), 0.5f * (fy0 + fy1), 0.5f * (fy1 - fy0));
+        dst[kPlane + tid] = make_float4(-0.5f * kLog2e * cc, op, cr, cg);
+        dst[2 * kPlane + tid] = make_float4(cb, __uint_as_float(xm | (ym << 16)), 0.5f * kLog2e * gs_footprint_tau(op, FLAT), 0.0f);
+        dst[3 * kPlane + tid] = make_float4(0.5f * (fx0 + fx1), 0.5f * (fx1 - fx0), 0.5f * (fy0 + fy1), 0.5f * (fy1 - fy0));
     };
     // splat record of filtered position `pos` into the registers; false if the list ended before it.  (Called right
     // after a barrier before which the producer made sure the position exists unless the list is exhausted.)
@@ -270,13 +273,13 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
                 if (s < cnt) {
                     // splat s against this warp's 8x4 sub-tile: extent-square overlap first, then the exact
                     // footprint test (can any pixel of the overlap reach alpha >= 1/255?)
-                    const float4 C = sSb[3 * kConsumers + s];
+                    const float4 C = sSb[3 * kPlane + s];
                     const float x0 = fmaxf(C.x - C.y, fwx0), x1 = fminf(C.x + C.y, fwx1);
                     const float y0 = fmaxf(C.z - C.w, fwy0), y1 = fminf(C.z + C.w, fwy1);
                     if (x0 <= x1 && y0 <= y1) {
                         const float4 A = sSb[s];
-                        const float tau = sSb[2 * kConsumers + s].z;
-                        const float pa = -A.z, pb = -0.5f * A.w, pc = -sSb[kConsumers + s].x;  // 0.5*log2e * (a, b, c)
+                        const float tau = sSb[2 * kPlane + s].z;
+                        const float pa = -A.z, pb = -0.5f * A.w, pc = -sSb[kPlane + s].x;  // 0.5*log2e * (a, b, c)
                         const float dx0 = x0 - A.x, dx1 = x1 - A.x, dy0 = y0 - A.y, dy1 = y1 - A.y;
                         const bool inx = dx0 <= 0.0f && dx1 >= 0.0f, iny = dy0 <= 0.0f && dy1 >= 0.0f;
                         float best = (inx && iny) ? 0.0f : 3.0e38f;
@@ -293,22 +296,25 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
                         ov = best <= tau;
                     }
                 }
-                uint32_t m = __ballot_sync(0xffffffffu, ov);
-                // two splats per trip: their alpha evaluations are independent (ILP), the blends are
-                // applied in order
-                while (m) {
-                    const int sa = (int)g + __ffs((int)m) - 1;
-                    m &= m - 1;
-                    const bool has_b = m != 0;
-                    const int sb = has_b ? (int)g + __ffs((int)m) - 1 : sa;
-                    m &= m - 1;  // no-op when m == 0
-                    const float4 Aa = sSb[sa], Ba = sSb[kConsumers + sa];
-                    const float4 Ab = sSb[sb], Bb = sSb[kConsumers + sb];
-                    const float2 Ca = *reinterpret_cast<const float2*>(&sSb[2 * kConsumers + sa]);   // {blue, extent masks}
-                    const float2 Cbb = *reinterpret_cast<const float2*>(&sSb[2 * kConsumers + sb]);
+                // The lanes whose splat hits write its shared-memory offset into the warp's hit list, in order (an odd count is
+                // padded with the NULL splat, whose extent masks are empty); the blend loop then walks the list two splats per
+                // trip — their alpha evaluations are independent (ILP), the blends are applied in order — and costs one 8-byte
+                // load per pair for "which splats" instead of a find-first-set chain on the ballot.
+                const uint32_t m = __ballot_sync(0xffffffffu, ov);
+                const int n_hit = __popc(m);
+                if (ov) s_hit[warp][__popc(m & lane_lt)] = s * 16u;
+                if (lane == 0 && (n_hit & 1)) s_hit[warp][n_hit] = (uint32_t)kConsumers * 16u;
+                __syncwarp();
+                const char* const pl = reinterpret_cast<const char*>(sSb);
+                for (int i = 0; i < n_hit; i += 2) {
+                    const uint2 h = *reinterpret_cast<const uint2*>(&s_hit[warp][i]);
+                    const float4 Aa = *reinterpret_cast<const float4*>(pl + h.x), Ba = *reinterpret_cast<const float4*>(pl + kPlane * 16 + h.x);
+                    const float4 Ab = *reinterpret_cast<const float4*>(pl + h.y), Bb = *reinterpret_cast<const float4*>(pl + kPlane * 16 + h.y);
+                    const float2 Ca = *reinterpret_cast<const float2*>(pl + 2 * kPlane * 16 + h.x);   // {blue, extent masks}
+                    const float2 Cbb = *reinterpret_cast<const float2*>(pl + 2 * kPlane * 16 + h.y);
                     const float dxa = fpx - Aa.x, dya = fpy - Aa.y, dxb = fpx - Ab.x, dyb = fpy - Ab.y;
                     const bool ina = (__float_as_uint(Ca.y) & sel) == sel;
-                    const bool inb = has_b && (__float_as_uint(Cbb.y) & sel) == sel;
+                    const bool inb = (__float_as_uint(Cbb.y) & sel) == sel;
                     const float pa2 = __fmaf_rn(__fmaf_rn(Aa.w, dya, Aa.z * dxa), dxa, (Ba.x * dya) * dya);
                     const float pb2 = __fmaf_rn(__fmaf_rn(Ab.w, dyb, Ab.z * dxb), dxb, (Bb.x * dyb) * dyb);
                     float ala, alb;
