@@ -33,6 +33,17 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// loads from a shared-memory window address (the hit list holds addresses, not indices)
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
 
 // The producer warp and the compositing warps run different code between barriers, so the barriers are spelled as PTX named
 // barriers with an explicit thread count (what warp-specialised kernels use) rather than as __syncthreads(), whose C++
@@ -213,7 +224,10 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
     const uint32_t sel = (1u << (px - tpx0)) | (0x10000u << (py - tpy0));   // this pixel's column bit | row bit << 16
 
     // A pixel has stopped when T < 1/1024; pixels outside the viewport start stopped (T = 0).  "Stopped" is always read off
-    // T itself: no separate flag to carry through the blend loop.
+    // T itself: no separate flag to carry through the blend loop.  Stopping is a property of the WARP and the CTA (they leave
+    // when all their pixels have stopped): a stopped pixel whose warp is still running keeps blending the splats the warp
+    // evaluates — contributions below 1/1024 that the back-to-front reference includes anyway — which takes the "has this
+    // pixel stopped" test out of the blend loop.
     float T = inside ? 1.0f : 0.0f, Cr = 0.0f, Cg = 0.0f, Cb = 0.0f;
     unsigned long long my_evals = 0;
     const float Wf = (float)W, Hf = (float)H;
@@ -265,6 +279,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
         const uint32_t cnt = min((uint32_t)kConsumers, produced - first);
         if (COUNT && tid == 0) atomicAdd(evals + 1, (unsigned long long)cnt);  // entries staged before the tile finished
         const float4* sSb = sS[buf];
+        const uint32_t plane0 = gs_smem_u32(sSb);   // shared-memory address of this round's first plane
 
         if (!__all_sync(0xffffffffu, T < GS_T_EPS)) {
             for (uint32_t g = 0; g < cnt; g += 32) {
@@ -302,16 +317,15 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
                 // load per pair for "which splats" instead of a find-first-set chain on the ballot.
                 const uint32_t m = __ballot_sync(0xffffffffu, ov);
                 const int n_hit = __popc(m);
-                if (ov) s_hit[warp][__popc(m & lane_lt)] = s * 16u;
-                if (lane == 0 && (n_hit & 1)) s_hit[warp][n_hit] = (uint32_t)kConsumers * 16u;
+                if (ov) s_hit[warp][__popc(m & lane_lt)] = plane0 + s * 16u;
+                if (lane == 0 && (n_hit & 1)) s_hit[warp][n_hit] = plane0 + (uint32_t)kConsumers * 16u;
                 __syncwarp();
-                const char* const pl = reinterpret_cast<const char*>(sSb);
                 for (int i = 0; i < n_hit; i += 2) {
                     const uint2 h = *reinterpret_cast<const uint2*>(&s_hit[warp][i]);
-                    const float4 Aa = *reinterpret_cast<const float4*>(pl + h.x), Ba = *reinterpret_cast<const float4*>(pl + kPlane * 16 + h.x);
-                    const float4 Ab = *reinterpret_cast<const float4*>(pl + h.y), Bb = *reinterpret_cast<const float4*>(pl + kPlane * 16 + h.y);
-                    const float2 Ca = *reinterpret_cast<const float2*>(pl + 2 * kPlane * 16 + h.x);   // {blue, extent masks}
-                    const float2 Cbb = *reinterpret_cast<const float2*>(pl + 2 * kPlane * 16 + h.y);
+                    const float4 Aa = lds128(h.x), Ba = lds128(h.x + kPlane * 16);
+                    const float4 Ab = lds128(h.y), Bb = lds128(h.y + kPlane * 16);
+                    const float2 Ca = lds64(h.x + 2 * kPlane * 16);   // {blue, extent masks}
+                    const float2 Cbb = lds64(h.y + 2 * kPlane * 16);
                     const float dxa = fpx - Aa.x, dya = fpy - Aa.y, dxb = fpx - Ab.x, dyb = fpy - Ab.y;
                     const bool ina = (__float_as_uint(Ca.y) & sel) == sel;
                     const bool inb = (__float_as_uint(Cbb.y) & sel) == sel;
@@ -326,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
                         alb = fminf(GS_ALPHA_MAX, Bb.y * ex2_approx(pb2));
                     }
                     if (COUNT) my_evals += (ina && T >= GS_T_EPS) ? 1ull : 0ull;
-                    if (ina && T >= GS_T_EPS && pa2 <= 0.0f && ala >= GS_ALPHA_MIN) {
+                    if (ina && pa2 <= 0.0f && ala >= GS_ALPHA_MIN) {
                         const float w = ala * T;
                         Cr = __fmaf_rn(Ba.z, w, Cr);
                         Cg = __fmaf_rn(Ba.w, w, Cg);
@@ -334,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
                         T -= w;
                     }
                     if (COUNT) my_evals += (inb && T >= GS_T_EPS) ? 1ull : 0ull;
-                    if (inb && T >= GS_T_EPS && pb2 <= 0.0f && alb >= GS_ALPHA_MIN) {
+                    if (inb && pb2 <= 0.0f && alb >= GS_ALPHA_MIN) {
                         const float w = alb * T;
                         Cr = __fmaf_rn(Bb.z, w, Cr);
                         Cg = __fmaf_rn(Bb.w, w, Cg);
