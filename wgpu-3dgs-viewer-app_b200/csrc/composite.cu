@@ -33,6 +33,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float rcp_approx(float x) {   // (operands here are conic entries: never denormal, never huge)
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 // loads from a shared-memory window address (the hit list holds addresses, not indices)
 __device__ __forceinline__ float4 lds128(uint32_t a) {
     float4 v;
@@ -284,32 +289,29 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
         if (!__all_sync(0xffffffffu, T < GS_T_EPS)) {
             for (uint32_t g = 0; g < cnt; g += 32) {
                 const uint32_t s = g + lane;
-                bool ov = false;
-                if (s < cnt) {
-                    // splat s against this warp's 8x4 sub-tile: extent-square overlap first, then the exact
-                    // footprint test (can any pixel of the overlap reach alpha >= 1/255?)
+                // splat s against this warp's 8x4 sub-tile: extent-square overlap, then the exact footprint test (can any
+                // pixel of the overlap reach alpha >= 1/255?: the minimum of the quadratic over the overlap rectangle is at
+                // the centre if it is inside, else on the edge nearest to it).  Straight-line code: lanes past the end of the
+                // list and splats that miss the square compute on whatever the slot holds and are masked at the end.
+                bool ov;
+                {
                     const float4 C = sSb[3 * kPlane + s];
                     const float x0 = fmaxf(C.x - C.y, fwx0), x1 = fminf(C.x + C.y, fwx1);
                     const float y0 = fmaxf(C.z - C.w, fwy0), y1 = fminf(C.z + C.w, fwy1);
-                    if (x0 <= x1 && y0 <= y1) {
-                        const float4 A = sSb[s];
-                        const float tau = sSb[2 * kPlane + s].z;
-                        const float pa = -A.z, pb = -0.5f * A.w, pc = -sSb[kPlane + s].x;  // 0.5*log2e * (a, b, c)
-                        const float dx0 = x0 - A.x, dx1 = x1 - A.x, dy0 = y0 - A.y, dy1 = y1 - A.y;
-                        const bool inx = dx0 <= 0.0f && dx1 >= 0.0f, iny = dy0 <= 0.0f && dy1 >= 0.0f;
-                        float best = (inx && iny) ? 0.0f : 3.0e38f;
-                        if (!inx) {
-                            const float dx = dx0 > 0.0f ? dx0 : dx1;
-                            const float dy = fminf(dy1, fmaxf(dy0, __fdividef(-pb * dx, pc)));
-                            best = pa * dx * dx + 2.0f * pb * dx * dy + pc * dy * dy;
-                        }
-                        if (!iny) {
-                            const float dy = dy0 > 0.0f ? dy0 : dy1;
-                            const float dx = fminf(dx1, fmaxf(dx0, __fdividef(-pb * dy, pa)));
-                            best = fminf(best, pa * dx * dx + 2.0f * pb * dx * dy + pc * dy * dy);
-                        }
-                        ov = best <= tau;
-                    }
+                    const float4 A = sSb[s];
+                    const float tau = sSb[2 * kPlane + s].z;
+                    const float pa = -A.z, pb = -0.5f * A.w, pc = -sSb[kPlane + s].x;  // 0.5*log2e * (a, b, c)
+                    const float dx0 = x0 - A.x, dx1 = x1 - A.x, dy0 = y0 - A.y, dy1 = y1 - A.y;
+                    const bool inx = dx0 <= 0.0f && dx1 >= 0.0f, iny = dy0 <= 0.0f && dy1 >= 0.0f;
+                    // the vertical edge nearest the centre, minimised over y; the horizontal edge nearest the centre, over x
+                    const float dxe = dx0 > 0.0f ? dx0 : dx1;
+                    const float dye = fminf(dy1, fmaxf(dy0, -pb * dxe * rcp_approx(pc)));
+                    const float qe = pa * dxe * dxe + 2.0f * pb * dxe * dye + pc * dye * dye;
+                    const float dyf = dy0 > 0.0f ? dy0 : dy1;
+                    const float dxf = fminf(dx1, fmaxf(dx0, -pb * dyf * rcp_approx(pa)));
+                    const float qf = pa * dxf * dxf + 2.0f * pb * dxf * dyf + pc * dyf * dyf;
+                    const float best = fminf(inx ? (iny ? 0.0f : 3.0e38f) : qe, iny ? 3.0e38f : qf);
+                    ov = s < cnt && x0 <= x1 && y0 <= y1 && best <= tau;
                 }
                 // The lanes whose splat hits write its shared-memory offset into the warp's hit list, in order (an odd count is
                 // padded with the NULL splat, whose extent masks are empty); the blend loop then walks the list two splats per
