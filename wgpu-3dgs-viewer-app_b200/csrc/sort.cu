@@ -122,8 +122,10 @@ __global__ void __launch_bounds__(kThreads, 3) k_sort_pass(uint32_t* __restrict_
 
     // exclusive prefix of the global histogram of this digit (thread d owns digit d)
     uint32_t gbase;
+    bool digit_used;   // does any key of the whole input carry this thread's digit?  (an unused digit takes no part in the look-back)
     {
         uint32_t c = hist[tid];
+        digit_used = c != 0u;
         uint32_t incl = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -173,7 +175,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_sort_pass(uint32_t* __restrict_
                 count += t;
             }
             // publish this tile's aggregate for digit `tid`
-            gs_st_status(&lb[(size_t)tile * kRadix], epoch, (tile == 0 ? GS_LOOKBACK_FLAG_INCL : GS_LOOKBACK_FLAG_AGG) | count);
+            if (digit_used)
+                gs_st_status(&lb[(size_t)tile * kRadix], epoch, (tile == 0 ? GS_LOOKBACK_FLAG_INCL : GS_LOOKBACK_FLAG_AGG) | count);
             // exclusive scan of the tile totals over digits
             uint32_t incl = count;
 #pragma unroll
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_sort_pass(uint32_t* __restrict_
             // ---- resolve the previous tile's look-back for digit `tid`, kLb status words per round trip
             const uint32_t pbuf = buf ^ 1u;
             uint32_t excl = 0;
-            if (p_tile > 0) {
+            if (p_tile > 0 && digit_used) {
                 constexpr int kLb = 4;
                 int64_t p = (int64_t)p_tile - 1;
                 bool done = false;
