@@ -614,7 +614,7 @@ static int model_create(b200gs_viewer* v, const char* key, uint64_t capacity, Gs
     if (rc == B200GS_OK) rc = dev_alloc(&m->vals_b, capacity, false, st);
     if (rc == B200GS_OK) rc = dev_alloc(&m->idx, capacity, false, st);
     if (rc == B200GS_OK) rc = dev_alloc(&m->binword, capacity, false, st);
-    if (rc == B200GS_OK) rc = dev_alloc(&m->lb_pre, (capacity + 255) / 256 + 1, true, st);
+    if (rc == B200GS_OK) rc = dev_alloc(&m->lb_pre, gs_preprocess_lookback_words(capacity), true, st);
     if (rc == B200GS_OK) rc = dev_alloc(&m->lb_sort, gs_sort_lookback_words((uint32_t)capacity, 4), true, st);
     if (rc != B200GS_OK) { free_model(m); return rc; }
     v->models.push_back(m);

@@ -82,6 +82,7 @@ struct GsPreprocessArgs {
 };
 cudaError_t gs_launch_preprocess(const GsPreprocessArgs& a, const GsFrame& f, const GsModelXf& m, int num_sms,
                                  cudaStream_t st);
+size_t gs_preprocess_lookback_words(uint64_t n);   // status words of the preprocess kernel for n Gaussians
 
 // K2 (sort.cu): onesweep LSD radix sort of (key,value) u32 pairs, 8-bit digits, CTA-local tiles; n is read from the
 // device (*d_n).  Sorts the depth keys.

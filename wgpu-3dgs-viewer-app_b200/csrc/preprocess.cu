@@ -29,7 +29,8 @@
 
 namespace {
 
-constexpr int kChunk = 256;
+constexpr int kChunk = 224;          // Gaussians per chunk = 7 compute warps: with 3 stages of 224 x 76 B a CTA needs 55 KB and 4 fit an SM
+constexpr int kCW = kChunk / 32;    // compute warps
 template <int SH> struct ShBytes { static constexpr int v = SH == 0 ? 180 : SH == 1 ? 92 : SH == 2 ? 48 : 0; };
 template <int COV> struct CovBytes { static constexpr int v = COV == 0 ? 24 : 12; };
 
@@ -107,7 +108,7 @@ __device__ void apply_edit(const b200gs_edit_pod& e, float rgb[3], float& op) {
 constexpr int kBarCounts = 1;   // compute warps -> control warp: per-warp visible counts of chunk j are in smem
 constexpr int kBarBase = 5;     // control warp -> compute warps: chunk j's output base is in smem
 constexpr int kBarFree = 9;     // compute warps -> control warp: chunk j's stage can be refilled
-constexpr int kThreads = kChunk + 32;  // 8 compute warps + 1 control warp
+constexpr int kThreads = kChunk + 32;  // the compute warps + 1 control warp
 
 __device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kThreads) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kThreads) : "memory"); }
@@ -240,7 +241,7 @@ __device__ __forceinline__ bool pre_tests(uint32_t i, uint32_t n, const uint32_t
 // selection / edit buffers, no selection query, Splat display, SH degree 3 with SH0 — and picks the instantiation in
 // which those uniform branches (and the loads of their operands) are compiled out.  Same arithmetic, same bits.
 template <int SH, int COV, bool FAST>
-__global__ void __launch_bounds__(kThreads, 3) k_preprocess(const uint8_t* __restrict__ recs, uint32_t n,
+__global__ void __launch_bounds__(kThreads, (16 + ShBytes<SH>::v + CovBytes<COV>::v) <= 76 ? 4 : 3) k_preprocess(const uint8_t* __restrict__ recs, uint32_t n,
                                                          const uint32_t* __restrict__ mask, uint32_t* selection,
                                                          const b200gs_edit_pod* __restrict__ edits,
                                                          const __grid_constant__ GsFrame f,
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_preprocess(const uint8_t* __res
         // (woff: this lane's warp's offset inside the chunk, lanes 0..7 — the exclusive scan of the 8 warp counts)
         auto publish = [&](uint32_t j, uint32_t c, uint32_t& woff) -> uint32_t {
             bar_sync(kBarCounts + (int)(j & 3u));  // counts of chunk j are in smem
-            const uint32_t cnt = lane < 8 ? s_wcount_all[(j & 3u) * 8 + lane] : 0u;
+            const uint32_t cnt = lane < kCW ? s_wcount_all[(j & 3u) * 8 + lane] : 0u;
             uint32_t incl = cnt;
 #pragma unroll
             for (int o = 1; o < 8; o <<= 1) {
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_preprocess(const uint8_t* __res
                 if (lane >= o) incl += t;
             }
             woff = incl - cnt;
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 7);
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, kCW - 1);
             if (lane == 0) gs_lookback_publish(lookback, epoch, c, total);
             return total;
         };
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_preprocess(const uint8_t* __res
                 __syncwarp();
             }
             const uint32_t excl = gs_lookback_resolve(lookback, epoch, c, total, lane);
-            if (lane < 8) s_base_all[(j & 3u) * 8 + lane] = excl + woff;   // output base of every warp of the chunk
+            if (lane < kCW) s_base_all[(j & 3u) * 8 + lane] = excl + woff;   // output base of every warp of the chunk
             if (lane == 0 && c == nchunks - 1) ctrl[GS_CTRL_VISIBLE] = excl + total;
             bar_arrive(kBarBase + (int)(j & 3u));
             c = c_next;
@@ -653,6 +654,8 @@ cudaError_t launch_t(const GsPreprocessArgs& a, const GsFrame& f, const GsModelX
 }
 
 }  // namespace
+
+size_t gs_preprocess_lookback_words(uint64_t n) { return (size_t)((n + kChunk - 1) / kChunk) + 1; }
 
 cudaError_t gs_launch_preprocess(const GsPreprocessArgs& a, const GsFrame& f, const GsModelXf& m, int num_sms,
                                  cudaStream_t st) {
