@@ -22,7 +22,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kKpt = 11;                       // keys per thread
+constexpr int kKpt = 12;                       // keys per thread
 constexpr int kTile = kThreads * kKpt;         // 3072 keys per tile
 constexpr int kRadix = 256;
 
@@ -85,7 +85,7 @@ struct PassSmem {
 // ones (the top bytes of depth keys, the row-band byte of tile ids).
 constexpr int kVoteBits = 5;
 template <int kVote>
-__global__ void __launch_bounds__(kThreads, 4) k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a,
+__global__ void __launch_bounds__(kThreads, 3) k_sort_pass(uint32_t* __restrict__ keys_a, uint32_t* __restrict__ vals_a,
                                                            uint32_t* __restrict__ keys_b, uint32_t* __restrict__ vals_b,
                                                            const uint32_t* d_n, uint32_t n_max,
                                                            const uint32_t* __restrict__ hist_all, uint32_t pass,
