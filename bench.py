@@ -51,7 +51,10 @@ def parse():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs stage timings (1M, 6M@4K, config 4)")
-    ap.add_argument("--no-gather", action="store_true", help="diagnostic: skip the NCCL image gather")
+    ap.add_argument("--no-gather", action="store_true", help="diagnostic: skip the image gather")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="how finished images reach rank 0: p2p = every rank copies its slot straight into rank 0's buffer over "
+                         "NVLink with the copy engines (symmetric memory, no SMs); nccl = dist.gather (SM kernels on every rank)")
     return ap.parse_args()
 
 
@@ -314,8 +317,32 @@ def run_ours(a, rank, world, local_rank):
 
     img_bytes = W * H * 4
     ring = [torch.empty((B, H, W, 4), dtype=torch.uint8, device=dev) for _ in range(2)]
+    # ---- image gather.  p2p: rank 0's (2, world, B, H, W, 4) buffer is symmetric memory mapped into every rank; a rank's
+    # finished slot is one peer-to-peer cudaMemcpyAsync over NVLink on a side stream (copy engines: no SM on either side is
+    # taken from the renderers, which NCCL's send / recv kernels do — rank 0 receives 7 x 531 MB per step at N = 8).  Falls
+    # back to the NCCL gather if symmetric memory cannot be set up on every rank.
+    gather_mode, gather_note, sym_local, sym_rank0, copy_stream = "none", "", None, None, None
+    if world > 1 and not a.no_gather:
+        gather_mode = "nccl"
+        if a.gather == "p2p":
+            ok = 1
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                shape = (2, world, B, H, W, 4)
+                sym_local = symm_mem.empty(shape, dtype=torch.uint8, device=dev)
+                hdl = symm_mem.rendezvous(sym_local, dist.group.WORLD)
+                sym_rank0 = hdl.get_buffer(0, shape, torch.uint8)
+                copy_stream = torch.cuda.Stream(device=dev)
+            except Exception as e:  # noqa: BLE001
+                ok, gather_note = 0, "symmetric memory unavailable: %r" % (e,)
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 1:
+                gather_mode = "p2p"
+            else:
+                sym_local = sym_rank0 = copy_stream = None
     gathered = [[torch.empty((B, H, W, 4), dtype=torch.uint8, device=dev) for _ in range(world)] for _ in range(2)] \
-        if (world > 1 and rank == 0) else None
+        if (gather_mode == "nccl" and rank == 0) else None
     pending = [None, None]
     rendered = [torch.cuda.Event() for _ in range(K)]
 
@@ -324,19 +351,32 @@ def run_ours(a, rank, world, local_rank):
         then hand the slot to an asynchronous NCCL gather that runs behind the next step's rendering"""
         slot = s % 2
         if pending[slot] is not None:
-            pending[slot].wait()                # (on `stream`: orders later work of viewer 0 behind the gather)
-            pending[slot] = None
-            done = torch.cuda.Event()
-            done.record(stream)
-            for st in streams[1:]:
-                st.wait_event(done)
+            if gather_mode == "p2p":
+                for st in streams:
+                    st.wait_event(pending[slot])    # the slot's previous copy has left before it is rendered into again
+                pending[slot] = None
+            else:
+                pending[slot].wait()            # (on `stream`: orders later work of viewer 0 behind the gather)
+                pending[slot] = None
+                done = torch.cuda.Event()
+                done.record(stream)
+                for st in streams[1:]:
+                    st.wait_event(done)
         base = ring[slot].data_ptr()
         for j in range(B):
             view, proj = mats[(s * B + j) % len(mats)]
             k = j % K
             viewers[k].update_camera_matrices(view, proj, (W, H))
             viewers[k].render_frame([models[k]], base + j * img_bytes, W * 4)
-        if world > 1 and not a.no_gather:
+        if gather_mode == "p2p":
+            for k in range(K):                  # the slot is complete when every viewer's last frame of it is
+                rendered[k].record(streams[k])
+                copy_stream.wait_event(rendered[k])
+            with torch.cuda.stream(copy_stream):
+                sym_rank0[slot, rank].copy_(ring[slot], non_blocking=True)
+                pending[slot] = torch.cuda.Event()
+                pending[slot].record(copy_stream)
+        elif gather_mode == "nccl":
             for k in range(1, K):               # the slot is complete when every viewer's last frame of it is
                 rendered[k].record(streams[k])
                 stream.wait_event(rendered[k])
@@ -350,7 +390,10 @@ def run_ours(a, rank, world, local_rank):
     def drain():
         for p in pending:
             if p is not None:
-                p.wait()
+                if gather_mode == "p2p":
+                    stream.wait_event(p)
+                else:
+                    p.wait()
         pending[0] = pending[1] = None
         for st in streams[1:]:
             stream.wait_stream(st)
@@ -384,7 +427,7 @@ def run_ours(a, rank, world, local_rank):
         # ---- are the gathered bytes right?  rank 0 re-renders, on its own GPU, a sample of the views every rank sent
         # in the last step and compares them byte for byte with what arrived (same view -> same bytes on every rank)
         gather_verified = None
-        if world > 1 and not a.no_gather:
+        if gather_mode != "none":
             ok = True
             if rank == 0:
                 s_last = a.warmup + a.steps - 1
@@ -396,7 +439,8 @@ def run_ours(a, rank, world, local_rank):
                         v.update_camera_matrices(c.view(), c.projection(asp), (W, H))
                         v.render_frame([m], check.data_ptr(), W * 4)
                         v.sync()
-                        ok = ok and bool(torch.equal(check, gathered[s_last % 2][r][j]))
+                        got = sym_local[s_last % 2, r, j] if gather_mode == "p2p" else gathered[s_last % 2][r][j]
+                        ok = ok and bool(torch.equal(check, got))
             flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
             dist.broadcast(flag, 0)
             gather_verified = bool(flag.item())
@@ -479,8 +523,9 @@ def run_ours(a, rank, world, local_rank):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "views_per_step_per_gpu": B, "viewers_per_gpu": K, "gaussians": N,
                        "record_bytes": rb, "scene_replicas_per_gpu": 1,
-                       "parallelism": "views partitioned over %d GPU(s), scene replicated; images gathered to rank 0 with NCCL "
-                                      "off the critical path" % world,
+                       "parallelism": "views partitioned over %d GPU(s), scene replicated (one NCCL broadcast); images gathered to rank 0 "
+                                      "off the critical path (%s)" % (world, {"p2p": "peer-to-peer copies over NVLink into rank 0's symmetric-memory "
+                                      "buffer, copy engines", "nccl": "async NCCL gather", "none": "no gather"}[gather_mode] + (("; " + gather_note) if gather_note else "")),
                        "l2": "inputs larger than L2: the %.0f MB packed scene is re-streamed every frame (L2 = 126 MB); "
                              "camera changes every frame" % (N * rb / 1e6)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 136, "d2h_bytes_per_step": B * img_bytes,
@@ -510,7 +555,7 @@ def run_ours(a, rank, world, local_rank):
         }
     for vv in viewers:
         vv.close()
-    del ring, gathered
+    del ring, gathered, sym_local, sym_rank0
     torch.cuda.empty_cache()
     if rank == 0:
         if world == 1 and not a.no_extra:
