@@ -184,6 +184,39 @@ def stage_times(G, v, m, mats, W, H, frames=14):
     return np.median(np.array(rows[2:], dtype=np.float64), axis=0)
 
 
+def ply_stream_rate(G, local_rank, n=1_000_000, chunk=65536):
+    """Row N1 of SURVEY.md §8: the loading loop of the reference (scene.rs:341-380 — read a chunk of the PLY, Gaussian::from,
+    gaussians_buffer.update_range, every frame while the file streams in) through this library: PLY file -> b200gs_ply_read ->
+    b200gs_gaussian_from_ply -> b200gs_model_update_range (host packer + pinned ring + H2D).  1M Gaussians (248 MB of PLY)."""
+    import tempfile
+    ply = G.synth_scene(0xB2000002, n)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "scene.ply")
+        G.write_ply(path, ply)
+        size = os.path.getsize(path)
+        del ply
+        with G.Viewer(640, 360, G.SH_NORM8, G.COV3D_HALF, device=local_rank) as v:
+            m = v.add_model("stream", n)
+            t0 = time.perf_counter()
+            start = parse_s = conv_s = up_s = 0.0
+            start = 0
+            ta = time.perf_counter()
+            for verts in G.read_ply(path, chunk=chunk):
+                tb = time.perf_counter()
+                g = G.gaussian_from_ply(verts)
+                tc = time.perf_counter()
+                m.update_range(start, g)
+                td_ = time.perf_counter()
+                parse_s += tb - ta; conv_s += tc - tb; up_s += td_ - tc
+                start += len(verts)
+                ta = time.perf_counter()
+            v.sync()
+            dt = time.perf_counter() - t0
+    return {"gaussians": n, "ply_bytes": size, "chunk": chunk, "seconds": dt, "ply_gb_per_s": size / dt / 1e9,
+            "mgaussians_per_s": n / dt / 1e6, "read_s": parse_s, "gaussian_from_ply_s": conv_s, "update_range_s": up_s,
+            "note": "file -> b200gs_ply_read -> b200gs_gaussian_from_ply -> b200gs_model_update_range (pack + pinned ring + H2D), one host thread"}
+
+
 def extra_config_times(G, local_rank):
     """The other BASELINE.json configs on one stream (CUDA events, median over views of the batch): configs[1]
     1M @ 1080p, configs[2] second leg 6M @ 3840x2160 (reuses nothing of the timed run), configs[3] three 2M models
@@ -559,6 +592,10 @@ def run_ours(a, rank, world, local_rank):
     torch.cuda.empty_cache()
     if rank == 0:
         if world == 1 and not a.no_extra:
+            try:
+                out["setup"]["ply_stream"] = ply_stream_rate(G, local_rank)
+            except Exception as e:  # noqa: BLE001
+                out["setup"]["ply_stream"] = {"error": repr(e)}
             try:
                 out["extra_configs"] = extra_config_times(G, local_rank)
             except Exception as e:  # noqa: BLE001  (a side table must never cost the headline line)
