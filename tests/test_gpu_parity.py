@@ -718,3 +718,32 @@ def test_partial_bins_and_quadrants_at_odd_viewports(G, O):
                 assert v.last_timings().overflow == 0
                 ref, _, _ = O.render_frame(f, [oms[i] for i in sel])
                 assert_image_close(img, ref)
+
+
+def test_long_translucent_lists_exercise_the_producer_ring(G, O):
+    """120 000 nearly transparent splats over a 2 x 2 block of 32-pixel bins (plus a thin veil over the whole frame): the
+    two central bins hold ~55 000 entries each — ~27x the compositor's id ring — and no pixel ever saturates (the oracle's
+    alpha stays below 215), so every quadrant CTA walks its whole list: the producer warp runs in steady state (ring
+    wrap-around, dozens of rounds) instead of stopping after the cooperative prologue.  Image vs oracle."""
+    W, H = 256, 160
+    rng = np.random.default_rng(7)
+    n_pile, n_veil = 120_000, 3_000
+    pile = np.stack([rng.uniform(-0.65, 0.65, n_pile), rng.uniform(-0.45, 0.45, n_pile), rng.uniform(-1.0, 1.0, n_pile)], 1)
+    veil = np.stack([rng.uniform(-1.6, 1.6, n_veil), rng.uniform(-1.0, 1.0, n_veil), rng.uniform(-1.0, 1.0, n_veil)], 1)
+    g = np.concatenate([make_gaussians(G.GAUSSIAN, pile, scale=0.01, color=(250, 120, 40, 2)),
+                        make_gaussians(G.GAUSSIAN, veil, scale=0.03, color=(30, 200, 240, 40))])
+    g["color"][:, :3] = rng.integers(0, 256, (len(g), 3), dtype=np.uint8)       # (so that a misordered blend shows)
+    cam = G.OrbitCamera(pos=(0, 0, 3.0))
+    with G.Viewer(W, H, G.SH_NONE, G.COV3D_SINGLE) as v:
+        m = v.add_model("pile", len(g))
+        m.update_range(0, g)
+        v.update_camera(cam)
+        v.enable_timings(True, True)
+        img = v.render_frame_host([m]).copy()
+        t = v.last_timings()
+        assert t.overflow == 0 and t.visible == len(g)
+        assert t.staged_entries > n_pile                          # every list was walked to its end (each splat is in >= 1 tile)
+    f = O.make_frame(cam.view(), cam.projection(np.float32(W) / np.float32(H)), W, H)
+    ref, _, _ = O.render_frame(f, [O.ModelRef(3, 0, G.pack_gaussians(3, 0, g), len(g))])
+    assert int(ref[..., 3].max()) < 230                           # (nothing saturates: no early exit anywhere)
+    assert_image_close(img, ref)
