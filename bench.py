@@ -214,7 +214,7 @@ def ply_stream_rate(G, local_rank, n=1_000_000, chunk=65536):
             dt = time.perf_counter() - t0
     return {"gaussians": n, "ply_bytes": size, "chunk": chunk, "seconds": dt, "ply_gb_per_s": size / dt / 1e9,
             "mgaussians_per_s": n / dt / 1e6, "read_s": parse_s, "gaussian_from_ply_s": conv_s, "update_range_s": up_s,
-            "note": "file -> b200gs_ply_read -> b200gs_gaussian_from_ply -> b200gs_model_update_range (pack + pinned ring + H2D), one host thread"}
+            "note": "file -> b200gs_ply_read -> b200gs_gaussian_from_ply -> b200gs_model_update_range (pack + pinned ring + H2D); the converters and the packer split large ranges over the host threads (host.cpp parallel_for)"}
 
 
 def extra_config_times(G, local_rank):
