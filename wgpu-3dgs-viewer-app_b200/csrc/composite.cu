@@ -358,6 +358,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_composite(const uint32_t* __res
                         T -= w;
                     }
                 }
+                __syncwarp();   // every lane is done reading the hit list before the next group overwrites it
                 if (__all_sync(0xffffffffu, T < GS_T_EPS)) break;
             }
         }
