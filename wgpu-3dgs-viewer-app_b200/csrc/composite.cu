@@ -5,17 +5,19 @@
 // to front in hardware; here one CTA owns a 16x16 pixel tile, stages the tile's depth-sorted
 // splats in shared memory 256 at a time and blends them FRONT TO BACK
 //     C += c·α·T,  T -= α·T,   α = min(0.99, o·exp(-½ dᵀQd)),
-// dropping α < 1/255 and power > 0, and stops a pixel when T < 1/1024 (whole warp / whole CTA
-// exit as soon as all their pixels stopped).  Each warp owns an 8x4 pixel sub-tile and first
+// dropping α < 1/255 and power > 0; a pixel has stopped when T < 1/1024, and a warp / the CTA
+// leave as soon as all their pixels have stopped.  Each warp owns an 8x4 pixel sub-tile and first
 // culls the staged splats against it 32 at a time with a ballot (exact ellipse-vs-rectangle
 // footprint test, one splat per lane), so only splats that can reach alpha >= 1/255 inside the
-// sub-tile are evaluated.  FP32-pipe + MUFU bound, not HBM bound.
+// sub-tile are evaluated; the hitting lanes leave the splats' shared-memory addresses in a per-warp
+// hit list that the blend loop walks two splats per trip.  Issue-slot and shared-memory-pipe bound,
+// not HBM bound.
 //
 // Lists are per 32x32-pixel BIN (bin.cu): the four tiles of a bin (its quadrants) are four CTAs that walk the same
 // list, and every entry's key says which quadrants its splat can reach.  A ninth PRODUCER warp per CTA streams the
 // bin's (key, splat id) entries, keeps the ids that carry this quadrant's bit and feeds them, in order, through a
 // shared-memory ring to the eight compositing warps — which therefore gather, convert and cull exactly the splats a
-// 16-pixel binning would have given them, while the binning stage and the bin sort handle ~40 % fewer entries.
+// 16-pixel binning would have given them, while the binning stage and the bin sort handle 26-40 % fewer entries.
 #include "common.cuh"
 
 namespace {
