@@ -9,8 +9,8 @@
 // stable sort is deterministic): depth key, Gaussian index, a 32-byte projected splat and a 4-byte
 // bin word (the splat's candidate tile rectangle, consumed by the binning kernel, common.cuh).
 //
-// Data movement: persistent CTAs of 8 compute warps + 1 control warp; each 256-Gaussian chunk
-// (256*R contiguous bytes, 16-byte aligned because 256*R is a multiple of 1024) is pulled into
+// Data movement: persistent CTAs of 7 compute warps + 1 control warp (4 per SM for records up to 76 bytes); each
+// 224-Gaussian chunk (224*R contiguous bytes, 16-byte aligned because R is a multiple of 4) is pulled into
 // shared memory with one 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) on an mbarrier, NSTAGE
 // chunks in flight per CTA; each compute thread then reads its own record from shared memory
 // (word stride R/4).  The control warp owns tickets, TMA issue and the decoupled look-back, so
