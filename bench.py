@@ -164,14 +164,15 @@ def plan_a_probe():
 
 
 # ------------------------------------------------------------------------------ our arm
-def stage_times(G, v, m, mats, W, H, frames=14):
+def stage_times(G, v, m, mats, W, H, frames=14, spread=None):
     """median per-stage device times (CUDA events on the viewer's stream) of `frames` consecutive views, timed with the
     production kernels; the work counters (evaluations) come from a second pass over the same views with the counting
-    instantiation of the compositor, whose atomics would otherwise sit inside the timed numbers"""
+    instantiation of the compositor, whose atomics would otherwise sit inside the timed numbers.  `spread`, if a dict, receives
+    the p10 / p90 of the frame time."""
     rows = []
     for counting in (False, True):
         v.enable_timings(True, counting)
-        for s in range(frames):
+        for s in range(frames if not counting else min(frames, 14)):
             view, proj = mats[s % len(mats)]
             v.update_camera_matrices(view, proj, (W, H))
             v.render_frame([m])
@@ -181,7 +182,13 @@ def stage_times(G, v, m, mats, W, H, frames=14):
             else:
                 rows[s][7] = tm.evals
     v.enable_timings(False, False)
-    return np.median(np.array(rows[2:], dtype=np.float64), axis=0)
+    arr = np.array(rows[2:], dtype=np.float64)
+    if spread is not None:
+        spread["frame_ms_p10"], spread["frame_ms_p90"] = float(np.percentile(arr[:, 4], 10)), float(np.percentile(arr[:, 4], 90))
+        spread["frames_timed"] = int(len(arr))
+    med = np.median(arr, axis=0)
+    med[7] = np.median(arr[:12, 7])      # (evaluation counts exist for the first frames only)
+    return med
 
 
 def ply_stream_rate(G, local_rank, n=1_000_000, chunk=65536):
@@ -237,6 +244,20 @@ def extra_config_times(G, local_rank):
         out[name] = {"frame_ms": tot, "frames_per_s_one_stream": 1e3 / tot, "preprocess_ms": pre, "sort_ms": srt, "bin_ms": bn,
                      "composite_ms": comp, "visible": int(vis), "tile_entries": int(ent)}
         del packed
+    # secondary layouts of SURVEY.md §8(d): the same 6M scene packed Half + Half (120 B) and Single + Single (220 B), 1080p
+    g6 = G.gaussian_from_ply(G.synth_scene(SEED, 6_000_000))
+    for name, sh, cov in (("6M@1920x1080 Half+Half (120 B/record)", G.SH_HALF, G.COV3D_HALF),
+                          ("6M@1920x1080 Single+Single (220 B/record)", G.SH_SINGLE, G.COV3D_SINGLE)):
+        W, H, n = 1920, 1080, 6_000_000
+        rb2 = G.record_bytes(sh, cov)
+        with G.Viewer(W, H, sh, cov, device=local_rank) as v:
+            m = v.add_model("scene", n)
+            m.upload_packed(0, G.pack_gaussians(sh, cov, g6))
+            pre, srt, bn, comp, tot, vis, ent, ev = stage_times(G, v, m, mats_for(W, H), W, H)
+        out[name] = {"frame_ms": tot, "frames_per_s_one_stream": 1e3 / tot, "preprocess_ms": pre, "sort_ms": srt, "bin_ms": bn,
+                     "composite_ms": comp, "visible": int(vis), "record_bytes": rb2,
+                     "preprocess_hbm_frac": ((n * rb2 + 8 * vis) / (pre * 1e-3) / 1e9) / peaks()[0]}
+    del g6
     # config 4
     W, H, n = 1920, 1080, 2_000_000
     xf = [((-2, 0, 0), (0, 30, 0), (1, 1, 1)), ((0, 0, 0), (10, 0, 45), (1.2, 0.8, 1)), ((2, 0.5, 0), (0, -60, 0), (0.7, 0.7, 0.7))]
@@ -532,7 +553,8 @@ def run_ours(a, rank, world, local_rank):
     e2e_value = frames / float(t.item())
 
     # ---- per-stage device times (CUDA events on the viewer's stream), separate short loop on one stream
-    pre_ms, sort_ms, bin_ms, comp_ms, tot_ms, vis, entries, evals = stage_times(G, v, m, mats, W, H)
+    spread = {}
+    pre_ms, sort_ms, bin_ms, comp_ms, tot_ms, vis, entries, evals = stage_times(G, v, m, mats, W, H, frames=122, spread=spread)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -570,7 +592,8 @@ def run_ours(a, rank, world, local_rank):
             "roofline": {"bound": "hbm", "kernel": "k_preprocess", "achieved": ach_pre, "peak": peak, "unit": "GB/s",
                          "frac": ach_pre / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": b_pre,
-                         "frac_with_intermediates": (b_pre_all / (pre_ms * 1e-3) / 1e9) / peak},
+                         "frac_with_intermediates": (b_pre_all / (pre_ms * 1e-3) / 1e9) / peak,
+                         "frac_of_nominal_8TBs": ach_pre / 8000.0},
             "stages": {
                 "preprocess_ms": pre_ms, "sort_ms": sort_ms, "bin_ms": bin_ms, "composite_ms": comp_ms, "frame_ms": tot_ms,
                 "frames_per_s_one_stream": 1e3 / tot_ms,   # one viewer, frames back to back on its stream
@@ -579,6 +602,10 @@ def run_ours(a, rank, world, local_rank):
                 "sort_hbm_frac": (b_sort / (sort_ms * 1e-3) / 1e9) / peak,
                 "pre_plus_sort_hbm_frac": ((b_pre + b_sort) / ((pre_ms + sort_ms) * 1e-3) / 1e9) / peak,
                 "composite_gevals_per_s": evals / (comp_ms * 1e-3) / 1e9,
+                # evaluations/s against min(FP32 ceiling 148 SMs x 128 lanes x f / ~10 instr, MUFU ceiling 148 x 16 x f)
+                "composite_frac_of_fp32_ceiling": (evals / (comp_ms * 1e-3) / 1e9) / min(148 * 128 * 1.965 / 10.0, 148 * 16 * 1.965),
+                "frame_ms_p10": spread.get("frame_ms_p10"), "frame_ms_p90": spread.get("frame_ms_p90"),
+                "frames_timed": spread.get("frames_timed"),
                 "sort_cluster": v.info("sort.cluster"), "sort_resident_clusters": v.info("sort.resident_clusters"),
             },
             "clocks": clocks,
