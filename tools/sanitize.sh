@@ -5,6 +5,7 @@
 TAG=${1:-r2}
 mkdir -p gpurun_out
 run() { echo "\$ compute-sanitizer --tool $1 --error-exitcode 9 python tools/sanitize_frame.py   [$2 build]"
+        if [ "$1" = racecheck ]; then export B200GS_SANITIZE_WIDE=0; else export B200GS_SANITIZE_WIDE=1; fi   # (see sanitize_frame.py)
         timeout 600 compute-sanitizer --tool $1 --error-exitcode 9 --print-limit 3 python tools/sanitize_frame.py 2>&1 | grep -v "Host Frame\|Saved host" | tail -5
         echo "exit code ${PIPESTATUS[0]}"; echo; }
 {
