@@ -65,7 +65,7 @@ __device__ __forceinline__ Rect huge_rect(const b200gs_splat* __restrict__ splat
 // the whole warp walks the bins of ONE big splat, 32 per round
 __device__ __forceinline__ void big_rounds(const Rect r, uint32_t bins_x, int lane, uint32_t o, uint32_t val,
                                            uint32_t capacity, uint32_t* tile_keys, uint32_t* tile_vals,
-                                           uint32_t* __restrict__ tile_count) {
+                                           uint32_t* __restrict__ tile_count, uint32_t count_off) {
     const uint32_t bx0 = r.tx0 >> 1, by0 = r.ty0 >> 1, nbx = (r.tx1 >> 1) - bx0 + 1u;
     const uint32_t total = nbx * ((r.ty1 >> 1) - by0 + 1u);
     const float inv_nx = __frcp_rn((float)nbx);
@@ -81,7 +81,65 @@ __device__ __forceinline__ void big_rounds(const Rect r, uint32_t bins_x, int la
             const uint32_t bin = by * bins_x + bx;
             tile_keys[g] = bin | (gs_quadrant_mask(bx, by, r.tx0, r.tx1, r.ty0, r.ty1) << GS_QMASK_SHIFT);
             tile_vals[g] = val;
-            atomicAdd(&tile_count[bin], 1u);
+            atomicAdd(&tile_count[count_off + bin], 1u);
+        }
+    }
+}
+
+// The entries of the kIpt ranks of one thread (bin word, slot, offset inside the chunk).  A small splat (<= GS_BIN_INLINE
+// bins: a run along a row, a run down a column, or a 2 x 2 block) is expanded by its thread, walking (bx, by, bin) from
+// entry to entry with per-splat steps, so that an entry costs three additions, the quadrant mask, two stores and the
+// counter bump; a bigger one by the whole warp.  Entries at offsets >= cap are dropped together with their counts.
+__device__ __forceinline__ void expand_ranks(const uint32_t (&p_w)[kIpt], const uint32_t (&p_slot)[kIpt], const uint32_t (&p_loc)[kIpt],
+                                             uint32_t obase, uint32_t cap, uint32_t splat_base, uint32_t* dst_k, uint32_t* dst_v,
+                                             uint32_t* __restrict__ tile_count, uint32_t count_off,
+                                             const b200gs_splat* __restrict__ splats, float W, float H, bool is_flat,
+                                             uint32_t bins_x, int lane) {
+#pragma unroll
+    for (int k = 0; k < kIpt; k++) {
+        const uint32_t wk = p_w[k];
+        const uint32_t o = obase + p_loc[k];
+        const uint32_t val = splat_base + p_slot[k];
+        Rect r = word_rect(wk);
+        const bool huge = (wk & GS_BIN_HUGE) != 0u;
+        uint32_t n = 0;
+        if (wk && !huge) {
+            const uint32_t bx0 = r.tx0 >> 1, by0 = r.ty0 >> 1, nbx = (r.tx1 >> 1) - bx0 + 1u;
+            n = nbx * ((r.ty1 >> 1) - by0 + 1u);
+            if (n <= GS_BIN_INLINE) {
+                const uint32_t ne = o < cap ? min(n, cap - o) : 0u;   // entries that fit
+                // step from entry e - 1 to entry e: along the row; down for a single column; back and down at the row end of
+                // a 2 x 2 block (n <= 4, so two columns and a third entry mean 2 x 2)
+                const bool column = nbx == 1u, two = nbx == 2u;
+                const uint32_t sx1 = column ? 0u : 1u, sy1 = column ? 1u : 0u;
+                const uint32_t sx2 = column ? 0u : (two ? 0xffffffffu : 1u), sy2 = (column || two) ? 1u : 0u;
+                const uint32_t sb1 = column ? bins_x : 1u, sb2 = column ? bins_x : (two ? bins_x - 1u : 1u);
+                uint32_t bx = bx0, by = by0, bin = by0 * bins_x + bx0;
+#pragma unroll
+                for (uint32_t e = 0; e < GS_BIN_INLINE; e++) {
+                    if (e == 1u || e == 3u) { bx += sx1; by += sy1; bin += sb1; }
+                    if (e == 2u) { bx += sx2; by += sy2; bin += sb2; }
+                    if (e < ne) {
+                        dst_k[o + e] = bin | (gs_quadrant_mask(bx, by, r.tx0, r.tx1, r.ty0, r.ty1) << GS_QMASK_SHIFT);
+                        dst_v[o + e] = val;
+                        atomicAdd(&tile_count[count_off + bin], 1u);
+                    }
+                }
+            }
+        }
+        uint32_t big = __ballot_sync(0xffffffffu, huge || n > GS_BIN_INLINE);
+        if (big) {
+            if (huge) r = huge_rect(splats, p_slot[k], W, H, is_flat);
+            while (big) {
+                const int src = __ffs((int)big) - 1;
+                big &= big - 1;
+                Rect rr;
+                rr.tx0 = __shfl_sync(0xffffffffu, r.tx0, src); rr.ty0 = __shfl_sync(0xffffffffu, r.ty0, src);
+                rr.tx1 = __shfl_sync(0xffffffffu, r.tx1, src); rr.ty1 = __shfl_sync(0xffffffffu, r.ty1, src);
+                if (rr.tx0 <= rr.tx1)
+                    big_rounds(rr, bins_x, lane, __shfl_sync(0xffffffffu, o, src), __shfl_sync(0xffffffffu, val, src), cap,
+                               dst_k, dst_v, tile_count, count_off);
+            }
         }
     }
 }
@@ -104,10 +162,14 @@ __global__ void __launch_bounds__(kThreads) k_bin(const uint32_t* __restrict__ s
     const uint32_t* __restrict__ sorted_slot = (sorted_in_b && *sorted_in_b) ? sorted_b : sorted_a;
     // per-bin entry counters are replicated (copy = SM id mod copies): same-address atomics from many SMs
     // serialise in L2 and the centre bins of a frame are hot
+    uint32_t count_off;
     {
         uint32_t smid;
         asm("mov.u32 %0, %%smid;" : "=r"(smid));
-        tile_count += (size_t)(smid & (count_copies - 1u)) * count_stride;
+        // (a 32-bit word offset, opaque to the compiler: it would otherwise re-derive the replica's 64-bit address from the
+        // parameters at every counter bump — seven instructions per entry — rather than hold it in registers)
+        count_off = (smid & (count_copies - 1u)) * count_stride;
+        asm volatile("" : "+r"(count_off));
     }
     uint32_t v = *d_v;
     if (v > v_max) v = v_max;
@@ -200,51 +262,12 @@ __global__ void __launch_bounds__(kThreads) k_bin(const uint32_t* __restrict__ s
             // are whole lines; a chunk that does not fit (the nearest, hugest splats) writes directly.  Either
             // way an entry past the capacity is dropped together with its count.
             const bool staged = p_total <= kStage;
-            uint32_t* const dst_k = staged ? s_keys : tile_keys;
-            uint32_t* const dst_v = staged ? s_vals : tile_vals;
             const uint32_t room = capacity > gbase ? capacity - gbase : 0u;
             const uint32_t cap = staged ? min(room, kStage) : capacity;
-            const uint32_t obase = staged ? 0u : gbase;
-#pragma unroll
-            for (int k = 0; k < kIpt; k++) {
-                const uint32_t wk = p_w[k];
-                const uint32_t o = obase + p_loc[k];
-                const uint32_t val = splat_base + p_slot[k];
-                Rect r = word_rect(wk);
-                const bool huge = (wk & GS_BIN_HUGE) != 0u;
-                uint32_t n = 0;
-                if (wk && !huge) {
-                    const uint32_t bx0 = r.tx0 >> 1, by0 = r.ty0 >> 1, nbx = (r.tx1 >> 1) - bx0 + 1u;
-                    n = nbx * ((r.ty1 >> 1) - by0 + 1u);
-                    if (n <= GS_BIN_INLINE) {
-                        // the <= 4 bins of a small splat: a 1xN / Nx1 run or a 2x2 block
-#pragma unroll
-                        for (uint32_t e = 0; e < GS_BIN_INLINE; e++) {
-                            if (e < n && o + e < cap) {
-                                const uint32_t y = (e >= nbx ? 1u : 0u) + (e >= 2u * nbx ? 1u : 0u) + (e >= 3u * nbx ? 1u : 0u);
-                                const uint32_t bx = bx0 + (e - y * nbx), by = by0 + y, bin = by * bins_x + bx;
-                                dst_k[o + e] = bin | (gs_quadrant_mask(bx, by, r.tx0, r.tx1, r.ty0, r.ty1) << GS_QMASK_SHIFT);
-                                dst_v[o + e] = val;
-                                atomicAdd(&tile_count[bin], 1u);
-                            }
-                        }
-                    }
-                }
-                uint32_t big = __ballot_sync(0xffffffffu, huge || n > GS_BIN_INLINE);
-                if (big) {
-                    if (huge) r = huge_rect(splats, p_slot[k], W, H, is_flat);
-                    while (big) {
-                        const int src = __ffs((int)big) - 1;
-                        big &= big - 1;
-                        Rect rr;
-                        rr.tx0 = __shfl_sync(0xffffffffu, r.tx0, src); rr.ty0 = __shfl_sync(0xffffffffu, r.ty0, src);
-                        rr.tx1 = __shfl_sync(0xffffffffu, r.tx1, src); rr.ty1 = __shfl_sync(0xffffffffu, r.ty1, src);
-                        if (rr.tx0 <= rr.tx1)
-                            big_rounds(rr, bins_x, lane, __shfl_sync(0xffffffffu, o, src), __shfl_sync(0xffffffffu, val, src), cap,
-                                       dst_k, dst_v, tile_count);
-                    }
-                }
-            }
+            // (two instantiations, so that the staged one stores with shared-memory instructions at immediate offsets
+            // instead of through a generic pointer chosen at run time)
+            if (staged) expand_ranks(p_w, p_slot, p_loc, 0u, cap, splat_base, s_keys, s_vals, tile_count, count_off, splats, W, H, is_flat, bins_x, lane);
+            else expand_ranks(p_w, p_slot, p_loc, gbase, cap, splat_base, tile_keys, tile_vals, tile_count, count_off, splats, W, H, is_flat, bins_x, lane);
             if (staged) {
                 __syncthreads();
                 const uint32_t nw = min(p_total, cap);
