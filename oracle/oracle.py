@@ -339,9 +339,12 @@ def orbit_camera(radius=4.5, elev_deg=20.0, azim_deg=35.0, width=1920, height=10
 
 def view_batch(width, height, n_az=32, n_el=8, radii=(3.0, 4.5, 6.0, 8.0), el_range=(-10.0, 60.0)):
     """(view, proj) of the 1024-view batch of SURVEY.md §8d in its fixed order (radius fastest, then elevation, then
-    azimuth) — the oracle's own copy, so that the reference arm of bench.py never imports the product."""
+    azimuth, the azimuths in bit-reversed order) — the oracle's own copy, so that the reference arm of bench.py never
+    imports the product."""
+    bits = max(1, (n_az - 1).bit_length())
+    az = [a for a in (int(format(i, "0%db" % bits)[::-1], 2) for i in range(1 << bits)) if a < n_az]
     out = []
-    for a in range(n_az):
+    for a in az:
         for e in range(n_el):
             el = el_range[0] + (el_range[1] - el_range[0]) * e / max(n_el - 1, 1)
             for r in radii:

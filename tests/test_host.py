@@ -51,7 +51,18 @@ def test_camera_and_euler_match_oracle(G, O):
     cam = G.OrbitCamera.orbit()
     v, p = O.orbit_camera()
     assert np.array_equal(cam.view(), v) and np.array_equal(cam.projection(np.float32(1920) / np.float32(1080)), p)
-    assert len(G.view_batch()) == 1024
+    # the 1024-view batch: same cameras in the same order from the product and from the oracle's own copy (the reference
+    # arm of bench.py uses the latter), azimuths in bit-reversed order so that contiguous per-rank blocks are balanced
+    cams, ocams = G.view_batch(), O.view_batch(1920, 1080)
+    assert len(cams) == 1024 == len(ocams)
+    asp = np.float32(1920) / np.float32(1080)
+    for i in range(0, 1024, 37):
+        assert np.array_equal(cams[i].view(), ocams[i][0]) and np.array_equal(cams[i].projection(asp), ocams[i][1])
+    assert G.azimuth_order(32)[:4] == [0, 16, 8, 24] and sorted(G.azimuth_order(32)) == list(range(32))
+    assert G.azimuth_order(3) == [0, 2, 1] and G.azimuth_order(1) == [0]
+    for n_az, kw in ((3, dict(n_el=2, radii=(4.5,))), (5, dict(n_el=1, radii=(3.0, 6.0)))):
+        a, b = G.view_batch(n_az=n_az, **kw), O.view_batch(64, 64, n_az=n_az, **kw)
+        assert len(a) == len(b) and all(np.array_equal(x.view(), y[0]) for x, y in zip(a, b))
 
 
 def test_unpack_recovers_what_the_kernels_decode(G):
