@@ -156,12 +156,22 @@ __global__ void __launch_bounds__(kThreads, 3) k_sort_pass(uint32_t* __restrict_
             const uint32_t tile_base = tile * kTile;
             valid = min((uint32_t)kTile, n - tile_base);
             // ---- load keys (warp-striped: slot = warp*32*KPT + k*32 + lane keeps index order inside a warp)
+            // (a full tile — every tile but the last — takes straight-line code: with a bounds test per element the compiler
+            // builds one branch region per element, and in the write-out below the dependent shared-memory loads of the
+            // twelve regions then run one after the other instead of overlapped)
             uint32_t key[kKpt];
             const uint32_t wbase_idx = warp * (32 * kKpt);
+            const bool full = valid == (uint32_t)kTile;
+            const uint32_t* __restrict__ kp = keys_in + tile_base + wbase_idx + lane;
+            if (full) {
 #pragma unroll
-            for (int k = 0; k < kKpt; k++) {
-                const uint32_t s = wbase_idx + k * 32 + lane;
-                key[k] = s < valid ? keys_in[tile_base + s] : 0xffffffffu;
+                for (int k = 0; k < kKpt; k++) key[k] = kp[k * 32];
+            } else {
+#pragma unroll
+                for (int k = 0; k < kKpt; k++) {
+                    const uint32_t s = wbase_idx + k * 32 + lane;
+                    key[k] = s < valid ? kp[k * 32] : 0xffffffffu;
+                }
             }
             // ---- early counts (per-warp histograms), so the aggregates can be published at once
 #pragma unroll
@@ -192,10 +202,21 @@ __global__ void __launch_bounds__(kThreads, 3) k_sort_pass(uint32_t* __restrict_
             __syncthreads();
             // ---- values (loaded late to keep registers low), then rank + scatter into the exchange buffer
             uint32_t val[kKpt];
+            if (synth_vals) {
 #pragma unroll
-            for (int k = 0; k < kKpt; k++) {
-                const uint32_t s = wbase_idx + k * 32 + lane;
-                val[k] = s < valid ? (synth_vals ? tile_base + s : vals_in[tile_base + s]) : 0u;
+                for (int k = 0; k < kKpt; k++) val[k] = tile_base + wbase_idx + k * 32 + lane;
+            } else {
+                const uint32_t* __restrict__ vp = vals_in + tile_base + wbase_idx + lane;
+                if (full) {
+#pragma unroll
+                    for (int k = 0; k < kKpt; k++) val[k] = vp[k * 32];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kKpt; k++) {
+                        const uint32_t s = wbase_idx + k * 32 + lane;
+                        val[k] = s < valid ? vp[k * 32] : 0u;
+                    }
+                }
             }
             // Two phases, so that the votes of all keys of a thread overlap (they touch no memory and do not depend on
             // each other) and only the short counter update runs as a dependent chain through shared memory.
@@ -262,14 +283,24 @@ __global__ void __launch_bounds__(kThreads, 3) k_sort_pass(uint32_t* __restrict_
             sm.global_off[tid] = (int32_t)(gbase + excl) - (int32_t)sm.tile_start[pbuf][tid];
             __syncthreads();
             // ---- write out the previous tile: consecutive positions of one digit are consecutive addresses
+            if (p_valid == (uint32_t)kTile) {
+                uint32_t kk[kKpt], vv[kKpt], g[kKpt];
 #pragma unroll
-            for (int k = 0; k < kKpt; k++) {
-                const uint32_t p = k * kThreads + tid;
-                if (p < p_valid) {
-                    const uint32_t kk = sm.exch_k[pbuf][p];
-                    const uint32_t g = (uint32_t)(sm.global_off[(kk >> shift) & 0xffu] + (int32_t)p);
-                    keys_out[g] = kk;
-                    vals_out[g] = sm.exch_v[pbuf][p];
+                for (int k = 0; k < kKpt; k++) { kk[k] = sm.exch_k[pbuf][k * kThreads + tid]; vv[k] = sm.exch_v[pbuf][k * kThreads + tid]; }
+#pragma unroll
+                for (int k = 0; k < kKpt; k++) g[k] = (uint32_t)(sm.global_off[(kk[k] >> shift) & 0xffu] + (int32_t)(k * kThreads + tid));
+#pragma unroll
+                for (int k = 0; k < kKpt; k++) { keys_out[g[k]] = kk[k]; vals_out[g[k]] = vv[k]; }
+            } else {
+#pragma unroll
+                for (int k = 0; k < kKpt; k++) {
+                    const uint32_t p = k * kThreads + tid;
+                    if (p < p_valid) {
+                        const uint32_t kk = sm.exch_k[pbuf][p];
+                        const uint32_t g = (uint32_t)(sm.global_off[(kk >> shift) & 0xffu] + (int32_t)p);
+                        keys_out[g] = kk;
+                        vals_out[g] = sm.exch_v[pbuf][p];
+                    }
                 }
             }
         }
