@@ -10,22 +10,16 @@ hdr = rows[hi]; col = {h: i for i, h in enumerate(hdr)}
 data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
 lines = open(sassp).read().split("\n")
 start = next(i for i, l in enumerate(lines) if l.startswith(".text.") and fn in l)
-ins = []   # (line number in the kernel's own file, opcode text)
+ins = []   # (file, line) of every instruction; helpers inlined from other files keep their own file:line
 cur = None
 base = srcfile.split("/")[-1]
+srcdir = "/".join(srcfile.split("/")[:-1])
 for l in lines[start + 1:]:
     if l.startswith(".text.") or l.startswith(".section"):
         break
-    m = re.search(r'//## File "([^"]+)", line (\d+)(.*)', l)
+    m = re.search(r'//## File "([^"]+)", line (\d+)', l)
     if m:
-        f, n, rest = m.group(1), int(m.group(2)), m.group(3)
-        if not f.endswith(base):
-            # inlined library code: attribute to the innermost frame of our file
-            mm = re.findall(r'inlined at "([^"]+)", line (\d+)', rest)
-            own = [int(b) for a, b in mm if a.endswith(base)]
-            cur = own[0] if own else cur
-        else:
-            cur = n
+        cur = (m.group(1).split("/")[-1], int(m.group(2)))
         continue
     if re.match(r'\s+/\*[0-9a-f]{4,}\*/\s+\S', l):
         ins.append(cur)
@@ -37,7 +31,22 @@ by_i = collections.Counter(); by_s = collections.Counter()
 for k, r in enumerate(data):
     by_i[ins[k]] += f(r, "Instructions Executed"); by_s[ins[k]] += f(r, "# Samples")
 ti = sum(by_i.values()); ts = sum(by_s.values())
-src = open(srcfile).read().split("\n")
+import os
+_src = {}
+def text(key):
+    if not key:
+        return "?"
+    f, ln = key
+    if f not in _src:
+        path = os.path.join(srcdir, f)
+        _src[f] = open(path).read().split("\n") if os.path.exists(path) else None
+    body = _src[f][ln - 1].strip()[:96] if _src[f] and ln <= len(_src[f]) else "(library header)"
+    return ("" if f == base else f + ": ") + body
 print("SASS %d (disasm %d), warp-instructions %.4g, samples %d" % (len(data), len(ins), ti, ts))
-for ln, c in sorted(by_i.items(), key=lambda x: -x[1])[:top]:
-    print("%5s %5.1f%% instr | %5.1f%% samples | %s" % (ln, 100 * c / ti, 100 * by_s[ln] / max(ts, 1), (src[ln - 1].strip()[:100] if ln else "?")))
+for key, c in sorted(by_i.items(), key=lambda x: -x[1])[:top]:
+    print("%5s %5.1f%% instr | %5.1f%% samples | %s" % (key[1] if key else "?", 100 * c / ti, 100 * by_s[key] / max(ts, 1), text(key)))
+# per file, and for this file per function-sized block of 25 lines, so that spread-out costs add up
+byfile = collections.Counter()
+for key, c in by_i.items():
+    byfile[key[0] if key else "?"] += c
+print("by file: " + ", ".join("%s %.1f%%" % (f, 100 * c / ti) for f, c in byfile.most_common(6)))
