@@ -6,7 +6,7 @@
 // reference sizes an indirect dispatch from it), here `*d_n`.
 //
 // Design: one histogram kernel (all digit histograms in one read of the keys), then one
-// kernel per 8-bit digit.  A digit pass is a single sweep: each 3072-key tile ranks its keys
+// kernel per 8-bit digit.  A digit pass is a single sweep: each 6144-key tile ranks its keys
 // with warp-level same-digit peer masks (ballots or MATCH.ANY), publishes its per-digit counts and resolves
 // its global offsets by decoupled look-back over epoch-tagged status words (chained scan, no
 // separate scan kernel, no second read of the keys), then scatters keys and values through
@@ -22,9 +22,10 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kKpt = 12;                       // keys per thread
-constexpr int kTile = kThreads * kKpt;         // 3072 keys per tile
+constexpr int kKpt = 24;                       // keys per thread
+constexpr int kTile = kThreads * kKpt;         // 6144 keys per tile
 constexpr int kRadix = 256;
+static_assert(kTile <= 65535, "tile_start holds 16-bit positions");
 
 // ------------------------------------------------------------------ histogram kernel
 // hist[pass][digit] += count, for `passes` digits.  Warp-aggregated (match_any) shared-memory
@@ -62,15 +63,28 @@ __global__ void __launch_bounds__(kThreads) k_sort_hist(const uint32_t* __restri
 }
 
 // ---------------------------------------------------------------------- digit pass
-// Software-pipelined by one tile with double-buffered shared memory: tile t+1 is loaded, counted
-// (its per-digit aggregates PUBLISHED), ranked and scattered into its exchange buffer BEFORE tile
-// t's look-back is resolved and tile t is written out, so a look-back only ever waits for
-// aggregates that were published a whole tile-time earlier.
+// One tile at a time per CTA (kNBuf = 1): load, count, publish, rank, scatter into the exchange buffer, resolve the
+// look-back, write out.  Until late in round 2 the pass was software-pipelined by one tile with double-buffered exchange
+// buffers (kNBuf = 2: tile t + 1 ranked before tile t is resolved), on the assumption that the look-back is what a tile
+// waits for.  It is not — with the look-back switched off the pipelined pass took the same time — and the second
+// buffer's shared memory is what capped the tile at 12 keys per thread and left nothing on the SM for another stream's
+// kernels.  Measured on the bench frame (1 viewer / 2 viewers, frames/s): pipelined 12 keys per thread 1221 / 1322,
+// 13: 1234 / 1339, 16: 1256 / 1295; one tile at a time 12: 1228 / 1367, 16: 1281 / 1400, 24 at 3 CTAs per SM (172 KB of
+// shared memory): **1290 / 1440**, 24 at 2 CTAs: 1258 / 1413, 32 at 2: 1254 / 1360 — bigger tiles mean fewer barrier
+// crossings per key, and what is left of the SM's shared memory decides how much of another viewer's frame overlaps.
+#ifndef GS_SORT_NBUF
+#define GS_SORT_NBUF 1
+#endif
+#ifndef GS_SORT_MAXCTAS
+#define GS_SORT_MAXCTAS 3
+#endif
+constexpr int kMaxCtasPerSm = GS_SORT_MAXCTAS;   // resident CTAs per SM the launcher asks for
+constexpr int kNBuf = GS_SORT_NBUF;               // exchange buffers: 1 = one tile at a time, 2 = pipelined by one tile
 struct PassSmem {
     uint32_t warp_hist[kWarps][kRadix];  // per-warp digit counts -> running per-warp offsets
-    uint32_t exch_k[2][kTile];           // keys / values in tile-sorted order, double-buffered
-    uint32_t exch_v[2][kTile];
-    uint32_t tile_start[2][kRadix];      // first position of each digit inside the sorted tile
+    uint32_t exch_k[kNBuf][kTile];       // keys / values in tile-sorted order
+    uint32_t exch_v[kNBuf][kTile];
+    uint16_t tile_start[kNBuf][kRadix];  // first position of each digit inside the sorted tile (< kTile <= 65535)
     int32_t global_off[kRadix];          // global index = global_off[digit] + position in sorted tile
     uint32_t scan_tmp[kWarps];
     uint32_t tile_id;
@@ -143,7 +157,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_sort_pass(uint32_t* __restrict_
     bool have_prev = false;
     uint32_t p_tile = 0, p_count = 0, p_valid = 0;
     for (uint32_t iter = 0;; iter++) {
-        const uint32_t buf = iter & 1u;
+        const uint32_t buf = kNBuf == 2 ? (iter & 1u) : 0u;
         __syncthreads();  // previous iteration's ranking / write-out are done
         if (tid == 0) sm.tile_id = atomicAdd(ticket, 1u);
 #pragma unroll
@@ -250,9 +264,10 @@ __global__ void __launch_bounds__(kThreads, 3) k_sort_pass(uint32_t* __restrict_
                 sm.exch_v[buf][pos] = val[k];
             }
         }
+        if (kNBuf == 1) { have_prev = valid_tile; p_tile = tile; p_count = count; p_valid = valid; }   // (no pipeline: this tile, now)
         if (have_prev) {
             // ---- resolve the previous tile's look-back for digit `tid`, kLb status words per round trip
-            const uint32_t pbuf = buf ^ 1u;
+            const uint32_t pbuf = kNBuf == 2 ? (buf ^ 1u) : 0u;
             uint32_t excl = 0;
             if (p_tile > 0 && digit_used) {
                 constexpr int kLb = 4;
@@ -305,10 +320,12 @@ __global__ void __launch_bounds__(kThreads, 3) k_sort_pass(uint32_t* __restrict_
             }
         }
         if (!valid_tile) break;
-        have_prev = true;
-        p_tile = tile;
-        p_count = count;
-        p_valid = valid;
+        if (kNBuf == 2) {
+            have_prev = true;
+            p_tile = tile;
+            p_count = count;
+            p_valid = valid;
+        }
     }
 }
 
@@ -347,6 +364,7 @@ cudaError_t gs_launch_sort(const GsSortArgs& a, int num_sms, cudaStream_t st) {
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_dev[dev], k_sort_pass<0>, kThreads, sizeof(PassSmem));
             if (e != cudaSuccess) { bps_dev[dev] = 0; return e; }
             if (bps_dev[dev] < 1) bps_dev[dev] = 1;
+            if (bps_dev[dev] > kMaxCtasPerSm) bps_dev[dev] = kMaxCtasPerSm;
         }
         blocks_per_sm = bps_dev[dev];
     }
