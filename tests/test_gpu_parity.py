@@ -305,7 +305,8 @@ def test_selection_highlight_hidden_and_unedited(G, O):
 
 
 # ------------------------------------------------------------------ sort
-@pytest.mark.parametrize("n", [1, 2, 255, 4095, 4096, 4097, 100_003, 1 << 20, 5_000_000])
+# (6143 / 6144 / 6145 / 12289: one key short of, exactly, and one past one and two of the sort's 6144-key tiles)
+@pytest.mark.parametrize("n", [1, 2, 255, 4095, 4096, 4097, 6143, 6144, 6145, 12289, 100_003, 1 << 20, 5_000_000])
 def test_sort_pairs_matches_stable_sort(G, O, n):
     rng = np.random.default_rng(n)
     keys = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
