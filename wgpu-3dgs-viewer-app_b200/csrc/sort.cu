@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_sort_pass(uint32_t* __restrict_
             // ---- load keys (warp-striped: slot = warp*32*KPT + k*32 + lane keeps index order inside a warp)
             // (a full tile — every tile but the last — takes straight-line code: with a bounds test per element the compiler
             // builds one branch region per element, and in the write-out below the dependent shared-memory loads of the
-            // twelve regions then run one after the other instead of overlapped)
+            // regions then run one after the other instead of overlapped)
             uint32_t key[kKpt];
             const uint32_t wbase_idx = warp * (32 * kKpt);
             const bool full = valid == (uint32_t)kTile;
